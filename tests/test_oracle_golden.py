@@ -1,0 +1,124 @@
+"""Pin the CPU oracle (oracle/*.py) to outputs of the real reference.
+
+The goldens were produced by tests/golden/make_golden.py, which imports the reference's
+own Squeeze_ErNET / Squeeze_RedConv (model/squeeze_ernet.py, model/squeeze_ernet_redconv.py)
+and the torchvision/Pillow eval transform (dataloaders/aider.py:421-426).
+"""
+import numpy as np
+import pytest
+
+import fixtures
+from oracle import ernet_numpy as E
+from oracle import ingest_numpy as I
+
+WSETS = ("shipped", "w3", "w3neg")
+
+
+@pytest.mark.parametrize("arch", fixtures.ARCHS)
+def test_param_and_mac_counts(arch):
+    # model_summary/squeeze_ernet.txt:45,48 and squeeze_redconv.txt:48,51
+    want_params = {"squeeze-ernet": 169241, "squeeze-redconv": 109569}[arch]
+    assert E.count_params(arch) == want_params
+    macs = E.count_macs(arch)
+    want_macs = {"squeeze-ernet": 45.64e6, "squeeze-redconv": 38.89e6}[arch]   # torchinfo adds bias terms
+    assert abs(macs - want_macs) / want_macs < 0.01
+    assert [k for k, _ in fixtures.key_shapes(arch)] == list(E.expected_keys(arch).keys()) or \
+        set(k for k, _ in fixtures.key_shapes(arch)) == set(E.expected_keys(arch).keys())
+    assert len(E.expected_keys(arch)) == {"squeeze-ernet": 56, "squeeze-redconv": 62}[arch]
+
+
+@pytest.mark.parametrize("arch", fixtures.ARCHS)
+def test_shipped_weights_layout(arch):
+    sd = fixtures.shipped_state_dict(arch)
+    want = E.expected_keys(arch)
+    assert set(sd.keys()) == set(want.keys())
+    for k, shp in want.items():
+        assert tuple(sd[k].shape) == tuple(shp), k
+
+
+@pytest.mark.parametrize("arch", fixtures.ARCHS)
+@pytest.mark.parametrize("wset", WSETS)
+def test_forward_fp64_matches_reference(arch, wset, model_golden):
+    sd = fixtures.get_state_dict(arch, wset)
+    for iname, x in (("norm", fixtures.normal_tensors(4, seed=7)), ("frames", model_golden["x_frames"])):
+        tag = f"{arch}/{wset}/{iname}"
+        res = E.forward(sd, x, arch, dtype=np.float64, want_taps=(iname == "norm"))
+        ref = model_golden[f"{tag}/logits64"]
+        scale = np.abs(ref).max()
+        assert np.abs(res["logits"] - ref).max() <= 1e-9 * scale, tag
+        assert np.abs(res["probs"] - model_golden[f"{tag}/probs64"]).max() <= 1e-9
+        assert (res["probs"].argmax(1) == model_golden[f"{tag}/probs64"].argmax(1)).all()
+        if iname == "norm":
+            names = {"conv1": None, "stem": None}
+            taps = res["taps"]
+            # oracle tap name -> reference module name
+            mapping = {"acff1": "acff1", "pool1": "pool1", "acff2": "acff2", "pool2": "pool2",
+                       "acff3": "acff3", "acff4": "acff4"}
+            mapping["stem"] = "conv_red1" if arch == "squeeze-redconv" else "conv1"
+            mapping["pool3"] = "conv_red3" if arch == "squeeze-redconv" else "pool3"
+            del names
+            for mine, theirs in mapping.items():
+                sub = model_golden[f"{tag}/tap/{theirs}/sub"]
+                got = taps[mine][0, :, ::5, ::5]
+                assert got.shape == sub.shape, (mine, got.shape, sub.shape)
+                s = max(np.abs(sub).max(), 1e-30)
+                assert np.abs(got - sub).max() <= 1e-9 * s, (tag, mine)
+                asum = float(model_golden[f"{tag}/tap/{theirs}/abs_sum"])
+                assert abs(np.abs(taps[mine]).sum() - asum) <= 1e-9 * asum, (tag, mine)
+
+
+@pytest.mark.parametrize("arch", fixtures.ARCHS)
+def test_forward_fp32_close_to_reference_fp32(arch, model_golden):
+    sd = fixtures.get_state_dict(arch, "shipped")
+    x = fixtures.normal_tensors(4, seed=7)
+    res = E.forward(sd, x, arch, dtype=np.float32)
+    ref = model_golden[f"{arch}/shipped/norm/logits32"]
+    assert np.abs(res["logits"] - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
+def test_forward_rejects_240():
+    # the reference cannot run the squeeze models at 240x240 (view(-1,20) fails / mixes images)
+    sd = fixtures.get_state_dict("squeeze-ernet", "w3")
+    with pytest.raises(ValueError):
+        E.forward(sd, np.zeros((1, 3, 240, 240), np.float32), "squeeze-ernet")
+    with pytest.raises(ValueError):
+        E.forward(sd, np.zeros((1, 3, 140, 140), np.float32), "ernet")
+
+
+def _case_frame(name):
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location(
+        "make_golden_cases", os.path.join(fixtures.GOLDEN, "make_golden.py"))
+    # parse INGEST_CASES without importing the reference: read the literal from the source
+    src = open(spec.origin).read()
+    start = src.index("INGEST_CASES = [")
+    end = src.index("]\n", start) + 1
+    ns = {}
+    exec(src[start:end], ns)
+    for n, kind, h, w, seed in ns["INGEST_CASES"]:
+        if n == name:
+            f = fixtures.noise_frames(1, h, w, seed) if kind == "noise" else fixtures.smooth_frames(1, h, w, seed)
+            return f[0]
+    raise KeyError(name)
+
+
+INGEST_NAMES = ["noise240", "smooth240", "noise480x640", "smooth350x372", "noise372x350",
+                "noise100x120_up", "noise159x159_id", "smooth720x1280", "noise161x300"]
+
+
+@pytest.mark.parametrize("name", INGEST_NAMES + ["real240"])
+def test_ingest_bit_exact(name, ingest_golden):
+    frame = ingest_golden["real240/frame"] if name == "real240" else _case_frame(name)
+    crop = I.crop_u8(frame)
+    assert np.array_equal(crop, ingest_golden[f"{name}/crop_u8"]), name
+    t = I.ingest(frame[None])[0]
+    ref = ingest_golden[f"{name}/tensor"]
+    assert t.dtype == np.float32 and np.array_equal(t, ref), name
+
+
+def test_ingest_constants():
+    assert I.resized_size(240, 240) == (159, 159)
+    assert I.resized_size(480, 640) == (159, 212)
+    assert I.center_crop_offset(159) == 10          # round(9.5) -> 10 (banker's)
+    xmin, xlen, kk = I.resample_coeffs(240, 159)
+    assert kk.shape == (159, 5) and int(kk.sum(1).min()) >= (1 << 22) - 3
