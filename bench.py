@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""Headline benchmark: images/sec of the Squeeze-ErNet hot path on synthetic 240x240 RGB frames.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one pass of the hot path over one batch: uint8 (B,240,240,3) frames -> eval transform
+(Resize 159 / CenterCrop 140 / Normalize) -> Squeeze_ErNET forward -> (B,5) probabilities.
+Workload = BASELINE.json configs[1]: Squeeze-ErNet, bf16, batch 256 per GPU (weak scaling: every rank
+owns its own 256-frame batches and weight copy; there is no collective on the hot path).
+
+  value   frames/s with the frames already resident in HBM, timed with CUDA events on the launch
+          stream, barrier + synchronize on both sides, max over ranks.
+  e2e     same metric through the host-buffer entry point (ernet_classify_frames_host): pinned host
+          frames -> H2D -> kernels -> D2H of the probabilities, every step.
+  roofline  dominant kernel, timed live with CUDA events around each of its launches (second pass
+          over the same steps with the library's per-stage timing switched on).
+  cpu_baseline / --impl reference: the reference's CPU path (torch.nn.functional restatement under
+          oracle/, plus the torchvision/Pillow transform) on the host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+ARCH = "squeeze-ernet"
+PRECISION = "bf16"
+BATCH = 256                     # per GPU
+FRAME = (240, 240)
+N_INPUT_SETS = 8                # 8 x 44 MB of frames > 126 MB L2: inputs never come from L2
+MACS_PER_IMAGE = {"squeeze-ernet": 45.48e6, "squeeze-redconv": 38.80e6}
+
+# algorithmic work per image of each stage: (flops, bytes moved at 16-bit)
+STAGE_WORK = {
+    "ingest": (0.0, 240 * 240 * 3 + 140 * 140 * 3 * 2),
+    "stem": (2 * 2.057e6, 140 * 140 * 3 * 2 + 69 * 69 * 16 * 2),
+    "dw1": (2 * 1.939e6, 69 * 69 * 16 * 2 + 66 * 66 * 48 * 2),
+    "pw1": (2 * 13.790e6 * (66 * 66) / (67 * 67), 66 * 66 * 48 * 2 + 33 * 33 * 64 * 2),
+    "dw2": (2 * 1.661e6, 33 * 33 * 64 * 2 + 30 * 30 * 192 * 2),
+    "pw2": (2 * 17.713e6 * (30 * 30) / (31 * 31), 30 * 30 * 192 * 2 + 15 * 15 * 96 * 2),
+    "dw3": (2 * 0.438e6, 15 * 15 * 96 * 2 + 12 * 12 * 288 * 2),
+    "pw3": (2 * 6.230e6 * (12 * 12) / (13 * 13), 12 * 12 * 288 * 2 + 6 * 6 * 128 * 2),
+    "dw4": (2 * 0.055e6, 6 * 6 * 128 * 2 + 4 * 4 * 384 * 2),
+    "pw4": (2 * 1.573e6, 4 * 4 * 384 * 2 + 4 * 4 * 256 * 2),
+    "head": (2 * 0.021e6, 4 * 4 * 256 * 2 + 20),
+}
+GEMM_STAGES = {"pw1", "pw2", "pw3", "pw4", "tc_block1", "tc_block2", "tc_block3", "tc_block4"}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_run(steps, warmup, sample_frames):
+    """Times the reference's CPU path on a bounded sample per step.  Returns (frames_per_s, info)."""
+    import fixtures
+    from oracle import ernet_torch as T
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = T.to_torch_sd(fixtures.get_state_dict(ARCH, "shipped"))
+    frames = fixtures.noise_frames(sample_frames, *FRAME, seed=1234)
+    how = ""
+    for _ in range(max(1, warmup)):
+        x, how = T.transform_frames(frames)
+        T.forward(sd, x, ARCH)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        x, how = T.transform_frames(frames)                 # aider-predict.py:57-66, per frame through PIL
+        probs, _ = T.forward(sd, x, ARCH)                   # aider-predict.py:76, fp32, all host threads
+        float(probs[0, 0])
+    dt = time.perf_counter() - t0
+    fps = steps * sample_frames / dt
+    info = {"value": fps, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} steps x {sample_frames} frames of 240x240x3 uint8: {how} + torch.nn.functional fp32 "
+                      f"forward (oracle/ernet_torch.py), torch.set_num_threads({cores})"}
+    return fps, dt, info
+
+
+def reference_main(args, rank):
+    if rank != 0:
+        return 0
+    sample = 32
+    steps = max(1, min(args.steps, 40))
+    fps, dt, info = cpu_reference_run(steps, min(args.warmup, 3), sample)
+    line = {
+        "impl": "reference", "metric": "images/sec", "value": fps, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "Squeeze-ErNet forward on 240x240x3 uint8 frames (transform + model), CPU reference "
+                               f"path, bounded sample of {sample} frames per step", "arch": ARCH},
+        "cpu_baseline": info,
+        "e2e": {"value": fps, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------- GPU arm
+def gpu_main(args, rank, local_rank, world):
+    import torch.distributed as dist
+    import fixtures
+    import rtdm_b200
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (the product path has no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sd = fixtures.get_state_dict(ARCH, "shipped")
+    model = rtdm_b200.from_state_dict(ARCH, sd, dev, PRECISION)
+    model.prepare_ingest(*FRAME)
+
+    # synthetic inputs: N_INPUT_SETS distinct batches per rank (seeded by rank), rotated so that a step
+    # never finds its frames in L2
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    host_sets = [torch.randint(0, 256, (BATCH, *FRAME, 3), dtype=torch.uint8, generator=g).pin_memory()
+                 for _ in range(N_INPUT_SETS)]
+    dev_sets = [h.to(dev) for h in host_sets]
+    stream = torch.cuda.current_stream(dev)
+
+    def step(i):
+        return model.forward_frames(dev_sets[i % N_INPUT_SETS])
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        out = step(i)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * BATCH * args.steps / (ms_max * 1e-3)
+    assert torch.isfinite(out).all()
+
+    # ---- e2e: host frames in, host probabilities out, through the C ABI host entry point
+    for i in range(min(args.warmup, 3)):
+        model.classify_host(host_sets[i % N_INPUT_SETS])
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 20))
+    for i in range(e2e_steps):
+        ph = model.classify_host(host_sets[i % N_INPUT_SETS])
+    torch.cuda.synchronize(dev)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * BATCH * e2e_steps / (float(t.item()) * 1e-3)
+    assert np.isfinite(ph).all()
+
+    # ---- live per-kernel timing: same steps again with CUDA events around every stage
+    barrier()
+    model.profile(True)
+    for i in range(args.steps):
+        step(i)
+    torch.cuda.synchronize(dev)
+    prof = model.profile_read()
+    model.profile(False)
+
+    if rank == 0:
+        peaks = load_peaks()
+        total_stage_ms = sum(v[0] for v in prof.values())
+        dom = max(prof, key=lambda k: prof[k][0])
+        dms, dcount = prof[dom]
+        per_launch_ms = dms / dcount
+        flops, nbytes = STAGE_WORK.get(dom, (0.0, 0.0))
+        if dom in GEMM_STAGES:
+            achieved = flops * BATCH / (per_launch_ms * 1e-3) / 1e12
+            peak = peaks["bf16_tflops_sustained"]
+            roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s"}
+        else:
+            achieved = nbytes * BATCH / (per_launch_ms * 1e-3) / 1e9
+            peak = peaks["hbm_gbs"]
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s"}
+        roof.update({"frac": achieved / peak, "traffic": None, "kernel": dom, "peak_source": peaks["source"],
+                     "launch_ms": per_launch_ms, "share_of_step": dms / total_stage_ms,
+                     "stage_ms_per_step": {k: round(v[0] / args.steps, 5) for k, v in prof.items()}})
+        launches = model.launches_per_forward(BATCH, True) * args.steps
+        cpu_fps, _, cpu_info = cpu_reference_run(6, 1, 32)
+        line = {
+            "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": PRECISION, "data": "synthetic",
+            "config": {"workload": f"Squeeze-ErNet bf16 batch {BATCH} per GPU on 1xB200 (BASELINE.json configs[1]): "
+                                   "240x240x3 uint8 frames -> eval transform -> forward -> probabilities",
+                       "arch": ARCH, "batch_per_gpu": BATCH, "global_batch": BATCH * world, "frame": "240x240x3 u8",
+                       "weights": "shipped squeeze-ernet-state_dict",
+                       "l2": f"inputs rotate over {N_INPUT_SETS} distinct batches "
+                             f"({N_INPUT_SETS * BATCH * 172800 / 1e6:.0f} MB > 126 MB L2)",
+                       "parallelism": f"dp{world}, no collective on the hot path"},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": BATCH * FRAME[0] * FRAME[1] * 3,
+                    "d2h_bytes_per_step": BATCH * 5 * 4, "steps": e2e_steps,
+                    "api": "Squeeze_ErNET.classify_host -> ernet_classify_frames_host (pinned host buffers)"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roof,
+            "model_flops_frac_of_tensor_peak": value / world * 2 * MACS_PER_IMAGE[ARCH] / 1e12 / peaks["bf16_tflops_sustained"],
+            "cpu_baseline": cpu_info,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return reference_main(args, rank)
+    if world == 1 and args.gpus > 1:
+        # convenience: re-launch under torchrun when called directly with --gpus N
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__),
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        return subprocess.call(cmd)
+    return gpu_main(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

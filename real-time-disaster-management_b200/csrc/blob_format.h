@@ -1,0 +1,42 @@
+// Packed-weights blob shared by the host-side packer (pack.py) and the CUDA library.
+//
+//   header   : ernet_blob_header (32 bytes)
+//   table    : n_entries x ernet_blob_entry (24 bytes each)
+//   payload  : tensors, each 256-byte aligned relative to the start of the blob
+//
+// The packer derives every tensor in fp64 from the reference's state_dict
+//  and stores it in the layout the kernels read.
+#pragma once
+#include <stdint.h>
+
+#define ERNET_BLOB_MAGIC 0x424E5245u /* 'ERNB' */
+#define ERNET_BLOB_VERSION 2u
+
+struct ernet_blob_header {
+  uint32_t magic, version, arch, precision, n_entries, reserved[3];
+};
+struct ernet_blob_entry {
+  uint32_t id, dtype;  // dtype: ernet_dtype, or 16 = raw bytes
+  uint64_t offset, nbytes;
+};
+
+// ---- tensor ids -----------------------------------------------------------------------------
+// CUDA-core ("simt") path, all fp32:
+#define ERNET_T_STEM_W 0        // [3][3][3][CS]  (ky,kx,cin,cout); RedConv: conv_red1 folded in, CS=8
+#define ERNET_T_STEM_B 1        // [CS]           (zeros for squeeze-ernet)
+#define ERNET_T_BLOCK_BASE 8    // + 8*k, k = 0..3 (acff1..acff4)
+#define ERNET_T_DW_W 0          //   [3][9][C]    branch, tap (ky*3+kx), channel
+#define ERNET_T_DW_B 1          //   [3][C]
+#define ERNET_T_PW_W 2          //   [3C][N]      k = branch*C + c  (concat order, acff.py:46)
+#define ERNET_T_PW_B 3          //   [N]
+#define ERNET_T_BN_S 4          //   [N]  gamma / sqrt(var + eps)
+#define ERNET_T_BN_T 5          //   [N]  beta - mean * scale
+#define ERNET_T_RED2_W 40       // [96][48]   conv_red2, k-major
+#define ERNET_T_RED2_B 41
+#define ERNET_T_RED3_W 42       // [128][64]  conv_red3
+#define ERNET_T_RED3_B 43
+#define ERNET_T_HEAD_W 44       // [5][256]   conv2 o avgpool o fc collapsed
+#define ERNET_T_HEAD_B 45       // [5]
+// tensor-core path (16-bit / int8 operand images), see tc_*.cuh:
+#define ERNET_T_TC_BASE 64
+#define ERNET_T_MAX 128

@@ -1,0 +1,614 @@
+// C ABI of the B200-native Squeeze-ErNet engine (see include/ernet_b200.h for the contract and the
+// reference interfaces each entry point replaces).
+#include <stdarg.h>
+
+#include <map>
+#include <new>
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+#include "ingest.cuh"
+#include "simt_layers.cuh"
+
+namespace ernet {
+
+thread_local char g_err[512] = "";
+
+struct Tensor {
+  const void* dev = nullptr;
+  size_t nbytes = 0;
+  int dtype = 0;
+};
+
+struct Plan {                 // byte offsets into the caller's workspace for one chunk
+  size_t ingest, stem, cat1, p1, cat2, a2, p2, cat3, p3, r3, cat4, a4, total;
+};
+
+}  // namespace ernet
+
+using namespace ernet;
+
+struct ernet_handle {
+  int arch = 0, precision = 0, device = 0;
+  int chunk = 1024;
+  bool loaded = false;
+  void* d_blob = nullptr;
+  size_t blob_bytes = 0;
+  Tensor t[ERNET_T_MAX];
+  std::map<std::pair<int, int>, IngestTables> ingest;
+  // host-buffer path (ernet_classify_frames_host)
+  cudaStream_t s_copy = nullptr, s_compute = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  uint8_t* d_frames[2] = {nullptr, nullptr};
+  size_t d_frames_bytes = 0;
+  void* d_ws = nullptr;
+  size_t d_ws_bytes = 0;
+  float* d_res = nullptr;       // probs then logits
+  size_t d_res_elems = 0;
+  // optional per-stage CUDA-event timing (ernet_profile_*)
+  bool profiling = false;
+  struct ProfRec { int stage; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> prof_pool;
+
+  bool red() const { return arch == ERNET_ARCH_REDCONV; }
+  int cs() const { return red() ? 8 : 16; }            // stem output channels
+  int c3() const { return red() ? 48 : 96; }           // acff3 input channels
+  int c4() const { return red() ? 64 : 128; }          // acff4 input channels
+  size_t esize() const { return precision == ERNET_PREC_FP32 ? 4 : 2; }
+  const float* f(int id) const { return static_cast<const float*>(t[id].dev); }
+  const float* blk(int k, int what) const { return f(ERNET_T_BLOCK_BASE + 8 * k + what); }
+};
+
+namespace ernet {
+
+static Plan make_plan(const ernet_handle* h, int n) {
+  const size_t e = h->esize(), N = (size_t)n;
+  Plan p{};
+  size_t o = 0;
+  auto take = [&](size_t elems) { size_t r = o; o += align_up(elems * e, 256); return r; };
+  p.ingest = take(N * 140 * 140 * 3);
+  p.stem = take(N * 69 * 69 * h->cs());
+  p.cat1 = take(N * 66 * 66 * 3 * h->cs());
+  p.p1 = take(N * 33 * 33 * 64);
+  p.cat2 = take(N * 30 * 30 * 192);
+  p.a2 = h->red() ? take(N * 30 * 30 * 96) : 0;
+  p.p2 = take(N * 15 * 15 * h->c3());
+  p.cat3 = take(N * 12 * 12 * 3 * h->c3());
+  p.p3 = take(N * 6 * 6 * 128);
+  p.r3 = h->red() ? take(N * 6 * 6 * 64) : 0;
+  p.cat4 = take(N * 4 * 4 * 3 * h->c4());
+  p.a4 = take(N * 4 * 4 * 256);
+  p.total = o;
+  return p;
+}
+
+static int check_tensor(const ernet_handle* h, int id, size_t elems) {
+  if (!h->t[id].dev) return fail(ERNET_ERR_BAD_BLOB, "packed weights: tensor id %d missing", id);
+  if (h->t[id].nbytes != elems * sizeof(float))
+    return fail(ERNET_ERR_BAD_BLOB, "packed weights: tensor id %d has %zu bytes, expected %zu", id, h->t[id].nbytes,
+                elems * sizeof(float));
+  return ERNET_OK;
+}
+
+static int validate_simt_tensors(const ernet_handle* h) {
+  int rc;
+  const int cs = h->cs();
+  if ((rc = check_tensor(h, ERNET_T_STEM_W, 27 * cs))) return rc;
+  if ((rc = check_tensor(h, ERNET_T_STEM_B, cs))) return rc;
+  const int cin[4] = {cs, 64, h->c3(), h->c4()}, cout[4] = {64, 96, 128, 256};
+  for (int k = 0; k < 4; ++k) {
+    const int base = ERNET_T_BLOCK_BASE + 8 * k;
+    if ((rc = check_tensor(h, base + ERNET_T_DW_W, 27 * cin[k]))) return rc;
+    if ((rc = check_tensor(h, base + ERNET_T_DW_B, 3 * cin[k]))) return rc;
+    if ((rc = check_tensor(h, base + ERNET_T_PW_W, (size_t)3 * cin[k] * cout[k]))) return rc;
+    if ((rc = check_tensor(h, base + ERNET_T_PW_B, cout[k]))) return rc;
+    if ((rc = check_tensor(h, base + ERNET_T_BN_S, cout[k]))) return rc;
+    if ((rc = check_tensor(h, base + ERNET_T_BN_T, cout[k]))) return rc;
+  }
+  if (h->red()) {
+    if ((rc = check_tensor(h, ERNET_T_RED2_W, 96 * 48))) return rc;
+    if ((rc = check_tensor(h, ERNET_T_RED2_B, 48))) return rc;
+    if ((rc = check_tensor(h, ERNET_T_RED3_W, 128 * 64))) return rc;
+    if ((rc = check_tensor(h, ERNET_T_RED3_B, 64))) return rc;
+  }
+  if ((rc = check_tensor(h, ERNET_T_HEAD_W, 5 * 256))) return rc;
+  if ((rc = check_tensor(h, ERNET_T_HEAD_B, 5))) return rc;
+  return ERNET_OK;
+}
+
+template <typename TI, typename T>
+static int launch_stem(const ernet_handle* h, const TI* x, long long sb, long long sc, long long sy, long long sx,
+                       T* out, int n, cudaStream_t s) {
+  const int total = n * 69 * 69;
+  const int grid = (total + 127) / 128;
+  if (h->red())
+    stem_kernel<TI, T, 8><<<grid, 128, 0, s>>>(x, sb, sc, sy, sx, h->f(ERNET_T_STEM_W), h->f(ERNET_T_STEM_B), out, total);
+  else
+    stem_kernel<TI, T, 16><<<grid, 128, 0, s>>>(x, sb, sc, sy, sx, h->f(ERNET_T_STEM_W), h->f(ERNET_T_STEM_B), out, total);
+  ERNET_LAUNCH_CHECK("stem_kernel");
+  return ERNET_OK;
+}
+
+// Brackets one stage with CUDA events on the launch stream when profiling is on.
+struct StageTimer {
+  ernet_handle* h; cudaStream_t s; cudaEvent_t a = nullptr, b = nullptr; int stage;
+  StageTimer(ernet_handle* h_, int stage_, cudaStream_t s_) : h(h_), s(s_), stage(stage_) {
+    if (!h->profiling) return;
+    auto get = [&]() { cudaEvent_t e = nullptr;
+      if (!h->prof_pool.empty()) { e = h->prof_pool.back(); h->prof_pool.pop_back(); } else cudaEventCreate(&e);
+      return e; };
+    a = get(); b = get();
+    cudaEventRecord(a, s);
+  }
+  ~StageTimer() {
+    if (!a) return;
+    cudaEventRecord(b, s);
+    h->prof.push_back({stage, a, b});
+  }
+};
+#define ERNET_STAGE(id, call)                                   \
+  do { StageTimer _t(h, id, s); if ((rc = (call))) return rc; } while (0)
+
+// One chunk of n images through the layer-wise CUDA-core pipeline.
+template <typename T>
+static int run_chunk_simt(ernet_handle* h, const void* x, int x_dtype, int x_layout, const uint8_t* frames,
+                          const IngestTables* tab, int order, int n, float* probs, float* logits, char* ws,
+                          cudaStream_t s) {
+  const Plan p = make_plan(h, n);
+  auto buf = [&](size_t off) { return reinterpret_cast<T*>(ws + off); };
+  int rc;
+  if (frames) {
+    ERNET_STAGE(ERNET_STAGE_INGEST, launch_ingest<T>(*tab, frames, n, order == ERNET_BGR, buf(p.ingest), 140LL * 140 * 3, 1, 140 * 3, 3, s));
+    ERNET_STAGE(ERNET_STAGE_STEM, (launch_stem<T, T>(h, buf(p.ingest), 140LL * 140 * 3, 1, 140 * 3, 3, buf(p.stem), n, s)));
+  } else {
+    long long sb = 3LL * 140 * 140, sc, sy, sx;
+    if (x_layout == ERNET_NCHW) { sc = 140 * 140; sy = 140; sx = 1; }
+    else                        { sc = 1; sy = 140 * 3; sx = 3; }
+    StageTimer _t(h, ERNET_STAGE_STEM, s);
+    if (x_dtype == ERNET_F32) rc = launch_stem<float, T>(h, static_cast<const float*>(x), sb, sc, sy, sx, buf(p.stem), n, s);
+    else if (x_dtype == ERNET_F16) rc = launch_stem<__half, T>(h, static_cast<const __half*>(x), sb, sc, sy, sx, buf(p.stem), n, s);
+    else rc = launch_stem<__nv_bfloat16, T>(h, static_cast<const __nv_bfloat16*>(x), sb, sc, sy, sx, buf(p.stem), n, s);
+    if (rc) return rc;
+  }
+  const int cs = h->cs(), c3 = h->c3(), c4 = h->c4();
+  // acff1 + pool1
+  ERNET_STAGE(ERNET_STAGE_DW1, launch_acff_dw<T>(buf(p.stem), n, 69, 69, cs, 66, 66, h->blk(0, ERNET_T_DW_W), h->blk(0, ERNET_T_DW_B), buf(p.cat1), s));
+  ERNET_STAGE(ERNET_STAGE_PW1, launch_pointwise<T>(buf(p.cat1), n, 66, 66, 3 * cs, 64, h->blk(0, ERNET_T_PW_W), h->blk(0, ERNET_T_PW_B),
+                                h->blk(0, ERNET_T_BN_S), h->blk(0, ERNET_T_BN_T), 1, 1, buf(p.p1), s));
+  // acff2 [+conv_red2] + pool2
+  ERNET_STAGE(ERNET_STAGE_DW2, launch_acff_dw<T>(buf(p.p1), n, 33, 33, 64, 30, 30, h->blk(1, ERNET_T_DW_W), h->blk(1, ERNET_T_DW_B), buf(p.cat2), s));
+  if (h->red()) {
+    ERNET_STAGE(ERNET_STAGE_PW2, launch_pointwise<T>(buf(p.cat2), n, 30, 30, 192, 96, h->blk(1, ERNET_T_PW_W), h->blk(1, ERNET_T_PW_B),
+                                  h->blk(1, ERNET_T_BN_S), h->blk(1, ERNET_T_BN_T), 1, 0, buf(p.a2), s));
+    ERNET_STAGE(ERNET_STAGE_RED2, launch_pointwise<T>(buf(p.a2), n, 30, 30, 96, 48, h->f(ERNET_T_RED2_W), h->f(ERNET_T_RED2_B), nullptr, nullptr,
+                                  0, 1, buf(p.p2), s));
+  } else {
+    ERNET_STAGE(ERNET_STAGE_PW2, launch_pointwise<T>(buf(p.cat2), n, 30, 30, 192, 96, h->blk(1, ERNET_T_PW_W), h->blk(1, ERNET_T_PW_B),
+                                  h->blk(1, ERNET_T_BN_S), h->blk(1, ERNET_T_BN_T), 1, 1, buf(p.p2), s));
+  }
+  // acff3 + pool3 [+conv_red3]
+  ERNET_STAGE(ERNET_STAGE_DW3, launch_acff_dw<T>(buf(p.p2), n, 15, 15, c3, 12, 12, h->blk(2, ERNET_T_DW_W), h->blk(2, ERNET_T_DW_B), buf(p.cat3), s));
+  ERNET_STAGE(ERNET_STAGE_PW3, launch_pointwise<T>(buf(p.cat3), n, 12, 12, 3 * c3, 128, h->blk(2, ERNET_T_PW_W), h->blk(2, ERNET_T_PW_B),
+                                h->blk(2, ERNET_T_BN_S), h->blk(2, ERNET_T_BN_T), 1, 1, buf(p.p3), s));
+  const T* in4 = buf(p.p3);
+  if (h->red()) {
+    ERNET_STAGE(ERNET_STAGE_RED3, launch_pointwise<T>(buf(p.p3), n, 6, 6, 128, 64, h->f(ERNET_T_RED3_W), h->f(ERNET_T_RED3_B), nullptr, nullptr,
+                                  0, 0, buf(p.r3), s));
+    in4 = buf(p.r3);
+  }
+  // acff4 + head
+  ERNET_STAGE(ERNET_STAGE_DW4, launch_acff_dw<T>(in4, n, 6, 6, c4, 4, 4, h->blk(3, ERNET_T_DW_W), h->blk(3, ERNET_T_DW_B), buf(p.cat4), s));
+  ERNET_STAGE(ERNET_STAGE_PW4, launch_pointwise<T>(buf(p.cat4), n, 4, 4, 3 * c4, 256, h->blk(3, ERNET_T_PW_W), h->blk(3, ERNET_T_PW_B),
+                                h->blk(3, ERNET_T_BN_S), h->blk(3, ERNET_T_BN_T), 1, 0, buf(p.a4), s));
+  {
+    StageTimer _t(h, ERNET_STAGE_HEAD, s);
+    head_kernel<T><<<n, 256, 0, s>>>(buf(p.a4), h->f(ERNET_T_HEAD_W), h->f(ERNET_T_HEAD_B), probs, logits);
+    ERNET_LAUNCH_CHECK("head_kernel");
+  }
+  return ERNET_OK;
+}
+
+static int run_chunk(ernet_handle* h, const void* x, int x_dtype, int x_layout, const uint8_t* frames,
+                     const IngestTables* tab, int order, int n, float* probs, float* logits, char* ws, cudaStream_t s) {
+  switch (h->precision) {
+    case ERNET_PREC_FP32: return run_chunk_simt<float>(h, x, x_dtype, x_layout, frames, tab, order, n, probs, logits, ws, s);
+    case ERNET_PREC_FP16: return run_chunk_simt<__half>(h, x, x_dtype, x_layout, frames, tab, order, n, probs, logits, ws, s);
+    case ERNET_PREC_BF16: return run_chunk_simt<__nv_bfloat16>(h, x, x_dtype, x_layout, frames, tab, order, n, probs, logits, ws, s);
+    default: return fail(ERNET_ERR_UNSUPPORTED, "precision %d is not implemented in this build", h->precision);
+  }
+}
+
+template <typename T>
+static int set_smem_attrs() {
+  ERNET_CUDA(cudaFuncSetAttribute(acff_dw_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  return ERNET_OK;
+}
+
+static int init_device_attrs() {
+  int rc;
+  if ((rc = set_smem_attrs<float>())) return rc;
+  if ((rc = set_smem_attrs<__half>())) return rc;
+  if ((rc = set_smem_attrs<__nv_bfloat16>())) return rc;
+  return ERNET_OK;
+}
+
+static int get_tables(ernet_handle* h, int H, int W, const IngestTables** out) {
+  auto key = std::make_pair(H, W);
+  auto it = h->ingest.find(key);
+  if (it == h->ingest.end()) {
+    IngestTables t;
+    int rc = build_ingest_tables(t, H, W);
+    if (rc) return rc;
+    it = h->ingest.emplace(key, t).first;
+  }
+  *out = &it->second;
+  return ERNET_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace ernet
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* ernet_last_error(void) { return g_err; }
+int ernet_abi_version(void) { return ERNET_ABI_VERSION; }
+
+int ernet_create(ernet_handle** out, int arch, int precision, int device) {
+  if (!out) return fail(ERNET_ERR_INVALID_ARG, "ernet_create: out is null");
+  *out = nullptr;
+  if (arch != ERNET_ARCH_SQUEEZE && arch != ERNET_ARCH_REDCONV)
+    return fail(ERNET_ERR_INVALID_ARG, "Unsupported model: arch=%d", arch);   // aider-predict.py:32
+  if (precision < ERNET_PREC_FP32 || precision > ERNET_PREC_INT8)
+    return fail(ERNET_ERR_INVALID_ARG, "unknown precision %d", precision);
+  int ndev = 0;
+  ERNET_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(ERNET_ERR_INVALID_ARG, "device %d out of range (%d visible)", device, ndev);
+  cudaDeviceProp prop;
+  ERNET_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(ERNET_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                prop.major, prop.minor);
+  DeviceGuard g(device);
+  if (!g.ok) return fail(ERNET_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  int rc = init_device_attrs();
+  if (rc) return rc;
+  ernet_handle* h = new (std::nothrow) ernet_handle();
+  if (!h) return fail(ERNET_ERR_INVALID_ARG, "out of host memory");
+  h->arch = arch; h->precision = precision; h->device = device;
+  *out = h;
+  return ERNET_OK;
+}
+
+void ernet_destroy(ernet_handle* h) {
+  if (!h) return;
+  DeviceGuard g(h->device);
+  if (h->d_blob) cudaFree(h->d_blob);
+  for (auto& kv : h->ingest) if (kv.second.d_base) cudaFree(kv.second.d_base);
+  for (int i = 0; i < 2; ++i) {
+    if (h->d_frames[i]) cudaFree(h->d_frames[i]);
+    if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+    if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+  }
+  for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : h->prof_pool) cudaEventDestroy(e);
+  if (h->d_ws) cudaFree(h->d_ws);
+  if (h->d_res) cudaFree(h->d_res);
+  if (h->s_copy) cudaStreamDestroy(h->s_copy);
+  if (h->s_compute) cudaStreamDestroy(h->s_compute);
+  delete h;
+}
+
+int ernet_load_packed(ernet_handle* h, const void* blob, size_t bytes) {
+  if (!h || !blob) return fail(ERNET_ERR_INVALID_ARG, "ernet_load_packed: null argument");
+  if (bytes < sizeof(ernet_blob_header)) return fail(ERNET_ERR_BAD_BLOB, "blob too small (%zu bytes)", bytes);
+  ernet_blob_header hd;
+  memcpy(&hd, blob, sizeof(hd));
+  if (hd.magic != ERNET_BLOB_MAGIC) return fail(ERNET_ERR_BAD_BLOB, "bad magic 0x%08x", hd.magic);
+  if (hd.version != ERNET_BLOB_VERSION) return fail(ERNET_ERR_BAD_BLOB, "blob version %u, library expects %u", hd.version, ERNET_BLOB_VERSION);
+  if ((int)hd.arch != h->arch || (int)hd.precision != h->precision)
+    return fail(ERNET_ERR_BAD_BLOB, "blob is arch=%u precision=%u, handle is arch=%d precision=%d", hd.arch, hd.precision, h->arch, h->precision);
+  const size_t table_end = sizeof(hd) + (size_t)hd.n_entries * sizeof(ernet_blob_entry);
+  if (hd.n_entries > 4096 || table_end > bytes) return fail(ERNET_ERR_BAD_BLOB, "entry table truncated");
+  std::vector<ernet_blob_entry> ent(hd.n_entries);
+  memcpy(ent.data(), static_cast<const char*>(blob) + sizeof(hd), hd.n_entries * sizeof(ernet_blob_entry));
+  for (auto& e : ent) {
+    if (e.id >= ERNET_T_MAX) return fail(ERNET_ERR_BAD_BLOB, "tensor id %u out of range", e.id);
+    if (e.offset % 256 || e.offset < table_end || e.offset + e.nbytes > bytes)
+      return fail(ERNET_ERR_BAD_BLOB, "tensor id %u: bad extent [%llu,+%llu) in a %zu-byte blob", e.id,
+                  (unsigned long long)e.offset, (unsigned long long)e.nbytes, bytes);
+  }
+  DeviceGuard g(h->device);
+  void* d = nullptr;
+  ERNET_CUDA(cudaMalloc(&d, bytes));
+  cudaError_t ce = cudaMemcpy(d, blob, bytes, cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) { cudaFree(d); return fail(ERNET_ERR_CUDA, "copying weights failed: %s", cudaGetErrorString(ce)); }
+  Tensor old[ERNET_T_MAX];
+  memcpy(old, h->t, sizeof(old));
+  for (auto& t : h->t) t = Tensor();
+  for (auto& e : ent) {
+    h->t[e.id].dev = static_cast<char*>(d) + e.offset;
+    h->t[e.id].nbytes = e.nbytes;
+    h->t[e.id].dtype = (int)e.dtype;
+  }
+  int rc = validate_simt_tensors(h);
+  if (rc) { memcpy(h->t, old, sizeof(old)); cudaFree(d); return rc; }
+  if (h->d_blob) { cudaDeviceSynchronize(); cudaFree(h->d_blob); }
+  h->d_blob = d; h->blob_bytes = bytes; h->loaded = true;
+  return ERNET_OK;
+}
+
+int ernet_set_chunk(ernet_handle* h, int n) {
+  if (!h || n < 1 || n > 65535) return fail(ERNET_ERR_INVALID_ARG, "chunk must be in [1,65535]");
+  h->chunk = n;
+  return ERNET_OK;
+}
+int ernet_get_chunk(const ernet_handle* h) { return h ? h->chunk : 0; }
+
+size_t ernet_workspace_bytes(const ernet_handle* h, int batch) {
+  if (!h || batch < 1) return 0;
+  return make_plan(h, batch < h->chunk ? batch : h->chunk).total;
+}
+
+static int forward_common(ernet_handle* h, const void* x, int x_dtype, int x_layout, const uint8_t* frames, int H, int W,
+                          int order, int batch, float* probs, float* logits, void* ws, size_t ws_bytes, void* stream) {
+  if (!h) return fail(ERNET_ERR_INVALID_ARG, "null handle");
+  if (!h->loaded) return fail(ERNET_ERR_NOT_LOADED, "no weights loaded (call ernet_load_packed first)");
+  if (batch < 1) return fail(ERNET_ERR_INVALID_ARG, "batch must be >= 1, got %d", batch);
+  if (!probs) return fail(ERNET_ERR_INVALID_ARG, "probs_out is null");
+  if (!frames) {
+    if (!x) return fail(ERNET_ERR_INVALID_ARG, "x is null");
+    if (x_dtype != ERNET_F32 && x_dtype != ERNET_F16 && x_dtype != ERNET_BF16)
+      return fail(ERNET_ERR_INVALID_ARG, "x_dtype %d must be fp32, fp16 or bf16", x_dtype);
+    if (x_layout != ERNET_NCHW && x_layout != ERNET_NHWC) return fail(ERNET_ERR_INVALID_ARG, "bad x_layout %d", x_layout);
+  } else if (order != ERNET_RGB && order != ERNET_BGR) {
+    return fail(ERNET_ERR_INVALID_ARG, "bad channel_order %d", order);
+  }
+  const size_t need = ernet_workspace_bytes(h, batch);
+  if (!ws || ws_bytes < need) return fail(ERNET_ERR_WORKSPACE, "workspace of %zu bytes needed, %zu given", need, ws ? ws_bytes : 0);
+  DeviceGuard g(h->device);
+  const IngestTables* tab = nullptr;
+  if (frames) { int rc = get_tables(h, H, W, &tab); if (rc) return rc; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t x_img = 3ull * 140 * 140 * dtype_size(x_dtype);
+  const size_t f_img = (size_t)H * W * 3;
+  for (int b0 = 0; b0 < batch; b0 += h->chunk) {
+    const int n = batch - b0 < h->chunk ? batch - b0 : h->chunk;
+    int rc = run_chunk(h, x ? static_cast<const char*>(x) + (size_t)b0 * x_img : nullptr, x_dtype, x_layout,
+                       frames ? frames + (size_t)b0 * f_img : nullptr, tab, order, n, probs + (size_t)b0 * 5,
+                       logits ? logits + (size_t)b0 * 5 : nullptr, static_cast<char*>(ws), s);
+    if (rc) return rc;
+  }
+  return ERNET_OK;
+}
+
+int ernet_forward(ernet_handle* h, const void* x, int x_dtype, int x_layout, int batch, float* probs_out,
+                  float* logits_out, void* workspace, size_t workspace_bytes, void* stream) {
+  return forward_common(h, x, x_dtype, x_layout, nullptr, 0, 0, 0, batch, probs_out, logits_out, workspace,
+                        workspace_bytes, stream);
+}
+
+int ernet_forward_frames(ernet_handle* h, const uint8_t* frames, int batch, int height, int width, int channel_order,
+                         float* probs_out, float* logits_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!frames) return fail(ERNET_ERR_INVALID_ARG, "frames is null");
+  return forward_common(h, nullptr, 0, 0, frames, height, width, channel_order, batch, probs_out, logits_out, workspace,
+                        workspace_bytes, stream);
+}
+
+int ernet_prepare_ingest(ernet_handle* h, int height, int width) {
+  if (!h) return fail(ERNET_ERR_INVALID_ARG, "null handle");
+  DeviceGuard g(h->device);
+  const IngestTables* tab;
+  return get_tables(h, height, width, &tab);
+}
+
+int ernet_ingest_u8(ernet_handle* h, const uint8_t* frames, int batch, int height, int width, int channel_order,
+                    void* x_out, int out_dtype, int out_layout, void* stream) {
+  if (!h || !frames || !x_out) return fail(ERNET_ERR_INVALID_ARG, "ernet_ingest_u8: null argument");
+  if (batch < 1) return fail(ERNET_ERR_INVALID_ARG, "batch must be >= 1, got %d", batch);
+  if (channel_order != ERNET_RGB && channel_order != ERNET_BGR) return fail(ERNET_ERR_INVALID_ARG, "bad channel_order");
+  DeviceGuard g(h->device);
+  const IngestTables* tab;
+  int rc = get_tables(h, height, width, &tab);
+  if (rc) return rc;
+  long long sb = 3LL * 140 * 140, sc, sy, sx;
+  if (out_layout == ERNET_NCHW) { sc = 140 * 140; sy = 140; sx = 1; }
+  else if (out_layout == ERNET_NHWC) { sc = 1; sy = 140 * 3; sx = 3; }
+  else return fail(ERNET_ERR_INVALID_ARG, "bad out_layout %d", out_layout);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool bgr = channel_order == ERNET_BGR;
+  for (int b0 = 0; b0 < batch; b0 += 32768) {     // gridDim.y limit
+    const int n = batch - b0 < 32768 ? batch - b0 : 32768;
+    const uint8_t* f = frames + (size_t)b0 * height * width * 3;
+    const size_t o = (size_t)b0 * sb;
+    if (out_dtype == ERNET_F32) rc = launch_ingest<float>(*tab, f, n, bgr, static_cast<float*>(x_out) + o, sb, sc, sy, sx, s);
+    else if (out_dtype == ERNET_F16) rc = launch_ingest<__half>(*tab, f, n, bgr, static_cast<__half*>(x_out) + o, sb, sc, sy, sx, s);
+    else if (out_dtype == ERNET_BF16) rc = launch_ingest<__nv_bfloat16>(*tab, f, n, bgr, static_cast<__nv_bfloat16*>(x_out) + o, sb, sc, sy, sx, s);
+    else return fail(ERNET_ERR_INVALID_ARG, "bad out_dtype %d", out_dtype);
+    if (rc) return rc;
+  }
+  return ERNET_OK;
+}
+
+int ernet_classify_frames_host(ernet_handle* h, const uint8_t* frames_host, int batch, int height, int width,
+                               int channel_order, float* probs_host, float* logits_host) {
+  if (!h || !frames_host || !probs_host) return fail(ERNET_ERR_INVALID_ARG, "ernet_classify_frames_host: null argument");
+  if (!h->loaded) return fail(ERNET_ERR_NOT_LOADED, "no weights loaded (call ernet_load_packed first)");
+  if (batch < 1) return fail(ERNET_ERR_INVALID_ARG, "batch must be >= 1, got %d", batch);
+  DeviceGuard g(h->device);
+  const IngestTables* tab;
+  int rc = get_tables(h, height, width, &tab);
+  if (rc) return rc;
+  if (!h->s_copy) {
+    ERNET_CUDA(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+    ERNET_CUDA(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      ERNET_CUDA(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+      ERNET_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    }
+  }
+  const int chunk = batch < h->chunk ? batch : h->chunk;
+  const size_t f_img = (size_t)height * width * 3;
+  const size_t fbytes = (size_t)chunk * f_img;
+  if (h->d_frames_bytes < fbytes) {
+    for (int i = 0; i < 2; ++i) {
+      if (h->d_frames[i]) { cudaFree(h->d_frames[i]); h->d_frames[i] = nullptr; }
+      ERNET_CUDA(cudaMalloc(&h->d_frames[i], fbytes));
+    }
+    h->d_frames_bytes = fbytes;
+  }
+  const size_t wbytes = ernet_workspace_bytes(h, chunk);
+  if (h->d_ws_bytes < wbytes) {
+    if (h->d_ws) { cudaFree(h->d_ws); h->d_ws = nullptr; }
+    ERNET_CUDA(cudaMalloc(&h->d_ws, wbytes));
+    h->d_ws_bytes = wbytes;
+  }
+  if (h->d_res_elems < (size_t)batch * 10) {
+    if (h->d_res) { cudaFree(h->d_res); h->d_res = nullptr; }
+    ERNET_CUDA(cudaMalloc(&h->d_res, (size_t)batch * 10 * sizeof(float)));
+    h->d_res_elems = (size_t)batch * 10;
+  }
+  float* d_probs = h->d_res;
+  float* d_logits = h->d_res + (size_t)batch * 5;
+  int it = 0;
+  for (int b0 = 0; b0 < batch; b0 += chunk, ++it) {
+    const int n = batch - b0 < chunk ? batch - b0 : chunk;
+    const int s = it & 1;
+    if (it >= 2) ERNET_CUDA(cudaStreamWaitEvent(h->s_copy, h->ev_done[s], 0));   // frame buffer s is free again
+    ERNET_CUDA(cudaMemcpyAsync(h->d_frames[s], frames_host + (size_t)b0 * f_img, (size_t)n * f_img,
+                               cudaMemcpyHostToDevice, h->s_copy));
+    ERNET_CUDA(cudaEventRecord(h->ev_copied[s], h->s_copy));
+    ERNET_CUDA(cudaStreamWaitEvent(h->s_compute, h->ev_copied[s], 0));
+    rc = run_chunk(h, nullptr, 0, 0, h->d_frames[s], tab, channel_order, n, d_probs + (size_t)b0 * 5,
+                   d_logits + (size_t)b0 * 5, static_cast<char*>(h->d_ws), h->s_compute);
+    if (rc) return rc;
+    ERNET_CUDA(cudaEventRecord(h->ev_done[s], h->s_compute));
+  }
+  ERNET_CUDA(cudaMemcpyAsync(probs_host, d_probs, (size_t)batch * 5 * sizeof(float), cudaMemcpyDeviceToHost, h->s_compute));
+  if (logits_host)
+    ERNET_CUDA(cudaMemcpyAsync(logits_host, d_logits, (size_t)batch * 5 * sizeof(float), cudaMemcpyDeviceToHost, h->s_compute));
+  ERNET_CUDA(cudaStreamSynchronize(h->s_compute));
+  return ERNET_OK;
+}
+
+int ernet_acff_depthwise(const void* x, int dtype, int batch, int H, int W, int C, int out_h, int out_w,
+                         const float* w, const float* b, void* out, void* stream) {
+  if (!x || !w || !b || !out || batch < 1) return fail(ERNET_ERR_INVALID_ARG, "ernet_acff_depthwise: bad argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  static thread_local bool attrs = false;
+  if (!attrs) { int rc = init_device_attrs(); if (rc) return rc; attrs = true; }
+  for (int b0 = 0; b0 < batch; b0 += 32768) {
+    const int n = batch - b0 < 32768 ? batch - b0 : 32768;
+    const size_t xi = (size_t)b0 * H * W * C, oi = (size_t)b0 * out_h * out_w * 3 * C;
+    int rc;
+    if (dtype == ERNET_F32) rc = launch_acff_dw<float>(static_cast<const float*>(x) + xi, n, H, W, C, out_h, out_w, w, b, static_cast<float*>(out) + oi, s);
+    else if (dtype == ERNET_F16) rc = launch_acff_dw<__half>(static_cast<const __half*>(x) + xi, n, H, W, C, out_h, out_w, w, b, static_cast<__half*>(out) + oi, s);
+    else if (dtype == ERNET_BF16) rc = launch_acff_dw<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(x) + xi, n, H, W, C, out_h, out_w, w, b, static_cast<__nv_bfloat16*>(out) + oi, s);
+    else return fail(ERNET_ERR_INVALID_ARG, "bad dtype %d", dtype);
+    if (rc) return rc;
+  }
+  return ERNET_OK;
+}
+
+int ernet_pointwise(const void* a, int dtype, int batch, int H, int W, int K, int N, const float* w, const float* bias,
+                    const float* bn_scale, const float* bn_shift, int leaky, int pool, void* out, void* stream) {
+  if (!a || !w || !out || batch < 1) return fail(ERNET_ERR_INVALID_ARG, "ernet_pointwise: bad argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == ERNET_F32) return launch_pointwise<float>(static_cast<const float*>(a), batch, H, W, K, N, w, bias, bn_scale, bn_shift, leaky, pool, static_cast<float*>(out), s);
+  if (dtype == ERNET_F16) return launch_pointwise<__half>(static_cast<const __half*>(a), batch, H, W, K, N, w, bias, bn_scale, bn_shift, leaky, pool, static_cast<__half*>(out), s);
+  if (dtype == ERNET_BF16) return launch_pointwise<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(a), batch, H, W, K, N, w, bias, bn_scale, bn_shift, leaky, pool, static_cast<__nv_bfloat16*>(out), s);
+  return fail(ERNET_ERR_INVALID_ARG, "bad dtype %d", dtype);
+}
+
+int ernet_debug_tap(ernet_handle* h, int tap, const void* workspace, int batch, float* out, size_t out_elems, void* stream) {
+  if (!h || !workspace || !out) return fail(ERNET_ERR_INVALID_ARG, "ernet_debug_tap: null argument");
+  if (batch < 1 || batch > h->chunk) return fail(ERNET_ERR_INVALID_ARG, "tap batch must be within one chunk");
+  const Plan p = make_plan(h, batch);
+  size_t off; int C, HW;
+  switch (tap) {
+    case ERNET_TAP_INGEST: off = p.ingest; C = 3; HW = 140 * 140; break;
+    case ERNET_TAP_STEM: off = p.stem; C = h->cs(); HW = 69 * 69; break;
+    case ERNET_TAP_POOL1: off = p.p1; C = 64; HW = 33 * 33; break;
+    case ERNET_TAP_POOL2: off = p.p2; C = h->c3(); HW = 15 * 15; break;
+    case ERNET_TAP_POOL3: off = h->red() ? p.r3 : p.p3; C = h->c4(); HW = 36; break;
+    case ERNET_TAP_ACFF4: off = p.a4; C = 256; HW = 16; break;
+    default: return fail(ERNET_ERR_INVALID_ARG, "unknown tap %d", tap);
+  }
+  const long long total = (long long)batch * C * HW;
+  if ((size_t)total != out_elems) return fail(ERNET_ERR_BAD_SHAPE, "tap %d has %lld elements, caller expects %zu", tap, total, out_elems);
+  DeviceGuard g(h->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const char* src = static_cast<const char*>(workspace) + off;
+  const int grid = (int)((total + 255) / 256);
+  if (h->precision == ERNET_PREC_FP32) tap_nhwc_to_nchw_f32<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(src), C, HW, total, out);
+  else if (h->precision == ERNET_PREC_FP16) tap_nhwc_to_nchw_f32<__half><<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(src), C, HW, total, out);
+  else tap_nhwc_to_nchw_f32<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), C, HW, total, out);
+  ERNET_LAUNCH_CHECK("tap_nhwc_to_nchw_f32");
+  return ERNET_OK;
+}
+
+int ernet_ingest_tables_host(int height, int width, int* meta, int* xmin, int* xlen, int* kx, int* ymin, int* ylen,
+                              int* ky, float* lut) {
+  if (!meta || !xmin || !xlen || !kx || !ymin || !ylen || !ky) return fail(ERNET_ERR_INVALID_ARG, "null argument");
+  IngestTables t;
+  if (height < 1 || width < 1) return fail(ERNET_ERR_INVALID_ARG, "bad frame size %dx%d", height, width);
+  if (width <= height) { t.new_w = kResizeShort; t.new_h = (int)((double)kResizeShort * height / width); }
+  else                 { t.new_h = kResizeShort; t.new_w = (int)((double)kResizeShort * width / height); }
+  if (t.new_h < kCrop || t.new_w < kCrop) return fail(ERNET_ERR_BAD_SHAPE, "resized frame smaller than crop");
+  t.top = py_round_half_even((t.new_h - kCrop) / 2.0);
+  t.left = py_round_half_even((t.new_w - kCrop) / 2.0);
+  std::vector<int> vxmin, vxlen, vkx, vymin, vylen, vky;
+  host_coeffs(width, t.new_w, t.left, kCrop, t.ksx, vxmin, vxlen, vkx);
+  host_coeffs(height, t.new_h, t.top, kCrop, t.ksy, vymin, vylen, vky);
+  if (t.ksx > kMaxTaps || t.ksy > kMaxTaps) return fail(ERNET_ERR_UNSUPPORTED, "too many taps");
+  meta[0] = t.new_h; meta[1] = t.new_w; meta[2] = t.top; meta[3] = t.left; meta[4] = t.ksy; meta[5] = t.ksx;
+  memcpy(xmin, vxmin.data(), kCrop * sizeof(int)); memcpy(xlen, vxlen.data(), kCrop * sizeof(int));
+  memcpy(ymin, vymin.data(), kCrop * sizeof(int)); memcpy(ylen, vylen.data(), kCrop * sizeof(int));
+  memcpy(kx, vkx.data(), vkx.size() * sizeof(int)); memcpy(ky, vky.data(), vky.size() * sizeof(int));
+  if (lut) host_lut(lut);
+  return ERNET_OK;
+}
+
+int ernet_profile_enable(ernet_handle* h, int on) {
+  if (!h) return fail(ERNET_ERR_INVALID_ARG, "null handle");
+  h->profiling = on != 0;
+  return ERNET_OK;
+}
+
+int ernet_profile_read(ernet_handle* h, double* ms_by_stage, int* launches_by_stage, int n_stages) {
+  if (!h || !ms_by_stage || !launches_by_stage || n_stages < ERNET_STAGE_COUNT)
+    return fail(ERNET_ERR_INVALID_ARG, "ernet_profile_read: need arrays of ERNET_STAGE_COUNT entries");
+  DeviceGuard g(h->device);
+  for (int i = 0; i < n_stages; ++i) { ms_by_stage[i] = 0.0; launches_by_stage[i] = 0; }
+  for (auto& r : h->prof) {
+    ERNET_CUDA(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    ERNET_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    ms_by_stage[r.stage] += ms;
+    launches_by_stage[r.stage] += 1;
+    h->prof_pool.push_back(r.a);
+    h->prof_pool.push_back(r.b);
+  }
+  h->prof.clear();
+  return ERNET_OK;
+}
+
+int ernet_launches_per_forward(const ernet_handle* h, int batch, int with_ingest) {
+  if (!h || batch < 1) return 0;
+  const int chunks = (batch + h->chunk - 1) / h->chunk;
+  const int per = (with_ingest ? 1 : 0) + 1 + 8 + (h->red() ? 2 : 0) + 1;
+  return chunks * per;
+}
+
+}  // extern "C"

@@ -1,0 +1,377 @@
+// CUDA-core ("simt") kernels of the Squeeze-ErNet forward pass: fp32 arithmetic, activations stored
+// NHWC in T (fp32 / fp16 / bf16).  This is the product path for precision=fp32 (tensor cores top out
+// at TF32, which cannot hold the 1e-4 logit bound) and the layer-wise reference implementation that
+// the fused tensor-core kernels are validated against on the device.
+//
+//   stem_kernel          conv1 3x3/s2 3->16            model/squeeze_ernet.py:11,25
+//                        (+conv_red1 folded, 3->8)     model/squeeze_ernet_redconv.py:12,28-29
+//   acff_dw_kernel       three dilated depthwise 3x3 + concat      model/acff.py:25-30,46
+//   pointwise_kernel     1x1 conv + bias [+LeakyReLU] [+BN affine] [+2x2 max-pool]
+//                                                      model/acff.py:31-34,51-53, squeeze_ernet.py:13
+//   head_kernel          conv2 -> AvgPool(5,1,1) -> view -> fc -> softmax, collapsed
+//                                                      model/squeeze_ernet.py:19-22,33-41
+#pragma once
+#include "common.cuh"
+
+namespace ernet {
+
+// ---------------------------------------------------------------------------------- stem
+// One thread = one output pixel, all CS output channels.  Input addressed through element strides so
+// NCHW (the reference's layout) and NHWC (the ingest kernel's) are both read in place.
+template <typename TI, typename TO, int CS>
+__global__ void __launch_bounds__(128)
+stem_kernel(const TI* __restrict__ x, long long sb, long long sc, long long sy, long long sx,
+            const float* __restrict__ w /*[27][CS]*/, const float* __restrict__ bias /*[CS]*/,
+            TO* __restrict__ out /*(B,69,69,CS)*/, int total) {
+  __shared__ float ws[27 * CS + CS];
+  for (int i = threadIdx.x; i < 27 * CS + CS; i += blockDim.x) ws[i] = i < 27 * CS ? w[i] : bias[i - 27 * CS];
+  __syncthreads();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int b = idx / (69 * 69);
+  const int r = idx - b * 69 * 69;
+  const int oy = r / 69, ox = r - oy * 69;
+  float acc[CS];
+#pragma unroll
+  for (int o = 0; o < CS; ++o) acc[o] = ws[27 * CS + o];
+  const TI* p = x + b * sb + (2 * oy) * sy + (2 * ox) * sx;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v = to_f32<TI>(p[ky * sy + kx * sx + c * sc]);
+        const float* wr = ws + ((ky * 3 + kx) * 3 + c) * CS;
+#pragma unroll
+        for (int o = 0; o < CS; ++o) acc[o] = fmaf(v, wr[o], acc[o]);
+      }
+  constexpr int NV = Vec16<TO>::NV;
+  uint4* o4 = reinterpret_cast<uint4*>(out + (size_t)idx * CS);
+#pragma unroll
+  for (int v = 0; v < CS / NV; ++v) {
+    float t[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) t[i] = acc[v * NV + i];
+    o4[v] = pack16<TO>(t);
+  }
+}
+
+// ---------------------------------------------------------------------------------- depthwise trio
+// CTA = one (th x tw) tile of output pixels of one image, all C channels.  The (th+6)x(tw+6) input halo
+// (rows/cols y-2 .. y+4: the union of the three dilations) is staged in shared memory with 16-byte
+// NHWC vectors, out-of-image taps read zeros (= the conv padding 0/1/2 of acff.py:25-30).  Each thread
+// then produces one 16-byte channel vector of one pixel for all three branches and stores them at
+// channel offsets 0, C, 2C (the concat of acff.py:46).
+template <typename T>
+__global__ void __launch_bounds__(256)
+acff_dw_kernel(const T* __restrict__ x, int H, int W, int C, int out_h, int out_w, int th, int tw,
+               const float* __restrict__ w /*[3][9][C]*/, const float* __restrict__ bias /*[3][C]*/,
+               T* __restrict__ out /*(B,out_h,out_w,3C)*/) {
+  constexpr int NV = Vec16<T>::NV;
+  extern __shared__ uint4 dw_smem[];
+  const int cv = C / NV;                       // vectors per pixel
+  const int hh = th + 6, hw = tw + 6;
+  uint4* tile = dw_smem;                       // [hh][hw][cv]
+  float* wsm = reinterpret_cast<float*>(dw_smem + (size_t)hh * hw * cv);  // [27][C] then bias [3][C]
+  const int b = blockIdx.z;
+  const int y0 = blockIdx.y * th, x0 = blockIdx.x * tw;
+  const T* xb = x + (size_t)b * H * W * C;
+
+  for (int i = threadIdx.x; i < 30 * C; i += blockDim.x) wsm[i] = i < 27 * C ? w[i] : bias[i - 27 * C];
+  for (int i = threadIdx.x; i < hh * hw * cv; i += blockDim.x) {
+    const int v = i % cv;
+    const int p = i / cv;
+    const int px = p % hw, py = p / hw;
+    const int gy = y0 - 2 + py, gx = x0 - 2 + px;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+      val = __ldg(reinterpret_cast<const uint4*>(xb + ((size_t)gy * W + gx) * C) + v);
+    tile[i] = val;
+  }
+  __syncthreads();
+
+  const int items = th * tw * cv;
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int v = i % cv;
+    const int p = i / cv;
+    const int lx = p % tw, ly = p / tw;
+    const int oy = y0 + ly, ox = x0 + lx;
+    if (oy >= out_h || ox >= out_w) continue;
+    float acc[3][NV];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) acc[d][k] = wsm[27 * C + d * C + v * NV + k];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const int dil = d + 1;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          // tap offset from the output coordinate: k*dil - (dil-1); +2 for the halo origin
+          const int ty = ly + 2 + ky * dil - (dil - 1);
+          const int tx = lx + 2 + kx * dil - (dil - 1);
+          float xv[NV];
+          unpack16<T>(tile[((size_t)ty * hw + tx) * cv + v], xv);
+          const float* wr = wsm + (d * 9 + ky * 3 + kx) * C + v * NV;
+#pragma unroll
+          for (int k = 0; k < NV; ++k) acc[d][k] = fmaf(xv[k], wr[k], acc[d][k]);
+        }
+    }
+    T* o = out + (((size_t)b * out_h + oy) * out_w + ox) * (3 * C) + v * NV;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) *reinterpret_cast<uint4*>(o + d * C) = pack16<T>(acc[d]);
+  }
+}
+
+inline void dw_pick_tile(int C, int esize, int out_h, int out_w, int& th, int& tw, size_t& smem) {
+  // largest square-ish tile whose halo fits in ~96 KB (two CTAs per SM)
+  static const int cand[] = {22, 16, 15, 12, 11, 10, 8, 6, 5, 4, 3, 2, 1};
+  for (int t : cand) {
+    int tth = t < out_h ? t : out_h, ttw = t < out_w ? t : out_w;
+    size_t s = (size_t)(tth + 6) * (ttw + 6) * C * esize + 30 * (size_t)C * sizeof(float);
+    if (s <= 96 * 1024) { th = tth; tw = ttw; smem = s; return; }
+  }
+  th = tw = 1;
+  smem = (size_t)49 * C * esize + 30 * (size_t)C * sizeof(float);
+}
+
+template <typename T>
+inline int launch_acff_dw(const T* x, int batch, int H, int W, int C, int out_h, int out_w,
+                          const float* w, const float* bias, T* out, cudaStream_t stream) {
+  if (C % Vec16<T>::NV) return fail(ERNET_ERR_INVALID_ARG, "depthwise: C=%d not a multiple of %d", C, Vec16<T>::NV);
+  if (out_h > H - 2 || out_w > W - 2 || out_h < 1 || out_w < 1)
+    return fail(ERNET_ERR_INVALID_ARG, "depthwise: bad output size %dx%d for input %dx%d", out_h, out_w, H, W);
+  int th, tw;
+  size_t smem;
+  dw_pick_tile(C, (int)sizeof(T), out_h, out_w, th, tw, smem);
+  dim3 grid((out_w + tw - 1) / tw, (out_h + th - 1) / th, batch);
+  acff_dw_kernel<T><<<grid, 256, smem, stream>>>(x, H, W, C, out_h, out_w, th, tw, w, bias, out);
+  ERNET_LAUNCH_CHECK("acff_dw_kernel");
+  return ERNET_OK;
+}
+
+// ---------------------------------------------------------------------------------- pointwise (1x1)
+// Register-tiled FFMA GEMM: rows = pixels, K = input channels, N = output channels.  CTA tile 128 x BN,
+// thread tile 8 x 4.  With POOL the 128 rows are 32 pooled pixels x their 2x2 quad, so the max-pool is an
+// in-thread max over 4 consecutive rows and the un-pooled map never reaches memory.
+struct PwGeom {
+  int H, W;        // spatial size of the input map (rows of A = B*H*W, compact NHWC)
+  int Hp, Wp;      // pooled size (floor(H/2), floor(W/2)) when pooling
+  int m_total;     // number of output rows (pooled pixels when pooling)
+};
+
+template <typename T, int BN, bool POOL>
+__global__ void __launch_bounds__(16 * BN / 4)
+pointwise_kernel(const T* __restrict__ A, int K, int N, const float* __restrict__ Wt /*[K][N]*/,
+                 const float* __restrict__ bias, const float* __restrict__ bn_s, const float* __restrict__ bn_t,
+                 int leaky, PwGeom g, T* __restrict__ out) {
+  constexpr int BM = 128, BK = 8, NT = 16 * BN / 4;
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN];
+  __shared__ long long rowoff[BM];   // element offset of each A row, -1 = out of range
+
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.y * BN;
+  const int out_rows_per_tile = POOL ? BM / 4 : BM;
+  const int o0 = blockIdx.x * out_rows_per_tile;
+
+  for (int r = tid; r < BM; r += NT) {
+    long long off = -1;
+    if (POOL) {
+      const int p = o0 + (r >> 2), q = r & 3;
+      if (p < g.m_total) {
+        const int b = p / (g.Hp * g.Wp);
+        const int rem = p - b * g.Hp * g.Wp;
+        const int py = rem / g.Wp, px = rem - py * g.Wp;
+        off = (((long long)b * g.H + (2 * py + (q >> 1))) * g.W + (2 * px + (q & 1))) * K;
+      }
+    } else {
+      const int m = o0 + r;
+      if (m < g.m_total) off = (long long)m * K;
+    }
+    rowoff[r] = off;
+  }
+  __syncthreads();
+
+  const int tr = tid / (BN / 4), tc = tid % (BN / 4);
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    for (int i = tid; i < BM * 2; i += NT) {
+      const int r = i >> 1, kh = (i & 1) * 4;
+      const long long off = rowoff[r];
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (off >= 0) {
+        const T* p = A + off + k0 + kh;
+        if constexpr (sizeof(T) == 4) {
+          const float4 f = __ldg(reinterpret_cast<const float4*>(p));
+          v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+        } else {
+          const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
+          const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = to_f32<T>(e[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) As[kh + j][r] = v[j];
+    }
+    for (int i = tid; i < BK * BN / 4; i += NT) {
+      const int kk = i / (BN / 4), c4 = i % (BN / 4);
+      const float4 f = __ldg(reinterpret_cast<const float4*>(Wt + (size_t)(k0 + kk) * N + n0) + c4);
+      *reinterpret_cast<float4*>(&Bs[kk][c4 * 4]) = f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][tr * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][tr * 8 + 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tc * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  float bsv[4], ssv[4], tsv[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int n = n0 + tc * 4 + j;
+    bsv[j] = bias ? bias[n] : 0.f;
+    ssv[j] = bn_s ? bn_s[n] : 1.f;
+    tsv[j] = bn_t ? bn_t[n] : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v = acc[i][j] + bsv[j];
+      if (leaky) v = leaky_relu(v);
+      acc[i][j] = fmaf(v, ssv[j], tsv[j]);
+    }
+
+  auto store4 = [&](int orow, const float (&v)[4]) {
+    T* o = out + (size_t)orow * N + n0 + tc * 4;
+    if constexpr (sizeof(T) == 4) {
+      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+      T e[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) e[j] = from_f32<T>(v[j]);
+      *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(e);
+    }
+  };
+  if (POOL) {
+#pragma unroll
+    for (int qd = 0; qd < 2; ++qd) {
+      const int p = o0 + tr * 2 + qd;
+      if (p < g.m_total) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          v[j] = fmaxf(fmaxf(acc[qd * 4][j], acc[qd * 4 + 1][j]), fmaxf(acc[qd * 4 + 2][j], acc[qd * 4 + 3][j]));
+        store4(p, v);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = o0 + tr * 8 + i;
+      if (m < g.m_total) store4(m, acc[i]);
+    }
+  }
+}
+
+template <typename T>
+inline int launch_pointwise(const T* a, int batch, int H, int W, int K, int N, const float* w, const float* bias,
+                            const float* bn_s, const float* bn_t, int leaky, int pool, T* out, cudaStream_t stream) {
+  if (K % 8) return fail(ERNET_ERR_INVALID_ARG, "pointwise: K=%d not a multiple of 8", K);
+  PwGeom g;
+  g.H = H; g.W = W; g.Hp = H / 2; g.Wp = W / 2;
+  g.m_total = pool ? batch * g.Hp * g.Wp : batch * H * W;
+  if (g.m_total <= 0) return fail(ERNET_ERR_INVALID_ARG, "pointwise: empty output");
+  const int rows_per_tile = pool ? 32 : 128;
+  const int bn = (N % 64 == 0) ? 64 : ((N % 48 == 0) ? 48 : ((N % 32 == 0) ? 32 : 0));
+  if (!bn) return fail(ERNET_ERR_INVALID_ARG, "pointwise: N=%d must be a multiple of 32 or 48", N);
+  dim3 grid((g.m_total + rows_per_tile - 1) / rows_per_tile, N / bn);
+#define ERNET_PW(BN_)                                                                                        \
+  do {                                                                                                       \
+    if (pool) pointwise_kernel<T, BN_, true><<<grid, 16 * BN_ / 4, 0, stream>>>(a, K, N, w, bias, bn_s, bn_t, leaky, g, out); \
+    else      pointwise_kernel<T, BN_, false><<<grid, 16 * BN_ / 4, 0, stream>>>(a, K, N, w, bias, bn_s, bn_t, leaky, g, out); \
+  } while (0)
+  if (bn == 64) ERNET_PW(64); else if (bn == 48) ERNET_PW(48); else ERNET_PW(32);
+#undef ERNET_PW
+  ERNET_LAUNCH_CHECK("pointwise_kernel");
+  return ERNET_OK;
+}
+
+// ---------------------------------------------------------------------------------- head
+// At 140x140 input acff4 yields a 4x4 map; AvgPool2d(5,1,1) on a 4x4 map gives a 2x2 map whose four
+// entries are all sum(4x4)/25, so conv2 -> pool -> view -> fc is logits = W_eff . sum_pixels(a4) + b_fc
+// with W_eff[5][256] precomputed by the packer.  One CTA of 256 threads per image.
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_kernel(const T* __restrict__ a4 /*(B,4,4,256)*/, const float* __restrict__ w_eff /*[5][256]*/,
+            const float* __restrict__ b_fc, float* __restrict__ probs, float* __restrict__ logits) {
+  __shared__ float red[8][5];
+  const int b = blockIdx.x, c = threadIdx.x;
+  const T* p = a4 + (size_t)b * 16 * 256 + c;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += to_f32<T>(p[i * 256]);
+  float part[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) part[j] = s * w_eff[j * 256 + c];
+#pragma unroll
+  for (int j = 0; j < 5; ++j)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part[j] += __shfl_xor_sync(0xffffffffu, part[j], o);
+  if ((c & 31) == 0)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) red[c >> 5][j] = part[j];
+  __syncthreads();
+  if (c == 0) {
+    float z[5], m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      float t = b_fc[j];
+#pragma unroll
+      for (int wv = 0; wv < 8; ++wv) t += red[wv][j];
+      z[j] = t;
+      m = fmaxf(m, t);
+    }
+    float e[5], sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { e[j] = expf(z[j] - m); sum += e[j]; }
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      probs[b * 5 + j] = e[j] / sum;
+      if (logits) logits[b * 5 + j] = z[j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- debug tap
+template <typename T>
+__global__ void tap_nhwc_to_nchw_f32(const T* __restrict__ src, int C, int HW, long long total, float* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // NCHW index
+  if (i >= total) return;
+  const int p = (int)(i % HW);
+  const long long bc = i / HW;
+  const int c = (int)(bc % C);
+  const long long b = bc / C;
+  dst[i] = to_f32<T>(src[(b * HW + p) * C + c]);
+}
+
+}  // namespace ernet

@@ -1,0 +1,318 @@
+"""Host-side mirror of the reference's model plugin surface, backed by the CUDA library.
+
+Drop-in for ``code/disaster_detection/model`` as used by ``aider-predict.py:22-45,76`` and
+``evaluate-classification-metrics.py:24-47,77``:
+
+    model = Squeeze_ErNET()                  # zero-arg constructor   (model/squeeze_ernet.py:8)
+    model.load_state_dict(torch.load(path))  # same 56 / 62 keys      
+    model = model.to(device); model.eval()
+    probs = model(x)                         # (B,3,140,140) -> (B,5) softmax probabilities
+
+The ``torch.nn`` leaf modules created here are parameter *containers* only (so ``state_dict``,
+``load_state_dict``, ``parameters``, ``to``, ``half``, ``apply`` behave exactly like the
+reference's); none of them is ever called.  All arithmetic happens in ``libernet_b200.so``
+through the C ABI of ``include/ernet_b200.h``.  Without that library, or without a CUDA device,
+``forward`` raises: there is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .pack import pack_state_dict, widths
+
+_PREC_OF_DTYPE = {torch.float32: "fp32", torch.float16: "fp16", torch.bfloat16: "bf16"}
+_DTYPE_CODE = {torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16, torch.bfloat16: _lib.DTYPE_BF16}
+_TAP_SHAPES = {  # name -> lambda(arch) -> (C, H, W)
+    "ingest": lambda a: (3, 140, 140),
+    "stem": lambda a: (widths(a)[0][0], 69, 69),
+    "pool1": lambda a: (64, 33, 33),
+    "pool2": lambda a: (widths(a)[2][0], 15, 15),
+    "pool3": lambda a: (widths(a)[3][0], 6, 6),
+    "acff4": lambda a: (256, 4, 4),
+}
+
+
+class _ACFFParams(nn.Module):
+    """Parameter container with the child names of the reference's ACFF block (acff.py:25-35)."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        for j, d in ((1, 1), (2, 2), (3, 3)):
+            setattr(self, f"conv{j}", nn.Conv2d(cin, cin, 3, 1, d - 1, d, groups=cin, bias=True))
+        self.fused_conv = nn.Conv2d(3 * cin, cout, 1, bias=True)
+        self.batch_norm = nn.BatchNorm2d(cout)
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter container: compute happens in libernet_b200.so")
+
+
+class _ErnetB200(nn.Module):
+    ARCH = None
+
+    def __init__(self, *, precision=None, device=None):
+        super().__init__()
+        arch = self.ARCH
+        red = arch == "squeeze-redconv"
+        w = widths(arch)
+        self.conv1 = nn.Conv2d(3, 16, 3, 2, 0, bias=False)
+        if red:
+            self.conv_red1 = nn.Conv2d(16, 8, 1)
+        self.acff1 = _ACFFParams(*w[0])
+        self.acff2 = _ACFFParams(*w[1])
+        if red:
+            self.conv_red2 = nn.Conv2d(96, 48, 1)
+        self.acff3 = _ACFFParams(*w[2])
+        if red:
+            self.conv_red3 = nn.Conv2d(128, 64, 1)
+        self.acff4 = _ACFFParams(*w[3])
+        self.conv2 = nn.Conv2d(256, 5, 1, bias=False)
+        self.fc = nn.Linear(2 * 2 * 5, 5)
+        if precision is not None and precision not in _lib.PRECISION:
+            raise ValueError(f"unknown precision {precision!r}; expected one of {sorted(_lib.PRECISION)}")
+        self._precision = precision          # None: follow the parameter dtype (fp32, or fp16 after .half())
+        self._engine = None                  # (handle, device_index, precision)
+        self._fingerprint = None
+        self._workspace = None
+        self._last_batch = 0
+        if device is not None:
+            self.to(device)
+
+    # ------------------------------------------------------------------ precision / engine
+    @property
+    def precision(self):
+        if self._precision is not None:
+            return self._precision
+        return _PREC_OF_DTYPE.get(self.conv1.weight.dtype, "fp32")
+
+    def set_precision(self, precision):
+        if precision not in _lib.PRECISION:
+            raise ValueError(f"unknown precision {precision!r}")
+        self._precision = precision
+        return self
+
+    def _weights_fingerprint(self):
+        fp = []
+        for t in list(self.parameters()) + list(self.buffers()):
+            fp.append((t.data_ptr(), t._version))
+        return tuple(fp)
+
+    def _release(self):
+        if self._engine is not None:
+            _lib.load().ernet_destroy(self._engine[0])
+            self._engine = None
+            self._fingerprint = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _ensure_engine(self):
+        dev = self.conv1.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("this model runs only on a CUDA device (B200, sm_100a); call .to('cuda') first — "
+                               "there is no CPU fallback")
+        if self.training:
+            raise RuntimeError("inference-only engine: call model.eval() first (train mode would need dropout and "
+                               "batch statistics, acff.py:34-35)")
+        lib = _lib.load()
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        prec = self.precision
+        if self._engine is None or self._engine[1:] != (idx, prec):
+            self._release()
+            h = C.c_void_p()
+            _lib.check(lib.ernet_create(C.byref(h), _lib.ARCH[self.ARCH], _lib.PRECISION[prec], idx))
+            self._engine = (h, idx, prec)
+        fp = self._weights_fingerprint()
+        if fp != self._fingerprint:
+            blob = pack_state_dict(self.state_dict(), self.ARCH, prec)
+            buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+            _lib.check(lib.ernet_load_packed(self._engine[0], buf, len(blob)))
+            self._fingerprint = fp
+        return lib, self._engine[0], idx
+
+    def _get_workspace(self, lib, h, batch, device):
+        need = lib.ernet_workspace_bytes(h, batch)
+        if self._workspace is None or self._workspace.numel() < need or self._workspace.device != device:
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=device)
+        return self._workspace
+
+    def set_chunk(self, n):
+        """Images processed per internal pass (bounds the workspace; default 1024)."""
+        lib, h, _ = self._ensure_engine()
+        _lib.check(lib.ernet_set_chunk(h, int(n)))
+        return self
+
+    # ------------------------------------------------------------------ model(x)
+    def _run(self, x, want_logits):
+        if not isinstance(x, torch.Tensor):
+            raise TypeError("expected a torch.Tensor")
+        if x.dim() != 4 or tuple(x.shape[1:]) != (3, 140, 140):
+            # the reference fails (or silently mixes images) for any other size, squeeze_ernet.py:39
+            raise ValueError(f"expected input of shape (B,3,140,140), got {tuple(x.shape)}")
+        if x.dtype not in _DTYPE_CODE:
+            raise ValueError(f"unsupported input dtype {x.dtype}")
+        lib, h, idx = self._ensure_engine()
+        if x.device.type != "cuda" or (x.device.index or 0) != idx:
+            raise RuntimeError(f"input is on {x.device} but the model is on cuda:{idx}")
+        B = x.shape[0]
+        if B < 1:
+            raise ValueError("empty batch")
+        layout = _lib.NCHW
+        if not x.is_contiguous():
+            if x.is_contiguous(memory_format=torch.channels_last):
+                layout = _lib.NHWC
+            else:
+                x = x.contiguous()
+        ws = self._get_workspace(lib, h, B, x.device)
+        probs = torch.empty((B, 5), dtype=torch.float32, device=x.device)
+        logits = torch.empty((B, 5), dtype=torch.float32, device=x.device) if want_logits else None
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(lib.ernet_forward(h, x.data_ptr(), _DTYPE_CODE[x.dtype], layout, B, probs.data_ptr(),
+                                     logits.data_ptr() if want_logits else None, ws.data_ptr(), ws.numel(), stream))
+        self._last_batch = B
+        return probs, logits
+
+    def forward(self, x):
+        """Softmax probabilities (B,5) in the dtype of ``x`` (squeeze_ernet.py:41)."""
+        probs, _ = self._run(x, False)
+        return probs if x.dtype == torch.float32 else probs.to(x.dtype)
+
+    def logits(self, x):
+        """Pre-softmax ``fc`` output (B,5) fp32 — what parity is judged on."""
+        return self._run(x, True)[1]
+
+    def forward_with_logits(self, x):
+        return self._run(x, True)
+
+    # ------------------------------------------------------------------ frames -> probabilities
+    def forward_frames(self, frames, *, bgr=False, return_logits=False):
+        """uint8 (B,H,W,3) device frames -> probabilities: the eval transform
+        (dataloaders/aider.py:421-426) and the model in one call."""
+        if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[3] != 3:
+            raise ValueError(f"expected uint8 frames of shape (B,H,W,3), got {frames.dtype} {tuple(frames.shape)}")
+        lib, h, idx = self._ensure_engine()
+        if frames.device.type != "cuda" or (frames.device.index or 0) != idx:
+            raise RuntimeError(f"frames are on {frames.device} but the model is on cuda:{idx}")
+        frames = frames.contiguous()
+        B, H, W, _ = frames.shape
+        ws = self._get_workspace(lib, h, B, frames.device)
+        probs = torch.empty((B, 5), dtype=torch.float32, device=frames.device)
+        logits = torch.empty((B, 5), dtype=torch.float32, device=frames.device) if return_logits else None
+        stream = torch.cuda.current_stream(frames.device).cuda_stream
+        _lib.check(lib.ernet_forward_frames(h, frames.data_ptr(), B, H, W, _lib.BGR if bgr else _lib.RGB,
+                                            probs.data_ptr(), logits.data_ptr() if return_logits else None,
+                                            ws.data_ptr(), ws.numel(), stream))
+        self._last_batch = B
+        return (probs, logits) if return_logits else probs
+
+    def classify_host(self, frames, *, bgr=False, return_logits=False):
+        """Host uint8 frames (numpy array or CPU tensor, (B,H,W,3)) -> numpy probabilities.  Copies in
+        and out happen inside the library, overlapped with the kernels (``predict()`` of
+        aider-predict.py:47-86 for a batch)."""
+        if isinstance(frames, torch.Tensor):
+            if frames.device.type != "cpu":
+                raise ValueError("classify_host expects host memory; use forward_frames for device tensors")
+            arr = frames.contiguous().numpy()
+        else:
+            arr = np.ascontiguousarray(frames)
+        if arr.dtype != np.uint8 or arr.ndim != 4 or arr.shape[3] != 3:
+            raise ValueError(f"expected uint8 frames of shape (B,H,W,3), got {arr.dtype} {arr.shape}")
+        lib, h, _ = self._ensure_engine()
+        B, H, W, _c = arr.shape
+        probs = np.empty((B, 5), dtype=np.float32)
+        logits = np.empty((B, 5), dtype=np.float32) if return_logits else None
+        _lib.check(lib.ernet_classify_frames_host(h, arr.ctypes.data, B, H, W, _lib.BGR if bgr else _lib.RGB,
+                                                  probs.ctypes.data, logits.ctypes.data if return_logits else None))
+        return (probs, logits) if return_logits else probs
+
+    def prepare_ingest(self, height, width):
+        lib, h, _ = self._ensure_engine()
+        _lib.check(lib.ernet_prepare_ingest(h, int(height), int(width)))
+
+    def ingest(self, frames, *, bgr=False, dtype=torch.float32):
+        """The eval transform alone: uint8 (B,H,W,3) device frames -> (B,3,140,140) tensor."""
+        lib, h, _ = self._ensure_engine()
+        frames = frames.contiguous()
+        B, H, W, _c = frames.shape
+        out = torch.empty((B, 3, 140, 140), dtype=dtype, device=frames.device)
+        stream = torch.cuda.current_stream(frames.device).cuda_stream
+        _lib.check(lib.ernet_ingest_u8(h, frames.data_ptr(), B, H, W, _lib.BGR if bgr else _lib.RGB,
+                                       out.data_ptr(), _DTYPE_CODE[dtype], _lib.NCHW, stream))
+        return out
+
+    # ------------------------------------------------------------------ introspection (tests)
+    def tap(self, name):
+        """fp32 NCHW copy of an intermediate of the most recent forward (B <= chunk)."""
+        lib, h, idx = self._ensure_engine()
+        Cc, H, W = _TAP_SHAPES[name](self.ARCH)
+        B = self._last_batch
+        out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=self._workspace.device)
+        stream = torch.cuda.current_stream(out.device).cuda_stream
+        _lib.check(lib.ernet_debug_tap(h, _lib.TAPS[name], self._workspace.data_ptr(), B, out.data_ptr(),
+                                       out.numel(), stream))
+        return out
+
+    def profile(self, on=True):
+        """Turn per-stage CUDA-event timing on/off (see ernet_profile_enable)."""
+        lib, h, _ = self._ensure_engine()
+        _lib.check(lib.ernet_profile_enable(h, 1 if on else 0))
+
+    def profile_read(self):
+        """{stage: (total_ms, launches)} since the previous read."""
+        lib, h, _ = self._ensure_engine()
+        n = len(_lib.STAGES)
+        ms = (C.c_double * n)()
+        cnt = (C.c_int * n)()
+        _lib.check(lib.ernet_profile_read(h, ms, cnt, n))
+        return {_lib.STAGES[i]: (ms[i], cnt[i]) for i in range(n) if cnt[i]}
+
+    def launches_per_forward(self, batch, with_ingest=True):
+        lib, h, _ = self._ensure_engine()
+        return lib.ernet_launches_per_forward(h, int(batch), 1 if with_ingest else 0)
+
+
+class Squeeze_ErNET(_ErnetB200):
+    """B200 engine behind the reference's ``Squeeze_ErNET`` surface (model/squeeze_ernet.py:7-46)."""
+    ARCH = "squeeze-ernet"
+
+
+class Squeeze_RedConv(_ErnetB200):
+    """B200 engine behind the reference's ``Squeeze_RedConv`` surface (model/squeeze_ernet_redconv.py:7-52)."""
+    ARCH = "squeeze-redconv"
+
+
+def load_model(model_name, weights_path, device, *, precision=None):
+    """Mirror of ``load_model`` in aider-predict.py:22-45 / evaluate-classification-metrics.py:24-47."""
+    if model_name == "squeeze-ernet":
+        model = Squeeze_ErNET(precision=precision)
+    elif model_name == "squeeze-redconv":
+        model = Squeeze_RedConv(precision=precision)
+    else:
+        raise ValueError(f"Unsupported model: {model_name}")
+    checkpoint = torch.load(weights_path, map_location="cpu", weights_only=True)
+    if isinstance(checkpoint, dict) and "model_state_dict" in checkpoint:
+        model.load_state_dict(checkpoint["model_state_dict"])
+    else:
+        model.load_state_dict(checkpoint)
+    model = model.to(device)
+    model.eval()
+    return model
+
+
+def from_state_dict(arch, sd, device="cuda", precision="fp32"):
+    """Build an eval-mode engine from a mapping of numpy arrays / tensors."""
+    cls = {"squeeze-ernet": Squeeze_ErNET, "squeeze-redconv": Squeeze_RedConv}.get(arch)
+    if cls is None:
+        raise ValueError(f"Unsupported model: {arch}")
+    m = cls(precision=precision)
+    m.load_state_dict({k: torch.as_tensor(np.asarray(v)) for k, v in sd.items()})
+    m = m.to(device)
+    m.eval()
+    return m

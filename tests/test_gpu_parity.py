@@ -1,0 +1,253 @@
+"""GPU parity tests: every call goes through the C ABI (ctypes -> libernet_b200.so) and is compared with
+the CPU oracle / the goldens produced by the real reference.  Run with `pytest -m gpu` on a B200."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import fixtures
+import rtdm_b200
+from oracle import ernet_numpy as E
+from oracle import ingest_numpy as I
+from rtdm_b200 import _lib
+from test_oracle_golden import INGEST_NAMES, _case_frame
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "fp16": 2e-2, "bf16": 2e-2}     # BASELINE.json north_star tolerances (relative, on logits)
+TDT = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
+DCODE = {"fp32": 0, "fp16": 1, "bf16": 2}
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _rel(a, ref):
+    return float(np.abs(a - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def _top1_ok(logits, ref_logits, rel_err_budget):
+    """Top-1 must match unless the reference's own top-2 margin is inside the error budget."""
+    got, want = logits.argmax(1), ref_logits.argmax(1)
+    srt = np.sort(ref_logits, axis=1)
+    margin = (srt[:, -1] - srt[:, -2]) / np.abs(ref_logits).max()
+    bad = (got != want) & (margin > 2 * rel_err_budget)
+    return not bad.any()
+
+
+# ------------------------------------------------------------------------------------ ingest
+@pytest.mark.parametrize("name", INGEST_NAMES + ["real240"])
+def test_ingest_bit_exact(name, ingest_golden, dev):
+    frame = ingest_golden["real240/frame"] if name == "real240" else _case_frame(name)
+    m = rtdm_b200.from_state_dict("squeeze-ernet", fixtures.get_state_dict("squeeze-ernet", "w3"), dev, "fp32")
+    f = torch.from_numpy(frame[None]).to(dev)
+    out = m.ingest(f).cpu().numpy()[0]
+    assert np.array_equal(out, ingest_golden[f"{name}/tensor"]), name
+    # BGR input with the flag set == RGB input
+    out_bgr = m.ingest(torch.from_numpy(frame[None, :, :, ::-1].copy()).to(dev), bgr=True).cpu().numpy()[0]
+    assert np.array_equal(out_bgr, out)
+    # 16-bit outputs are the correctly rounded fp32 values
+    for dt in (torch.float16, torch.bfloat16):
+        o16 = m.ingest(f, dtype=dt).float().cpu().numpy()[0]
+        assert np.array_equal(o16, torch.from_numpy(out).to(dt).float().numpy())
+
+
+def test_ingest_batch_matches_oracle(dev):
+    frames = np.concatenate([fixtures.noise_frames(5, seed=21), fixtures.smooth_frames(4, seed=22)], 0)
+    m = rtdm_b200.from_state_dict("squeeze-ernet", fixtures.get_state_dict("squeeze-ernet", "w3"), dev, "fp32")
+    out = m.ingest(torch.from_numpy(frames).to(dev)).cpu().numpy()
+    assert np.array_equal(out, I.ingest(frames))
+
+
+# ------------------------------------------------------------------------------------ building blocks
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "fp16"])
+@pytest.mark.parametrize("shape", [(2, 69, 69, 16, 66), (2, 33, 33, 64, 30), (3, 15, 15, 96, 12), (5, 6, 6, 128, 4),
+                                   (1, 69, 69, 8, 67), (2, 15, 15, 48, 13), (1, 9, 11, 32, 7)])
+def test_acff_depthwise_kernel(prec, shape, dev):
+    B, H, W, Cc, out_h = shape
+    out_w = min(out_h, W - 2)
+    rs = np.random.RandomState(H * 100 + Cc)
+    x = rs.standard_normal((B, Cc, H, W)).astype(np.float32)
+    w = (rs.standard_normal((3, Cc, 1, 3, 3)) * 0.4).astype(np.float32)
+    b = (rs.standard_normal((3, Cc)) * 0.1).astype(np.float32)
+    xt = torch.from_numpy(x).to(dev).to(TDT[prec])
+    x_used = xt.float().cpu().numpy().astype(np.float64)          # the kernel sees the rounded input
+    ref = np.concatenate([E.conv2d_depthwise3x3(x_used, w[d].astype(np.float64), b[d].astype(np.float64), d + 1)
+                          for d in range(3)], axis=1)[:, :, :out_h, :out_w]
+    x_nhwc = xt.permute(0, 2, 3, 1).contiguous()
+    wp = torch.from_numpy(np.stack([w[d][:, 0].reshape(Cc, 9).T for d in range(3)], 0).copy()).to(dev)
+    bp = torch.from_numpy(b).to(dev)
+    out = torch.empty((B, out_h, out_w, 3 * Cc), dtype=TDT[prec], device=dev)
+    lib = _lib.load()
+    _lib.check(lib.ernet_acff_depthwise(x_nhwc.data_ptr(), DCODE[prec], B, H, W, Cc, out_h, out_w, wp.data_ptr(),
+                                        bp.data_ptr(), out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    got = out.float().permute(0, 3, 1, 2).cpu().numpy()
+    tol = {"fp32": 2e-6, "fp16": 1.5e-3, "bf16": 1e-2}[prec]       # fp32 accumulate, one output rounding
+    assert _rel(got, ref) <= tol
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("cfg", [(2, 66, 66, 48, 64, 1, 1), (2, 30, 30, 192, 96, 1, 1), (3, 12, 12, 288, 128, 1, 1),
+                                 (5, 4, 4, 384, 256, 1, 0), (2, 30, 30, 96, 48, 0, 1), (7, 6, 6, 128, 64, 0, 0),
+                                 (1, 66, 66, 24, 64, 1, 1), (1, 7, 5, 144, 128, 1, 1)])
+def test_pointwise_kernel(prec, cfg, dev):
+    B, H, W, K, N, leaky, pool = cfg
+    rs = np.random.RandomState(K + N)
+    a = rs.standard_normal((B, H, W, K)).astype(np.float32)
+    w = (rs.standard_normal((K, N)) / np.sqrt(K)).astype(np.float32)
+    bias = (rs.standard_normal(N) * 0.1).astype(np.float32)
+    s = rs.uniform(0.5, 1.5, N).astype(np.float32) * np.where(rs.rand(N) < 0.2, -1, 1).astype(np.float32)
+    t = (rs.standard_normal(N) * 0.1).astype(np.float32)
+    at = torch.from_numpy(a).to(dev).to(TDT[prec])
+    a_used = at.float().cpu().numpy().astype(np.float64)
+    z = a_used @ w.astype(np.float64) + bias
+    if leaky:
+        z = np.where(z > 0, z, 0.01 * z)
+    z = z * s + t
+    if pool:
+        Hp, Wp = H // 2, W // 2
+        z = z[:, :2 * Hp, :2 * Wp].reshape(B, Hp, 2, Wp, 2, N).max(axis=(2, 4))
+    out = torch.empty(z.shape, dtype=TDT[prec], device=dev)
+    lib = _lib.load()
+    tw, tb, ts, tt = (torch.from_numpy(v).to(dev) for v in (w, bias, s, t))
+    _lib.check(lib.ernet_pointwise(at.data_ptr(), DCODE[prec], B, H, W, K, N, tw.data_ptr(), tb.data_ptr(),
+                                   ts.data_ptr(), tt.data_ptr(), leaky, pool, out.data_ptr(),
+                                   torch.cuda.current_stream().cuda_stream))
+    got = out.float().cpu().numpy()
+    assert _rel(got, z) <= {"fp32": 3e-6, "bf16": 1e-2}[prec]
+
+
+# ------------------------------------------------------------------------------------ whole network
+@pytest.mark.parametrize("arch", fixtures.ARCHS)
+@pytest.mark.parametrize("wset", ["shipped", "w3", "w3neg"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "fp16"])
+def test_logits_match_reference(arch, wset, prec, model_golden, dev):
+    sd = fixtures.get_state_dict(arch, wset)
+    m = rtdm_b200.from_state_dict(arch, sd, dev, prec)
+    for iname, x in (("norm", fixtures.normal_tensors(4, seed=7)), ("frames", model_golden["x_frames"])):
+        ref = model_golden[f"{arch}/{wset}/{iname}/logits64"]
+        probs, logits = m.forward_with_logits(torch.from_numpy(x).to(dev))
+        lg = logits.double().cpu().numpy()
+        err = _rel(lg, ref)
+        assert err <= TOL[prec], (arch, wset, prec, iname, err)
+        assert _top1_ok(lg, ref, TOL[prec]), (arch, wset, prec, iname)
+        pr = probs.double().cpu().numpy()
+        assert np.allclose(pr.sum(1), 1.0, atol=1e-5)
+        if prec == "fp32":
+            assert np.abs(pr - model_golden[f"{arch}/{wset}/{iname}/probs64"]).max() <= 2e-3
+            assert (pr.argmax(1) == model_golden[f"{arch}/{wset}/{iname}/probs64"].argmax(1)).all()
+
+
+@pytest.mark.parametrize("arch", fixtures.ARCHS)
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_intermediates_match_oracle(arch, prec, dev):
+    sd = fixtures.get_state_dict(arch, "w3neg")
+    x = fixtures.normal_tensors(2, seed=5)
+    ref = E.forward(sd, x, arch, dtype=np.float64, want_taps=True)["taps"]
+    m = rtdm_b200.from_state_dict(arch, sd, dev, prec)
+    m(torch.from_numpy(x).to(dev))
+    tol = {"fp32": 2e-5, "bf16": 3e-2}[prec]
+    for name, oname in (("stem", "stem"), ("pool1", "pool1"), ("pool2", "pool2"), ("pool3", "pool3"), ("acff4", "acff4")):
+        got = m.tap(name).double().cpu().numpy()
+        assert got.shape == ref[oname].shape, name
+        assert _rel(got, ref[oname]) <= tol, (name, _rel(got, ref[oname]))
+
+
+@pytest.mark.parametrize("arch", fixtures.ARCHS)
+def test_model_call_surface(arch, dev):
+    """`model(x)` semantics of the reference: probabilities, dtype follows the input, .half() works,
+    channels_last input is accepted, wrong shapes raise."""
+    sd = fixtures.get_state_dict(arch, "w3")
+    m = rtdm_b200.from_state_dict(arch, sd, dev, None)
+    x = torch.from_numpy(fixtures.normal_tensors(3, seed=9)).to(dev)
+    with torch.no_grad():
+        p = m(x)
+    assert p.shape == (3, 5) and p.dtype == torch.float32 and p.device == x.device
+    ref = E.forward(sd, x.cpu().numpy(), arch, dtype=np.float64)["probs"]
+    assert np.abs(p.double().cpu().numpy() - ref).max() <= 1e-4
+    p_cl = m(x.contiguous(memory_format=torch.channels_last))
+    assert torch.allclose(p_cl, p, atol=1e-6)
+    mh = rtdm_b200.from_state_dict(arch, sd, dev, None).half()
+    ph = mh(x.half())
+    assert ph.dtype == torch.float16 and np.abs(ph.double().cpu().numpy() - ref).max() <= 2e-2
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 3, 240, 240, device=dev))
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 140, 140))                       # CPU tensor: no fallback
+    m.train()
+    with pytest.raises(RuntimeError):
+        m(x)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_frames_path_and_chunking(prec, dev):
+    arch = "squeeze-ernet"
+    sd = fixtures.get_state_dict(arch, "shipped")
+    frames = np.concatenate([fixtures.noise_frames(9, seed=31), fixtures.smooth_frames(8, seed=32)], 0)
+    ft = torch.from_numpy(frames).to(dev)
+    m = rtdm_b200.from_state_dict(arch, sd, dev, prec)
+    probs, logits = m.forward_frames(ft, return_logits=True)
+    # same as transform-then-model
+    x = m.ingest(ft, dtype=TDT[prec])
+    p2, l2 = m.forward_with_logits(x)
+    assert torch.equal(logits, l2) and torch.equal(probs, p2)
+    ref = E.forward(sd, I.ingest(frames), arch, dtype=np.float64)
+    assert _rel(logits.double().cpu().numpy(), ref["logits"]) <= TOL[prec]
+    # ragged chunking (17 = 5+5+5+2) gives bit-identical results; so does B=1
+    m.set_chunk(5)
+    p3, l3 = m.forward_frames(ft, return_logits=True)
+    assert torch.equal(l3, logits) and torch.equal(p3, probs)
+    p1, l1 = m.forward_frames(ft[3:4], return_logits=True)
+    assert torch.equal(l1, logits[3:4])
+    # host-buffer entry point
+    ph, lh = m.classify_host(frames, return_logits=True)
+    assert np.array_equal(lh, logits.cpu().numpy()) and np.array_equal(ph, probs.cpu().numpy())
+
+
+def test_abi_error_paths(dev):
+    lib = _lib.load()
+    h = C.c_void_p()
+    _lib.check(lib.ernet_create(C.byref(h), 0, 0, 0))
+    x = torch.zeros(1, 3, 140, 140, device=dev)
+    out = torch.zeros(1, 5, device=dev)
+    ws = torch.zeros(16, dtype=torch.uint8, device=dev)
+    assert lib.ernet_forward(h, x.data_ptr(), 0, 0, 1, out.data_ptr(), None, ws.data_ptr(), 16, None) == _lib.ERR_NOT_LOADED
+    blob = rtdm_b200.pack_state_dict(fixtures.get_state_dict("squeeze-ernet", "w3"), "squeeze-ernet", "fp32")
+    bad = bytearray(blob); bad[0] ^= 0xFF
+    buf = (C.c_char * len(bad)).from_buffer(bad)
+    assert lib.ernet_load_packed(h, buf, len(bad)) == _lib.ERR_BAD_BLOB
+    wrong = rtdm_b200.pack_state_dict(fixtures.get_state_dict("squeeze-redconv", "w3"), "squeeze-redconv", "fp32")
+    assert lib.ernet_load_packed(h, (C.c_char * len(wrong)).from_buffer_copy(wrong), len(wrong)) == _lib.ERR_BAD_BLOB
+    _lib.check(lib.ernet_load_packed(h, (C.c_char * len(blob)).from_buffer_copy(blob), len(blob)))
+    assert lib.ernet_forward(h, x.data_ptr(), 0, 0, 1, out.data_ptr(), None, ws.data_ptr(), 16, None) == _lib.ERR_WORKSPACE
+    assert lib.ernet_forward(h, x.data_ptr(), 0, 0, 0, out.data_ptr(), None, ws.data_ptr(), 16, None) == _lib.ERR_INVALID_ARG
+    assert lib.ernet_forward(h, x.data_ptr(), 3, 0, 1, out.data_ptr(), None, ws.data_ptr(), 16, None) == _lib.ERR_INVALID_ARG
+    assert lib.ernet_workspace_bytes(h, 1) > 0
+    assert lib.ernet_workspace_bytes(h, 4096) == lib.ernet_workspace_bytes(h, 1024)      # saturates at the chunk
+    lib.ernet_destroy(h)
+
+
+def test_full_size_properties(dev):
+    """BASELINE config 2 size (bf16, B=256): determinism, shard equivalence (two halves == whole, the
+    multi-GPU partitioning rule) and oracle parity on a sub-sample."""
+    arch = "squeeze-ernet"
+    sd = fixtures.get_state_dict(arch, "shipped")
+    frames = np.concatenate([fixtures.noise_frames(128, seed=41), fixtures.smooth_frames(128, seed=42)], 0)
+    ft = torch.from_numpy(frames).to(dev)
+    m = rtdm_b200.from_state_dict(arch, sd, dev, "bf16")
+    p, l = m.forward_frames(ft, return_logits=True)
+    p_again, l_again = m.forward_frames(ft, return_logits=True)
+    assert torch.equal(l, l_again) and torch.equal(p, p_again)
+    la = m.forward_frames(ft[:128], return_logits=True)[1]
+    lb = m.forward_frames(ft[128:], return_logits=True)[1]
+    assert torch.equal(torch.cat([la, lb]), l)
+    idx = np.arange(0, 256, 16)
+    ref = E.forward(sd, I.ingest(frames[idx]), arch, dtype=np.float64)
+    lg = l.double().cpu().numpy()[idx]
+    assert _rel(lg, ref["logits"]) <= TOL["bf16"]
+    assert _top1_ok(lg, ref["logits"], TOL["bf16"])
+    assert torch.allclose(p.sum(1), torch.ones(256, device=dev), atol=1e-5)
