@@ -85,6 +85,13 @@ size_t ernet_workspace_bytes(const ernet_handle* h, int batch);
 int ernet_set_chunk(ernet_handle* h, int images_per_chunk);
 int ernet_get_chunk(const ernet_handle* h);
 
+/* Kernel family.  AUTO (default): tcgen05 tensor-core block kernels where they exist (16-bit
+ * Squeeze_ErNET), CUDA-core kernels otherwise (fp32: tensor cores top out at TF32, which cannot hold
+ * the 1e-4 logit bound).  SIMT forces the CUDA-core kernels (used to cross-check the two on device).   */
+typedef enum ernet_engine { ERNET_ENGINE_AUTO = 0, ERNET_ENGINE_SIMT = 1, ERNET_ENGINE_TC = 2 } ernet_engine;
+int ernet_set_engine(ernet_handle* h, int engine);
+int ernet_get_engine(const ernet_handle* h);   /* the family the next forward will use (SIMT or TC) */
+
 /* ---- the hot path ------------------------------------------------------------------------------
  * Replaces `output = model(data)` (aider-predict.py:76, evaluate-classification-metrics.py:77):
  * Squeeze_ErNET.forward (model/squeeze_ernet.py:24-46) / Squeeze_RedConv.forward

@@ -17,6 +17,7 @@ PRECISION = {"fp32": 0, "fp16": 1, "bf16": 2, "int8": 3}
 DTYPE_F32, DTYPE_F16, DTYPE_BF16, DTYPE_U8 = 0, 1, 2, 3
 NCHW, NHWC = 0, 1
 RGB, BGR = 0, 1
+ENGINE = {"auto": 0, "simt": 1, "tc": 2}
 TAPS = {"ingest": 0, "stem": 1, "pool1": 2, "pool2": 3, "pool3": 4, "acff4": 5}
 
 _vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
@@ -27,6 +28,8 @@ SIGNATURES = {
     "ernet_workspace_bytes": (_sz, [_vp, _i]),
     "ernet_set_chunk": (_i, [_vp, _i]),
     "ernet_get_chunk": (_i, [_vp]),
+    "ernet_set_engine": (_i, [_vp, _i]),
+    "ernet_get_engine": (_i, [_vp]),
     "ernet_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "ernet_ingest_u8": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "ernet_prepare_ingest": (_i, [_vp, _i, _i]),

@@ -38,5 +38,7 @@ struct ernet_blob_entry {
 #define ERNET_T_HEAD_W 44       // [5][256]   conv2 o avgpool o fc collapsed
 #define ERNET_T_HEAD_B 45       // [5]
 // tensor-core path (16-bit / int8 operand images), see tc_*.cuh:
-#define ERNET_T_TC_BASE 64
+#define ERNET_T_TC_BASE 64      // + 4*k, k = 0..2 (acff1..acff3)
+#define ERNET_T_TC_WIMG 0       //   [25 taps][C/8][N][8] 16-bit: folded depthwise x 1x1 weights (pack_tc.py)
+#define ERNET_T_TC_BIAS 1       //   [N] fp32: b_f + W_f . cat(b_d)
 #define ERNET_T_MAX 128

@@ -3,6 +3,7 @@
 #include <stdarg.h>
 
 #include <map>
+#include <type_traits>
 #include <new>
 #include <utility>
 #include <vector>
@@ -10,6 +11,7 @@
 #include "common.cuh"
 #include "ingest.cuh"
 #include "simt_layers.cuh"
+#include "tc_block.cuh"
 
 namespace ernet {
 
@@ -23,6 +25,7 @@ struct Tensor {
 
 struct Plan {                 // byte offsets into the caller's workspace for one chunk
   size_t ingest, stem, cat1, p1, cat2, a2, p2, cat3, p3, r3, cat4, a4, total;
+  bool tc;                    // stem/p1/p2 are in the padded P8 layout of tc_block.cuh
 };
 
 }  // namespace ernet
@@ -32,7 +35,9 @@ using namespace ernet;
 struct ernet_handle {
   int arch = 0, precision = 0, device = 0;
   int chunk = 1024;
+  int engine = ERNET_ENGINE_AUTO;
   bool loaded = false;
+  bool has_tc = false;          // blob carries the tensor-core operand images
   void* d_blob = nullptr;
   size_t blob_bytes = 0;
   Tensor t[ERNET_T_MAX];
@@ -57,6 +62,11 @@ struct ernet_handle {
   int c3() const { return red() ? 48 : 96; }           // acff3 input channels
   int c4() const { return red() ? 64 : 128; }          // acff4 input channels
   size_t esize() const { return precision == ERNET_PREC_FP32 ? 4 : 2; }
+  // tensor-core path: 16-bit Squeeze_ErNET (RedConv's chained reductions still run on the CUDA-core path)
+  bool use_tc() const {
+    if (engine == ERNET_ENGINE_SIMT) return false;
+    return has_tc && !red() && (precision == ERNET_PREC_BF16 || precision == ERNET_PREC_FP16);
+  }
   const float* f(int id) const { return static_cast<const float*>(t[id].dev); }
   const float* blk(int k, int what) const { return f(ERNET_T_BLOCK_BASE + 8 * k + what); }
 };
@@ -68,7 +78,18 @@ static Plan make_plan(const ernet_handle* h, int n) {
   Plan p{};
   size_t o = 0;
   auto take = [&](size_t elems) { size_t r = o; o += align_up(elems * e, 256); return r; };
+  p.tc = h->use_tc();
   p.ingest = take(N * 140 * 140 * 3);
+  if (p.tc) {
+    p.stem = take(N * 2 * 72 * 72 * 8);        // P8 (B,2,72,72,8)
+    p.p1 = take(N * 8 * 36 * 36 * 8);          // P8 (B,8,36,36,8)
+    p.p2 = take(N * 12 * 18 * 18 * 8 + 12 * 18 * 18 * 8);   // P8 (B,12,18,18,8) + one image of slack (2 images per CTA)
+    p.p3 = take(N * 6 * 6 * 128);              // NHWC
+    p.cat4 = take(N * 4 * 4 * 3 * h->c4());
+    p.a4 = take(N * 4 * 4 * 256);
+    p.total = o;
+    return p;
+  }
   p.stem = take(N * 69 * 69 * h->cs());
   p.cat1 = take(N * 66 * 66 * 3 * h->cs());
   p.p1 = take(N * 33 * 33 * 64);
@@ -210,8 +231,57 @@ static int run_chunk_simt(ernet_handle* h, const void* x, int x_dtype, int x_lay
   return ERNET_OK;
 }
 
+// One chunk through the tensor-core pipeline: ingest -> stem (P8) -> blocks 1-3 on tcgen05 -> block 4 + head.
+template <typename T>
+static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layout, const uint8_t* frames,
+                        const IngestTables* tab, int order, int n, float* probs, float* logits, char* ws,
+                        cudaStream_t s) {
+  constexpr bool BF16 = std::is_same<T, __nv_bfloat16>::value;
+  const Plan p = make_plan(h, n);
+  auto buf = [&](size_t off) { return reinterpret_cast<T*>(ws + off); };
+  auto u16 = [&](size_t off) { return reinterpret_cast<uint16_t*>(ws + off); };
+  int rc;
+  const int total = n * 72 * 72, grid = (total + 127) / 128;
+  const float* sw = h->f(ERNET_T_STEM_W);
+  const float* sb_ = h->f(ERNET_T_STEM_B);
+  if (frames) {
+    ERNET_STAGE(ERNET_STAGE_INGEST, launch_ingest<T>(*tab, frames, n, order == ERNET_BGR, buf(p.ingest), 140LL * 140 * 3, 1, 140 * 3, 3, s));
+    StageTimer _t(h, ERNET_STAGE_STEM, s);
+    tc::stem_p8_kernel<T, 16, BF16><<<grid, 128, 0, s>>>(buf(p.ingest), 140LL * 140 * 3, 1, 140 * 3, 3, sw, sb_, u16(p.stem), total);
+    ERNET_LAUNCH_CHECK("stem_p8_kernel");
+  } else {
+    long long sb = 3LL * 140 * 140, sc, sy, sx;
+    if (x_layout == ERNET_NCHW) { sc = 140 * 140; sy = 140; sx = 1; }
+    else                        { sc = 1; sy = 140 * 3; sx = 3; }
+    StageTimer _t(h, ERNET_STAGE_STEM, s);
+    if (x_dtype == ERNET_F32) tc::stem_p8_kernel<float, 16, BF16><<<grid, 128, 0, s>>>(static_cast<const float*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total);
+    else if (x_dtype == ERNET_F16) tc::stem_p8_kernel<__half, 16, BF16><<<grid, 128, 0, s>>>(static_cast<const __half*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total);
+    else tc::stem_p8_kernel<__nv_bfloat16, 16, BF16><<<grid, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total);
+    ERNET_LAUNCH_CHECK("stem_p8_kernel");
+  }
+  auto wimg = [&](int k) { return h->t[ERNET_T_TC_BASE + 4 * k + ERNET_T_TC_WIMG].dev; };
+  auto beff = [&](int k) { return h->f(ERNET_T_TC_BASE + 4 * k + ERNET_T_TC_BIAS); };
+  ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_block<tc::CfgBlock1, true>(BF16, u16(p.stem), wimg(0), beff(0), h->blk(0, ERNET_T_BN_S), h->blk(0, ERNET_T_BN_T), u16(p.p1), n, s)));
+  ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_block<tc::CfgBlock2, true>(BF16, u16(p.p1), wimg(1), beff(1), h->blk(1, ERNET_T_BN_S), h->blk(1, ERNET_T_BN_T), u16(p.p2), n, s)));
+  ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_block<tc::CfgBlock3, false>(BF16, u16(p.p2), wimg(2), beff(2), h->blk(2, ERNET_T_BN_S), h->blk(2, ERNET_T_BN_T), u16(p.p3), n, s)));
+  const int c4 = h->c4();
+  ERNET_STAGE(ERNET_STAGE_DW4, launch_acff_dw<T>(buf(p.p3), n, 6, 6, c4, 4, 4, h->blk(3, ERNET_T_DW_W), h->blk(3, ERNET_T_DW_B), buf(p.cat4), s));
+  ERNET_STAGE(ERNET_STAGE_PW4, launch_pointwise<T>(buf(p.cat4), n, 4, 4, 3 * c4, 256, h->blk(3, ERNET_T_PW_W), h->blk(3, ERNET_T_PW_B),
+                                h->blk(3, ERNET_T_BN_S), h->blk(3, ERNET_T_BN_T), 1, 0, buf(p.a4), s));
+  {
+    StageTimer _t(h, ERNET_STAGE_HEAD, s);
+    head_kernel<T><<<n, 256, 0, s>>>(buf(p.a4), h->f(ERNET_T_HEAD_W), h->f(ERNET_T_HEAD_B), probs, logits);
+    ERNET_LAUNCH_CHECK("head_kernel");
+  }
+  return ERNET_OK;
+}
+
 static int run_chunk(ernet_handle* h, const void* x, int x_dtype, int x_layout, const uint8_t* frames,
                      const IngestTables* tab, int order, int n, float* probs, float* logits, char* ws, cudaStream_t s) {
+  if (h->use_tc()) {
+    if (h->precision == ERNET_PREC_BF16) return run_chunk_tc<__nv_bfloat16>(h, x, x_dtype, x_layout, frames, tab, order, n, probs, logits, ws, s);
+    return run_chunk_tc<__half>(h, x, x_dtype, x_layout, frames, tab, order, n, probs, logits, ws, s);
+  }
   switch (h->precision) {
     case ERNET_PREC_FP32: return run_chunk_simt<float>(h, x, x_dtype, x_layout, frames, tab, order, n, probs, logits, ws, s);
     case ERNET_PREC_FP16: return run_chunk_simt<__half>(h, x, x_dtype, x_layout, frames, tab, order, n, probs, logits, ws, s);
@@ -232,6 +302,9 @@ static int init_device_attrs() {
   if ((rc = set_smem_attrs<float>())) return rc;
   if ((rc = set_smem_attrs<__half>())) return rc;
   if ((rc = set_smem_attrs<__nv_bfloat16>())) return rc;
+  if ((rc = tc::set_block_attrs<tc::CfgBlock1, true>())) return rc;
+  if ((rc = tc::set_block_attrs<tc::CfgBlock2, true>())) return rc;
+  if ((rc = tc::set_block_attrs<tc::CfgBlock3, false>())) return rc;
   return ERNET_OK;
 }
 
@@ -344,6 +417,17 @@ int ernet_load_packed(ernet_handle* h, const void* blob, size_t bytes) {
   }
   int rc = validate_simt_tensors(h);
   if (rc) { memcpy(h->t, old, sizeof(old)); cudaFree(d); return rc; }
+  {
+    const size_t wimg_bytes[3] = {tc::CfgBlock1::W_BYTES, tc::CfgBlock2::W_BYTES, tc::CfgBlock3::W_BYTES};
+    const size_t nout[3] = {64, 96, 128};
+    bool all = !h->red();
+    for (int k = 0; k < 3 && all; ++k) {
+      const Tensor& w = h->t[ERNET_T_TC_BASE + 4 * k + ERNET_T_TC_WIMG];
+      const Tensor& b = h->t[ERNET_T_TC_BASE + 4 * k + ERNET_T_TC_BIAS];
+      all = w.dev && b.dev && w.nbytes == wimg_bytes[k] && b.nbytes == nout[k] * sizeof(float);
+    }
+    h->has_tc = all;
+  }
   if (h->d_blob) { cudaDeviceSynchronize(); cudaFree(h->d_blob); }
   h->d_blob = d; h->blob_bytes = bytes; h->loaded = true;
   return ERNET_OK;
@@ -355,6 +439,15 @@ int ernet_set_chunk(ernet_handle* h, int n) {
   return ERNET_OK;
 }
 int ernet_get_chunk(const ernet_handle* h) { return h ? h->chunk : 0; }
+
+int ernet_set_engine(ernet_handle* h, int engine) {
+  if (!h || engine < ERNET_ENGINE_AUTO || engine > ERNET_ENGINE_TC) return fail(ERNET_ERR_INVALID_ARG, "bad engine %d", engine);
+  if (engine == ERNET_ENGINE_TC && h->loaded && !(h->has_tc && !h->red() && h->precision != ERNET_PREC_FP32 && h->precision != ERNET_PREC_INT8))
+    return fail(ERNET_ERR_UNSUPPORTED, "tensor-core engine needs a 16-bit Squeeze_ErNET handle");
+  h->engine = engine;
+  return ERNET_OK;
+}
+int ernet_get_engine(const ernet_handle* h) { return h ? (h->use_tc() ? ERNET_ENGINE_TC : ERNET_ENGINE_SIMT) : -1; }
 
 size_t ernet_workspace_bytes(const ernet_handle* h, int batch) {
   if (!h || batch < 1) return 0;
@@ -551,6 +644,14 @@ int ernet_debug_tap(ernet_handle* h, int tap, const void* workspace, int batch, 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const char* src = static_cast<const char*>(workspace) + off;
   const int grid = (int)((total + 255) / 256);
+  if (p.tc && (tap == ERNET_TAP_STEM || tap == ERNET_TAP_POOL1 || tap == ERNET_TAP_POOL2)) {
+    const int Hh = tap == ERNET_TAP_STEM ? 69 : (tap == ERNET_TAP_POOL1 ? 33 : 15);
+    const int NCc = tap == ERNET_TAP_STEM ? 2 : (tap == ERNET_TAP_POOL1 ? 8 : 12);
+    if (h->precision == ERNET_PREC_BF16) tc::tap_p8_to_nchw_f32<true><<<grid, 256, 0, s>>>(reinterpret_cast<const uint16_t*>(src), NCc, C, Hh, total, out);
+    else tc::tap_p8_to_nchw_f32<false><<<grid, 256, 0, s>>>(reinterpret_cast<const uint16_t*>(src), NCc, C, Hh, total, out);
+    ERNET_LAUNCH_CHECK("tap_p8_to_nchw_f32");
+    return ERNET_OK;
+  }
   if (h->precision == ERNET_PREC_FP32) tap_nhwc_to_nchw_f32<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(src), C, HW, total, out);
   else if (h->precision == ERNET_PREC_FP16) tap_nhwc_to_nchw_f32<__half><<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(src), C, HW, total, out);
   else tap_nhwc_to_nchw_f32<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), C, HW, total, out);
@@ -607,7 +708,8 @@ int ernet_profile_read(ernet_handle* h, double* ms_by_stage, int* launches_by_st
 int ernet_launches_per_forward(const ernet_handle* h, int batch, int with_ingest) {
   if (!h || batch < 1) return 0;
   const int chunks = (batch + h->chunk - 1) / h->chunk;
-  const int per = (with_ingest ? 1 : 0) + 1 + 8 + (h->red() ? 2 : 0) + 1;
+  const int per = h->use_tc() ? (with_ingest ? 1 : 0) + 1 + 3 + 2 + 1
+                              : (with_ingest ? 1 : 0) + 1 + 8 + (h->red() ? 2 : 0) + 1;
   return chunks * per;
 }
 

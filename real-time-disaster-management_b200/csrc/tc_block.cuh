@@ -1,0 +1,347 @@
+// Fused ACFF block on the 5th-gen tensor cores (tcgen05 + TMEM), sm_100a.
+//
+//   ACFF(x) = BN(LeakyReLU(W_f . cat(dw_1(x), dw_2(x), dw_3(x)) + b_f))      model/acff.py:37-59
+//
+// The three dilated depthwise convs and the 1x1 conv are both linear with nothing in between, so the
+// block is ONE dense convolution over the 25 distinct taps of the three stencils:
+//   z[n,y,x] = b_eff[n] + sum_{tap} sum_c W_eff[n,tap,c] * X[c, y+dy(tap), x+dx(tap)]
+//   W_eff[n,tap,c] = sum_{d : tap in stencil d} W_f[n, d*C + c] * w_d[c,ky,kx],  b_eff = b_f + W_f . cat(b_d)
+// (packer: pack_tc.py).  That turns the bandwidth-bound depthwise stage + concat into tensor-core work
+// with zero CUDA-core instructions: the input image is staged ONCE in shared memory in the "P8" layout
+// [channel chunk of 8][padded row][padded col][8 ch] (16 B per pixel-chunk), which is exactly the
+// un-swizzled K-major UMMA operand layout with 16 B row stride - so each tap is the same staged image
+// read through a descriptor whose start address is shifted by (dy*P + dx)*16 B, the zero padding of
+// acff.py:25-30 is the zero halo of the staged image, and an MMA tile of 128 rows is a 16x8 block of
+// output pixels (SBO = one image row).
+//
+// Warp roles (192 threads, one CTA per SM):
+//   warp 0    producer: one 1-D bulk copy (UBLKCP) of the whole P8 image(s); weight images either
+//             resident (block 1) or streamed tap by tap through a small ring; then zero-fills the halo
+//             of the output tensor
+//   warp 1    allocates TMEM, one lane issues tcgen05.mma (M=128, N=Cout, K=16) for
+//             group-of-tiles x 25 taps x C/16 k-steps, commits to mbarriers
+//   warps 2-5 epilogue: tcgen05.ld -> +b_eff -> LeakyReLU -> BN affine -> bf16/fp16 -> 2x2 max-pool with
+//             warp shuffles (a warp owns 4 rows x 8 cols of the tile) -> 16-byte stores in the next
+//             block's P8 layout (or NHWC)
+#pragma once
+#include "tc_common.cuh"
+
+namespace ernet {
+namespace tc {
+
+template <int NC_, int N_, int HIN_, int HU_, int IMGS_, int G_, int NBUF_, bool WRES_, int WSTAGES_>
+struct BlockCfg {
+  static constexpr int NC = NC_, N = N_, HIN = HIN_, HU = HU_, IMGS = IMGS_, G = G_, NBUF = NBUF_, WSTAGES = WSTAGES_;
+  static constexpr bool WRES = WRES_;
+  static constexpr int P = HIN + 3;                       // padded pitch: cols -2 .. HIN
+  static constexpr int CHUNK_BYTES = P * P * 16;
+  static constexpr int IMG_BYTES = NC * CHUNK_BYTES;
+  static constexpr int IN_BYTES = IMGS * IMG_BYTES;
+  static constexpr int TR = (HU + 15) / 16, TCOLS = (HU + 7) / 8;
+  static constexpr int TILES_PER_IMG = TR * TCOLS;
+  static constexpr int T = IMGS * TILES_PER_IMG;
+  static constexpr int NG = (T + G - 1) / G;
+  static constexpr int KSTEPS = NC / 2;
+  static constexpr int TAP_BYTES = NC * N * 16;
+  static constexpr int W_BYTES = 25 * TAP_BYTES;
+  static constexpr int W_SMEM = WRES ? W_BYTES : WSTAGES * TAP_BYTES;
+  static constexpr int OUT_H = HU / 2, OP = OUT_H + 3;
+  static constexpr int OFF_W = IN_BYTES;
+  static constexpr int OFF_PAR = OFF_W + W_SMEM;
+  static constexpr int OFF_BAR = OFF_PAR + 3 * N * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128;
+  static_assert(NC % 2 == 0, "K step is 16 channels");
+  static_assert(N % 32 == 0 && N <= 256, "N must be a multiple of 32");
+  static_assert(G * N * NBUF <= 512, "TMEM has 512 columns");
+  static_assert(HU % 2 == 0, "pooling needs an even used size");
+  static_assert(IN_BYTES % 128 == 0 && TAP_BYTES % 128 == 0, "alignment");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+template <class Cfg, bool OUT_P8, bool BF16>
+__global__ void __launch_bounds__(192, 1)
+acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ wimg, const float* __restrict__ bias,
+                  const float* __restrict__ bn_s, const float* __restrict__ bn_t, uint16_t* __restrict__ out, int batch) {
+  constexpr int NC = Cfg::NC, N = Cfg::N, P = Cfg::P, G = Cfg::G, NBUF = Cfg::NBUF, T = Cfg::T, NG = Cfg::NG;
+  constexpr int OP = Cfg::OP, OUT_H = Cfg::OUT_H;
+  constexpr uint32_t IDESC = instr_desc(1u, BF16 ? 1u : 0u, 128u, (uint32_t)N);
+
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* s_in = smem;
+  uint8_t* s_w = smem + Cfg::OFF_W;
+  float* s_par = reinterpret_cast<float*>(smem + Cfg::OFF_PAR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* bar_in = bars;            // [1]
+  uint64_t* w_full = bars + 1;        // [4]
+  uint64_t* w_empty = bars + 5;       // [4]
+  uint64_t* acc_full = bars + 9;      // [2]
+  uint64_t* acc_empty = bars + 11;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int img0 = blockIdx.x * Cfg::IMGS;
+  const int nimg = min(Cfg::IMGS, batch - img0);
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_in, 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < N; i += 128) {
+      s_par[i] = bias[i]; s_par[N + i] = bn_s[i]; s_par[2 * N + i] = bn_t[i];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer
+    if (lane == 0) {
+      mbar_expect_tx(bar_in, (uint32_t)(nimg * Cfg::IMG_BYTES + (Cfg::WRES ? Cfg::W_BYTES : 0)));
+      bulk_g2s(s_in, reinterpret_cast<const uint8_t*>(in) + (size_t)img0 * Cfg::IMG_BYTES, (uint32_t)(nimg * Cfg::IMG_BYTES), bar_in);
+      if (Cfg::WRES) {
+        bulk_g2s(s_w, wimg, Cfg::W_BYTES, bar_in);
+      } else {
+        for (int it = 0; it < NG * 25; ++it) {
+          const int s = it % Cfg::WSTAGES, use = it / Cfg::WSTAGES;
+          if (use > 0) mbar_wait(&w_empty[s], (use - 1) & 1);
+          mbar_expect_tx(&w_full[s], Cfg::TAP_BYTES);
+          bulk_g2s(s_w + s * Cfg::TAP_BYTES, reinterpret_cast<const uint8_t*>(wimg) + (size_t)(it % 25) * Cfg::TAP_BYTES,
+                   Cfg::TAP_BYTES, &w_full[s]);
+        }
+      }
+    }
+    __syncwarp();
+    if (OUT_P8) {
+      // zero halo of the output images (rows 0,1,OP-1 and cols 0,1,OP-1 of every chunk): the next block's
+      // conv padding.  Done by the otherwise idle producer warp.
+      constexpr int BORDER = 3 * OP + (OP - 3) * 3;
+      for (int im = 0; im < nimg; ++im) {
+        uint4* oimg = reinterpret_cast<uint4*>(out) + (size_t)(img0 + im) * (N / 8) * OP * OP;
+        for (int i = lane; i < (N / 8) * BORDER; i += 32) {
+          const int ch = i / BORDER, k = i - ch * BORDER;
+          int r, c;
+          if (k < 3 * OP) { r = k / OP; c = k - r * OP; if (r == 2) r = OP - 1; }
+          else { const int k2 = k - 3 * OP; r = 2 + k2 / 3; c = k2 % 3; if (c == 2) c = OP - 1; }
+          oimg[(ch * OP + r) * OP + c] = make_uint4(0, 0, 0, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      mbar_wait(bar_in, 0);
+      tc_fence_after();
+      const uint32_t in_addr = smem_u32(s_in), w_addr = smem_u32(s_w);
+      int it = 0;
+      for (int g = 0; g < NG; ++g) {
+        const int buf = g % NBUF, use = g / NBUF;
+        if (use > 0) { mbar_wait(&acc_empty[buf], (use - 1) & 1); tc_fence_after(); }
+        const int ntile = min(G, T - g * G);
+        for (int tap = 0; tap < 25; ++tap) {
+          uint32_t wb;
+          int s = 0;
+          if (Cfg::WRES) {
+            wb = w_addr + tap * Cfg::TAP_BYTES;
+          } else {
+            s = it % Cfg::WSTAGES;
+            mbar_wait(&w_full[s], (it / Cfg::WSTAGES) & 1);
+            tc_fence_after();
+            wb = w_addr + s * Cfg::TAP_BYTES;
+          }
+          const int dy = kTapDy[tap], dx = kTapDx[tap];
+          for (int tl = 0; tl < ntile; ++tl) {
+            const int t = g * G + tl;
+            const int im = t / Cfg::TILES_PER_IMG, rem = t - im * Cfg::TILES_PER_IMG;
+            const int ty = rem / Cfg::TCOLS, tx = rem - ty * Cfg::TCOLS;
+            const uint32_t a0 = in_addr + im * Cfg::IMG_BYTES + (uint32_t)(((ty * 16 + 2 + dy) * P + tx * 8 + 2 + dx) * 16);
+            const uint32_t d = tmem_base + (uint32_t)(buf * G * N + tl * N);
+#pragma unroll
+            for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+              const uint64_t ad = smem_desc(a0 + ks * 2 * Cfg::CHUNK_BYTES, Cfg::CHUNK_BYTES, P * 16);
+              const uint64_t bd = smem_desc(wb + ks * 2 * N * 16, N * 16, 128);
+              mma_f16(d, ad, bd, IDESC, (tap | ks) != 0 ? 1u : 0u);
+            }
+          }
+          if (!Cfg::WRES) { mma_commit(&w_empty[s]); ++it; }
+        }
+        mma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    asm volatile("bar.sync 1, 128;" ::: "memory");          // s_par visible to all epilogue warps
+    const int q4 = warp & 3;                                 // TMEM lane quarter this warp may read
+    const int rr = 4 * q4 + (lane >> 3), cc = lane & 7;
+    const int qm = (lane & 1) | (((lane >> 3) & 1) << 1);    // position inside the 2x2 pooling quad
+    for (int g = 0; g < NG; ++g) {
+      const int buf = g % NBUF, use = g / NBUF;
+      mbar_wait(&acc_full[buf], use & 1);
+      tc_fence_after();
+      const int ntile = min(G, T - g * G);
+      for (int tl = 0; tl < ntile; ++tl) {
+        const int t = g * G + tl;
+        const int im = t / Cfg::TILES_PER_IMG, rem = t - im * Cfg::TILES_PER_IMG;
+        const int ty = rem / Cfg::TCOLS, tx = rem - ty * Cfg::TCOLS;
+        const int y = ty * 16 + rr, x = tx * 8 + cc;
+        const bool valid = (y < Cfg::HU) && (x < Cfg::HU) && (im < nimg);
+        const int py = y >> 1, px = x >> 1;
+        const uint32_t tbase = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * G * N + tl * N);
+#pragma unroll 1
+        for (int cb = 0; cb < N / 32; ++cb) {
+          uint32_t v[32];
+          tmem_ld32(tbase + cb * 32, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = cb * 32 + 2 * j;
+            float z0 = __uint_as_float(v[2 * j]) + s_par[n];
+            float z1 = __uint_as_float(v[2 * j + 1]) + s_par[n + 1];
+            z0 = fmaxf(z0, 0.01f * z0);                       // LeakyReLU(0.01), acff.py:33
+            z1 = fmaxf(z1, 0.01f * z1);
+            z0 = fmaf(z0, s_par[N + n], s_par[2 * N + n]);    // eval BatchNorm, acff.py:34
+            z1 = fmaf(z1, s_par[N + n + 1], s_par[2 * N + n + 1]);
+            if (BF16) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(z0, z1);
+              __nv_bfloat162 o = __shfl_xor_sync(0xffffffffu, h, 1);
+              h = __hmax2(h, o);
+              o = __shfl_xor_sync(0xffffffffu, h, 8);
+              h = __hmax2(h, o);
+              pk[j] = *reinterpret_cast<uint32_t*>(&h);
+            } else {
+              __half2 h = __floats2half2_rn(z0, z1);
+              __half2 o = __shfl_xor_sync(0xffffffffu, h, 1);
+              h = __hmax2(h, o);
+              o = __shfl_xor_sync(0xffffffffu, h, 8);
+              h = __hmax2(h, o);
+              pk[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+          }
+          // every lane of a quad now holds the pooled values of 32 channels; lane qm stores channels
+          // [8*qm, 8*qm+8) of this 32-channel block
+          uint4 o4;
+          o4.x = qm == 0 ? pk[0] : qm == 1 ? pk[4] : qm == 2 ? pk[8] : pk[12];
+          o4.y = qm == 0 ? pk[1] : qm == 1 ? pk[5] : qm == 2 ? pk[9] : pk[13];
+          o4.z = qm == 0 ? pk[2] : qm == 1 ? pk[6] : qm == 2 ? pk[10] : pk[14];
+          o4.w = qm == 0 ? pk[3] : qm == 1 ? pk[7] : qm == 2 ? pk[11] : pk[15];
+          if (valid) {
+            const int ch = cb * 4 + qm;
+            if (OUT_P8) {
+              uint4* oimg = reinterpret_cast<uint4*>(out) + (size_t)(img0 + im) * (N / 8) * OP * OP;
+              oimg[(ch * OP + py + 2) * OP + px + 2] = o4;
+            } else {
+              uint16_t* o = out + ((size_t)((img0 + im) * OUT_H + py) * OUT_H + px) * N + ch * 8;
+              *reinterpret_cast<uint4*>(o) = o4;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// Block configurations (SURVEY.md section 7.5 sizes, Squeeze_ErNET):
+//   block 1: 16(+pad) -> 64, 69x69 in, 66x66 used, 45 tiles/img, weights resident (51 KB), 2 x 4-tile TMEM buffers
+//   block 2: 64 -> 96,  33x33 in, 30x30 used,  8 tiles/img, weights streamed (12 KB per tap, 3-stage ring)
+//   block 3: 96 -> 128, 15x15 in, 12x12 used,  2 tiles/img, 2 images per CTA, weights streamed (24 KB per tap)
+using CfgBlock1 = BlockCfg<2, 64, 69, 66, 1, 4, 2, true, 1>;
+using CfgBlock2 = BlockCfg<8, 96, 33, 30, 1, 4, 1, false, 3>;
+using CfgBlock3 = BlockCfg<12, 128, 15, 12, 2, 4, 1, false, 2>;
+
+template <class Cfg, bool OUT_P8>
+inline int launch_acff_block(bool bf16, const void* in, const void* wimg, const float* bias, const float* s, const float* t,
+                             void* out, int batch, cudaStream_t stream) {
+  const int grid = (batch + Cfg::IMGS - 1) / Cfg::IMGS;
+  auto* i16 = static_cast<const uint16_t*>(in);
+  auto* w16 = static_cast<const uint16_t*>(wimg);
+  auto* o16 = static_cast<uint16_t*>(out);
+  if (bf16) acff_block_kernel<Cfg, OUT_P8, true><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(i16, w16, bias, s, t, o16, batch);
+  else      acff_block_kernel<Cfg, OUT_P8, false><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(i16, w16, bias, s, t, o16, batch);
+  ERNET_LAUNCH_CHECK("acff_block_kernel");
+  return ERNET_OK;
+}
+
+template <class Cfg, bool OUT_P8>
+inline int set_block_attrs() {
+  ERNET_CUDA(cudaFuncSetAttribute(acff_block_kernel<Cfg, OUT_P8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  ERNET_CUDA(cudaFuncSetAttribute(acff_block_kernel<Cfg, OUT_P8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  return ERNET_OK;
+}
+
+// ---------------------------------------------------------------------------------- stem -> P8
+// conv1 3x3/s2 (model/squeeze_ernet.py:11,25; RedConv: conv_red1 folded in) writing the P8 layout block 1
+// stages: (B, 2 chunks, 72, 72, 8) with the zero halo included.  One thread per padded pixel.
+template <typename TI, int CS, bool BF16>
+__global__ void __launch_bounds__(128)
+stem_p8_kernel(const TI* __restrict__ x, long long sb, long long sc, long long sy, long long sx,
+               const float* __restrict__ w /*[27][CS]*/, const float* __restrict__ bias, uint16_t* __restrict__ out, int total) {
+  __shared__ float ws[27 * CS + CS];
+  for (int i = threadIdx.x; i < 27 * CS + CS; i += blockDim.x) ws[i] = i < 27 * CS ? w[i] : bias[i - 27 * CS];
+  __syncthreads();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  constexpr int P = 72;
+  const int b = idx / (P * P);
+  const int r = idx - b * P * P;
+  const int pr = r / P, pc = r - pr * P;
+  const int oy = pr - 2, ox = pc - 2;
+  uint4* o = reinterpret_cast<uint4*>(out) + (size_t)b * 2 * P * P + pr * P + pc;
+  if (oy < 0 || oy >= 69 || ox < 0 || ox >= 69) {
+    o[0] = make_uint4(0, 0, 0, 0);
+    o[P * P] = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  float acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = c < CS ? ws[27 * CS + c] : 0.f;
+  const TI* p = x + b * sb + (2 * oy) * sy + (2 * ox) * sx;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v = to_f32<TI>(p[ky * sy + kx * sx + c * sc]);
+        const float* wr = ws + ((ky * 3 + kx) * 3 + c) * CS;
+#pragma unroll
+        for (int k = 0; k < CS; ++k) acc[k] = fmaf(v, wr[k], acc[k]);
+      }
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    float t8[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t8[k] = acc[ch * 8 + k];
+    o[ch * P * P] = BF16 ? pack16<__nv_bfloat16>(t8) : pack16<__half>(t8);
+  }
+}
+
+// debug: P8 (B, NC, H+3, W+3, 8) 16-bit -> fp32 NCHW (B, NC*8 [first C], H, W)
+template <bool BF16>
+__global__ void tap_p8_to_nchw_f32(const uint16_t* __restrict__ src, int NC, int C, int H, long long total, float* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int P = H + 3;
+  const int x = (int)(i % H);
+  const int y = (int)((i / H) % H);
+  const int c = (int)((i / ((long long)H * H)) % C);
+  const long long b = i / ((long long)H * H * C);
+  const uint16_t raw = src[(((b * NC + (c >> 3)) * P + y + 2) * P + x + 2) * 8 + (c & 7)];
+  dst[i] = BF16 ? __uint_as_float((uint32_t)raw << 16) : __half2float(*reinterpret_cast<const __half*>(&raw));
+}
+
+}  // namespace tc
+}  // namespace ernet

@@ -143,6 +143,18 @@ class _ErnetB200(nn.Module):
             self._workspace = torch.empty(need, dtype=torch.uint8, device=device)
         return self._workspace
 
+    def set_engine(self, engine):
+        """'auto' (default), 'simt' (CUDA-core kernels) or 'tc' (tcgen05 block kernels)."""
+        lib, h, _ = self._ensure_engine()
+        _lib.check(lib.ernet_set_engine(h, _lib.ENGINE[engine]))
+        self._workspace = None
+        return self
+
+    @property
+    def engine(self):
+        lib, h, _ = self._ensure_engine()
+        return {1: "simt", 2: "tc"}[lib.ernet_get_engine(h)]
+
     def set_chunk(self, n):
         """Images processed per internal pass (bounds the workspace; default 1024)."""
         lib, h, _ = self._ensure_engine()

@@ -1,6 +1,78 @@
-"""Operand images for the tensor-core (tcgen05) kernels.  Filled in as those kernels land."""
+"""Operand images for the tensor-core (tcgen05) ACFF block kernels (csrc/tc_block.cuh).
+
+Each ACFF block (model/acff.py:25-31,46,51) is linear up to the LeakyReLU, so its three dilated
+depthwise convs, the concat and the 1x1 conv fold into one dense conv over the 25 distinct taps:
+
+    W_eff[n, tap, c] = sum_{d in {1,2,3} : tap in stencil d} W_f[n, (d-1)*C + c] * w_d[c, ky, kx]
+    b_eff[n]         = b_f[n] + sum_{d,c} W_f[n, (d-1)*C + c] * b_d[c]
+
+computed in fp64 and rounded once to bf16 / fp16.  The image is laid out exactly as the kernel's
+shared-memory B operand: [tap][channel chunk of 8][n][8], so one 1-D bulk copy per tap stages it.
+"""
 from __future__ import annotations
+
+import numpy as np
+
+T_TC_BASE = 64
+T_TC_WIMG, T_TC_BIAS = 0, 1          # + 4*k for block k
+DT_F32, DT_RAW = 0, 16
+
+# offsets from the output coordinate, sorted by (dy, dx); mirrored by kTapDy/kTapDx in csrc/tc_common.cuh
+TAPS = sorted({(ky * d - (d - 1), kx * d - (d - 1)) for d in (1, 2, 3) for ky in range(3) for kx in range(3)})
+assert len(TAPS) == 25
+
+
+def to_bits16(a, precision):
+    a32 = np.ascontiguousarray(a, dtype=np.float32)
+    if precision == "fp16":
+        return a32.astype(np.float16).view(np.uint16)
+    u = a32.view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)      # round-to-nearest-even bf16
+    return r
+
+
+def from_bits16(bits, precision):
+    bits = np.asarray(bits, dtype=np.uint16)
+    if precision == "fp16":
+        return bits.view(np.float16).astype(np.float64)
+    return (bits.astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+
+
+def fold_block(sd, prefix, c_real, c_pad):
+    """-> (W_eff [N][25][c_pad] fp64, b_eff [N] fp64)."""
+    from .pack import _np64
+    wf = _np64(sd, f"{prefix}.fused_conv.weight")[:, :, 0, 0]               # (N, 3C)
+    n_out = wf.shape[0]
+    weff = np.zeros((n_out, 25, c_pad))
+    beff = _np64(sd, f"{prefix}.fused_conv.bias").copy()
+    for d in (1, 2, 3):
+        wd = _np64(sd, f"{prefix}.conv{d}.weight")[:, 0]                     # (C,3,3)
+        bd = _np64(sd, f"{prefix}.conv{d}.bias")
+        wfd = wf[:, (d - 1) * c_real:d * c_real]                             # (N, C)
+        beff += wfd @ bd
+        for ky in range(3):
+            for kx in range(3):
+                tap = TAPS.index((ky * d - (d - 1), kx * d - (d - 1)))
+                weff[:, tap, :c_real] += wfd * wd[:, ky, kx][None, :]
+    return weff, beff
+
+
+def weight_image(weff, precision):
+    """[N][25][C] -> uint16 image [25][C/8][N][8]."""
+    n_out, _, c = weff.shape
+    img = weff.transpose(1, 2, 0).reshape(25, c // 8, 8, n_out).transpose(0, 1, 3, 2)   # [tap][chunk][n][8]
+    return to_bits16(img, precision)
 
 
 def derive_tc(sd, arch, precision):
-    return {}
+    from .pack import widths
+    if precision not in ("fp16", "bf16"):
+        return {}
+    out = {}
+    for k, (c, _co) in enumerate(widths(arch)[:3]):
+        c_pad = max(16, c)
+        weff, beff = fold_block(sd, f"acff{k + 1}", c, c_pad)
+        base = T_TC_BASE + 4 * k
+        out[base + T_TC_WIMG] = (weight_image(weff, precision), DT_RAW)
+        out[base + T_TC_BIAS] = (beff.astype(np.float32), DT_F32)
+    return out

@@ -251,3 +251,46 @@ def test_full_size_properties(dev):
     assert _rel(lg, ref["logits"]) <= TOL["bf16"]
     assert _top1_ok(lg, ref["logits"], TOL["bf16"])
     assert torch.allclose(p.sum(1), torch.ones(256, device=dev), atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------ tensor-core engine
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("wset", ["w3neg", "shipped"])
+def test_tc_engine_blocks_match_oracle(prec, wset, dev):
+    """16-bit Squeeze_ErNET runs blocks 1-3 as tcgen05 kernels; check every block boundary against the
+    fp64 oracle and the whole result against the CUDA-core engine on the same device."""
+    arch = "squeeze-ernet"
+    sd = fixtures.get_state_dict(arch, wset)
+    x = fixtures.normal_tensors(3, seed=11)          # odd batch: block 3 packs two images per CTA
+    ref = E.forward(sd, x, arch, dtype=np.float64, want_taps=True)
+    m = rtdm_b200.from_state_dict(arch, sd, dev, prec)
+    assert m.engine == "tc"
+    xt = torch.from_numpy(x).to(dev)
+    probs, logits = m.forward_with_logits(xt)
+    torch.cuda.synchronize()
+    tol = {"bf16": 3e-2, "fp16": 4e-3}[prec]
+    for name in ("stem", "pool1", "pool2", "pool3", "acff4"):
+        got = m.tap(name).double().cpu().numpy()
+        assert got.shape == ref["taps"][name].shape, name
+        err = _rel(got, ref["taps"][name])
+        assert err <= tol, (name, err)
+    lg = logits.double().cpu().numpy()
+    assert _rel(lg, ref["logits"]) <= TOL[prec]
+    assert _top1_ok(lg, ref["logits"], TOL[prec])
+    m2 = rtdm_b200.from_state_dict(arch, sd, dev, prec).set_engine("simt")
+    assert m2.engine == "simt"
+    l2 = m2.forward_with_logits(xt)[1].double().cpu().numpy()
+    assert _rel(lg, l2) <= TOL[prec]
+
+
+def test_tc_engine_p8_halo_is_rewritten(dev):
+    """The zero halo of the P8 activation tensors is produced by the kernels themselves, so a dirty
+    workspace (here: filled with NaN bit patterns) must not change the result."""
+    arch = "squeeze-ernet"
+    sd = fixtures.get_state_dict(arch, "w3")
+    x = torch.from_numpy(fixtures.normal_tensors(5, seed=13)).to(dev)
+    m = rtdm_b200.from_state_dict(arch, sd, dev, "bf16")
+    l0 = m.forward_with_logits(x)[1].clone()
+    m._workspace.fill_(0xFF)
+    l1 = m.forward_with_logits(x)[1]
+    assert torch.equal(l0, l1)

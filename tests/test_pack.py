@@ -59,3 +59,50 @@ def test_blob_layout():
     assert pz["arch"] == 1 and pz["precision"] == 0
     assert P.T_RED2_W in pz["tensors"] and P.T_HEAD_W in pz["tensors"]
     assert len(pz["tensors"][P.T_STEM_W][1]) == 27 * 8 * 4
+
+
+# ---------------------------------------------------------------- tensor-core operand images
+def test_tap_table_matches_device_header():
+    import rtdm_b200.pack_tc as PT
+    hdr = open(os.path.join(ROOT, "real-time-disaster-management_b200", "csrc", "tc_common.cuh")).read()
+    dy = [int(v) for v in re.search(r"kTapDy\[25\]\s*=\s*\{([^}]*)\}", hdr).group(1).split(",")]
+    dx = [int(v) for v in re.search(r"kTapDx\[25\]\s*=\s*\{([^}]*)\}", hdr).group(1).split(",")]
+    assert list(zip(dy, dx)) == PT.TAPS
+
+
+@pytest.mark.parametrize("arch", fixtures.ARCHS)
+def test_25_tap_fold_is_exact(arch):
+    """depthwise trio + concat + 1x1 == one dense 25-tap conv with the folded weights (fp64)."""
+    import rtdm_b200.pack_tc as PT
+    sd = fixtures.get_state_dict(arch, "w3neg")
+    for k, (c, co) in enumerate(P.widths(arch)[:3], start=1):
+        rs = np.random.RandomState(k)
+        H = {1: 19, 2: 13, 3: 15}[k]
+        x = rs.standard_normal((2, c, H, H))
+        cat = E.acff_concat(x, {kk: np.asarray(v, np.float64) for kk, v in sd.items() if kk.startswith(f"acff{k}.conv")}, f"acff{k}")
+        ref = E.conv2d_pointwise(cat, np.asarray(sd[f"acff{k}.fused_conv.weight"], np.float64),
+                                 np.asarray(sd[f"acff{k}.fused_conv.bias"], np.float64))
+        weff, beff = PT.fold_block(sd, f"acff{k}", c, max(16, c))
+        Ho = H - 2
+        xp = np.zeros((2, max(16, c), H + 6, H + 6))
+        xp[:, :c, 2:2 + H, 2:2 + H] = x
+        z = np.zeros((2, co, Ho, Ho)) + beff.reshape(1, -1, 1, 1)
+        for t, (dy, dx) in enumerate(PT.TAPS):
+            z += np.einsum("nc,bchw->bnhw", weff[:, t, :], xp[:, :, 2 + dy:2 + dy + Ho, 2 + dx:2 + dx + Ho])
+        assert np.abs(z - ref).max() <= 1e-11 * np.abs(ref).max()
+        # image layout [tap][chunk][n][8] round-trips
+        img = PT.weight_image(weff, "bf16")
+        assert img.shape == (25, max(16, c) // 8, co, 8) and img.dtype == np.uint16
+        back = PT.from_bits16(img, "bf16").transpose(2, 0, 1, 3).reshape(co, 25, -1)
+        assert np.abs(back - weff).max() <= 2 ** -8 * np.abs(weff).max()
+        img16 = PT.weight_image(weff, "fp16")
+        back16 = PT.from_bits16(img16, "fp16").transpose(2, 0, 1, 3).reshape(co, 25, -1)
+        assert np.abs(back16 - weff).max() <= 2 ** -10 * np.abs(weff).max()
+
+
+def test_bf16_rounding_is_nearest_even():
+    import rtdm_b200.pack_tc as PT
+    import torch
+    x = np.random.RandomState(0).standard_normal(4096).astype(np.float32) * 3
+    want = torch.from_numpy(x).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    assert np.array_equal(PT.to_bits16(x, "bf16"), want)
