@@ -134,44 +134,56 @@ acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      mbar_wait(bar_in, 0);
-      tc_fence_after();
-      const uint32_t in_addr = smem_u32(s_in), w_addr = smem_u32(s_w);
-      int it = 0;
-      for (int g = 0; g < NG; ++g) {
-        const int buf = g % NBUF, use = g / NBUF;
-        if (use > 0) { mbar_wait(&acc_empty[buf], (use - 1) & 1); tc_fence_after(); }
-        const int ntile = min(G, T - g * G);
-        for (int tap = 0; tap < 25; ++tap) {
-          uint32_t wb;
-          int s = 0;
-          if (Cfg::WRES) {
-            wb = w_addr + tap * Cfg::TAP_BYTES;
-          } else {
-            s = it % Cfg::WSTAGES;
-            mbar_wait(&w_full[s], (it / Cfg::WSTAGES) & 1);
-            tc_fence_after();
-            wb = w_addr + s * Cfg::TAP_BYTES;
-          }
-          const int dy = kTapDy[tap], dx = kTapDx[tap];
-          for (int tl = 0; tl < ntile; ++tl) {
-            const int t = g * G + tl;
-            const int im = t / Cfg::TILES_PER_IMG, rem = t - im * Cfg::TILES_PER_IMG;
-            const int ty = rem / Cfg::TCOLS, tx = rem - ty * Cfg::TCOLS;
-            const uint32_t a0 = in_addr + im * Cfg::IMG_BYTES + (uint32_t)(((ty * 16 + 2 + dy) * P + tx * 8 + 2 + dx) * 16);
-            const uint32_t d = tmem_base + (uint32_t)(buf * G * N + tl * N);
+    // The whole warp walks the loop (warp-uniform control flow and descriptors); one elected lane issues.
+    mbar_wait(bar_in, 0);
+    tc_fence_after();
+    const uint32_t in_addr = smem_u32(s_in), w_addr = smem_u32(s_w);
+    constexpr uint32_t A_HI = desc_hi(P * 16), B_HI = desc_hi(128);
+    constexpr uint32_t A_KSTEP = (2 * Cfg::CHUNK_BYTES) >> 4, B_KSTEP = (2 * N * 16) >> 4;
+    int it = 0;
+    for (int g = 0; g < NG; ++g) {
+      const int buf = g % NBUF, use = g / NBUF;
+      if (use > 0) { mbar_wait(&acc_empty[buf], (use - 1) & 1); tc_fence_after(); }
+      const int ntile = min(G, T - g * G);
+      uint32_t a_lo[G];                     // descriptor low word of each tile of the group at tap (0,0), k-step 0
 #pragma unroll
-            for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
-              const uint64_t ad = smem_desc(a0 + ks * 2 * Cfg::CHUNK_BYTES, Cfg::CHUNK_BYTES, P * 16);
-              const uint64_t bd = smem_desc(wb + ks * 2 * N * 16, N * 16, 128);
-              mma_f16(d, ad, bd, IDESC, (tap | ks) != 0 ? 1u : 0u);
+      for (int tl = 0; tl < G; ++tl) {
+        const int t = min(g * G + tl, T - 1);
+        const int im = t / Cfg::TILES_PER_IMG, rem = t - im * Cfg::TILES_PER_IMG;
+        const int ty = rem / Cfg::TCOLS, tx = rem - ty * Cfg::TCOLS;
+        a_lo[tl] = desc_lo(in_addr + im * Cfg::IMG_BYTES + (uint32_t)(((ty * 16 + 2) * P + tx * 8 + 2) * 16), Cfg::CHUNK_BYTES);
+      }
+      const uint32_t d0 = tmem_base + (uint32_t)(buf * G * N);
+#pragma unroll 1
+      for (int tap = 0; tap < 25; ++tap) {
+        uint32_t b_lo;
+        int s = 0;
+        if (Cfg::WRES) {
+          b_lo = desc_lo(w_addr + tap * Cfg::TAP_BYTES, N * 16);
+        } else {
+          s = it % Cfg::WSTAGES;
+          mbar_wait(&w_full[s], (it / Cfg::WSTAGES) & 1);
+          tc_fence_after();
+          b_lo = desc_lo(w_addr + s * Cfg::TAP_BYTES, N * 16);
+        }
+        const int toff = (int)kTapDy[tap] * P + (int)kTapDx[tap];      // tap shift in 16-byte units
+        if (elect_one()) {
+#pragma unroll
+          for (int tl = 0; tl < G; ++tl) {
+            if (tl < ntile) {
+#pragma unroll
+              for (int ks = 0; ks < Cfg::KSTEPS; ++ks)
+                mma_f16(d0 + tl * N, desc_make(a_lo[tl] + (uint32_t)toff + ks * A_KSTEP, A_HI),
+                        desc_make(b_lo + ks * B_KSTEP, B_HI), IDESC, (tap | ks) != 0 ? 1u : 0u);
             }
           }
-          if (!Cfg::WRES) { mma_commit(&w_empty[s]); ++it; }
+          if (!Cfg::WRES) mma_commit(&w_empty[s]);
         }
-        mma_commit(&acc_full[buf]);
+        __syncwarp();
+        if (!Cfg::WRES) ++it;
       }
+      if (elect_one()) mma_commit(&acc_full[buf]);
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------------ epilogue

@@ -44,6 +44,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a converged warp (elect.sync): keeps the surrounding code warp-uniform so that descriptors
+// live in uniform registers instead of going through R2UR + retry loops.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- async proxy ------------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -111,6 +119,13 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
+// Split form for hot loops: the low word is (start>>4) | LBO field, so moving the start address by a
+// multiple of 16 bytes is one 32-bit add of (bytes>>4); the high word (SBO, version) is loop-invariant.
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint64_t desc_make(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 // cute::UMMA::InstrDescriptor: [4,6) D format (1 = f32, 2 = s32), [7,10) A format, [10,13) B format
 // (kind::f16: 0 = f16, 1 = bf16; kind::i8: 0 = u8, 1 = s8), [15] A major (0 = K), [16] B major (0 = K),
 // [17,23) N>>3, [24,29) M>>4.
