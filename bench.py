@@ -56,6 +56,11 @@ STAGE_WORK = {
     "dw4": (2 * 0.055e6, 6 * 6 * 128 * 2 + 4 * 4 * 384 * 2),
     "pw4": (2 * 1.573e6, 4 * 4 * 384 * 2 + 4 * 4 * 256 * 2),
     "head": (2 * 0.021e6, 4 * 4 * 256 * 2 + 20),
+    # fused tensor-core blocks: algorithmic flops = depthwise + 1x1 MACs of the region the pool keeps
+    # (NOT the 25-tap dense flops the kernel actually issues), bytes = P8 image in + P8 / NHWC image out
+    "tc_block1": (2 * (66 * 66 * 16 * 27 + 66 * 66 * 48 * 64), 2 * 72 * 72 * 16 + 8 * 36 * 36 * 16),
+    "tc_block2": (2 * (30 * 30 * 64 * 27 + 30 * 30 * 192 * 96), 8 * 36 * 36 * 16 + 12 * 18 * 18 * 16),
+    "tc_block3": (2 * (12 * 12 * 96 * 27 + 12 * 12 * 288 * 128), 12 * 18 * 18 * 16 + 6 * 6 * 128 * 2),
 }
 GEMM_STAGES = {"pw1", "pw2", "pw3", "pw4", "tc_block1", "tc_block2", "tc_block3", "tc_block4"}
 

@@ -154,6 +154,11 @@ int ernet_debug_tap(ernet_handle* h, int tap, const void* workspace, int batch,
 int ernet_ingest_tables_host(int height, int width, int* meta, int* xmin, int* xlen, int* kx,
                              int* ymin, int* ylen, int* ky, float* lut);
 
+/* Device-side watchdog record of the tensor-core kernels on the current device: out8[0] = number of
+ * pipeline waits that timed out since the last reset (0 in a healthy run), out8[1..3] = tag / block /
+ * aux of the first one.  A timed-out kernel terminates normally but its results are invalid.          */
+int ernet_debug_device_status(unsigned int* out8, int reset);
+
 /* Per-stage device timing with CUDA events recorded on the launch stream around every kernel of the
  * forward path (bench.py's live roofline measurement).  Off by default; when on, each forward adds
  * two event records per stage.  ernet_profile_read() synchronises on the recorded events, sums the

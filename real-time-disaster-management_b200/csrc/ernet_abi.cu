@@ -38,6 +38,9 @@ struct ernet_handle {
   int engine = ERNET_ENGINE_AUTO;
   bool loaded = false;
   bool has_tc = false;          // blob carries the tensor-core operand images
+  tc::EpiParams<64> epi1;       // host copies of the per-channel epilogue constants (kernel parameters)
+  tc::EpiParams<96> epi2;
+  tc::EpiParams<128> epi3;
   void* d_blob = nullptr;
   size_t blob_bytes = 0;
   Tensor t[ERNET_T_MAX];
@@ -260,10 +263,9 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
     ERNET_LAUNCH_CHECK("stem_p8_kernel");
   }
   auto wimg = [&](int k) { return h->t[ERNET_T_TC_BASE + 4 * k + ERNET_T_TC_WIMG].dev; };
-  auto beff = [&](int k) { return h->f(ERNET_T_TC_BASE + 4 * k + ERNET_T_TC_BIAS); };
-  ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_block<tc::CfgBlock1, true>(BF16, u16(p.stem), wimg(0), beff(0), h->blk(0, ERNET_T_BN_S), h->blk(0, ERNET_T_BN_T), u16(p.p1), n, s)));
-  ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_block<tc::CfgBlock2, true>(BF16, u16(p.p1), wimg(1), beff(1), h->blk(1, ERNET_T_BN_S), h->blk(1, ERNET_T_BN_T), u16(p.p2), n, s)));
-  ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_block<tc::CfgBlock3, false>(BF16, u16(p.p2), wimg(2), beff(2), h->blk(2, ERNET_T_BN_S), h->blk(2, ERNET_T_BN_T), u16(p.p3), n, s)));
+  ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_block<tc::CfgBlock1, true>(BF16, u16(p.stem), wimg(0), h->epi1, u16(p.p1), n, s)));
+  ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_block<tc::CfgBlock2, true>(BF16, u16(p.p1), wimg(1), h->epi2, u16(p.p2), n, s)));
+  ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_block<tc::CfgBlock3, false>(BF16, u16(p.p2), wimg(2), h->epi3, u16(p.p3), n, s)));
   const int c4 = h->c4();
   ERNET_STAGE(ERNET_STAGE_DW4, launch_acff_dw<T>(buf(p.p3), n, 6, 6, c4, 4, 4, h->blk(3, ERNET_T_DW_W), h->blk(3, ERNET_T_DW_B), buf(p.cat4), s));
   ERNET_STAGE(ERNET_STAGE_PW4, launch_pointwise<T>(buf(p.cat4), n, 4, 4, 3 * c4, 256, h->blk(3, ERNET_T_PW_W), h->blk(3, ERNET_T_PW_B),
@@ -427,6 +429,17 @@ int ernet_load_packed(ernet_handle* h, const void* blob, size_t bytes) {
       all = w.dev && b.dev && w.nbytes == wimg_bytes[k] && b.nbytes == nout[k] * sizeof(float);
     }
     h->has_tc = all;
+    if (all) {
+      auto host_f32 = [&](int id) { return reinterpret_cast<const float*>(static_cast<const char*>(blob) + (static_cast<const char*>(h->t[id].dev) - static_cast<const char*>(d))); };
+      auto fill = [&](int k, float* bias, float* scale, float* shift, int n) {
+        memcpy(bias, host_f32(ERNET_T_TC_BASE + 4 * k + ERNET_T_TC_BIAS), n * sizeof(float));
+        memcpy(scale, host_f32(ERNET_T_BLOCK_BASE + 8 * k + ERNET_T_BN_S), n * sizeof(float));
+        memcpy(shift, host_f32(ERNET_T_BLOCK_BASE + 8 * k + ERNET_T_BN_T), n * sizeof(float));
+      };
+      fill(0, h->epi1.bias, h->epi1.scale, h->epi1.shift, 64);
+      fill(1, h->epi2.bias, h->epi2.scale, h->epi2.shift, 96);
+      fill(2, h->epi3.bias, h->epi3.scale, h->epi3.shift, 128);
+    }
   }
   if (h->d_blob) { cudaDeviceSynchronize(); cudaFree(h->d_blob); }
   h->d_blob = d; h->blob_bytes = bytes; h->loaded = true;
@@ -678,6 +691,16 @@ int ernet_ingest_tables_host(int height, int width, int* meta, int* xmin, int* x
   memcpy(ymin, vymin.data(), kCrop * sizeof(int)); memcpy(ylen, vylen.data(), kCrop * sizeof(int));
   memcpy(kx, vkx.data(), vkx.size() * sizeof(int)); memcpy(ky, vky.data(), vky.size() * sizeof(int));
   if (lut) host_lut(lut);
+  return ERNET_OK;
+}
+
+int ernet_debug_device_status(unsigned int* out8, int reset) {
+  if (!out8) return fail(ERNET_ERR_INVALID_ARG, "null argument");
+  ERNET_CUDA(cudaMemcpyFromSymbol(out8, tc::g_tc_status, 8 * sizeof(unsigned int)));
+  if (reset) {
+    unsigned int z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    ERNET_CUDA(cudaMemcpyToSymbol(tc::g_tc_status, z, sizeof(z)));
+  }
   return ERNET_OK;
 }
 

@@ -14,15 +14,17 @@
 // acff.py:25-30 is the zero halo of the staged image, and an MMA tile of 128 rows is a 16x8 block of
 // output pixels (SBO = one image row).
 //
-// Warp roles (192 threads, one CTA per SM):
+// Warp roles (320 threads, one CTA per SM):
 //   warp 0    producer: one 1-D bulk copy (UBLKCP) of the whole P8 image(s); weight images either
 //             resident (block 1) or streamed tap by tap through a small ring; then zero-fills the halo
 //             of the output tensor
 //   warp 1    allocates TMEM, one lane issues tcgen05.mma (M=128, N=Cout, K=16) for
 //             group-of-tiles x 25 taps x C/16 k-steps, commits to mbarriers
-//   warps 2-5 epilogue: tcgen05.ld -> +b_eff -> LeakyReLU -> BN affine -> bf16/fp16 -> 2x2 max-pool with
-//             warp shuffles (a warp owns 4 rows x 8 cols of the tile) -> 16-byte stores in the next
-//             block's P8 layout (or NHWC)
+//   warps 2-9 epilogue (two warps per TMEM lane quarter, alternating tiles): tcgen05.ld -> +b_eff ->
+//             LeakyReLU -> BN affine (per-channel constants come from the kernel-parameter constant bank,
+//             so they are instruction operands, not loads) -> bf16/fp16 -> 2x2 max-pool by exchanging
+//             register halves with the x- and y-neighbour lanes (a warp owns 4 rows x 8 cols of the
+//             tile) -> one 16-byte store per lane per 32 channels in the next block's P8 layout (or NHWC)
 #pragma once
 #include "tc_common.cuh"
 
@@ -47,8 +49,7 @@ struct BlockCfg {
   static constexpr int W_SMEM = WRES ? W_BYTES : WSTAGES * TAP_BYTES;
   static constexpr int OUT_H = HU / 2, OP = OUT_H + 3;
   static constexpr int OFF_W = IN_BYTES;
-  static constexpr int OFF_PAR = OFF_W + W_SMEM;
-  static constexpr int OFF_BAR = OFF_PAR + 3 * N * 4;
+  static constexpr int OFF_BAR = OFF_W + W_SMEM;
   static constexpr int SMEM_BYTES = OFF_BAR + 128;
   static_assert(NC % 2 == 0, "K step is 16 channels");
   static_assert(N % 32 == 0 && N <= 256, "N must be a multiple of 32");
@@ -58,18 +59,27 @@ struct BlockCfg {
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
+// Per-output-channel epilogue constants, passed by value so they sit in the kernel-parameter constant bank.
+template <int N>
+struct EpiParams {
+  float bias[N];    // b_eff
+  float scale[N];   // BN gamma / sqrt(var + eps)
+  float shift[N];   // BN beta - mean * scale
+};
+
+constexpr int kBlockThreads = 320;   // producer + MMA + 8 epilogue warps
+
 template <class Cfg, bool OUT_P8, bool BF16>
-__global__ void __launch_bounds__(192, 1)
-acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ wimg, const float* __restrict__ bias,
-                  const float* __restrict__ bn_s, const float* __restrict__ bn_t, uint16_t* __restrict__ out, int batch) {
-  constexpr int NC = Cfg::NC, N = Cfg::N, P = Cfg::P, G = Cfg::G, NBUF = Cfg::NBUF, T = Cfg::T, NG = Cfg::NG;
+__global__ void __launch_bounds__(kBlockThreads, 1)
+acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ wimg,
+                  const __grid_constant__ EpiParams<Cfg::N> par, uint16_t* __restrict__ out, int batch) {
+  constexpr int N = Cfg::N, P = Cfg::P, G = Cfg::G, NBUF = Cfg::NBUF, T = Cfg::T, NG = Cfg::NG;
   constexpr int OP = Cfg::OP, OUT_H = Cfg::OUT_H;
   constexpr uint32_t IDESC = instr_desc(1u, BF16 ? 1u : 0u, 128u, (uint32_t)N);
 
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* s_in = smem;
   uint8_t* s_w = smem + Cfg::OFF_W;
-  float* s_par = reinterpret_cast<float*>(smem + Cfg::OFF_PAR);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* bar_in = bars;            // [1]
   uint64_t* w_full = bars + 1;        // [4]
@@ -77,23 +87,20 @@ acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ 
   uint64_t* acc_full = bars + 9;      // [2]
   uint64_t* acc_empty = bars + 11;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  volatile uint32_t* abort_flag = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int img0 = blockIdx.x * Cfg::IMGS;
   const int nimg = min(Cfg::IMGS, batch - img0);
 
   if (threadIdx.x == 0) {
+    *abort_flag = 0u;
     mbar_init(bar_in, 1);
     for (int i = 0; i < 4; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
-  if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < N; i += 128) {
-      s_par[i] = bias[i]; s_par[N + i] = bn_s[i]; s_par[2 * N + i] = bn_t[i];
-    }
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -109,7 +116,7 @@ acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ 
       } else {
         for (int it = 0; it < NG * 25; ++it) {
           const int s = it % Cfg::WSTAGES, use = it / Cfg::WSTAGES;
-          if (use > 0) mbar_wait(&w_empty[s], (use - 1) & 1);
+          if (use > 0 && !mbar_wait(&w_empty[s], (use - 1) & 1, abort_flag, 0x100u, it)) break;
           mbar_expect_tx(&w_full[s], Cfg::TAP_BYTES);
           bulk_g2s(s_w + s * Cfg::TAP_BYTES, reinterpret_cast<const uint8_t*>(wimg) + (size_t)(it % 25) * Cfg::TAP_BYTES,
                    Cfg::TAP_BYTES, &w_full[s]);
@@ -134,69 +141,76 @@ acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    // The whole warp walks the loop (warp-uniform control flow and descriptors); one elected lane issues.
-    mbar_wait(bar_in, 0);
-    tc_fence_after();
-    const uint32_t in_addr = smem_u32(s_in), w_addr = smem_u32(s_w);
-    constexpr uint32_t A_HI = desc_hi(P * 16), B_HI = desc_hi(128);
-    constexpr uint32_t A_KSTEP = (2 * Cfg::CHUNK_BYTES) >> 4, B_KSTEP = (2 * N * 16) >> 4;
-    int it = 0;
-    for (int g = 0; g < NG; ++g) {
-      const int buf = g % NBUF, use = g / NBUF;
-      if (use > 0) { mbar_wait(&acc_empty[buf], (use - 1) & 1); tc_fence_after(); }
-      const int ntile = min(G, T - g * G);
-      uint32_t a_lo[G];                     // descriptor low word of each tile of the group at tap (0,0), k-step 0
+    // ONE elected lane runs the whole issue loop.  Per MMA it spends an add on each descriptor's low word:
+    // tile bases are computed once per group, the tap shift is a compile-time constant (block 1: loop fully
+    // unrolled) or one multiply-add per tap, k-steps are immediates.
+    if (elect_one()) {
+      bool ok = mbar_wait(bar_in, 0, abort_flag, 0x200u);
+      tc_fence_after();
+      const uint32_t in_addr = smem_u32(s_in), w_addr = smem_u32(s_w);
+      constexpr uint32_t A_HI = desc_hi(P * 16), B_HI = desc_hi(128);
+      constexpr uint32_t A_KSTEP = (2 * Cfg::CHUNK_BYTES) >> 4, B_KSTEP = (2 * N * 16) >> 4;
+      constexpr int TAP_UNROLL = Cfg::KSTEPS == 1 ? 25 : 1;
+      const uint32_t w_lo0 = desc_lo(w_addr, N * 16);
+      int ws = 0;                 // weight ring stage and its phase (streamed weights)
+      uint32_t wphase = 0;
+      for (int g = 0; g < NG && ok; ++g) {
+        const int buf = g % NBUF, use = g / NBUF;
+        if (use > 0) { ok = mbar_wait(&acc_empty[buf], (use - 1) & 1, abort_flag, 0x201u, g); tc_fence_after(); }
+        if (!ok) break;
+        const int ntile = min(G, T - g * G);
+        uint32_t a_lo[G];         // descriptor low word of each tile of the group at tap shift 0, k-step 0
 #pragma unroll
-      for (int tl = 0; tl < G; ++tl) {
-        const int t = min(g * G + tl, T - 1);
-        const int im = t / Cfg::TILES_PER_IMG, rem = t - im * Cfg::TILES_PER_IMG;
-        const int ty = rem / Cfg::TCOLS, tx = rem - ty * Cfg::TCOLS;
-        a_lo[tl] = desc_lo(in_addr + im * Cfg::IMG_BYTES + (uint32_t)(((ty * 16 + 2) * P + tx * 8 + 2) * 16), Cfg::CHUNK_BYTES);
-      }
-      const uint32_t d0 = tmem_base + (uint32_t)(buf * G * N);
-#pragma unroll 1
-      for (int tap = 0; tap < 25; ++tap) {
-        uint32_t b_lo;
-        int s = 0;
-        if (Cfg::WRES) {
-          b_lo = desc_lo(w_addr + tap * Cfg::TAP_BYTES, N * 16);
-        } else {
-          s = it % Cfg::WSTAGES;
-          mbar_wait(&w_full[s], (it / Cfg::WSTAGES) & 1);
-          tc_fence_after();
-          b_lo = desc_lo(w_addr + s * Cfg::TAP_BYTES, N * 16);
+        for (int tl = 0; tl < G; ++tl) {
+          const int t = min(g * G + tl, T - 1);
+          const int im = t / Cfg::TILES_PER_IMG, rem = t - im * Cfg::TILES_PER_IMG;
+          const int ty = rem / Cfg::TCOLS, tx = rem - ty * Cfg::TCOLS;
+          a_lo[tl] = desc_lo(in_addr + im * Cfg::IMG_BYTES + (uint32_t)(((ty * 16 + 2) * P + tx * 8 + 2) * 16), Cfg::CHUNK_BYTES);
         }
-        const int toff = (int)kTapDy[tap] * P + (int)kTapDx[tap];      // tap shift in 16-byte units
-        if (elect_one()) {
+        const uint32_t d0 = tmem_base + (uint32_t)(buf * G * N);
+#pragma unroll TAP_UNROLL
+        for (int tap = 0; tap < 25; ++tap) {
+          uint32_t b_lo;
+          if (Cfg::WRES) {
+            b_lo = w_lo0 + (uint32_t)(tap * (Cfg::TAP_BYTES >> 4));
+          } else {
+            ok = mbar_wait(&w_full[ws], wphase, abort_flag, 0x202u, g * 32 + tap);
+            if (!ok) break;
+            tc_fence_after();
+            b_lo = w_lo0 + (uint32_t)(ws * (Cfg::TAP_BYTES >> 4));
+          }
+          const uint32_t toff = (uint32_t)(tap_dy(tap) * P + tap_dx(tap));      // tap shift in 16-byte units
 #pragma unroll
           for (int tl = 0; tl < G; ++tl) {
             if (tl < ntile) {
 #pragma unroll
               for (int ks = 0; ks < Cfg::KSTEPS; ++ks)
-                mma_f16(d0 + tl * N, desc_make(a_lo[tl] + (uint32_t)toff + ks * A_KSTEP, A_HI),
+                mma_f16(d0 + tl * N, desc_make(a_lo[tl] + toff + ks * A_KSTEP, A_HI),
                         desc_make(b_lo + ks * B_KSTEP, B_HI), IDESC, (tap | ks) != 0 ? 1u : 0u);
             }
           }
-          if (!Cfg::WRES) mma_commit(&w_empty[s]);
+          if (!Cfg::WRES) {
+            mma_commit(&w_empty[ws]);
+            if (++ws == Cfg::WSTAGES) { ws = 0; wphase ^= 1; }
+          }
         }
-        __syncwarp();
-        if (!Cfg::WRES) ++it;
+        if (ok) mma_commit(&acc_full[buf]);
       }
-      if (elect_one()) mma_commit(&acc_full[buf]);
-      __syncwarp();
     }
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue
-    asm volatile("bar.sync 1, 128;" ::: "memory");          // s_par visible to all epilogue warps
     const int q4 = warp & 3;                                 // TMEM lane quarter this warp may read
+    const int ehalf = (warp - 2) >> 2;                       // this warp takes tiles with (tl & 1) == ehalf
     const int rr = 4 * q4 + (lane >> 3), cc = lane & 7;
-    const int qm = (lane & 1) | (((lane >> 3) & 1) << 1);    // position inside the 2x2 pooling quad
+    const bool xodd = (lane & 1) != 0, yodd = ((lane >> 3) & 1) != 0;
+    const int qsel = (xodd ? 2 : 0) + (yodd ? 1 : 0);        // which 8-channel chunk of a 32-channel block this lane keeps
     for (int g = 0; g < NG; ++g) {
       const int buf = g % NBUF, use = g / NBUF;
-      mbar_wait(&acc_full[buf], use & 1);
+      if (!mbar_wait(&acc_full[buf], use & 1, abort_flag, 0x300u + warp, g)) break;
       tc_fence_after();
       const int ntile = min(G, T - g * G);
-      for (int tl = 0; tl < ntile; ++tl) {
+      for (int tl = ehalf; tl < ntile; tl += 2) {
         const int t = g * G + tl;
         const int im = t / Cfg::TILES_PER_IMG, rem = t - im * Cfg::TILES_PER_IMG;
         const int ty = rem / Cfg::TCOLS, tx = rem - ty * Cfg::TCOLS;
@@ -204,46 +218,49 @@ acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ 
         const bool valid = (y < Cfg::HU) && (x < Cfg::HU) && (im < nimg);
         const int py = y >> 1, px = x >> 1;
         const uint32_t tbase = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * G * N + tl * N);
-#pragma unroll 1
+        uint32_t v[2][32];
+        tmem_ld32(tbase, v[0]);
+#pragma unroll
         for (int cb = 0; cb < N / 32; ++cb) {
-          uint32_t v[32];
-          tmem_ld32(tbase + cb * 32, v);
-          tmem_ld_wait();
+          tmem_ld_wait();                                     // block cb has landed
+          if (cb + 1 < N / 32) tmem_ld32(tbase + (cb + 1) * 32, v[(cb + 1) & 1]);   // prefetch the next 32 columns
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int n = cb * 32 + 2 * j;
-            float z0 = __uint_as_float(v[2 * j]) + s_par[n];
-            float z1 = __uint_as_float(v[2 * j + 1]) + s_par[n + 1];
+            float z0 = __uint_as_float(v[cb & 1][2 * j]) + par.bias[n];
+            float z1 = __uint_as_float(v[cb & 1][2 * j + 1]) + par.bias[n + 1];
             z0 = fmaxf(z0, 0.01f * z0);                       // LeakyReLU(0.01), acff.py:33
             z1 = fmaxf(z1, 0.01f * z1);
-            z0 = fmaf(z0, s_par[N + n], s_par[2 * N + n]);    // eval BatchNorm, acff.py:34
-            z1 = fmaf(z1, s_par[N + n + 1], s_par[2 * N + n + 1]);
-            if (BF16) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(z0, z1);
-              __nv_bfloat162 o = __shfl_xor_sync(0xffffffffu, h, 1);
-              h = __hmax2(h, o);
-              o = __shfl_xor_sync(0xffffffffu, h, 8);
-              h = __hmax2(h, o);
-              pk[j] = *reinterpret_cast<uint32_t*>(&h);
-            } else {
-              __half2 h = __floats2half2_rn(z0, z1);
-              __half2 o = __shfl_xor_sync(0xffffffffu, h, 1);
-              h = __hmax2(h, o);
-              o = __shfl_xor_sync(0xffffffffu, h, 8);
-              h = __hmax2(h, o);
-              pk[j] = *reinterpret_cast<uint32_t*>(&h);
-            }
+            z0 = fmaf(z0, par.scale[n], par.shift[n]);        // eval BatchNorm, acff.py:34
+            z1 = fmaf(z1, par.scale[n + 1], par.shift[n + 1]);
+            if (BF16) { __nv_bfloat162 h = __floats2bfloat162_rn(z0, z1); pk[j] = *reinterpret_cast<uint32_t*>(&h); }
+            else      { __half2 h = __floats2half2_rn(z0, z1);            pk[j] = *reinterpret_cast<uint32_t*>(&h); }
           }
-          // every lane of a quad now holds the pooled values of 32 channels; lane qm stores channels
-          // [8*qm, 8*qm+8) of this 32-channel block
-          uint4 o4;
-          o4.x = qm == 0 ? pk[0] : qm == 1 ? pk[4] : qm == 2 ? pk[8] : pk[12];
-          o4.y = qm == 0 ? pk[1] : qm == 1 ? pk[5] : qm == 2 ? pk[9] : pk[13];
-          o4.z = qm == 0 ? pk[2] : qm == 1 ? pk[6] : qm == 2 ? pk[10] : pk[14];
-          o4.w = qm == 0 ? pk[3] : qm == 1 ? pk[7] : qm == 2 ? pk[11] : pk[15];
+          // 2x2 max-pool (squeeze_ernet.py:13).  x-neighbour = lane^1, y-neighbour = lane^8.  Each step the
+          // lane keeps one half of its channels, ships the other half to the neighbour, and maxes what it
+          // receives: 8 + 4 shuffles instead of 2 x 16, and the lane ends with exactly the 8 channels it stores.
+          uint32_t m1[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t keep = xodd ? pk[j + 8] : pk[j];
+            const uint32_t send = xodd ? pk[j] : pk[j + 8];
+            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+            if (BF16) { __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&keep), *reinterpret_cast<const __nv_bfloat162*>(&recv)); m1[j] = *reinterpret_cast<uint32_t*>(&r); }
+            else      { __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&keep), *reinterpret_cast<const __half2*>(&recv)); m1[j] = *reinterpret_cast<uint32_t*>(&r); }
+          }
+          uint32_t m2[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t keep = yodd ? m1[j + 4] : m1[j];
+            const uint32_t send = yodd ? m1[j] : m1[j + 4];
+            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 8);
+            if (BF16) { __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&keep), *reinterpret_cast<const __nv_bfloat162*>(&recv)); m2[j] = *reinterpret_cast<uint32_t*>(&r); }
+            else      { __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&keep), *reinterpret_cast<const __half2*>(&recv)); m2[j] = *reinterpret_cast<uint32_t*>(&r); }
+          }
           if (valid) {
-            const int ch = cb * 4 + qm;
+            const uint4 o4 = make_uint4(m2[0], m2[1], m2[2], m2[3]);
+            const int ch = cb * 4 + qsel;
             if (OUT_P8) {
               uint4* oimg = reinterpret_cast<uint4*>(out) + (size_t)(img0 + im) * (N / 8) * OP * OP;
               oimg[(ch * OP + py + 2) * OP + px + 2] = o4;
@@ -255,7 +272,8 @@ acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ 
         }
       }
       tc_fence_before();
-      mbar_arrive(&acc_empty[buf]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
   }
   tc_fence_before();
@@ -275,14 +293,14 @@ using CfgBlock2 = BlockCfg<8, 96, 33, 30, 1, 4, 1, false, 3>;
 using CfgBlock3 = BlockCfg<12, 128, 15, 12, 2, 4, 1, false, 2>;
 
 template <class Cfg, bool OUT_P8>
-inline int launch_acff_block(bool bf16, const void* in, const void* wimg, const float* bias, const float* s, const float* t,
-                             void* out, int batch, cudaStream_t stream) {
+inline int launch_acff_block(bool bf16, const void* in, const void* wimg, const EpiParams<Cfg::N>& par, void* out, int batch,
+                             cudaStream_t stream) {
   const int grid = (batch + Cfg::IMGS - 1) / Cfg::IMGS;
   auto* i16 = static_cast<const uint16_t*>(in);
   auto* w16 = static_cast<const uint16_t*>(wimg);
   auto* o16 = static_cast<uint16_t*>(out);
-  if (bf16) acff_block_kernel<Cfg, OUT_P8, true><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(i16, w16, bias, s, t, o16, batch);
-  else      acff_block_kernel<Cfg, OUT_P8, false><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(i16, w16, bias, s, t, o16, batch);
+  if (bf16) acff_block_kernel<Cfg, OUT_P8, true><<<grid, kBlockThreads, Cfg::SMEM_BYTES, stream>>>(i16, w16, par, o16, batch);
+  else      acff_block_kernel<Cfg, OUT_P8, false><<<grid, kBlockThreads, Cfg::SMEM_BYTES, stream>>>(i16, w16, par, o16, batch);
   ERNET_LAUNCH_CHECK("acff_block_kernel");
   return ERNET_OK;
 }

@@ -35,13 +35,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Spin with a watchdog: a protocol bug traps (-> CUDA error at the next sync) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// Soft watchdog.  A wait that exceeds ~0.15 s records {tag, block, aux} in a global debug buffer, raises a
+// CTA-wide abort flag in shared memory, and returns false; every other wait in the CTA then returns false
+// as soon as it sees the flag, the roles fall through to the common exit, and the kernel terminates
+// normally (a __trap() here was observed to wedge the process instead of surfacing an error).  The host
+// reads the buffer with ernet_debug_device_status().
+__device__ unsigned int g_tc_status[8];   // [0] = number of timeouts, [1] = first tag, [2] = blockIdx.x, [3] = aux
+
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile uint32_t* abort_flag, uint32_t tag,
+                                          uint32_t aux = 0) {
+  if (mbar_try_wait(bar, parity)) return true;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if (*abort_flag) return false;
+    if (clock64() - t0 > 300000000LL) {
+      if (atomicAdd(&g_tc_status[0], 1u) == 0) { g_tc_status[1] = tag; g_tc_status[2] = blockIdx.x; g_tc_status[3] = aux; }
+      *abort_flag = 1u;
+      return false;
+    }
   }
+  return true;
 }
 
 // One lane of a converged warp (elect.sync): keeps the surrounding code warp-uniform so that descriptors
@@ -137,6 +150,13 @@ __host__ __device__ constexpr uint32_t instr_desc(uint32_t d_fmt, uint32_t ab_fm
 // Union of the three dilated 3x3 stencils of acff.py:25-30 expressed as offsets from the OUTPUT
 // coordinate: d=1 -> {0,1,2}, d=2 -> {-1,1,3}, d=3 -> {-2,1,4}; (1,1) is shared by all three.
 // Sorted by (dy, dx); pack_tc.py builds the weight images in the same order.
+// Arithmetic form (compile-time foldable in unrolled loops): rows of the table are
+//   dy=-2:{-2,1,4} dy=-1:{-1,1,3} dy=0:{0,1,2} dy=1:{-2..4} dy=2:{0,1,2} dy=3:{-1,1,3} dy=4:{-2,1,4}
+__host__ __device__ constexpr int tap_dy(int t) { return t < 3 ? -2 : t < 6 ? -1 : t < 9 ? 0 : t < 16 ? 1 : t < 19 ? 2 : t < 22 ? 3 : 4; }
+__host__ __device__ constexpr int tap_dx(int t) {
+  return t < 3 ? -2 + 3 * t : t < 6 ? -1 + 2 * (t - 3) : t < 9 ? (t - 6) : t < 16 ? (t - 9) - 2 : t < 19 ? (t - 16)
+         : t < 22 ? -1 + 2 * (t - 19) : -2 + 3 * (t - 22);
+}
 __device__ constexpr int8_t kTapDy[25] = {-2, -2, -2, -1, -1, -1, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4};
 __device__ constexpr int8_t kTapDx[25] = {-2, 1, 4, -1, 1, 3, 0, 1, 2, -2, -1, 0, 1, 2, 3, 4, 0, 1, 2, -1, 1, 3, -2, 1, 4};
 
