@@ -67,9 +67,12 @@ struct ernet_handle {
   size_t esize() const { return precision == ERNET_PREC_FP32 ? 4 : 2; }
   // tensor-core path: 16-bit Squeeze_ErNET (RedConv's chained reductions still run on the CUDA-core path)
   bool use_tc() const {
+    if (precision == ERNET_PREC_INT8) return has_tc && !red();      // int8 exists only as tensor-core kernels
     if (engine == ERNET_ENGINE_SIMT) return false;
     return has_tc && !red() && (precision == ERNET_PREC_BF16 || precision == ERNET_PREC_FP16);
   }
+  float q_scales[16 + 64 + 96];          // int8: per-channel int8 step of the stem / pool1 / pool2 tensors
+  tc::StemInv stem_inv;
   const float* f(int id) const { return static_cast<const float*>(t[id].dev); }
   const float* blk(int k, int what) const { return f(ERNET_T_BLOCK_BASE + 8 * k + what); }
 };
@@ -83,6 +86,16 @@ static Plan make_plan(const ernet_handle* h, int n) {
   auto take = [&](size_t elems) { size_t r = o; o += align_up(elems * e, 256); return r; };
   p.tc = h->use_tc();
   p.ingest = take(N * 140 * 140 * 3);
+  if (p.tc && h->precision == ERNET_PREC_INT8) {   // P16 images: 16 int8 channels per 16-byte chunk (sizes in 2-byte units)
+    p.stem = take(N * 2 * 72 * 72 * 8);        // (B,2,72,72,16) int8
+    p.p1 = take(N * 4 * 36 * 36 * 8);          // (B,4,36,36,16)
+    p.p2 = take(N * 6 * 18 * 18 * 8 + 6 * 18 * 18 * 8);     // (B,6,18,18,16) + slack
+    p.p3 = take(N * 6 * 6 * 128);              // NHWC fp16
+    p.cat4 = take(N * 4 * 4 * 3 * h->c4());
+    p.a4 = take(N * 4 * 4 * 256);
+    p.total = o;
+    return p;
+  }
   if (p.tc) {
     p.stem = take(N * 2 * 72 * 72 * 8);        // P8 (B,2,72,72,8)
     p.p1 = take(N * 8 * 36 * 36 * 8);          // P8 (B,8,36,36,8)
@@ -234,12 +247,12 @@ static int run_chunk_simt(ernet_handle* h, const void* x, int x_dtype, int x_lay
   return ERNET_OK;
 }
 
-// One chunk through the tensor-core pipeline: ingest -> stem (P8) -> blocks 1-3 on tcgen05 -> block 4 + head.
-template <typename T>
+// One chunk through the tensor-core pipeline: ingest -> stem (P8/P16) -> blocks 1-3 on tcgen05 -> block 4 + head.
+// T is the 16-bit element type of the non-quantised tensors (int8 engine: fp16).
+template <typename T, int KIND>
 static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layout, const uint8_t* frames,
                         const IngestTables* tab, int order, int n, float* probs, float* logits, char* ws,
                         cudaStream_t s) {
-  constexpr bool BF16 = std::is_same<T, __nv_bfloat16>::value;
   const Plan p = make_plan(h, n);
   auto buf = [&](size_t off) { return reinterpret_cast<T*>(ws + off); };
   auto u16 = [&](size_t off) { return reinterpret_cast<uint16_t*>(ws + off); };
@@ -247,25 +260,33 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
   const int total = n * 72 * 72, grid = (total + 127) / 128;
   const float* sw = h->f(ERNET_T_STEM_W);
   const float* sb_ = h->f(ERNET_T_STEM_B);
+  const tc::StemInv& s_inv = h->stem_inv;
   if (frames) {
     ERNET_STAGE(ERNET_STAGE_INGEST, launch_ingest<T>(*tab, frames, n, order == ERNET_BGR, buf(p.ingest), 140LL * 140 * 3, 1, 140 * 3, 3, s));
     StageTimer _t(h, ERNET_STAGE_STEM, s);
-    tc::stem_p8_kernel<T, 16, BF16><<<grid, 128, 0, s>>>(buf(p.ingest), 140LL * 140 * 3, 1, 140 * 3, 3, sw, sb_, u16(p.stem), total);
+    tc::stem_p8_kernel<T, 16, KIND><<<grid, 128, 0, s>>>(buf(p.ingest), 140LL * 140 * 3, 1, 140 * 3, 3, sw, sb_, u16(p.stem), total, s_inv);
     ERNET_LAUNCH_CHECK("stem_p8_kernel");
   } else {
     long long sb = 3LL * 140 * 140, sc, sy, sx;
     if (x_layout == ERNET_NCHW) { sc = 140 * 140; sy = 140; sx = 1; }
     else                        { sc = 1; sy = 140 * 3; sx = 3; }
     StageTimer _t(h, ERNET_STAGE_STEM, s);
-    if (x_dtype == ERNET_F32) tc::stem_p8_kernel<float, 16, BF16><<<grid, 128, 0, s>>>(static_cast<const float*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total);
-    else if (x_dtype == ERNET_F16) tc::stem_p8_kernel<__half, 16, BF16><<<grid, 128, 0, s>>>(static_cast<const __half*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total);
-    else tc::stem_p8_kernel<__nv_bfloat16, 16, BF16><<<grid, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total);
+    if (x_dtype == ERNET_F32) tc::stem_p8_kernel<float, 16, KIND><<<grid, 128, 0, s>>>(static_cast<const float*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total, s_inv);
+    else if (x_dtype == ERNET_F16) tc::stem_p8_kernel<__half, 16, KIND><<<grid, 128, 0, s>>>(static_cast<const __half*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total, s_inv);
+    else tc::stem_p8_kernel<__nv_bfloat16, 16, KIND><<<grid, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total, s_inv);
     ERNET_LAUNCH_CHECK("stem_p8_kernel");
   }
   auto wimg = [&](int k) { return h->t[ERNET_T_TC_BASE + 4 * k + ERNET_T_TC_WIMG].dev; };
-  ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_block<tc::CfgBlock1, true>(BF16, u16(p.stem), wimg(0), h->epi1, u16(p.p1), n, s)));
-  ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_block<tc::CfgBlock2, true>(BF16, u16(p.p1), wimg(1), h->epi2, u16(p.p2), n, s)));
-  ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_block<tc::CfgBlock3, false>(BF16, u16(p.p2), wimg(2), h->epi3, u16(p.p3), n, s)));
+  if (KIND == tc::KIND_I8) {
+    ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_block<tc::CfgBlock1Q, tc::KIND_I8, tc::OUT_P16>(u16(p.stem), wimg(0), h->epi1, u16(p.p1), n, s)));
+    ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_block<tc::CfgBlock2Q, tc::KIND_I8, tc::OUT_P16>(u16(p.p1), wimg(1), h->epi2, u16(p.p2), n, s)));
+    ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_block<tc::CfgBlock3Q, tc::KIND_I8, tc::OUT_NHWC>(u16(p.p2), wimg(2), h->epi3, u16(p.p3), n, s)));
+  } else {
+    constexpr int K16 = KIND == tc::KIND_I8 ? tc::KIND_F16 : KIND;
+    ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_block<tc::CfgBlock1, K16, tc::OUT_P8>(u16(p.stem), wimg(0), h->epi1, u16(p.p1), n, s)));
+    ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_block<tc::CfgBlock2, K16, tc::OUT_P8>(u16(p.p1), wimg(1), h->epi2, u16(p.p2), n, s)));
+    ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_block<tc::CfgBlock3, K16, tc::OUT_NHWC>(u16(p.p2), wimg(2), h->epi3, u16(p.p3), n, s)));
+  }
   const int c4 = h->c4();
   ERNET_STAGE(ERNET_STAGE_DW4, launch_acff_dw<T>(buf(p.p3), n, 6, 6, c4, 4, 4, h->blk(3, ERNET_T_DW_W), h->blk(3, ERNET_T_DW_B), buf(p.cat4), s));
   ERNET_STAGE(ERNET_STAGE_PW4, launch_pointwise<T>(buf(p.cat4), n, 4, 4, 3 * c4, 256, h->blk(3, ERNET_T_PW_W), h->blk(3, ERNET_T_PW_B),
@@ -281,8 +302,9 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
 static int run_chunk(ernet_handle* h, const void* x, int x_dtype, int x_layout, const uint8_t* frames,
                      const IngestTables* tab, int order, int n, float* probs, float* logits, char* ws, cudaStream_t s) {
   if (h->use_tc()) {
-    if (h->precision == ERNET_PREC_BF16) return run_chunk_tc<__nv_bfloat16>(h, x, x_dtype, x_layout, frames, tab, order, n, probs, logits, ws, s);
-    return run_chunk_tc<__half>(h, x, x_dtype, x_layout, frames, tab, order, n, probs, logits, ws, s);
+    if (h->precision == ERNET_PREC_BF16) return run_chunk_tc<__nv_bfloat16, tc::KIND_BF16>(h, x, x_dtype, x_layout, frames, tab, order, n, probs, logits, ws, s);
+    if (h->precision == ERNET_PREC_INT8) return run_chunk_tc<__half, tc::KIND_I8>(h, x, x_dtype, x_layout, frames, tab, order, n, probs, logits, ws, s);
+    return run_chunk_tc<__half, tc::KIND_F16>(h, x, x_dtype, x_layout, frames, tab, order, n, probs, logits, ws, s);
   }
   switch (h->precision) {
     case ERNET_PREC_FP32: return run_chunk_simt<float>(h, x, x_dtype, x_layout, frames, tab, order, n, probs, logits, ws, s);
@@ -304,9 +326,7 @@ static int init_device_attrs() {
   if ((rc = set_smem_attrs<float>())) return rc;
   if ((rc = set_smem_attrs<__half>())) return rc;
   if ((rc = set_smem_attrs<__nv_bfloat16>())) return rc;
-  if ((rc = tc::set_block_attrs<tc::CfgBlock1, true>())) return rc;
-  if ((rc = tc::set_block_attrs<tc::CfgBlock2, true>())) return rc;
-  if ((rc = tc::set_block_attrs<tc::CfgBlock3, false>())) return rc;
+  if ((rc = tc::set_all_block_attrs())) return rc;
   return ERNET_OK;
 }
 
@@ -420,25 +440,48 @@ int ernet_load_packed(ernet_handle* h, const void* blob, size_t bytes) {
   int rc = validate_simt_tensors(h);
   if (rc) { memcpy(h->t, old, sizeof(old)); cudaFree(d); return rc; }
   {
-    const size_t wimg_bytes[3] = {tc::CfgBlock1::W_BYTES, tc::CfgBlock2::W_BYTES, tc::CfgBlock3::W_BYTES};
+    const bool q = h->precision == ERNET_PREC_INT8;
+    const size_t wimg_bytes[3] = {q ? (size_t)tc::CfgBlock1Q::W_BYTES : (size_t)tc::CfgBlock1::W_BYTES,
+                                  q ? (size_t)tc::CfgBlock2Q::W_BYTES : (size_t)tc::CfgBlock2::W_BYTES,
+                                  q ? (size_t)tc::CfgBlock3Q::W_BYTES : (size_t)tc::CfgBlock3::W_BYTES};
     const size_t nout[3] = {64, 96, 128};
-    bool all = !h->red();
+    bool all = !h->red() && h->precision != ERNET_PREC_FP32;
     for (int k = 0; k < 3 && all; ++k) {
       const Tensor& w = h->t[ERNET_T_TC_BASE + 4 * k + ERNET_T_TC_WIMG];
       const Tensor& b = h->t[ERNET_T_TC_BASE + 4 * k + ERNET_T_TC_BIAS];
       all = w.dev && b.dev && w.nbytes == wimg_bytes[k] && b.nbytes == nout[k] * sizeof(float);
+      if (q) {
+        const Tensor& dq = h->t[ERNET_T_TC_BASE + 4 * k + ERNET_T_TC_DEQ];
+        all = all && dq.dev && dq.nbytes == nout[k] * sizeof(float);
+      }
     }
+    if (q) all = all && h->t[ERNET_T_Q_SCALES].dev && h->t[ERNET_T_Q_SCALES].nbytes == sizeof(h->q_scales);
     h->has_tc = all;
     if (all) {
       auto host_f32 = [&](int id) { return reinterpret_cast<const float*>(static_cast<const char*>(blob) + (static_cast<const char*>(h->t[id].dev) - static_cast<const char*>(d))); };
-      auto fill = [&](int k, float* bias, float* scale, float* shift, int n) {
+      if (q) {
+        memcpy(h->q_scales, host_f32(ERNET_T_Q_SCALES), sizeof(h->q_scales));
+        for (int i = 0; i < 16; ++i) h->stem_inv.v[i] = 1.f / h->q_scales[i];
+      } else {
+        for (int i = 0; i < 16; ++i) h->stem_inv.v[i] = 1.f;
+      }
+      auto fill = [&](int k, float* bias, float* scale, float* shift, float* deq, float* out_inv, int n) {
         memcpy(bias, host_f32(ERNET_T_TC_BASE + 4 * k + ERNET_T_TC_BIAS), n * sizeof(float));
         memcpy(scale, host_f32(ERNET_T_BLOCK_BASE + 8 * k + ERNET_T_BN_S), n * sizeof(float));
         memcpy(shift, host_f32(ERNET_T_BLOCK_BASE + 8 * k + ERNET_T_BN_T), n * sizeof(float));
+        if (q) memcpy(deq, host_f32(ERNET_T_TC_BASE + 4 * k + ERNET_T_TC_DEQ), n * sizeof(float));
+        else for (int i = 0; i < n; ++i) deq[i] = 1.f;
+        const float* qs = h->q_scales + (k == 0 ? 16 : 16 + 64);      // blocks 1, 2 requantise for the next int8 block
+        for (int i = 0; i < n; ++i) out_inv[i] = (q && k < 2) ? 1.f / qs[i] : 1.f;
       };
-      fill(0, h->epi1.bias, h->epi1.scale, h->epi1.shift, 64);
-      fill(1, h->epi2.bias, h->epi2.scale, h->epi2.shift, 96);
-      fill(2, h->epi3.bias, h->epi3.scale, h->epi3.shift, 128);
+      fill(0, h->epi1.bias, h->epi1.scale, h->epi1.shift, h->epi1.deq, h->epi1.out_inv, 64);
+      fill(1, h->epi2.bias, h->epi2.scale, h->epi2.shift, h->epi2.deq, h->epi2.out_inv, 96);
+      fill(2, h->epi3.bias, h->epi3.scale, h->epi3.shift, h->epi3.deq, h->epi3.out_inv, 128);
+    }
+    if (q && !all) {
+      memcpy(h->t, old, sizeof(old)); cudaFree(d);
+      return fail(ERNET_ERR_BAD_BLOB, h->red() ? "int8 is implemented for Squeeze_ErNET only"
+                                                : "int8 blob lacks the calibrated tensor-core images (pack with act_scales)");
     }
   }
   if (h->d_blob) { cudaDeviceSynchronize(); cudaFree(h->d_blob); }
@@ -657,6 +700,14 @@ int ernet_debug_tap(ernet_handle* h, int tap, const void* workspace, int batch, 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const char* src = static_cast<const char*>(workspace) + off;
   const int grid = (int)((total + 255) / 256);
+  if (p.tc && h->precision == ERNET_PREC_INT8 && (tap == ERNET_TAP_STEM || tap == ERNET_TAP_POOL1 || tap == ERNET_TAP_POOL2)) {
+    const int Hh = tap == ERNET_TAP_STEM ? 69 : (tap == ERNET_TAP_POOL1 ? 33 : 15);
+    const int NCc = tap == ERNET_TAP_STEM ? 2 : (tap == ERNET_TAP_POOL1 ? 4 : 6);
+    const float* sc = h->f(ERNET_T_Q_SCALES) + (tap == ERNET_TAP_STEM ? 0 : (tap == ERNET_TAP_POOL1 ? 16 : 16 + 64));
+    tc::tap_p16_to_nchw_f32<<<grid, 256, 0, s>>>(reinterpret_cast<const int8_t*>(src), NCc, C, Hh, total, sc, out);
+    ERNET_LAUNCH_CHECK("tap_p16_to_nchw_f32");
+    return ERNET_OK;
+  }
   if (p.tc && (tap == ERNET_TAP_STEM || tap == ERNET_TAP_POOL1 || tap == ERNET_TAP_POOL2)) {
     const int Hh = tap == ERNET_TAP_STEM ? 69 : (tap == ERNET_TAP_POOL1 ? 33 : 15);
     const int NCc = tap == ERNET_TAP_STEM ? 2 : (tap == ERNET_TAP_POOL1 ? 8 : 12);
@@ -666,7 +717,7 @@ int ernet_debug_tap(ernet_handle* h, int tap, const void* workspace, int batch, 
     return ERNET_OK;
   }
   if (h->precision == ERNET_PREC_FP32) tap_nhwc_to_nchw_f32<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(src), C, HW, total, out);
-  else if (h->precision == ERNET_PREC_FP16) tap_nhwc_to_nchw_f32<__half><<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(src), C, HW, total, out);
+  else if (h->precision == ERNET_PREC_FP16 || h->precision == ERNET_PREC_INT8) tap_nhwc_to_nchw_f32<__half><<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(src), C, HW, total, out);
   else tap_nhwc_to_nchw_f32<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), C, HW, total, out);
   ERNET_LAUNCH_CHECK("tap_nhwc_to_nchw_f32");
   return ERNET_OK;

@@ -65,17 +65,30 @@ struct EpiParams {
   float bias[N];    // b_eff
   float scale[N];   // BN gamma / sqrt(var + eps)
   float shift[N];   // BN beta - mean * scale
+  float deq[N];     // int8 only: s_w[n] (int32 accumulator -> real value; the per-input-channel activation
+                    // scales are folded into the quantised weights)
+  float out_inv[N]; // int8 output only: 1 / (real value of one int8 step of output channel n)
 };
+
+// operand kind and output format of a block kernel instance
+enum : int { KIND_F16 = 0, KIND_BF16 = 1, KIND_I8 = 2 };
+enum : int { OUT_P8 = 0,      // 16-bit, (B, N/8, OP, OP, 8) with zero halo: next block's staged image
+             OUT_NHWC = 1,    // 16-bit, (B, OUT_H, OUT_H, N): input of the CUDA-core ACFF4 kernels
+             OUT_P16 = 2 };   // int8,   (B, N/16, OP, OP, 16) with zero halo: next int8 block's staged image
 
 constexpr int kBlockThreads = 320;   // producer + MMA + 8 epilogue warps
 
-template <class Cfg, bool OUT_P8, bool BF16>
+// KIND_I8 with a 16-bit output writes fp16 (the int8 engine keeps its non-quantised tensors in fp16).
+template <class Cfg, int KIND, int OUT>
 __global__ void __launch_bounds__(kBlockThreads, 1)
 acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ wimg,
                   const __grid_constant__ EpiParams<Cfg::N> par, uint16_t* __restrict__ out, int batch) {
   constexpr int N = Cfg::N, P = Cfg::P, G = Cfg::G, NBUF = Cfg::NBUF, T = Cfg::T, NG = Cfg::NG;
   constexpr int OP = Cfg::OP, OUT_H = Cfg::OUT_H;
-  constexpr uint32_t IDESC = instr_desc(1u, BF16 ? 1u : 0u, 128u, (uint32_t)N);
+  constexpr bool BF16 = KIND == KIND_BF16;                       // 16-bit output element type
+  constexpr uint32_t IDESC = KIND == KIND_I8 ? instr_desc(2u, 1u, 128u, (uint32_t)N)      // s8 x s8 -> s32
+                                             : instr_desc(1u, BF16 ? 1u : 0u, 128u, (uint32_t)N);
+  constexpr int OUT_CHUNKS = OUT == OUT_P16 ? N / 16 : N / 8;     // 16-byte chunks per output pixel
 
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* s_in = smem;
@@ -124,13 +137,13 @@ acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ 
       }
     }
     __syncwarp();
-    if (OUT_P8) {
+    if (OUT != OUT_NHWC) {
       // zero halo of the output images (rows 0,1,OP-1 and cols 0,1,OP-1 of every chunk): the next block's
       // conv padding.  Done by the otherwise idle producer warp.
       constexpr int BORDER = 3 * OP + (OP - 3) * 3;
       for (int im = 0; im < nimg; ++im) {
-        uint4* oimg = reinterpret_cast<uint4*>(out) + (size_t)(img0 + im) * (N / 8) * OP * OP;
-        for (int i = lane; i < (N / 8) * BORDER; i += 32) {
+        uint4* oimg = reinterpret_cast<uint4*>(out) + (size_t)(img0 + im) * OUT_CHUNKS * OP * OP;
+        for (int i = lane; i < OUT_CHUNKS * BORDER; i += 32) {
           const int ch = i / BORDER, k = i - ch * BORDER;
           int r, c;
           if (k < 3 * OP) { r = k / OP; c = k - r * OP; if (r == 2) r = OP - 1; }
@@ -185,8 +198,12 @@ acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ 
             if (tl < ntile) {
 #pragma unroll
               for (int ks = 0; ks < Cfg::KSTEPS; ++ks)
-                mma_f16(d0 + tl * N, desc_make(a_lo[tl] + toff + ks * A_KSTEP, A_HI),
-                        desc_make(b_lo + ks * B_KSTEP, B_HI), IDESC, (tap | ks) != 0 ? 1u : 0u);
+                if (KIND == KIND_I8)
+                  mma_i8(d0 + tl * N, desc_make(a_lo[tl] + toff + ks * A_KSTEP, A_HI),
+                         desc_make(b_lo + ks * B_KSTEP, B_HI), IDESC, (tap | ks) != 0 ? 1u : 0u);
+                else
+                  mma_f16(d0 + tl * N, desc_make(a_lo[tl] + toff + ks * A_KSTEP, A_HI),
+                          desc_make(b_lo + ks * B_KSTEP, B_HI), IDESC, (tap | ks) != 0 ? 1u : 0u);
             }
           }
           if (!Cfg::WRES) {
@@ -224,49 +241,86 @@ acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ 
         for (int cb = 0; cb < N / 32; ++cb) {
           tmem_ld_wait();                                     // block cb has landed
           if (cb + 1 < N / 32) tmem_ld32(tbase + (cb + 1) * 32, v[(cb + 1) & 1]);   // prefetch the next 32 columns
-          uint32_t pk[16];
+          float yv[32];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = cb * 32 + 2 * j;
-            float z0 = __uint_as_float(v[cb & 1][2 * j]) + par.bias[n];
-            float z1 = __uint_as_float(v[cb & 1][2 * j + 1]) + par.bias[n + 1];
-            z0 = fmaxf(z0, 0.01f * z0);                       // LeakyReLU(0.01), acff.py:33
-            z1 = fmaxf(z1, 0.01f * z1);
-            z0 = fmaf(z0, par.scale[n], par.shift[n]);        // eval BatchNorm, acff.py:34
-            z1 = fmaf(z1, par.scale[n + 1], par.shift[n + 1]);
-            if (BF16) { __nv_bfloat162 h = __floats2bfloat162_rn(z0, z1); pk[j] = *reinterpret_cast<uint32_t*>(&h); }
-            else      { __half2 h = __floats2half2_rn(z0, z1);            pk[j] = *reinterpret_cast<uint32_t*>(&h); }
+          for (int j = 0; j < 32; ++j) {
+            const int n = cb * 32 + j;
+            float z = KIND == KIND_I8 ? fmaf(__int2float_rn((int)v[cb & 1][j]), par.deq[n], par.bias[n])
+                                      : __uint_as_float(v[cb & 1][j]) + par.bias[n];
+            z = fmaxf(z, 0.01f * z);                           // LeakyReLU(0.01), acff.py:33
+            yv[j] = fmaf(z, par.scale[n], par.shift[n]);       // eval BatchNorm, acff.py:34
           }
           // 2x2 max-pool (squeeze_ernet.py:13).  x-neighbour = lane^1, y-neighbour = lane^8.  Each step the
           // lane keeps one half of its channels, ships the other half to the neighbour, and maxes what it
-          // receives: 8 + 4 shuffles instead of 2 x 16, and the lane ends with exactly the 8 channels it stores.
-          uint32_t m1[8];
+          // receives, so the lane ends with exactly the 8 channels it stores.  Rounding / quantisation is
+          // monotone, so it commutes with the max and is done first (fewer registers to exchange).
+          if (OUT == OUT_P16) {
+            uint32_t pk[8];                                    // 32 channels as packed int8
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t keep = xodd ? pk[j + 8] : pk[j];
-            const uint32_t send = xodd ? pk[j] : pk[j + 8];
-            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
-            if (BF16) { __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&keep), *reinterpret_cast<const __nv_bfloat162*>(&recv)); m1[j] = *reinterpret_cast<uint32_t*>(&r); }
-            else      { __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&keep), *reinterpret_cast<const __half2*>(&recv)); m1[j] = *reinterpret_cast<uint32_t*>(&r); }
-          }
-          uint32_t m2[4];
+            for (int j = 0; j < 8; ++j) {
+              uint32_t w = 0;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t keep = yodd ? m1[j + 4] : m1[j];
-            const uint32_t send = yodd ? m1[j] : m1[j + 4];
-            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 8);
-            if (BF16) { __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&keep), *reinterpret_cast<const __nv_bfloat162*>(&recv)); m2[j] = *reinterpret_cast<uint32_t*>(&r); }
-            else      { __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&keep), *reinterpret_cast<const __half2*>(&recv)); m2[j] = *reinterpret_cast<uint32_t*>(&r); }
-          }
-          if (valid) {
-            const uint4 o4 = make_uint4(m2[0], m2[1], m2[2], m2[3]);
-            const int ch = cb * 4 + qsel;
-            if (OUT_P8) {
-              uint4* oimg = reinterpret_cast<uint4*>(out) + (size_t)(img0 + im) * (N / 8) * OP * OP;
-              oimg[(ch * OP + py + 2) * OP + px + 2] = o4;
-            } else {
-              uint16_t* o = out + ((size_t)((img0 + im) * OUT_H + py) * OUT_H + px) * N + ch * 8;
-              *reinterpret_cast<uint4*>(o) = o4;
+              for (int e = 0; e < 4; ++e) {
+                int q = __float2int_rn(yv[4 * j + e] * par.out_inv[cb * 32 + 4 * j + e]);
+                q = max(-127, min(127, q));
+                w |= ((uint32_t)q & 0xffu) << (8 * e);
+              }
+              pk[j] = w;
+            }
+            uint32_t m1[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t keep = xodd ? pk[j + 4] : pk[j];
+              const uint32_t send = xodd ? pk[j] : pk[j + 4];
+              m1[j] = __vmaxs4(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+            }
+            uint32_t m2[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint32_t keep = yodd ? m1[j + 2] : m1[j];
+              const uint32_t send = yodd ? m1[j] : m1[j + 2];
+              m2[j] = __vmaxs4(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+            }
+            if (valid) {                                       // 8 channels = half of a 16-channel chunk
+              const int ch = cb * 2 + (qsel >> 1);
+              uint2* oimg = reinterpret_cast<uint2*>(out) + ((size_t)(img0 + im) * OUT_CHUNKS * OP * OP) * 2;
+              oimg[((size_t)(ch * OP + py + 2) * OP + px + 2) * 2 + (qsel & 1)] = make_uint2(m2[0], m2[1]);
+            }
+          } else {
+            uint32_t pk[16];                                   // 32 channels as packed bf16x2 / half2
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (BF16) { __nv_bfloat162 h = __floats2bfloat162_rn(yv[2 * j], yv[2 * j + 1]); pk[j] = *reinterpret_cast<uint32_t*>(&h); }
+              else      { __half2 h = __floats2half2_rn(yv[2 * j], yv[2 * j + 1]);            pk[j] = *reinterpret_cast<uint32_t*>(&h); }
+            }
+            uint32_t m1[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t keep = xodd ? pk[j + 8] : pk[j];
+              const uint32_t send = xodd ? pk[j] : pk[j + 8];
+              const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+              if (BF16) { __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&keep), *reinterpret_cast<const __nv_bfloat162*>(&recv)); m1[j] = *reinterpret_cast<uint32_t*>(&r); }
+              else      { __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&keep), *reinterpret_cast<const __half2*>(&recv)); m1[j] = *reinterpret_cast<uint32_t*>(&r); }
+            }
+            uint32_t m2[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t keep = yodd ? m1[j + 4] : m1[j];
+              const uint32_t send = yodd ? m1[j] : m1[j + 4];
+              const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 8);
+              if (BF16) { __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&keep), *reinterpret_cast<const __nv_bfloat162*>(&recv)); m2[j] = *reinterpret_cast<uint32_t*>(&r); }
+              else      { __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&keep), *reinterpret_cast<const __half2*>(&recv)); m2[j] = *reinterpret_cast<uint32_t*>(&r); }
+            }
+            if (valid) {
+              const uint4 o4 = make_uint4(m2[0], m2[1], m2[2], m2[3]);
+              const int ch = cb * 4 + qsel;
+              if (OUT == OUT_P8) {
+                uint4* oimg = reinterpret_cast<uint4*>(out) + (size_t)(img0 + im) * OUT_CHUNKS * OP * OP;
+                oimg[(ch * OP + py + 2) * OP + px + 2] = o4;
+              } else {
+                uint16_t* o = out + ((size_t)((img0 + im) * OUT_H + py) * OUT_H + px) * N + ch * 8;
+                *reinterpret_cast<uint4*>(o) = o4;
+              }
             }
           }
         }
@@ -284,41 +338,58 @@ acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ 
   }
 }
 
-// Block configurations (SURVEY.md section 7.5 sizes, Squeeze_ErNET):
-//   block 1: 16(+pad) -> 64, 69x69 in, 66x66 used, 45 tiles/img, weights resident (51 KB), 2 x 4-tile TMEM buffers
-//   block 2: 64 -> 96,  33x33 in, 30x30 used,  8 tiles/img, weights streamed (12 KB per tap, 3-stage ring)
-//   block 3: 96 -> 128, 15x15 in, 12x12 used,  2 tiles/img, 2 images per CTA, weights streamed (24 KB per tap)
+// Block configurations (SURVEY.md section 7.5 sizes, Squeeze_ErNET).  NC counts 16-byte chunks per pixel:
+// 8 channels at 16 bit, 16 channels at int8 (block 1 int8: 16 real channels + one zero chunk, K step = 32).
+//   block 1: 16 -> 64,  69x69 in, 66x66 used, 45 tiles/img, weights resident, 2 x 4-tile TMEM buffers
+//   block 2: 64 -> 96,  33x33 in, 30x30 used,  8 tiles/img, weights streamed through a ring
+//   block 3: 96 -> 128, 15x15 in, 12x12 used,  2 tiles/img, 2 images per CTA, weights streamed
 using CfgBlock1 = BlockCfg<2, 64, 69, 66, 1, 4, 2, true, 1>;
 using CfgBlock2 = BlockCfg<8, 96, 33, 30, 1, 4, 1, false, 3>;
 using CfgBlock3 = BlockCfg<12, 128, 15, 12, 2, 4, 1, false, 2>;
+using CfgBlock1Q = BlockCfg<2, 64, 69, 66, 1, 4, 2, true, 1>;
+using CfgBlock2Q = BlockCfg<4, 96, 33, 30, 1, 4, 1, false, 4>;
+using CfgBlock3Q = BlockCfg<6, 128, 15, 12, 2, 4, 1, false, 3>;
 
-template <class Cfg, bool OUT_P8>
-inline int launch_acff_block(bool bf16, const void* in, const void* wimg, const EpiParams<Cfg::N>& par, void* out, int batch,
+template <class Cfg, int KIND, int OUT>
+inline int launch_acff_block(const void* in, const void* wimg, const EpiParams<Cfg::N>& par, void* out, int batch,
                              cudaStream_t stream) {
   const int grid = (batch + Cfg::IMGS - 1) / Cfg::IMGS;
-  auto* i16 = static_cast<const uint16_t*>(in);
-  auto* w16 = static_cast<const uint16_t*>(wimg);
-  auto* o16 = static_cast<uint16_t*>(out);
-  if (bf16) acff_block_kernel<Cfg, OUT_P8, true><<<grid, kBlockThreads, Cfg::SMEM_BYTES, stream>>>(i16, w16, par, o16, batch);
-  else      acff_block_kernel<Cfg, OUT_P8, false><<<grid, kBlockThreads, Cfg::SMEM_BYTES, stream>>>(i16, w16, par, o16, batch);
+  acff_block_kernel<Cfg, KIND, OUT><<<grid, kBlockThreads, Cfg::SMEM_BYTES, stream>>>(
+      static_cast<const uint16_t*>(in), static_cast<const uint16_t*>(wimg), par, static_cast<uint16_t*>(out), batch);
   ERNET_LAUNCH_CHECK("acff_block_kernel");
   return ERNET_OK;
 }
 
-template <class Cfg, bool OUT_P8>
-inline int set_block_attrs() {
-  ERNET_CUDA(cudaFuncSetAttribute(acff_block_kernel<Cfg, OUT_P8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  ERNET_CUDA(cudaFuncSetAttribute(acff_block_kernel<Cfg, OUT_P8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+template <class Cfg, int KIND, int OUT>
+inline int set_block_attr() {
+  ERNET_CUDA(cudaFuncSetAttribute(acff_block_kernel<Cfg, KIND, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  return ERNET_OK;
+}
+
+inline int set_all_block_attrs() {
+  int rc;
+  if ((rc = set_block_attr<CfgBlock1, KIND_BF16, OUT_P8>())) return rc;
+  if ((rc = set_block_attr<CfgBlock1, KIND_F16, OUT_P8>())) return rc;
+  if ((rc = set_block_attr<CfgBlock2, KIND_BF16, OUT_P8>())) return rc;
+  if ((rc = set_block_attr<CfgBlock2, KIND_F16, OUT_P8>())) return rc;
+  if ((rc = set_block_attr<CfgBlock3, KIND_BF16, OUT_NHWC>())) return rc;
+  if ((rc = set_block_attr<CfgBlock3, KIND_F16, OUT_NHWC>())) return rc;
+  if ((rc = set_block_attr<CfgBlock1Q, KIND_I8, OUT_P16>())) return rc;
+  if ((rc = set_block_attr<CfgBlock2Q, KIND_I8, OUT_P16>())) return rc;
+  if ((rc = set_block_attr<CfgBlock3Q, KIND_I8, OUT_NHWC>())) return rc;
   return ERNET_OK;
 }
 
 // ---------------------------------------------------------------------------------- stem -> P8
 // conv1 3x3/s2 (model/squeeze_ernet.py:11,25; RedConv: conv_red1 folded in) writing the P8 layout block 1
 // stages: (B, 2 chunks, 72, 72, 8) with the zero halo included.  One thread per padded pixel.
-template <typename TI, int CS, bool BF16>
+// KIND_I8: channel c is quantised with out_inv.v[c] (= 1 / its int8 step) into chunk 0 of a P16 image, chunk 1 is zero.
+struct StemInv { float v[16]; };
+template <typename TI, int CS, int KIND>
 __global__ void __launch_bounds__(128)
 stem_p8_kernel(const TI* __restrict__ x, long long sb, long long sc, long long sy, long long sx,
-               const float* __restrict__ w /*[27][CS]*/, const float* __restrict__ bias, uint16_t* __restrict__ out, int total) {
+               const float* __restrict__ w /*[27][CS]*/, const float* __restrict__ bias, uint16_t* __restrict__ out, int total,
+               const __grid_constant__ StemInv out_inv) {
   __shared__ float ws[27 * CS + CS];
   for (int i = threadIdx.x; i < 27 * CS + CS; i += blockDim.x) ws[i] = i < 27 * CS ? w[i] : bias[i - 27 * CS];
   __syncthreads();
@@ -350,13 +421,43 @@ stem_p8_kernel(const TI* __restrict__ x, long long sb, long long sc, long long s
 #pragma unroll
         for (int k = 0; k < CS; ++k) acc[k] = fmaf(v, wr[k], acc[k]);
       }
+  if (KIND == KIND_I8) {
+    uint32_t wq[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t wv = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        int q = __float2int_rn(acc[4 * j + e] * out_inv.v[4 * j + e]);
+        q = max(-127, min(127, q));
+        wv |= ((uint32_t)q & 0xffu) << (8 * e);
+      }
+      wq[j] = wv;
+    }
+    o[0] = make_uint4(wq[0], wq[1], wq[2], wq[3]);
+    o[P * P] = make_uint4(0, 0, 0, 0);
+    return;
+  }
 #pragma unroll
   for (int ch = 0; ch < 2; ++ch) {
     float t8[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) t8[k] = acc[ch * 8 + k];
-    o[ch * P * P] = BF16 ? pack16<__nv_bfloat16>(t8) : pack16<__half>(t8);
+    o[ch * P * P] = KIND == KIND_BF16 ? pack16<__nv_bfloat16>(t8) : pack16<__half>(t8);
   }
+}
+
+// debug: P16 (B, NC, H+3, W+3, 16) int8 -> dequantised fp32 NCHW (first C channels)
+__global__ void tap_p16_to_nchw_f32(const int8_t* __restrict__ src, int NC, int C, int H, long long total,
+                                    const float* __restrict__ scale /*[C]*/, float* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int P = H + 3;
+  const int x = (int)(i % H);
+  const int y = (int)((i / H) % H);
+  const int c = (int)((i / ((long long)H * H)) % C);
+  const long long b = i / ((long long)H * H * C);
+  dst[i] = scale[c] * (float)src[(((b * NC + (c >> 4)) * P + y + 2) * P + x + 2) * 16 + (c & 15)];
 }
 
 // debug: P8 (B, NC, H+3, W+3, 8) 16-bit -> fp32 NCHW (B, NC*8 [first C], H, W)

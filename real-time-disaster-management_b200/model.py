@@ -79,6 +79,7 @@ class _ErnetB200(nn.Module):
         self._fingerprint = None
         self._workspace = None
         self._last_batch = 0
+        self._act_scales = None              # int8: calibrated per-tensor activation scales (stem, pool1, pool2)
         if device is not None:
             self.to(device)
 
@@ -129,9 +130,11 @@ class _ErnetB200(nn.Module):
             h = C.c_void_p()
             _lib.check(lib.ernet_create(C.byref(h), _lib.ARCH[self.ARCH], _lib.PRECISION[prec], idx))
             self._engine = (h, idx, prec)
-        fp = self._weights_fingerprint()
+        if prec == "int8" and self._act_scales is None:
+            self.calibrate()                 # default synthetic calibration set
+        fp = (self._weights_fingerprint(), self._act_scales)
         if fp != self._fingerprint:
-            blob = pack_state_dict(self.state_dict(), self.ARCH, prec)
+            blob = pack_state_dict(self.state_dict(), self.ARCH, prec, self._act_scales)
             buf = (C.c_char * len(blob)).from_buffer_copy(blob)
             _lib.check(lib.ernet_load_packed(self._engine[0], buf, len(blob)))
             self._fingerprint = fp
@@ -142,6 +145,65 @@ class _ErnetB200(nn.Module):
         if self._workspace is None or self._workspace.numel() < need or self._workspace.device != device:
             self._workspace = torch.empty(need, dtype=torch.uint8, device=device)
         return self._workspace
+
+    # ------------------------------------------------------------------ int8 calibration
+    def calibrate(self, frames=None, *, percentile=100.0, per_channel=True, batch=128):
+        """Activation scales for the int8 engine (the TensorRT scheme behind the reference's int8 artefacts:
+        symmetric int8, activation scales from a calibration set, per-output-channel weight scale
+        max|W|/127, int32 accumulate, fp32 dequant + bias).
+
+        ``frames``: uint8 (N,H,W,3) calibration frames (numpy / tensor); default = 512 synthetic 240x240
+        frames, seed 99 (half uniform noise, half smooth).  An fp32 twin of this model runs them through the
+        CUDA-core engine; at the three quantised tensors (stem, pool1, pool2 outputs) the ``percentile`` of
+        |activation| becomes 127 int8 steps - per channel when ``per_channel`` (cross-layer equalisation:
+        the per-channel factors are folded into the producer's epilogue constants and the consumer's weights
+        at pack time, the runtime tensor keeps one scale), else per tensor.  Returns the three scale arrays."""
+        dev = self.conv1.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("calibration runs on the GPU; call .to('cuda') first")
+        if frames is None:
+            frames = default_calibration_frames()
+        frames = torch.as_tensor(np.asarray(frames) if not isinstance(frames, torch.Tensor) else frames)
+        twin = type(self)(precision="fp32")
+        twin.load_state_dict({k: v.detach().float() if v.is_floating_point() else v.detach()
+                              for k, v in self.state_dict().items()})
+        twin = twin.to(dev)
+        twin.eval()
+        names = ("stem", "pool1", "pool2")
+        amax = {n: None for n in names}
+        samples = {n: [] for n in names}
+        for i in range(0, frames.shape[0], batch):
+            twin.forward_frames(frames[i:i + batch].to(dev))
+            for n in names:
+                t = twin.tap(n).abs()                                     # (b,C,H,W)
+                tc_ = t.permute(1, 0, 2, 3).reshape(t.shape[1], -1)       # (C, b*H*W)
+                m = tc_.max(dim=1).values
+                amax[n] = m if amax[n] is None else torch.maximum(amax[n], m)
+                if percentile < 100:
+                    step = max(1, tc_.shape[1] // 20_000)
+                    samples[n].append(tc_[:, ::step].clone())
+        scales = []
+        for n in names:
+            if percentile < 100:
+                v = torch.cat(samples[n], dim=1).double()
+                r = torch.quantile(v, percentile / 100.0, dim=1) if per_channel else \
+                    torch.quantile(v.flatten()[: 16_000_000], percentile / 100.0).expand(v.shape[0])
+            else:
+                r = amax[n].double() if per_channel else amax[n].double().max().expand(amax[n].shape[0])
+            floor = float(amax[n].max()) * 1e-6 + 1e-30                   # dead channels: keep the step finite
+            scales.append(tuple((torch.clamp(r, min=floor) / 127.0).cpu().tolist()))
+        twin._release()
+        self._act_scales = tuple(scales)
+        return self._act_scales
+
+    @property
+    def act_scales(self):
+        return self._act_scales
+
+    def set_act_scales(self, scales):
+        from .pack_tc import normalize_act_scales
+        self._act_scales = tuple(tuple(float(x) for x in a) for a in normalize_act_scales(scales))
+        return self
 
     def set_engine(self, engine):
         """'auto' (default), 'simt' (CUDA-core kernels) or 'tc' (tcgen05 block kernels)."""
@@ -288,6 +350,16 @@ class _ErnetB200(nn.Module):
     def launches_per_forward(self, batch, with_ingest=True):
         lib, h, _ = self._ensure_engine()
         return lib.ernet_launches_per_forward(h, int(batch), 1 if with_ingest else 0)
+
+
+def default_calibration_frames(n=512, seed=99):
+    """Synthetic calibration set: half i.i.d. uniform uint8 frames, half smooth frames (coarse noise
+    upsampled by pixel replication), 240x240x3."""
+    rs = np.random.RandomState(seed)
+    noise = rs.randint(0, 256, (n // 2, 240, 240, 3)).astype(np.uint8)
+    coarse = rs.randint(0, 256, (n - n // 2, 15, 15, 3)).astype(np.uint8)
+    smooth = np.repeat(np.repeat(coarse, 16, axis=1), 16, axis=2)
+    return np.concatenate([noise, smooth], 0)
 
 
 class Squeeze_ErNET(_ErnetB200):

@@ -138,8 +138,9 @@ def assemble(arch, precision, tensors):
     return blob
 
 
-def pack_state_dict(sd, arch, precision):
-    """Build the blob for ernet_load_packed()."""
+def pack_state_dict(sd, arch, precision, act_scales=None):
+    """Build the blob for ernet_load_packed().  ``act_scales`` (int8 only): the three calibrated
+    per-tensor activation scales, see pack_tc.derive_tc_int8."""
     if arch not in ARCH_ID:
         raise ValueError(f"Unsupported model: {arch}")                 # aider-predict.py:32
     if precision not in PREC_ID:
@@ -148,5 +149,5 @@ def pack_state_dict(sd, arch, precision):
     tensors = {i: (v.astype(np.float32), DT_F32) for i, v in derive_simt(sd, arch).items()}
     if precision in ("fp16", "bf16", "int8"):
         from . import pack_tc
-        tensors.update(pack_tc.derive_tc(sd, arch, precision))
+        tensors.update(pack_tc.derive_tc(sd, arch, precision, act_scales))
     return assemble(arch, precision, tensors)

@@ -14,7 +14,8 @@ from __future__ import annotations
 import numpy as np
 
 T_TC_BASE = 64
-T_TC_WIMG, T_TC_BIAS = 0, 1          # + 4*k for block k
+T_TC_WIMG, T_TC_BIAS, T_TC_DEQ = 0, 1, 2   # + 4*k for block k
+T_Q_SCALES = 80
 DT_F32, DT_RAW = 0, 16
 
 # offsets from the output coordinate, sorted by (dy, dx); mirrored by kTapDy/kTapDx in csrc/tc_common.cuh
@@ -64,9 +65,71 @@ def weight_image(weff, precision):
     return to_bits16(img, precision)
 
 
-def derive_tc(sd, arch, precision):
+def quantize_weights(weff):
+    """TensorRT-style symmetric per-output-channel int8: s_w[n] = max|W_eff[n]| / 127, q = round(W / s_w).
+    -> (int8 [N][25][C], s_w [N])."""
+    amax = np.abs(weff).reshape(weff.shape[0], -1).max(axis=1)
+    s_w = np.where(amax > 0, amax / 127.0, 1.0)
+    q = np.clip(np.rint(weff / s_w[:, None, None]), -127, 127).astype(np.int8)
+    return q, s_w
+
+
+def weight_image_i8(wq):
+    """int8 [N][25][C] (C multiple of 32) -> image [25][C/16][N][16]: the K-major operand with 16 int8
+    channels per 16-byte chunk."""
+    n_out, _, c = wq.shape
+    return np.ascontiguousarray(wq.transpose(1, 2, 0).reshape(25, c // 16, 16, n_out).transpose(0, 1, 3, 2))
+
+
+ACT_CHANNELS = (16, 64, 96)      # channels of the three quantised tensors: stem, pool1, pool2 outputs
+
+
+def normalize_act_scales(act_scales):
+    """-> three fp64 arrays of per-channel int8 steps.  Accepts three scalars (plain per-tensor scales) or
+    three arrays (per-channel equalised)."""
+    if act_scales is None or len(act_scales) != 3:
+        raise ValueError("act_scales must have three entries (stem, pool1, pool2)")
+    out = []
+    for v, c in zip(act_scales, ACT_CHANNELS):
+        a = np.asarray(v, dtype=np.float64)
+        a = np.full(c, float(a)) if a.ndim == 0 else a.reshape(-1)
+        if a.shape != (c,) or not np.all(np.isfinite(a)) or np.any(a <= 0):
+            raise ValueError(f"activation scales for a {c}-channel tensor must be {c} positive numbers")
+        out.append(a)
+    return out
+
+
+def derive_tc_int8(sd, arch, act_scales):
+    """int8 operand images.  ``act_scales[k][c]`` = real value of one int8 step of channel c of the k-th
+    quantised tensor (stem, pool1, pool2 outputs; from calibration).  The producer divides channel c by its
+    step in its epilogue (for pool1/pool2 that is a change of the BN affine constants), the consumer's
+    folded weights are multiplied by it, so at run time the int8 tensor has ONE scale (1.0) - the
+    per-channel part is cross-layer equalisation done at pack time."""
     from .pack import widths
-    if precision not in ("fp16", "bf16"):
+    if arch != "squeeze-ernet":
+        raise ValueError("int8 is implemented for squeeze-ernet only")
+    s_act = normalize_act_scales(act_scales)
+    out = {}
+    for k, (c, _co) in enumerate(widths(arch)[:3]):
+        c_pad = max(32, c)                      # K step of kind::i8 is 32
+        weff, beff = fold_block(sd, f"acff{k + 1}", c, c_pad)
+        weff[:, :, :c] *= s_act[k].reshape(1, 1, -1)
+        wq, s_w = quantize_weights(weff)
+        base = T_TC_BASE + 4 * k
+        out[base + T_TC_WIMG] = (weight_image_i8(wq), DT_RAW)
+        out[base + T_TC_BIAS] = (beff.astype(np.float32), DT_F32)
+        out[base + T_TC_DEQ] = (s_w.astype(np.float32), DT_F32)
+    out[T_Q_SCALES] = (np.concatenate(s_act).astype(np.float32), DT_F32)
+    return out
+
+
+def derive_tc(sd, arch, precision, act_scales=None):
+    from .pack import widths
+    if precision == "int8":
+        if act_scales is None:
+            raise ValueError("int8 needs calibrated activation scales (model.calibrate(frames))")
+        return derive_tc_int8(sd, arch, act_scales)
+    if arch != "squeeze-ernet" or precision not in ("fp16", "bf16"):
         return {}
     out = {}
     for k, (c, _co) in enumerate(widths(arch)[:3]):

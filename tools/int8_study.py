@@ -1,0 +1,82 @@
+"""Offline study of int8 calibration choices with an exact numpy emulation of the int8 engine."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import fixtures
+from oracle import ernet_numpy as E, ingest_numpy as I
+import rtdm_b200.pack as P, rtdm_b200.pack_tc as PT
+
+arch = "squeeze-ernet"
+
+
+def conv25(xq, w, hu):
+    """xq (B,C,H,H) float64 (integers), w (N,25,Cpad) -> (B,N,hu,hu) exact."""
+    B, C, H, _ = xq.shape
+    xp = np.zeros((B, w.shape[2], H + 6, H + 6)); xp[:, :C, 2:2 + H, 2:2 + H] = xq
+    out = np.zeros((B, w.shape[0], hu, hu))
+    for t, (dy, dx) in enumerate(PT.TAPS):
+        out += np.einsum("nc,bchw->bnhw", w[:, t, :], xp[:, :, 2 + dy:2 + dy + hu, 2 + dx:2 + dx + hu], optimize=True)
+    return out
+
+
+def pool(y):
+    B, N, H, _ = y.shape
+    return y.reshape(B, N, H // 2, 2, H // 2, 2).max(axis=(3, 5))
+
+
+def run(sd, x, chan_scales, mode):
+    """chan_scales: list of 3 arrays (per-channel real value of one int8 step) for stem/pool1/pool2."""
+    sd64 = {k: np.asarray(v, np.float64) for k, v in sd.items()}
+    a = E.conv2d_dense(x.astype(np.float64), sd64["conv1.weight"], None, 2)
+    hus = [66, 30, 12]
+    for k in range(3):
+        c, co = P.widths(arch)[k]
+        s_in = chan_scales[k]                                   # (C,)
+        q = np.clip(np.rint(a / s_in.reshape(1, -1, 1, 1)), -127, 127)
+        weff, beff = PT.fold_block(sd, f"acff{k+1}", c, max(32, c))
+        weff = weff.copy(); weff[:, :, :c] *= s_in.reshape(1, 1, -1)    # fold per-input-channel scale
+        wq, s_w = PT.quantize_weights(weff)
+        z = conv25(q, wq.astype(np.float64), hus[k]) * s_w.reshape(1, -1, 1, 1) + beff.reshape(1, -1, 1, 1)
+        z = np.maximum(z, 0.01 * z)
+        p = f"acff{k+1}.batch_norm"
+        s = sd64[f"{p}.weight"] / np.sqrt(sd64[f"{p}.running_var"] + 1e-5)
+        t = sd64[f"{p}.bias"] - sd64[f"{p}.running_mean"] * s
+        a = pool(z * s.reshape(1, -1, 1, 1) + t.reshape(1, -1, 1, 1))
+    a = a.astype(np.float16).astype(np.float64)
+    z = E.acff(a, sd64, "acff4")
+    out = E.conv2d_pointwise(z, sd64["conv2.weight"], None)
+    out = E.avg_pool_5x5_s1_p1(out)
+    return out.reshape(-1, 20) @ sd64["fc.weight"].T + sd64["fc.bias"]
+
+
+def calib(sd, xcal, mode, pct):
+    taps = E.forward(sd, xcal, arch, dtype=np.float64, want_taps=True)["taps"]
+    out = []
+    for name in ("stem", "pool1", "pool2"):
+        v = np.abs(taps[name])
+        if mode == "tensor":
+            r = np.percentile(v, pct) if pct < 100 else v.max()
+            out.append(np.full(v.shape[1], max(r, 1e-12) / 127.0))
+        else:
+            vc = v.transpose(1, 0, 2, 3).reshape(v.shape[1], -1)
+            r = np.percentile(vc, pct, axis=1) if pct < 100 else vc.max(axis=1)
+            out.append(np.maximum(r, 1e-12) / 127.0)
+    return out
+
+
+for wset in sys.argv[1:] or ["shipped", "w3neg"]:
+    sd = fixtures.get_state_dict(arch, wset)
+    fcal = np.concatenate([fixtures.noise_frames(12, seed=99), fixtures.smooth_frames(4, seed=98)], 0)
+    ftest = np.concatenate([fixtures.noise_frames(24, seed=61), fixtures.smooth_frames(24, seed=62)], 0)
+    xcal, xtest = I.ingest(fcal), I.ingest(ftest)
+    ref = E.forward(sd, xtest, arch, dtype=np.float64)["logits"]
+    srt = np.sort(ref, 1); margin = (srt[:, -1] - srt[:, -2]) / np.abs(ref).max()
+    print(wset, "ref top1 hist", np.bincount(ref.argmax(1), minlength=5), "min/median margin", margin.min(), np.median(margin))
+    for mode in ("tensor", "channel"):
+        for pct in (99.9, 99.99, 99.999, 100):
+            cs = calib(sd, xcal, mode, pct)
+            lg = run(sd, xtest, cs, mode)
+            agree = (lg.argmax(1) == ref.argmax(1)).mean()
+            err = np.abs(lg - ref).max() / np.abs(ref).max()
+            print(f"  {mode:8s} pct {pct:7.3f}: agreement {agree:.3f}  rel logit err {err:.3e}", flush=True)
