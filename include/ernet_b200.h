@@ -91,6 +91,9 @@ int ernet_get_chunk(const ernet_handle* h);
 typedef enum ernet_engine { ERNET_ENGINE_AUTO = 0, ERNET_ENGINE_SIMT = 1, ERNET_ENGINE_TC = 2 } ernet_engine;
 int ernet_set_engine(ernet_handle* h, int engine);
 int ernet_get_engine(const ernet_handle* h);   /* the family the next forward will use (SIMT or TC) */
+/* Fused kernels keep some intermediates on chip (acff4 inside the ACFF4+head kernel).  With debug taps
+ * on they are also written to the workspace so that ernet_debug_tap() can read them (test use).      */
+int ernet_set_debug_taps(ernet_handle* h, int on);
 
 /* ---- the hot path ------------------------------------------------------------------------------
  * Replaces `output = model(data)` (aider-predict.py:76, evaluate-classification-metrics.py:77):

@@ -30,6 +30,7 @@ SIGNATURES = {
     "ernet_get_chunk": (_i, [_vp]),
     "ernet_set_engine": (_i, [_vp, _i]),
     "ernet_get_engine": (_i, [_vp]),
+    "ernet_set_debug_taps": (_i, [_vp, _i]),
     "ernet_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "ernet_ingest_u8": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "ernet_prepare_ingest": (_i, [_vp, _i, _i]),

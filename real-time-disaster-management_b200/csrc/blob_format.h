@@ -42,6 +42,7 @@ struct ernet_blob_entry {
 #define ERNET_T_TC_WIMG 0       //   [25 taps][C/8][N][8] 16-bit: folded depthwise x 1x1 weights (pack_tc.py)
 #define ERNET_T_TC_BIAS 1       //   [N] fp32: b_f + W_f . cat(b_d)
 #define ERNET_T_TC_DEQ 2        //   [N] fp32, int8 only: per-output-channel weight scale s_w[n] = max|W'_eff[n]|/127
+#define ERNET_T_TC4_WIMG 76     // [3*C4/8][256][8] 16-bit: acff4.fused_conv.weight as the K-major UMMA B operand (tc_tail.cuh)
 #define ERNET_T_Q_SCALES 80     // [16+64+96] fp32, int8 only: real value of one int8 step of every channel of the stem /
                                 // pool1 / pool2 tensors (per-channel equalisation of a per-tensor int8 scale; folded into
                                 // the producer's epilogue and the consumer's weights, so the runtime tensor scale is 1)

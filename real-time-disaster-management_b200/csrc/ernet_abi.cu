@@ -12,6 +12,7 @@
 #include "ingest.cuh"
 #include "simt_layers.cuh"
 #include "tc_block.cuh"
+#include "tc_tail.cuh"
 
 namespace ernet {
 
@@ -41,6 +42,9 @@ struct ernet_handle {
   tc::EpiParams<64> epi1;       // host copies of the per-channel epilogue constants (kernel parameters)
   tc::EpiParams<96> epi2;
   tc::EpiParams<128> epi3;
+  bool has_tail = false;        // blob carries the ACFF4+head tensor-core image
+  bool debug_taps = false;      // keep intermediates the fused kernels would not write (acff4)
+  tc::TailParams tail;
   void* d_blob = nullptr;
   size_t blob_bytes = 0;
   Tensor t[ERNET_T_MAX];
@@ -188,6 +192,31 @@ struct StageTimer {
 #define ERNET_STAGE(id, call)                                   \
   do { StageTimer _t(h, id, s); if ((rc = (call))) return rc; } while (0)
 
+// ACFF4 + head: one fused tensor-core kernel when the blob has its weight image (16-bit / int8 handles),
+// else depthwise + pointwise + head CUDA-core kernels.
+template <typename T>
+static int run_tail(ernet_handle* h, const T* in4, T* cat4, T* a4, int n, float* probs, float* logits, cudaStream_t s) {
+  int rc;
+  const int c4 = h->c4();
+  if (h->has_tail && h->engine != ERNET_ENGINE_SIMT && sizeof(T) == 2) {
+    constexpr bool BF16 = std::is_same<T, __nv_bfloat16>::value;
+    StageTimer _t(h, ERNET_STAGE_TC_BLOCK4, s);
+    void* dbg = h->debug_taps ? a4 : nullptr;
+    if (c4 == 128) rc = tc::launch_acff4_head<tc::TailCfg128>(BF16, in4, h->blk(3, ERNET_T_DW_W), h->blk(3, ERNET_T_DW_B), h->t[ERNET_T_TC4_WIMG].dev, h->tail, probs, logits, dbg, n, s);
+    else           rc = tc::launch_acff4_head<tc::TailCfg64>(BF16, in4, h->blk(3, ERNET_T_DW_W), h->blk(3, ERNET_T_DW_B), h->t[ERNET_T_TC4_WIMG].dev, h->tail, probs, logits, dbg, n, s);
+    return rc;
+  }
+  ERNET_STAGE(ERNET_STAGE_DW4, launch_acff_dw<T>(in4, n, 6, 6, c4, 4, 4, h->blk(3, ERNET_T_DW_W), h->blk(3, ERNET_T_DW_B), cat4, s));
+  ERNET_STAGE(ERNET_STAGE_PW4, launch_pointwise<T>(cat4, n, 4, 4, 3 * c4, 256, h->blk(3, ERNET_T_PW_W), h->blk(3, ERNET_T_PW_B),
+                                h->blk(3, ERNET_T_BN_S), h->blk(3, ERNET_T_BN_T), 1, 0, a4, s));
+  {
+    StageTimer _t(h, ERNET_STAGE_HEAD, s);
+    head_kernel<T><<<n, 256, 0, s>>>(a4, h->f(ERNET_T_HEAD_W), h->f(ERNET_T_HEAD_B), probs, logits);
+    ERNET_LAUNCH_CHECK("head_kernel");
+  }
+  return ERNET_OK;
+}
+
 // One chunk of n images through the layer-wise CUDA-core pipeline.
 template <typename T>
 static int run_chunk_simt(ernet_handle* h, const void* x, int x_dtype, int x_layout, const uint8_t* frames,
@@ -236,15 +265,8 @@ static int run_chunk_simt(ernet_handle* h, const void* x, int x_dtype, int x_lay
     in4 = buf(p.r3);
   }
   // acff4 + head
-  ERNET_STAGE(ERNET_STAGE_DW4, launch_acff_dw<T>(in4, n, 6, 6, c4, 4, 4, h->blk(3, ERNET_T_DW_W), h->blk(3, ERNET_T_DW_B), buf(p.cat4), s));
-  ERNET_STAGE(ERNET_STAGE_PW4, launch_pointwise<T>(buf(p.cat4), n, 4, 4, 3 * c4, 256, h->blk(3, ERNET_T_PW_W), h->blk(3, ERNET_T_PW_B),
-                                h->blk(3, ERNET_T_BN_S), h->blk(3, ERNET_T_BN_T), 1, 0, buf(p.a4), s));
-  {
-    StageTimer _t(h, ERNET_STAGE_HEAD, s);
-    head_kernel<T><<<n, 256, 0, s>>>(buf(p.a4), h->f(ERNET_T_HEAD_W), h->f(ERNET_T_HEAD_B), probs, logits);
-    ERNET_LAUNCH_CHECK("head_kernel");
-  }
-  return ERNET_OK;
+  (void)c4;
+  return run_tail<T>(h, in4, buf(p.cat4), buf(p.a4), n, probs, logits, s);
 }
 
 // One chunk through the tensor-core pipeline: ingest -> stem (P8/P16) -> blocks 1-3 on tcgen05 -> block 4 + head.
@@ -287,16 +309,7 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
     ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_block<tc::CfgBlock2, K16, tc::OUT_P8>(u16(p.p1), wimg(1), h->epi2, u16(p.p2), n, s)));
     ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_block<tc::CfgBlock3, K16, tc::OUT_NHWC>(u16(p.p2), wimg(2), h->epi3, u16(p.p3), n, s)));
   }
-  const int c4 = h->c4();
-  ERNET_STAGE(ERNET_STAGE_DW4, launch_acff_dw<T>(buf(p.p3), n, 6, 6, c4, 4, 4, h->blk(3, ERNET_T_DW_W), h->blk(3, ERNET_T_DW_B), buf(p.cat4), s));
-  ERNET_STAGE(ERNET_STAGE_PW4, launch_pointwise<T>(buf(p.cat4), n, 4, 4, 3 * c4, 256, h->blk(3, ERNET_T_PW_W), h->blk(3, ERNET_T_PW_B),
-                                h->blk(3, ERNET_T_BN_S), h->blk(3, ERNET_T_BN_T), 1, 0, buf(p.a4), s));
-  {
-    StageTimer _t(h, ERNET_STAGE_HEAD, s);
-    head_kernel<T><<<n, 256, 0, s>>>(buf(p.a4), h->f(ERNET_T_HEAD_W), h->f(ERNET_T_HEAD_B), probs, logits);
-    ERNET_LAUNCH_CHECK("head_kernel");
-  }
-  return ERNET_OK;
+  return run_tail<T>(h, buf(p.p3), buf(p.cat4), buf(p.a4), n, probs, logits, s);
 }
 
 static int run_chunk(ernet_handle* h, const void* x, int x_dtype, int x_layout, const uint8_t* frames,
@@ -327,6 +340,8 @@ static int init_device_attrs() {
   if ((rc = set_smem_attrs<__half>())) return rc;
   if ((rc = set_smem_attrs<__nv_bfloat16>())) return rc;
   if ((rc = tc::set_all_block_attrs())) return rc;
+  if ((rc = tc::set_tail_attrs<tc::TailCfg128>())) return rc;
+  if ((rc = tc::set_tail_attrs<tc::TailCfg64>())) return rc;
   return ERNET_OK;
 }
 
@@ -484,6 +499,18 @@ int ernet_load_packed(ernet_handle* h, const void* blob, size_t bytes) {
                                                 : "int8 blob lacks the calibrated tensor-core images (pack with act_scales)");
     }
   }
+  {
+    const Tensor& w4 = h->t[ERNET_T_TC4_WIMG];
+    h->has_tail = h->precision != ERNET_PREC_FP32 && w4.dev && w4.nbytes == (size_t)3 * h->c4() * 256 * 2;
+    if (h->has_tail) {
+      auto host_f32 = [&](int id) { return reinterpret_cast<const float*>(static_cast<const char*>(blob) + (static_cast<const char*>(h->t[id].dev) - static_cast<const char*>(d))); };
+      memcpy(h->tail.bias, host_f32(ERNET_T_BLOCK_BASE + 24 + ERNET_T_PW_B), 256 * sizeof(float));
+      memcpy(h->tail.scale, host_f32(ERNET_T_BLOCK_BASE + 24 + ERNET_T_BN_S), 256 * sizeof(float));
+      memcpy(h->tail.shift, host_f32(ERNET_T_BLOCK_BASE + 24 + ERNET_T_BN_T), 256 * sizeof(float));
+      memcpy(h->tail.weff, host_f32(ERNET_T_HEAD_W), 5 * 256 * sizeof(float));
+      memcpy(h->tail.bfc, host_f32(ERNET_T_HEAD_B), 5 * sizeof(float));
+    }
+  }
   if (h->d_blob) { cudaDeviceSynchronize(); cudaFree(h->d_blob); }
   h->d_blob = d; h->blob_bytes = bytes; h->loaded = true;
   return ERNET_OK;
@@ -501,6 +528,11 @@ int ernet_set_engine(ernet_handle* h, int engine) {
   if (engine == ERNET_ENGINE_TC && h->loaded && !(h->has_tc && !h->red() && h->precision != ERNET_PREC_FP32 && h->precision != ERNET_PREC_INT8))
     return fail(ERNET_ERR_UNSUPPORTED, "tensor-core engine needs a 16-bit Squeeze_ErNET handle");
   h->engine = engine;
+  return ERNET_OK;
+}
+int ernet_set_debug_taps(ernet_handle* h, int on) {
+  if (!h) return fail(ERNET_ERR_INVALID_ARG, "null handle");
+  h->debug_taps = on != 0;
   return ERNET_OK;
 }
 int ernet_get_engine(const ernet_handle* h) { return h ? (h->use_tc() ? ERNET_ENGINE_TC : ERNET_ENGINE_SIMT) : -1; }
@@ -691,7 +723,10 @@ int ernet_debug_tap(ernet_handle* h, int tap, const void* workspace, int batch, 
     case ERNET_TAP_POOL1: off = p.p1; C = 64; HW = 33 * 33; break;
     case ERNET_TAP_POOL2: off = p.p2; C = h->c3(); HW = 15 * 15; break;
     case ERNET_TAP_POOL3: off = h->red() ? p.r3 : p.p3; C = h->c4(); HW = 36; break;
-    case ERNET_TAP_ACFF4: off = p.a4; C = 256; HW = 16; break;
+    case ERNET_TAP_ACFF4:
+      if (h->has_tail && h->engine != ERNET_ENGINE_SIMT && !h->debug_taps)
+        return fail(ERNET_ERR_UNSUPPORTED, "the fused ACFF4+head kernel keeps acff4 on chip; call ernet_set_debug_taps(h, 1) before the forward");
+      off = p.a4; C = 256; HW = 16; break;
     default: return fail(ERNET_ERR_INVALID_ARG, "unknown tap %d", tap);
   }
   const long long total = (long long)batch * C * HW;
@@ -782,8 +817,10 @@ int ernet_profile_read(ernet_handle* h, double* ms_by_stage, int* launches_by_st
 int ernet_launches_per_forward(const ernet_handle* h, int batch, int with_ingest) {
   if (!h || batch < 1) return 0;
   const int chunks = (batch + h->chunk - 1) / h->chunk;
-  const int per = h->use_tc() ? (with_ingest ? 1 : 0) + 1 + 3 + 2 + 1
-                              : (with_ingest ? 1 : 0) + 1 + 8 + (h->red() ? 2 : 0) + 1;
+  const bool tail = h->has_tail && h->engine != ERNET_ENGINE_SIMT;
+  const int tail_launches = tail ? 1 : 3;
+  const int per = h->use_tc() ? (with_ingest ? 1 : 0) + 1 + 3 + tail_launches
+                              : (with_ingest ? 1 : 0) + 1 + 6 + (h->red() ? 2 : 0) + tail_launches;
   return chunks * per;
 }
 

@@ -16,6 +16,7 @@ import numpy as np
 T_TC_BASE = 64
 T_TC_WIMG, T_TC_BIAS, T_TC_DEQ = 0, 1, 2   # + 4*k for block k
 T_Q_SCALES = 80
+T_TC4_WIMG = 76
 DT_F32, DT_RAW = 0, 16
 
 # offsets from the output coordinate, sorted by (dy, dx); mirrored by kTapDy/kTapDx in csrc/tc_common.cuh
@@ -123,14 +124,27 @@ def derive_tc_int8(sd, arch, act_scales):
     return out
 
 
+def tail_weight_image(sd, precision):
+    """acff4.fused_conv.weight (256, 3*C4, 1, 1) -> uint16 image [3*C4/8][256][8] (K-major B operand of the
+    ACFF4+head kernel; K order = concat order [branch][channel], acff.py:46)."""
+    from .pack import _np64
+    w = _np64(sd, "acff4.fused_conv.weight")[:, :, 0, 0]                  # (256, K)
+    n, k = w.shape
+    return to_bits16(w.reshape(n, k // 8, 8).transpose(1, 0, 2), precision)
+
+
 def derive_tc(sd, arch, precision, act_scales=None):
     from .pack import widths
     if precision == "int8":
         if act_scales is None:
             raise ValueError("int8 needs calibrated activation scales (model.calibrate(frames))")
-        return derive_tc_int8(sd, arch, act_scales)
-    if arch != "squeeze-ernet" or precision not in ("fp16", "bf16"):
+        out = derive_tc_int8(sd, arch, act_scales)
+        out[T_TC4_WIMG] = (tail_weight_image(sd, "fp16"), DT_RAW)        # the int8 engine's tail runs in fp16
+        return out
+    if precision not in ("fp16", "bf16"):
         return {}
+    if arch != "squeeze-ernet":
+        return {T_TC4_WIMG: (tail_weight_image(sd, precision), DT_RAW)}   # RedConv: tensor-core tail only
     out = {}
     for k, (c, _co) in enumerate(widths(arch)[:3]):
         c_pad = max(16, c)
@@ -138,4 +152,5 @@ def derive_tc(sd, arch, precision, act_scales=None):
         base = T_TC_BASE + 4 * k
         out[base + T_TC_WIMG] = (weight_image(weff, precision), DT_RAW)
         out[base + T_TC_BIAS] = (beff.astype(np.float32), DT_F32)
+    out[T_TC4_WIMG] = (tail_weight_image(sd, precision), DT_RAW)
     return out
