@@ -225,7 +225,12 @@ static int run_chunk_simt(ernet_handle* h, const void* x, int x_dtype, int x_lay
   const Plan p = make_plan(h, n);
   auto buf = [&](size_t off) { return reinterpret_cast<T*>(ws + off); };
   int rc;
-  if (frames) {
+  if (frames && tab->fs_max_in_rows > 0 && !h->debug_taps) {
+    // transform + conv1 fused (the transformed tensor never reaches HBM)
+    StemQ q{};
+    if (h->red()) ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem<T, 8, FS_NHWC>(*tab, frames, n, order == ERNET_BGR, h->f(ERNET_T_STEM_W), h->f(ERNET_T_STEM_B), q, buf(p.stem), s)));
+    else          ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem<T, 16, FS_NHWC>(*tab, frames, n, order == ERNET_BGR, h->f(ERNET_T_STEM_W), h->f(ERNET_T_STEM_B), q, buf(p.stem), s)));
+  } else if (frames) {
     ERNET_STAGE(ERNET_STAGE_INGEST, launch_ingest<T>(*tab, frames, n, order == ERNET_BGR, buf(p.ingest), 140LL * 140 * 3, 1, 140 * 3, 3, s));
     ERNET_STAGE(ERNET_STAGE_STEM, (launch_stem<T, T>(h, buf(p.ingest), 140LL * 140 * 3, 1, 140 * 3, 3, buf(p.stem), n, s)));
   } else {
@@ -283,7 +288,12 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
   const float* sw = h->f(ERNET_T_STEM_W);
   const float* sb_ = h->f(ERNET_T_STEM_B);
   const tc::StemInv& s_inv = h->stem_inv;
-  if (frames) {
+  if (frames && tab->fs_max_in_rows > 0 && !h->debug_taps) {
+    StemQ q{};
+    for (int i = 0; i < 16; ++i) q.inv[i] = s_inv.v[i];
+    constexpr int FSOUT = KIND == tc::KIND_I8 ? FS_P16 : FS_P8;
+    ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem<T, 16, FSOUT>(*tab, frames, n, order == ERNET_BGR, sw, sb_, q, u16(p.stem), s)));
+  } else if (frames) {
     ERNET_STAGE(ERNET_STAGE_INGEST, launch_ingest<T>(*tab, frames, n, order == ERNET_BGR, buf(p.ingest), 140LL * 140 * 3, 1, 140 * 3, 3, s));
     StageTimer _t(h, ERNET_STAGE_STEM, s);
     tc::stem_p8_kernel<T, 16, KIND><<<grid, 128, 0, s>>>(buf(p.ingest), 140LL * 140 * 3, 1, 140 * 3, 3, sw, sb_, u16(p.stem), total, s_inv);
@@ -328,6 +338,14 @@ static int run_chunk(ernet_handle* h, const void* x, int x_dtype, int x_layout, 
 }
 
 template <typename T>
+static int set_fused_ingest_attrs() {
+  const int lim = 200 * 1024;
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<T, 16, FS_NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<T, 8, FS_NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  return ERNET_OK;
+}
+
+template <typename T>
 static int set_smem_attrs() {
   ERNET_CUDA(cudaFuncSetAttribute(acff_dw_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   ERNET_CUDA(cudaFuncSetAttribute(ingest_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -339,6 +357,12 @@ static int init_device_attrs() {
   if ((rc = set_smem_attrs<float>())) return rc;
   if ((rc = set_smem_attrs<__half>())) return rc;
   if ((rc = set_smem_attrs<__nv_bfloat16>())) return rc;
+  if ((rc = set_fused_ingest_attrs<float>())) return rc;
+  if ((rc = set_fused_ingest_attrs<__half>())) return rc;
+  if ((rc = set_fused_ingest_attrs<__nv_bfloat16>())) return rc;
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__half, 16, FS_P8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__nv_bfloat16, 16, FS_P8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__half, 16, FS_P16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   if ((rc = tc::set_all_block_attrs())) return rc;
   if ((rc = tc::set_tail_attrs<tc::TailCfg128>())) return rc;
   if ((rc = tc::set_tail_attrs<tc::TailCfg64>())) return rc;
@@ -718,7 +742,9 @@ int ernet_debug_tap(ernet_handle* h, int tap, const void* workspace, int batch, 
   const Plan p = make_plan(h, batch);
   size_t off; int C, HW;
   switch (tap) {
-    case ERNET_TAP_INGEST: off = p.ingest; C = 3; HW = 140 * 140; break;
+    case ERNET_TAP_INGEST:
+      if (!h->debug_taps) return fail(ERNET_ERR_UNSUPPORTED, "the fused transform+conv1 kernel keeps the transformed tensor on chip; call ernet_set_debug_taps(h, 1) before the forward");
+      off = p.ingest; C = 3; HW = 140 * 140; break;
     case ERNET_TAP_STEM: off = p.stem; C = h->cs(); HW = 69 * 69; break;
     case ERNET_TAP_POOL1: off = p.p1; C = 64; HW = 33 * 33; break;
     case ERNET_TAP_POOL2: off = p.p2; C = h->c3(); HW = 15 * 15; break;
@@ -819,8 +845,9 @@ int ernet_launches_per_forward(const ernet_handle* h, int batch, int with_ingest
   const int chunks = (batch + h->chunk - 1) / h->chunk;
   const bool tail = h->has_tail && h->engine != ERNET_ENGINE_SIMT;
   const int tail_launches = tail ? 1 : 3;
-  const int per = h->use_tc() ? (with_ingest ? 1 : 0) + 1 + 3 + tail_launches
-                              : (with_ingest ? 1 : 0) + 1 + 6 + (h->red() ? 2 : 0) + tail_launches;
+  // frames path: transform + conv1 are one kernel (two with debug taps on); tensor path: conv1 only
+  const int front = with_ingest ? (h->debug_taps ? 2 : 1) : 1;
+  const int per = h->use_tc() ? front + 3 + tail_launches : front + 6 + (h->red() ? 2 : 0) + tail_launches;
   return chunks * per;
 }
 

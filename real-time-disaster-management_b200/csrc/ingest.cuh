@@ -18,12 +18,18 @@ constexpr int kCrop = 140;
 constexpr int kResizeShort = 159;
 constexpr int kPrecisionBits = 22;
 constexpr int kMaxTaps = 64;  // frames up to ~31x down-scaling
+constexpr int kStemBand = 14;                 // conv1 output rows per CTA of the fused transform+stem kernel
+constexpr int kStemXnRows = 2 * kStemBand + 1;
+constexpr size_t kRawStageBytes = 48 * 1024;
 
 struct IngestTables {
   int H = 0, W = 0, new_h = 0, new_w = 0, top = 0, left = 0;
   int ksx = 0, ksy = 0;          // taps per output column / row (padded table width)
   int band_rows = 0;             // output rows per CTA
   int max_in_rows = 0;           // input rows a band needs at most
+  // fused transform+stem kernel: bands of kStemBand conv1 rows
+  int fs_max_in_rows = 0;        // input rows such a band needs at most
+  int fs_stage_raw = 0;          // 1: the raw rows of a band fit in shared memory and are staged with 16-byte loads
   // device arrays (one allocation): per crop column / row
   int* d_base = nullptr;
   int *d_xmin = nullptr, *d_xlen = nullptr, *d_kx = nullptr;
@@ -145,6 +151,209 @@ ingest_kernel(const uint8_t* __restrict__ frames, int H, int W, int bgr,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Fused eval transform + conv1 (model/squeeze_ernet.py:11,25; RedConv: conv_red1 folded in) for the frames
+// path.  One CTA = one band of kStemBand conv1 output rows of one frame:
+//   phase 0  the raw uint8 rows the band needs are contiguous in HBM: staged with 16-byte loads
+//   phase 1  horizontal resample pass  -> smem uint8 [rows][140][3]
+//   phase 2  vertical pass + ToTensor/Normalize table -> smem T [<=29][140][3]  (rounded to the engine's
+//            element type exactly like the standalone ingest kernel, so both paths agree bit for bit)
+//   phase 3  3x3/s2 conv, fp32 accumulate in the same order as stem_kernel -> stem tensor
+// Output formats: FS_NHWC (B,69,69,CS) T | FS_P8 (B,2,72,72,8) 16-bit + zero halo | FS_P16 (B,2,72,72,16) int8.
+enum : int { FS_NHWC = 0, FS_P8 = 1, FS_P16 = 2 };
+struct StemQ { float inv[16]; };   // FS_P16: 1 / int8 step of each stem channel
+
+template <typename T, int CS, int OUT>
+__global__ void __launch_bounds__(256)
+ingest_stem_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restrict__ frames_end, int H, int W, int bgr, int stage_raw,
+                   const int* __restrict__ xmin, const int* __restrict__ xlen, const int* __restrict__ kx, int ksx,
+                   const int* __restrict__ ymin, const int* __restrict__ ylen, const int* __restrict__ ky, int ksy,
+                   const float* __restrict__ lut, const float* __restrict__ w /*[27][CS]*/, const float* __restrict__ bias,
+                   const __grid_constant__ StemQ q, int hbuf_bytes, void* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t fs_smem[];
+  // layout: [xn: kStemXnRows*140*3 T][weights: 28*CS float][hbuf: hbuf_bytes][raw: rest]
+  T* xn = reinterpret_cast<T*>(fs_smem);
+  constexpr int XN_BYTES = (kStemXnRows * kCrop * 3 * (int)sizeof(T) + 15) / 16 * 16;
+  float* ws = reinterpret_cast<float*>(fs_smem + XN_BYTES);
+  uint8_t* hbuf = fs_smem + XN_BYTES + 28 * CS * 4;
+  uint8_t* raw = hbuf + hbuf_bytes;
+
+  const int b = blockIdx.y;
+  const int y0 = blockIdx.x * kStemBand;
+  const int y1 = min(y0 + kStemBand, 69);
+  const int n0 = 2 * y0, n1 = 2 * (y1 - 1) + 2;          // transform rows n0 .. n1 (inclusive)
+  const int r0 = ymin[n0];
+  const int r1 = ymin[n1] + ylen[n1];
+  const int in_rows = r1 - r0;
+  const uint8_t* src = frames + (size_t)b * H * W * 3;
+
+  for (int i = threadIdx.x; i < 28 * CS; i += blockDim.x) ws[i] = i < 27 * CS ? w[i] : bias[i - 27 * CS];
+
+  // ---- phase 0: stage raw rows
+  const uint8_t* band = src + (size_t)r0 * W * 3;
+  int raw_off = 0;
+  if (stage_raw) {
+    const size_t a0 = reinterpret_cast<size_t>(band) & ~(size_t)15;
+    raw_off = (int)(reinterpret_cast<size_t>(band) - a0);
+    const int nvec = (raw_off + in_rows * W * 3 + 15) / 16;
+    const uint8_t* g = reinterpret_cast<const uint8_t*>(a0);
+    // vectors that would touch bytes outside [frames, frames_end) are assembled byte-wise
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+      const uint8_t* pv = g + (size_t)i * 16;
+      if (pv >= frames && pv + 16 <= frames_end) {
+        reinterpret_cast<uint4*>(raw)[i] = __ldg(reinterpret_cast<const uint4*>(pv));
+      } else {
+        for (int e = 0; e < 16; ++e) raw[i * 16 + e] = (pv + e >= frames && pv + e < frames_end) ? __ldg(pv + e) : (uint8_t)0;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- phase 1: horizontal pass
+  for (int idx = threadIdx.x; idx < in_rows * kCrop; idx += blockDim.x) {
+    const int r = idx / kCrop, ox = idx - r * kCrop;
+    const int x0 = xmin[ox], n = xlen[ox];
+    const int* k = kx + ox * ksx;
+    int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+    if (stage_raw) {
+      const uint8_t* p = raw + raw_off + (r * W + x0) * 3;
+      for (int t = 0; t < n; ++t) {
+        const int c = __ldg(k + t);
+        a0 += c * (int)p[3 * t]; a1 += c * (int)p[3 * t + 1]; a2 += c * (int)p[3 * t + 2];
+      }
+    } else {
+      const uint8_t* p = band + ((size_t)r * W + x0) * 3;
+      for (int t = 0; t < n; ++t) {
+        const int c = __ldg(k + t);
+        a0 += c * (int)__ldg(p + 3 * t); a1 += c * (int)__ldg(p + 3 * t + 1); a2 += c * (int)__ldg(p + 3 * t + 2);
+      }
+    }
+    uint8_t* h = hbuf + (size_t)idx * 3;
+    h[0] = (uint8_t)min(max(a0 >> kPrecisionBits, 0), 255);
+    h[1] = (uint8_t)min(max(a1 >> kPrecisionBits, 0), 255);
+    h[2] = (uint8_t)min(max(a2 >> kPrecisionBits, 0), 255);
+  }
+  __syncthreads();
+
+  // ---- phase 2: vertical pass + normalise -> xn
+  const int nrows = n1 - n0 + 1;
+  for (int idx = threadIdx.x; idx < nrows * kCrop; idx += blockDim.x) {
+    const int rn = idx / kCrop, ox = idx - rn * kCrop;
+    const int oy = n0 + rn;
+    const int yy = ymin[oy] - r0, n = ylen[oy];
+    const int* k = ky + oy * ksy;
+    int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+    for (int t = 0; t < n; ++t) {
+      const int c = __ldg(k + t);
+      const uint8_t* h = hbuf + ((size_t)(yy + t) * kCrop + ox) * 3;
+      a0 += c * (int)h[0]; a1 += c * (int)h[1]; a2 += c * (int)h[2];
+    }
+    int v[3] = {min(max(a0 >> kPrecisionBits, 0), 255), min(max(a1 >> kPrecisionBits, 0), 255),
+                min(max(a2 >> kPrecisionBits, 0), 255)};
+    if (bgr) { int t = v[0]; v[0] = v[2]; v[2] = t; }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) xn[idx * 3 + c] = from_f32<T>(__ldg(lut + v[c] * 3 + c));
+  }
+  __syncthreads();
+
+  // ---- phase 3: conv1 (3x3, stride 2) out of shared memory
+  const int brow = y1 - y0;
+  constexpr int PW = OUT == FS_NHWC ? 69 : 72;           // pixels per output row handled here (incl. halo cols)
+  for (int idx = threadIdx.x; idx < brow * PW; idx += blockDim.x) {
+    const int ly = idx / PW, pc = idx - ly * PW;
+    const int oy = y0 + ly;
+    const int ox = OUT == FS_NHWC ? pc : pc - 2;
+    if (OUT != FS_NHWC && (ox < 0 || ox >= 69)) {          // zero halo columns of this row
+      uint4* o = reinterpret_cast<uint4*>(out) + (size_t)b * 2 * 72 * 72 + (oy + 2) * 72 + pc;
+      o[0] = make_uint4(0, 0, 0, 0);
+      o[72 * 72] = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = c < CS ? ws[27 * CS + c] : 0.f;
+    const T* p = xn + ((2 * ly) * kCrop + 2 * ox) * 3;
+#pragma unroll
+    for (int kyy = 0; kyy < 3; ++kyy)
+#pragma unroll
+      for (int kxx = 0; kxx < 3; ++kxx)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float v = to_f32<T>(p[(kyy * kCrop + kxx) * 3 + c]);
+          const float* wr = ws + ((kyy * 3 + kxx) * 3 + c) * CS;
+#pragma unroll
+          for (int k = 0; k < CS; ++k) acc[k] = fmaf(v, wr[k], acc[k]);
+        }
+    if (OUT == FS_NHWC) {
+      constexpr int NV = Vec16<T>::NV;
+      uint4* o4 = reinterpret_cast<uint4*>(static_cast<T*>(out) + ((size_t)(b * 69 + oy) * 69 + ox) * CS);
+#pragma unroll
+      for (int v = 0; v < CS / NV; ++v) {
+        float t[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) t[i] = acc[v * NV + i];
+        o4[v] = pack16<T>(t);
+      }
+    } else {
+      uint4* o = reinterpret_cast<uint4*>(out) + (size_t)b * 2 * 72 * 72 + (oy + 2) * 72 + pc;
+      if (OUT == FS_P16) {
+        uint32_t wq[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t wv = 0;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            int qq = __float2int_rn(acc[4 * j + e] * q.inv[4 * j + e]);
+            qq = max(-127, min(127, qq));
+            wv |= ((uint32_t)qq & 0xffu) << (8 * e);
+          }
+          wq[j] = wv;
+        }
+        o[0] = make_uint4(wq[0], wq[1], wq[2], wq[3]);
+        o[72 * 72] = make_uint4(0, 0, 0, 0);
+      } else {
+        if constexpr (sizeof(T) == 2) {
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            float t8[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t8[k] = acc[ch * 8 + k];
+            o[ch * 72 * 72] = pack16<T>(t8);
+          }
+        }
+      }
+    }
+  }
+  if (OUT != FS_NHWC) {                                     // zero halo rows 0,1 (first band) and 71 (last band)
+    uint4* img = reinterpret_cast<uint4*>(out) + (size_t)b * 2 * 72 * 72;
+    if (blockIdx.x == 0)
+      for (int i = threadIdx.x; i < 2 * 2 * 72; i += blockDim.x) img[(i / 144) * 72 * 72 + (i % 144)] = make_uint4(0, 0, 0, 0);
+    if (y1 == 69)
+      for (int i = threadIdx.x; i < 2 * 72; i += blockDim.x) img[(i / 72) * 72 * 72 + 71 * 72 + (i % 72)] = make_uint4(0, 0, 0, 0);
+  }
+}
+
+template <typename T, int CS, int OUT>
+inline size_t ingest_stem_smem(const IngestTables& t) {
+  const size_t xn = ((size_t)kStemXnRows * kCrop * 3 * sizeof(T) + 15) / 16 * 16;
+  const size_t hb = ((size_t)t.fs_max_in_rows * kCrop * 3 + 15) / 16 * 16;
+  const size_t raw = t.fs_stage_raw ? ((size_t)t.fs_max_in_rows * t.W * 3 + 32 + 15) / 16 * 16 : 0;
+  return xn + 28 * CS * 4 + hb + raw;
+}
+
+template <typename T, int CS, int OUT>
+inline int launch_ingest_stem(const IngestTables& t, const uint8_t* frames, int batch, int bgr, const float* w,
+                              const float* bias, const StemQ& q, void* out, cudaStream_t stream) {
+  const size_t hb = ((size_t)t.fs_max_in_rows * kCrop * 3 + 15) / 16 * 16;
+  dim3 grid((69 + kStemBand - 1) / kStemBand, batch);
+  ingest_stem_kernel<T, CS, OUT><<<grid, 256, ingest_stem_smem<T, CS, OUT>(t), stream>>>(
+      frames, frames + (size_t)batch * t.H * t.W * 3, t.H, t.W, bgr, t.fs_stage_raw, t.d_xmin, t.d_xlen, t.d_kx, t.ksx, t.d_ymin, t.d_ylen, t.d_ky, t.ksy, t.d_lut,
+      w, bias, q, (int)hb, out);
+  ERNET_LAUNCH_CHECK("ingest_stem_kernel");
+  return ERNET_OK;
+}
+
 // ToTensor + Normalize as a 256x3 table, each step rounded to fp32 like torch (aider.py:424-425).
 inline void host_lut(float* lut) {
   const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
@@ -182,6 +391,18 @@ inline int build_ingest_tables(IngestTables& t, int H, int W) {
     if ((size_t)worst * kCrop * 3 <= 64 * 1024) { t.band_rows = br; t.max_in_rows = worst; break; }
   }
   if (t.max_in_rows == 0) return fail(ERNET_ERR_UNSUPPORTED, "frame %dx%d too large for the ingest row buffer", H, W);
+  {  // geometry of the fused transform+stem bands (kStemBand conv1 rows -> 2*band+1 transform rows)
+    int worst = 0;
+    for (int y0 = 0; y0 < 69; y0 += kStemBand) {
+      const int y1 = y0 + kStemBand < 69 ? y0 + kStemBand : 69;
+      const int n0 = 2 * y0, n1 = 2 * (y1 - 1) + 2;
+      const int rows = ymin[n1] + ylen[n1] - ymin[n0];
+      if (rows > worst) worst = rows;
+    }
+    t.fs_max_in_rows = worst;
+    t.fs_stage_raw = ((size_t)worst * W * 3 + 32 <= kRawStageBytes) ? 1 : 0;
+    if ((size_t)worst * kCrop * 3 > 72 * 1024) t.fs_max_in_rows = 0;      // fused kernel unavailable: fall back to two kernels
+  }
 
   float lut[256 * 3];
   host_lut(lut);

@@ -416,3 +416,26 @@ def test_int8_rejects_redconv_and_needs_calibration(dev):
     m = rtdm_b200.from_state_dict("squeeze-redconv", fixtures.get_state_dict("squeeze-redconv", "w3"), dev, "int8")
     with pytest.raises(ValueError):
         m(torch.zeros(1, 3, 140, 140, device=dev))
+
+
+@pytest.mark.parametrize("hw", [(240, 240), (161, 300), (480, 640), (100, 120), (372, 350), (720, 1280), (159, 159)])
+@pytest.mark.parametrize("arch,prec", [("squeeze-ernet", "fp32"), ("squeeze-ernet", "bf16"), ("squeeze-redconv", "fp16")])
+def test_fused_transform_conv1_equals_two_kernel_path(hw, arch, prec, dev):
+    """forward_frames() runs transform + conv1 as one kernel; it must agree bit for bit with the standalone
+    (Pillow-exact) transform followed by model(x), for aligned, unaligned, up-scaled and large frames."""
+    H, W = hw
+    sd = fixtures.get_state_dict(arch, "w3")
+    frames = np.concatenate([fixtures.noise_frames(2, H, W, seed=H + W), fixtures.smooth_frames(1, H, W, seed=H * W)], 0)
+    ft = torch.from_numpy(frames).to(dev)
+    m = rtdm_b200.from_state_dict(arch, sd, dev, prec)
+    l_fused = m.forward_frames(ft, return_logits=True)[1]
+    l_bgr = m.forward_frames(torch.from_numpy(frames[..., ::-1].copy()).to(dev), bgr=True, return_logits=True)[1]
+    x = m.ingest(ft, dtype=TDT[prec])
+    l_two = m.forward_with_logits(x)[1]
+    assert torch.equal(l_fused, l_two)
+    assert torch.equal(l_bgr, l_fused)
+    # a view into a larger buffer (unaligned start for odd sizes) gives the same answer
+    big = torch.zeros(frames.size + 7, dtype=torch.uint8, device=dev)
+    big[7:] = ft.flatten()
+    l_view = m.forward_frames(big[7:].view(ft.shape), return_logits=True)[1]
+    assert torch.equal(l_view, l_fused)
