@@ -164,8 +164,10 @@ ingest_kernel(const uint8_t* __restrict__ frames, int H, int W, int bgr,
 enum : int { FS_NHWC = 0, FS_P8 = 1, FS_P16 = 2 };
 struct StemQ { float inv[16]; };   // FS_P16: 1 / int8 step of each stem channel
 
+constexpr int kFusedThreads = 512;
+
 template <typename T, int CS, int OUT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kFusedThreads)
 ingest_stem_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restrict__ frames_end, int H, int W, int bgr, int stage_raw,
                    const int* __restrict__ xmin, const int* __restrict__ xlen, const int* __restrict__ kx, int ksx,
                    const int* __restrict__ ymin, const int* __restrict__ ylen, const int* __restrict__ ky, int ksy,
@@ -347,7 +349,7 @@ inline int launch_ingest_stem(const IngestTables& t, const uint8_t* frames, int 
                               const float* bias, const StemQ& q, void* out, cudaStream_t stream) {
   const size_t hb = ((size_t)t.fs_max_in_rows * kCrop * 3 + 15) / 16 * 16;
   dim3 grid((69 + kStemBand - 1) / kStemBand, batch);
-  ingest_stem_kernel<T, CS, OUT><<<grid, 256, ingest_stem_smem<T, CS, OUT>(t), stream>>>(
+  ingest_stem_kernel<T, CS, OUT><<<grid, kFusedThreads, ingest_stem_smem<T, CS, OUT>(t), stream>>>(
       frames, frames + (size_t)batch * t.H * t.W * 3, t.H, t.W, bgr, t.fs_stage_raw, t.d_xmin, t.d_xlen, t.d_kx, t.ksx, t.d_ymin, t.d_ylen, t.d_ky, t.ksy, t.d_lut,
       w, bias, q, (int)hb, out);
   ERNET_LAUNCH_CHECK("ingest_stem_kernel");

@@ -4,8 +4,8 @@
 //   logits = W_eff . sum_{4x4}(a4) + b_fc ; probs = softmax(logits)              model/squeeze_ernet.py:33-41
 //
 // The map is only 6x6 -> 4x4 here, so unlike blocks 1-3 the 25-tap fold would waste the tensor cores on
-// padding.  Instead ("design D"): a CTA takes 8 images = 128 output pixels = one M=128 MMA tile;
-//   1. one bulk copy stages the 8 input images (NHWC, contiguous in HBM),
+// padding.  Instead ("design D"): a CTA takes IMGS images x 16 output pixels as rows of one M=128 MMA tile;
+//   1. one bulk copy stages the input images (NHWC, contiguous in HBM),
 //   2. all 8 warps compute the three dilated depthwise convs on CUDA cores (fp32 accumulate) and write
 //      the results, rounded to 16 bit, directly as the A operand in the un-swizzled K-major UMMA layout
 //      [k-chunk of 8][128 rows][8] - the concat of acff.py:46 is just the K order [branch][channel],
@@ -30,20 +30,29 @@ struct TailParams {          // kernel-parameter constant bank
 
 template <int C4_>
 struct TailCfg {
-  static constexpr int C4 = C4_, K = 3 * C4, N = 256, IMGS = 8;
+  static constexpr int C4 = C4_, K = 3 * C4, N = 256;
+  // images per CTA: 4 fill only rows 0..63 of the M=128 tile (the MMA is a negligible part of this kernel), which
+  // doubles the number of CTAs sharing the CUDA-core depthwise stage
+  static constexpr int IMGS = 4;
   static constexpr int KCHUNKS = K / 8, KSTEPS = K / 16;
   static constexpr int IN_BYTES = IMGS * 36 * C4 * 2;              // 8 images (6,6,C4) 16-bit
   static constexpr int A_BYTES = KCHUNKS * 128 * 16;               // [k-chunk][128 rows][16 B]
   static constexpr int DW_FLOATS = 30 * C4;                        // [3][9][C4] weights + [3][C4] bias
-  static constexpr int KS_PER_STAGE = 2, WSTAGES = 2;
+  static constexpr int KS_PER_STAGE = 2;
   static constexpr int STAGE_BYTES = KS_PER_STAGE * 2 * N * 16;    // 16 KB
+  // weight ring: WPRE dedicated stages are filled while the depthwise stage runs; once that stage is done the
+  // staged input is dead and its region provides WREUSE more stages (deep enough to cover L2 latency)
+  static constexpr int WPRE = 2;
+  static constexpr int WREUSE = (IMGS * 36 * C4_ * 2) / STAGE_BYTES;
+  static constexpr int WSTAGES = WPRE + WREUSE;
   static constexpr int NSTAGE_LOADS = KSTEPS / KS_PER_STAGE;
   static constexpr int OFF_A = IN_BYTES;
   static constexpr int OFF_DW = OFF_A + A_BYTES;
   static constexpr int OFF_W = OFF_DW + DW_FLOATS * 4;
-  static constexpr int OFF_BAR = OFF_W + WSTAGES * STAGE_BYTES;
-  static constexpr int SMEM_BYTES = OFF_BAR + 128;
+  static constexpr int OFF_BAR = OFF_W + WPRE * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256;
   static_assert(KSTEPS % KS_PER_STAGE == 0, "stage granularity");
+  static_assert(WSTAGES <= 8, "barrier array size");
   static_assert(OFF_W % 128 == 0 && OFF_A % 128 == 0, "alignment");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
@@ -67,10 +76,10 @@ acff4_head_kernel(const uint16_t* __restrict__ in /*(B,6,6,C4)*/, const float* _
   uint8_t* s_w = smem + Cfg::OFF_W;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* bar_in = bars;          // [1]
-  uint64_t* w_full = bars + 1;      // [2]
-  uint64_t* w_empty = bars + 3;     // [2]
-  uint64_t* acc_full = bars + 5;    // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* w_full = bars + 1;      // [8]
+  uint64_t* w_empty = bars + 9;     // [8]
+  uint64_t* acc_full = bars + 17;   // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
   volatile uint32_t* abort_flag = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -80,12 +89,14 @@ acff4_head_kernel(const uint16_t* __restrict__ in /*(B,6,6,C4)*/, const float* _
   if (threadIdx.x == 0) {
     *abort_flag = 0u;
     mbar_init(bar_in, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 256);
-  for (int i = threadIdx.x; i < Cfg::DW_FLOATS; i += kTailThreads) s_dw[i] = i < 27 * C4 ? dw_w[i] : dw_b[i - 27 * C4];
+  for (int i = threadIdx.x; i < Cfg::DW_FLOATS / 4; i += kTailThreads)       // 27*C4 and 3*C4 are multiples of 4
+    reinterpret_cast<float4*>(s_dw)[i] = i < 27 * C4 / 4 ? __ldg(reinterpret_cast<const float4*>(dw_w) + i)
+                                                          : __ldg(reinterpret_cast<const float4*>(dw_b) + (i - 27 * C4 / 4));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -95,7 +106,7 @@ acff4_head_kernel(const uint16_t* __restrict__ in /*(B,6,6,C4)*/, const float* _
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar_in, (uint32_t)(nimg * 36 * C4 * 2));
     bulk_g2s(smem, reinterpret_cast<const uint8_t*>(in) + (size_t)img0 * 36 * C4 * 2, (uint32_t)(nimg * 36 * C4 * 2), bar_in);
-    for (int st = 0; st < Cfg::WSTAGES; ++st) {
+    for (int st = 0; st < Cfg::WPRE; ++st) {
       mbar_expect_tx(&w_full[st], Cfg::STAGE_BYTES);
       bulk_g2s(s_w + st * Cfg::STAGE_BYTES, reinterpret_cast<const uint8_t*>(wimg) + (size_t)st * Cfg::STAGE_BYTES,
                Cfg::STAGE_BYTES, &w_full[st]);
@@ -105,7 +116,7 @@ acff4_head_kernel(const uint16_t* __restrict__ in /*(B,6,6,C4)*/, const float* _
   // ---- depthwise trio -> A operand (all warps)
   bool ok = mbar_wait(bar_in, 0, abort_flag, 0x400u);
   if (ok) {
-    for (int item = threadIdx.x; item < 128 * CV; item += kTailThreads) {
+    for (int item = threadIdx.x; item < Cfg::IMGS * 16 * CV; item += kTailThreads) {
       const int v = item % CV, row = item / CV;
       const int im = row >> 4, oy = (row >> 2) & 3, ox = row & 3;
       float acc[3][8];
@@ -140,20 +151,20 @@ acff4_head_kernel(const uint16_t* __restrict__ in /*(B,6,6,C4)*/, const float* _
   __syncthreads();
 
   if (warp == 0) {
-    // ---- weight ring producer: remaining stages
+    // ---- weight ring producer: remaining loads; stages >= WPRE live in the (now dead) input region
     if (lane == 0) {
-      for (int ld = Cfg::WSTAGES; ld < Cfg::NSTAGE_LOADS; ++ld) {
+      for (int ld = Cfg::WPRE; ld < Cfg::NSTAGE_LOADS; ++ld) {
         const int st = ld % Cfg::WSTAGES, use = ld / Cfg::WSTAGES;
-        if (!mbar_wait(&w_empty[st], (use - 1) & 1, abort_flag, 0x401u, ld)) break;
+        if (use > 0 && !mbar_wait(&w_empty[st], (use - 1) & 1, abort_flag, 0x401u, ld)) break;
+        uint8_t* dst = st < Cfg::WPRE ? s_w + st * Cfg::STAGE_BYTES : smem + (st - Cfg::WPRE) * Cfg::STAGE_BYTES;
         mbar_expect_tx(&w_full[st], Cfg::STAGE_BYTES);
-        bulk_g2s(s_w + st * Cfg::STAGE_BYTES, reinterpret_cast<const uint8_t*>(wimg) + (size_t)ld * Cfg::STAGE_BYTES,
-                 Cfg::STAGE_BYTES, &w_full[st]);
+        bulk_g2s(dst, reinterpret_cast<const uint8_t*>(wimg) + (size_t)ld * Cfg::STAGE_BYTES, Cfg::STAGE_BYTES, &w_full[st]);
       }
     }
   } else if (warp == 1) {
     // ---- MMA issuer
     if (elect_one()) {
-      const uint32_t a_lo0 = desc_lo(smem_u32(s_a), 128 * 16), w_lo0 = desc_lo(smem_u32(s_w), N * 16);
+      const uint32_t a_lo0 = desc_lo(smem_u32(s_a), 128 * 16);
       constexpr uint32_t AB_HI = desc_hi(128);
       bool okm = ok;
       for (int ld = 0; ld < Cfg::NSTAGE_LOADS && okm; ++ld) {
@@ -164,8 +175,9 @@ acff4_head_kernel(const uint16_t* __restrict__ in /*(B,6,6,C4)*/, const float* _
 #pragma unroll
         for (int j = 0; j < Cfg::KS_PER_STAGE; ++j) {
           const int ks = ld * Cfg::KS_PER_STAGE + j;
+          const uint8_t* wst = st < Cfg::WPRE ? s_w + st * Cfg::STAGE_BYTES : smem + (st - Cfg::WPRE) * Cfg::STAGE_BYTES;
           mma_f16(tmem_base, desc_make(a_lo0 + (uint32_t)(ks * ((2 * 128 * 16) >> 4)), AB_HI),
-                  desc_make(w_lo0 + (uint32_t)((st * Cfg::STAGE_BYTES + j * 2 * N * 16) >> 4), AB_HI), IDESC, ks != 0 ? 1u : 0u);
+                  desc_make(desc_lo(smem_u32(wst) + (uint32_t)(j * 2 * N * 16), N * 16), AB_HI), IDESC, ks != 0 ? 1u : 0u);
         }
         mma_commit(&w_empty[st]);
       }
@@ -176,7 +188,7 @@ acff4_head_kernel(const uint16_t* __restrict__ in /*(B,6,6,C4)*/, const float* _
     // ---- epilogue: lane = pixel (row of the tile), 16 consecutive lanes = one image
     const int q4 = warp & 3;
     const int row = q4 * 32 + lane, im = row >> 4;
-    if (mbar_wait(acc_full, 0, abort_flag, 0x403u, warp)) {
+    if (q4 * 32 < Cfg::IMGS * 16 && mbar_wait(acc_full, 0, abort_flag, 0x403u, warp)) {
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q4 * 32) << 16);
       float dot[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
