@@ -340,8 +340,10 @@ static int run_chunk(ernet_handle* h, const void* x, int x_dtype, int x_layout, 
 template <typename T>
 static int set_fused_ingest_attrs() {
   const int lim = 200 * 1024;
-  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<T, 16, FS_NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<T, 8, FS_NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<T, 16, FS_NHWC, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<T, 8, FS_NHWC, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<T, 16, FS_NHWC, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<T, 8, FS_NHWC, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
   return ERNET_OK;
 }
 
@@ -360,9 +362,12 @@ static int init_device_attrs() {
   if ((rc = set_fused_ingest_attrs<float>())) return rc;
   if ((rc = set_fused_ingest_attrs<__half>())) return rc;
   if ((rc = set_fused_ingest_attrs<__nv_bfloat16>())) return rc;
-  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__half, 16, FS_P8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__nv_bfloat16, 16, FS_P8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__half, 16, FS_P16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__half, 16, FS_P8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__nv_bfloat16, 16, FS_P8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__half, 16, FS_P16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__half, 16, FS_P8, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__nv_bfloat16, 16, FS_P8, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__half, 16, FS_P16, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   if ((rc = tc::set_all_block_attrs())) return rc;
   if ((rc = tc::set_tail_attrs<tc::TailCfg128>())) return rc;
   if ((rc = tc::set_tail_attrs<tc::TailCfg64>())) return rc;
@@ -663,7 +668,9 @@ int ernet_classify_frames_host(ernet_handle* h, const uint8_t* frames_host, int 
       ERNET_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
     }
   }
-  const int chunk = batch < h->chunk ? batch : h->chunk;
+  // sub-chunks so that the H2D copy of one overlaps the kernels of the previous one even inside a single call
+  int chunk = batch < h->chunk ? batch : h->chunk;
+  if (batch >= 128) { const int q = (batch + 3) / 4; chunk = q < chunk ? q : chunk; if (chunk < 32) chunk = 32; }
   const size_t f_img = (size_t)height * width * 3;
   const size_t fbytes = (size_t)chunk * f_img;
   if (h->d_frames_bytes < fbytes) {

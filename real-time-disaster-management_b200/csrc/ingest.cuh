@@ -164,10 +164,15 @@ ingest_kernel(const uint8_t* __restrict__ frames, int H, int W, int bgr,
 enum : int { FS_NHWC = 0, FS_P8 = 1, FS_P16 = 2 };
 struct StemQ { float inv[16]; };   // FS_P16: 1 / int8 step of each stem channel
 
-constexpr int kFusedThreads = 512;
+constexpr int kFusedThreads = 512;   // 2 CTAs per SM (<= 64 registers); the 5-tap fast path uses 3 row groups x 140 columns
+constexpr int kFusedRowGroups = 3;
 
-template <typename T, int CS, int OUT>
-__global__ void __launch_bounds__(kFusedThreads)
+// KS = 5: specialisation for frames whose resample needs exactly 5 taps per axis (e.g. 240x240 -> 159) with the raw
+// rows staged in shared memory: every thread owns one output column, keeps its 5 horizontal coefficients in
+// registers and walks down the rows with fully unrolled taps (tables are zero-padded to 5 taps, so border columns
+// just multiply neighbouring bytes by 0).  KS = 0: generic run-time tap counts.
+template <typename T, int CS, int OUT, int KS>
+__global__ void __launch_bounds__(kFusedThreads, 2)
 ingest_stem_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restrict__ frames_end, int H, int W, int bgr, int stage_raw,
                    const int* __restrict__ xmin, const int* __restrict__ xlen, const int* __restrict__ kx, int ksx,
                    const int* __restrict__ ymin, const int* __restrict__ ylen, const int* __restrict__ ky, int ksy,
@@ -213,6 +218,26 @@ ingest_stem_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restrict
   }
 
   // ---- phase 1: horizontal pass
+  if (KS == 5) {
+    if (threadIdx.x < kFusedRowGroups * kCrop) {
+      const int ox = threadIdx.x % kCrop, rg = threadIdx.x / kCrop;
+      int kc[5];
+#pragma unroll
+      for (int t = 0; t < 5; ++t) kc[t] = __ldg(kx + ox * 5 + t);
+      const uint8_t* p = raw + raw_off + (rg * W + xmin[ox]) * 3;
+      uint8_t* h = hbuf + (rg * kCrop + ox) * 3;
+      for (int r = rg; r < in_rows; r += kFusedRowGroups, p += kFusedRowGroups * W * 3, h += kFusedRowGroups * kCrop * 3) {
+        int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {
+          a0 += kc[t] * (int)p[3 * t]; a1 += kc[t] * (int)p[3 * t + 1]; a2 += kc[t] * (int)p[3 * t + 2];
+        }
+        h[0] = (uint8_t)min(max(a0 >> kPrecisionBits, 0), 255);
+        h[1] = (uint8_t)min(max(a1 >> kPrecisionBits, 0), 255);
+        h[2] = (uint8_t)min(max(a2 >> kPrecisionBits, 0), 255);
+      }
+    }
+  } else
   for (int idx = threadIdx.x; idx < in_rows * kCrop; idx += blockDim.x) {
     const int r = idx / kCrop, ox = idx - r * kCrop;
     const int x0 = xmin[ox], n = xlen[ox];
@@ -240,6 +265,26 @@ ingest_stem_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restrict
 
   // ---- phase 2: vertical pass + normalise -> xn
   const int nrows = n1 - n0 + 1;
+  if (KS == 5) {
+    if (threadIdx.x < kFusedRowGroups * kCrop) {
+      const int ox = threadIdx.x % kCrop, rg = threadIdx.x / kCrop;
+      for (int rn = rg; rn < nrows; rn += kFusedRowGroups) {
+        const int oy = n0 + rn;
+        const uint8_t* h = hbuf + ((ymin[oy] - r0) * kCrop + ox) * 3;
+        int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {
+          const int c = __ldg(ky + oy * 5 + t);
+          a0 += c * (int)h[t * kCrop * 3]; a1 += c * (int)h[t * kCrop * 3 + 1]; a2 += c * (int)h[t * kCrop * 3 + 2];
+        }
+        int v[3] = {min(max(a0 >> kPrecisionBits, 0), 255), min(max(a1 >> kPrecisionBits, 0), 255),
+                    min(max(a2 >> kPrecisionBits, 0), 255)};
+        if (bgr) { int t = v[0]; v[0] = v[2]; v[2] = t; }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) xn[(rn * kCrop + ox) * 3 + c] = from_f32<T>(__ldg(lut + v[c] * 3 + c));
+      }
+    }
+  } else
   for (int idx = threadIdx.x; idx < nrows * kCrop; idx += blockDim.x) {
     const int rn = idx / kCrop, ox = idx - rn * kCrop;
     const int oy = n0 + rn;
@@ -339,17 +384,19 @@ ingest_stem_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restrict
 template <typename T, int CS, int OUT>
 inline size_t ingest_stem_smem(const IngestTables& t) {
   const size_t xn = ((size_t)kStemXnRows * kCrop * 3 * sizeof(T) + 15) / 16 * 16;
-  const size_t hb = ((size_t)t.fs_max_in_rows * kCrop * 3 + 15) / 16 * 16;
-  const size_t raw = t.fs_stage_raw ? ((size_t)t.fs_max_in_rows * t.W * 3 + 32 + 15) / 16 * 16 : 0;
+  const size_t hb = ((size_t)(t.fs_max_in_rows + 5) * kCrop * 3 + 15) / 16 * 16;   // +5 rows: zero-weight taps past the band
+  const size_t raw = t.fs_stage_raw ? ((size_t)t.fs_max_in_rows * t.W * 3 + 64 + 15) / 16 * 16 : 0;
   return xn + 28 * CS * 4 + hb + raw;
 }
 
 template <typename T, int CS, int OUT>
 inline int launch_ingest_stem(const IngestTables& t, const uint8_t* frames, int batch, int bgr, const float* w,
                               const float* bias, const StemQ& q, void* out, cudaStream_t stream) {
-  const size_t hb = ((size_t)t.fs_max_in_rows * kCrop * 3 + 15) / 16 * 16;
+  const size_t hb = ((size_t)(t.fs_max_in_rows + 5) * kCrop * 3 + 15) / 16 * 16;
   dim3 grid((69 + kStemBand - 1) / kStemBand, batch);
-  ingest_stem_kernel<T, CS, OUT><<<grid, kFusedThreads, ingest_stem_smem<T, CS, OUT>(t), stream>>>(
+  const bool fast5 = t.fs_stage_raw && t.ksx == 5 && t.ksy == 5;
+  auto kern = fast5 ? ingest_stem_kernel<T, CS, OUT, 5> : ingest_stem_kernel<T, CS, OUT, 0>;
+  kern<<<grid, kFusedThreads, ingest_stem_smem<T, CS, OUT>(t), stream>>>(
       frames, frames + (size_t)batch * t.H * t.W * 3, t.H, t.W, bgr, t.fs_stage_raw, t.d_xmin, t.d_xlen, t.d_kx, t.ksx, t.d_ymin, t.d_ylen, t.d_ky, t.ksy, t.d_lut,
       w, bias, q, (int)hb, out);
   ERNET_LAUNCH_CHECK("ingest_stem_kernel");
@@ -402,7 +449,7 @@ inline int build_ingest_tables(IngestTables& t, int H, int W) {
       if (rows > worst) worst = rows;
     }
     t.fs_max_in_rows = worst;
-    t.fs_stage_raw = ((size_t)worst * W * 3 + 32 <= kRawStageBytes) ? 1 : 0;
+    t.fs_stage_raw = ((size_t)worst * W * 3 + 64 <= kRawStageBytes) ? 1 : 0;
     if ((size_t)worst * kCrop * 3 > 72 * 1024) t.fs_max_in_rows = 0;      // fused kernel unavailable: fall back to two kernels
   }
 
