@@ -45,7 +45,8 @@ MACS_PER_IMAGE = {"squeeze-ernet": 45.48e6, "squeeze-redconv": 38.80e6}      # S
 
 # algorithmic work per image of each stage: (flops, bytes moved at 16-bit)
 STAGE_WORK = {
-    "ingest": (0.0, 240 * 240 * 3 + 140 * 140 * 3 * 2),
+    # frames path: transform + conv1 fused (uint8 frame in, stem tensor out; the 140x140 tensor stays on chip)
+    "ingest": (2 * 2.057e6, 240 * 240 * 3 + 69 * 69 * 16 * 2),
     "stem": (2 * 2.057e6, 140 * 140 * 3 * 2 + 69 * 69 * 16 * 2),
     "dw1": (2 * 1.939e6, 69 * 69 * 16 * 2 + 66 * 66 * 48 * 2),
     "pw1": (2 * 13.790e6 * (66 * 66) / (67 * 67), 66 * 66 * 48 * 2 + 33 * 33 * 64 * 2),
@@ -163,8 +164,9 @@ def reference_main(args, rank):
         "impl": "reference", "metric": "images/sec", "value": fps, "unit": "images/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "Squeeze-ErNet forward on 240x240x3 uint8 frames (transform + model), CPU reference "
-                               f"path, bounded sample of {sample} frames per step", "arch": ARCH},
+        "config": {"workload": f"Squeeze-ErNet bf16 batch {BATCH} per GPU on 1xB200 (BASELINE.json configs[1]): "
+                               "240x240x3 uint8 frames -> eval transform -> forward -> probabilities",
+                   "arch": ARCH, "reference_arm": f"CPU fp32, bounded sample of {sample} of those frames per step"},
         "cpu_baseline": info,
         "e2e": {"value": fps, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -204,12 +206,12 @@ def gpu_main(args, rank, local_rank, world):
     def step(i):
         return model.forward_frames(dev_sets[i % N_INPUT_SETS])
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                       # sampled from the warm-up on, so short runs still see the GPU under load
     for i in range(args.warmup):
         step(i)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(args.steps):
@@ -244,7 +246,8 @@ def gpu_main(args, rank, local_rank, world):
     # ---- live per-kernel timing: same steps again with CUDA events around every stage
     barrier()
     model.profile(True)
-    for i in range(args.steps):
+    prof_steps = min(args.steps, 200)
+    for i in range(prof_steps):
         step(i)
     torch.cuda.synchronize(dev)
     prof = model.profile_read()
@@ -257,6 +260,12 @@ def gpu_main(args, rank, local_rank, world):
         dms, dcount = prof[dom]
         per_launch_ms = dms / dcount
         flops, nbytes = STAGE_WORK.get(dom, (0.0, 0.0))
+        per_kernel = {}
+        for k, (kms, kcnt) in prof.items():
+            kf, kb = STAGE_WORK.get(k, (0.0, 0.0))
+            t_s = kms / kcnt * 1e-3
+            per_kernel[k] = {"ms": round(kms / kcnt, 5), "tflops": round(kf * BATCH / t_s / 1e12, 2),
+                             "gbs": round(kb * BATCH / t_s / 1e9, 1)}
         if dom in GEMM_STAGES:
             achieved = flops * BATCH / (per_launch_ms * 1e-3) / 1e12
             peak = peaks["bf16_tflops_sustained"]
@@ -265,9 +274,16 @@ def gpu_main(args, rank, local_rank, world):
             achieved = nbytes * BATCH / (per_launch_ms * 1e-3) / 1e9
             peak = peaks["hbm_gbs"]
             roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s"}
-        roof.update({"frac": achieved / peak, "traffic": None, "kernel": dom, "peak_source": peaks["source"],
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_dram_bytes_per_launch.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if dom in tj.get("stages", {}) and tj.get("batch") == BATCH:
+                traffic = tj["stages"][dom]        # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full)
+        roof.update({"frac": achieved / peak, "traffic": traffic, "kernel": dom, "peak_source": peaks["source"],
                      "launch_ms": per_launch_ms, "share_of_step": dms / total_stage_ms,
-                     "stage_ms_per_step": {k: round(v[0] / args.steps, 5) for k, v in prof.items()}})
+                     "stage_ms_per_step": {k: round(v[0] / prof_steps, 5) for k, v in prof.items()},
+                     "per_kernel": per_kernel})
         launches = model.launches_per_forward(BATCH, True) * args.steps
         cpu_fps, _, cpu_info = cpu_reference_run(6, 1, 32)
         line = {
@@ -300,8 +316,8 @@ def gpu_main(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
