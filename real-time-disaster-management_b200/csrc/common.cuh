@@ -109,6 +109,26 @@ __device__ __forceinline__ uint4 pack16<__nv_bfloat16>(const float (&v)[8]) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------
+// Every kernel of the forward chain is launched with programmatic stream serialisation: the next kernel's
+// CTAs may become resident while the previous kernel drains, run their prologue (barrier init, TMEM
+// allocation, prefetch of constant weights) and then block in pdl_wait() until the previous grid has
+// completed and its writes are visible.  RULE: nothing that reads or writes an activation buffer may be
+// issued before pdl_wait().  Both instructions are no-ops for a normally launched kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float leaky_relu(float v) { return v > 0.f ? v : 0.01f * v; }  // acff.py:33
 
 }  // namespace ernet

@@ -178,6 +178,8 @@ ingest_stem_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restrict
                    const int* __restrict__ ymin, const int* __restrict__ ylen, const int* __restrict__ ky, int ksy,
                    const float* __restrict__ lut, const float* __restrict__ w /*[27][CS]*/, const float* __restrict__ bias,
                    const __grid_constant__ StemQ q, int hbuf_bytes, void* __restrict__ out) {
+  pdl_wait();                 // writes the stem tensor the previous step's block 1 read: wait before anything else
+  pdl_launch_dependents();
   extern __shared__ __align__(16) uint8_t fs_smem[];
   // layout: [xn: kStemXnRows*140*3 T][weights: 28*CS float][hbuf: hbuf_bytes][raw: rest]
   T* xn = reinterpret_cast<T*>(fs_smem);
@@ -396,10 +398,9 @@ inline int launch_ingest_stem(const IngestTables& t, const uint8_t* frames, int 
   dim3 grid((69 + kStemBand - 1) / kStemBand, batch);
   const bool fast5 = t.fs_stage_raw && t.ksx == 5 && t.ksy == 5;
   auto kern = fast5 ? ingest_stem_kernel<T, CS, OUT, 5> : ingest_stem_kernel<T, CS, OUT, 0>;
-  kern<<<grid, kFusedThreads, ingest_stem_smem<T, CS, OUT>(t), stream>>>(
-      frames, frames + (size_t)batch * t.H * t.W * 3, t.H, t.W, bgr, t.fs_stage_raw, t.d_xmin, t.d_xlen, t.d_kx, t.ksx, t.d_ymin, t.d_ylen, t.d_ky, t.ksy, t.d_lut,
-      w, bias, q, (int)hb, out);
-  ERNET_LAUNCH_CHECK("ingest_stem_kernel");
+  ERNET_CUDA(launch_pdl(kern, grid, dim3(kFusedThreads), ingest_stem_smem<T, CS, OUT>(t), stream,
+                        frames, frames + (size_t)batch * t.H * t.W * 3, t.H, t.W, bgr, t.fs_stage_raw, t.d_xmin, t.d_xlen, t.d_kx, t.ksx,
+                        t.d_ymin, t.d_ylen, t.d_ky, t.ksy, t.d_lut, w, bias, q, (int)hb, out));
   return ERNET_OK;
 }
 

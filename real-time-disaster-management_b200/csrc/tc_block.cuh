@@ -118,16 +118,24 @@ acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
     if (lane == 0) {
+      // weights are constants: their copies are issued before waiting for the previous kernel (PDL)
       mbar_expect_tx(bar_in, (uint32_t)(nimg * Cfg::IMG_BYTES + (Cfg::WRES ? Cfg::W_BYTES : 0)));
+      if (Cfg::WRES) bulk_g2s(s_w, wimg, Cfg::W_BYTES, bar_in);
+      if (!Cfg::WRES) {
+        for (int it = 0; it < Cfg::WSTAGES; ++it) {
+          mbar_expect_tx(&w_full[it], Cfg::TAP_BYTES);
+          bulk_g2s(s_w + it * Cfg::TAP_BYTES, reinterpret_cast<const uint8_t*>(wimg) + (size_t)it * Cfg::TAP_BYTES, Cfg::TAP_BYTES, &w_full[it]);
+        }
+      }
+      pdl_wait();
       bulk_g2s(s_in, reinterpret_cast<const uint8_t*>(in) + (size_t)img0 * Cfg::IMG_BYTES, (uint32_t)(nimg * Cfg::IMG_BYTES), bar_in);
-      if (Cfg::WRES) {
-        bulk_g2s(s_w, wimg, Cfg::W_BYTES, bar_in);
-      } else {
-        for (int it = 0; it < NG * 25; ++it) {
+      if (!Cfg::WRES) {
+        for (int it = Cfg::WSTAGES; it < NG * 25; ++it) {
           const int s = it % Cfg::WSTAGES, use = it / Cfg::WSTAGES;
           if (use > 0 && !mbar_wait(&w_empty[s], (use - 1) & 1, abort_flag, 0x100u, it)) break;
           mbar_expect_tx(&w_full[s], Cfg::TAP_BYTES);
@@ -137,6 +145,7 @@ acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ 
       }
     }
     __syncwarp();
+    pdl_wait();
     if (OUT != OUT_NHWC) {
       // zero halo of the output images (rows 0,1,OP-1 and cols 0,1,OP-1 of every chunk): the next block's
       // conv padding.  Done by the otherwise idle producer warp.
@@ -354,9 +363,8 @@ template <class Cfg, int KIND, int OUT>
 inline int launch_acff_block(const void* in, const void* wimg, const EpiParams<Cfg::N>& par, void* out, int batch,
                              cudaStream_t stream) {
   const int grid = (batch + Cfg::IMGS - 1) / Cfg::IMGS;
-  acff_block_kernel<Cfg, KIND, OUT><<<grid, kBlockThreads, Cfg::SMEM_BYTES, stream>>>(
-      static_cast<const uint16_t*>(in), static_cast<const uint16_t*>(wimg), par, static_cast<uint16_t*>(out), batch);
-  ERNET_LAUNCH_CHECK("acff_block_kernel");
+  ERNET_CUDA(launch_pdl(acff_block_kernel<Cfg, KIND, OUT>, dim3(grid), dim3(kBlockThreads), Cfg::SMEM_BYTES, stream,
+                        static_cast<const uint16_t*>(in), static_cast<const uint16_t*>(wimg), par, static_cast<uint16_t*>(out), batch));
   return ERNET_OK;
 }
 

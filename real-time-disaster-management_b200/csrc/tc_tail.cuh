@@ -101,16 +101,19 @@ acff4_head_kernel(const uint16_t* __restrict__ in /*(B,6,6,C4)*/, const float* _
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
 
-  // ---- kick off the input copy and the first weight stages (they land while the depthwise stage runs)
+  // ---- kick off the first weight stages (constants: before the PDL wait), then the input copy; both land while
+  //      the depthwise stage runs
   if (threadIdx.x == 0) {
-    mbar_expect_tx(bar_in, (uint32_t)(nimg * 36 * C4 * 2));
-    bulk_g2s(smem, reinterpret_cast<const uint8_t*>(in) + (size_t)img0 * 36 * C4 * 2, (uint32_t)(nimg * 36 * C4 * 2), bar_in);
     for (int st = 0; st < Cfg::WPRE; ++st) {
       mbar_expect_tx(&w_full[st], Cfg::STAGE_BYTES);
       bulk_g2s(s_w + st * Cfg::STAGE_BYTES, reinterpret_cast<const uint8_t*>(wimg) + (size_t)st * Cfg::STAGE_BYTES,
                Cfg::STAGE_BYTES, &w_full[st]);
     }
+    pdl_wait();
+    mbar_expect_tx(bar_in, (uint32_t)(nimg * 36 * C4 * 2));
+    bulk_g2s(smem, reinterpret_cast<const uint8_t*>(in) + (size_t)img0 * 36 * C4 * 2, (uint32_t)(nimg * 36 * C4 * 2), bar_in);
   }
 
   // ---- depthwise trio -> A operand (all warps)
@@ -259,11 +262,12 @@ inline int launch_acff4_head(bool bf16, const void* in, const float* dw_w, const
   auto* i16 = static_cast<const uint16_t*>(in);
   auto* w16 = static_cast<const uint16_t*>(wimg);
   auto* a16 = static_cast<uint16_t*>(a4_out);
-#define ERNET_TAIL(BF, WA) acff4_head_kernel<Cfg, BF, WA><<<grid, kTailThreads, Cfg::SMEM_BYTES, stream>>>(i16, dw_w, dw_b, w16, par, probs, logits, a16, batch)
-  if (bf16) { if (a4_out) ERNET_TAIL(true, true); else ERNET_TAIL(true, false); }
-  else      { if (a4_out) ERNET_TAIL(false, true); else ERNET_TAIL(false, false); }
+#define ERNET_TAIL(BF, WA) launch_pdl(acff4_head_kernel<Cfg, BF, WA>, dim3(grid), dim3(kTailThreads), Cfg::SMEM_BYTES, stream, i16, dw_w, dw_b, w16, par, probs, logits, a16, batch)
+  cudaError_t ce;
+  if (bf16) { ce = a4_out ? ERNET_TAIL(true, true) : ERNET_TAIL(true, false); }
+  else      { ce = a4_out ? ERNET_TAIL(false, true) : ERNET_TAIL(false, false); }
 #undef ERNET_TAIL
-  ERNET_LAUNCH_CHECK("acff4_head_kernel");
+  if (ce != cudaSuccess) return fail(ERNET_ERR_CUDA, "launch of acff4_head_kernel failed: %s", cudaGetErrorString(ce));
   return ERNET_OK;
 }
 
