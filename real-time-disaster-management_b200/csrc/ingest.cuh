@@ -167,6 +167,29 @@ struct StemQ { float inv[16]; };   // FS_P16: 1 / int8 step of each stem channel
 constexpr int kFusedThreads = 512;   // 2 CTAs per SM (<= 64 registers); the 5-tap fast path uses 3 row groups x 140 columns
 constexpr int kFusedRowGroups = 3;
 
+
+// ---- warp-level tensor-core helper for the stem conv (legacy mma.sync path; the stem is 4.5 % of the MACs and
+// lives inside the CUDA-core transform kernel, so a TMEM pipeline would not pay) ------------------------------
+template <typename T> struct StemMma;
+template <> struct StemMma<__half> {
+  static __device__ __forceinline__ void mma(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+  }
+  static __device__ __forceinline__ uint32_t pack(float lo, float hi) { __half2 h = __floats2half2_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&h); }
+};
+template <> struct StemMma<__nv_bfloat16> {
+  static __device__ __forceinline__ void mma(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+  }
+  static __device__ __forceinline__ uint32_t pack(float lo, float hi) { __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&h); }
+};
+template <> struct StemMma<float> {   // never used (fp32 engine keeps FFMA); present so the template instantiates
+  static __device__ __forceinline__ void mma(float (&)[4], const uint32_t (&)[4], const uint32_t (&)[2]) {}
+  static __device__ __forceinline__ uint32_t pack(float, float) { return 0u; }
+};
+
 // KS = 5: specialisation for frames whose resample needs exactly 5 taps per axis (e.g. 240x240 -> 159) with the raw
 // rows staged in shared memory: every thread owns one output column, keeps its 5 horizontal coefficients in
 // registers and walks down the rows with fully unrolled taps (tables are zero-padded to 5 taps, so border columns
@@ -309,6 +332,98 @@ ingest_stem_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restrict
   // ---- phase 3: conv1 (3x3, stride 2) out of shared memory
   const int brow = y1 - y0;
   constexpr int PW = OUT == FS_NHWC ? 69 : 72;           // pixels per output row handled here (incl. halo cols)
+  if constexpr (sizeof(T) == 2) {
+    // 16-bit engines: im2col fragments gathered from the xn tile feed mma.sync m16n8k16 (16 pixels x 8 channels,
+    // K = 27 padded to 32, fp32 accumulate; weights rounded to T).  k = (ky*3+kx)*3+c, and inside one ky the 9
+    // values of a pixel are contiguous in xn, so element (k, ox) sits at  (2*ly + k/9)*420 + 6*ox + k%9.
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    constexpr int NT = CS / 8;                             // n-tiles of 8 output channels
+    int koff[2][4];                                        // smem offsets of this lane's k indices; -1 = zero padding
+#pragma unroll
+    for (int ss = 0; ss < 2; ++ss)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = 16 * ss + 2 * t + (e & 1) + (e >> 1) * 8;
+        koff[ss][e] = k < 27 ? (k / 9) * (kCrop * 3) + (k % 9) : -1;
+      }
+    uint32_t bfrag[2][NT][2];                              // B fragments: w[k][n], k = 2t(+1)(+8), n = 8j + g
+#pragma unroll
+    for (int ss = 0; ss < 2; ++ss)
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int k0 = 16 * ss + 2 * t + 8 * h2;
+          const float w0 = k0 < 27 ? ws[k0 * CS + 8 * j + g] : 0.f;
+          const float w1 = k0 + 1 < 27 ? ws[(k0 + 1) * CS + 8 * j + g] : 0.f;
+          bfrag[ss][j][h2] = StemMma<T>::pack(w0, w1);
+        }
+    const uint16_t* xs = reinterpret_cast<const uint16_t*>(xn);
+    const int ngroups = brow * 5;                          // 5 groups of 16 pixels cover the 69 columns
+    for (int grp = warp; grp < ngroups; grp += kFusedThreads / 32) {
+      const int ly = grp / 5, xg = grp - ly * 5;
+      const int oy = y0 + ly;
+      const int ox0 = xg * 16 + g, ox1 = ox0 + 8;
+      const int b0 = (2 * ly) * (kCrop * 3) + 6 * min(ox0, 68), b1 = (2 * ly) * (kCrop * 3) + 6 * min(ox1, 68);
+      uint32_t afrag[2][4];
+#pragma unroll
+      for (int ss = 0; ss < 2; ++ss) {
+        uint32_t e0[4], e1[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          e0[e] = koff[ss][e] >= 0 ? (uint32_t)xs[b0 + koff[ss][e]] : 0u;
+          e1[e] = koff[ss][e] >= 0 ? (uint32_t)xs[b1 + koff[ss][e]] : 0u;
+        }
+        afrag[ss][0] = e0[0] | (e0[1] << 16);              // row g,   k = 2t, 2t+1
+        afrag[ss][1] = e1[0] | (e1[1] << 16);              // row g+8
+        afrag[ss][2] = e0[2] | (e0[3] << 16);              // row g,   k = 2t+8, 2t+9
+        afrag[ss][3] = e1[2] | (e1[3] << 16);              // row g+8
+      }
+      float acc[NT][4];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        acc[j][0] = acc[j][2] = ws[27 * CS + 8 * j + 2 * t];
+        acc[j][1] = acc[j][3] = ws[27 * CS + 8 * j + 2 * t + 1];
+      }
+#pragma unroll
+      for (int ss = 0; ss < 2; ++ss)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) StemMma<T>::mma(acc[j], afrag[ss], bfrag[ss][j]);
+      // lane holds channels 8j+2t, 8j+2t+1 of pixels ox0 (acc[j][0..1]) and ox1 (acc[j][2..3])
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int ox = half ? ox1 : ox0;
+        if (ox >= 69) continue;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const float v0 = acc[j][2 * half], v1 = acc[j][2 * half + 1];
+          if (OUT == FS_NHWC) {
+            T* o = static_cast<T*>(out) + ((size_t)(b * 69 + oy) * 69 + ox) * CS + 8 * j + 2 * t;
+            *reinterpret_cast<uint32_t*>(o) = StemMma<T>::pack(v0, v1);
+          } else if (OUT == FS_P8) {
+            uint32_t* o = reinterpret_cast<uint32_t*>(reinterpret_cast<uint4*>(out) + (size_t)b * 2 * 72 * 72 + (size_t)j * 72 * 72 + (oy + 2) * 72 + ox + 2);
+            o[t] = StemMma<T>::pack(v0, v1);
+          } else {
+            int q0 = __float2int_rn(v0 * q.inv[8 * j + 2 * t]), q1 = __float2int_rn(v1 * q.inv[8 * j + 2 * t + 1]);
+            q0 = max(-127, min(127, q0)); q1 = max(-127, min(127, q1));
+            uint16_t* o = reinterpret_cast<uint16_t*>(reinterpret_cast<uint4*>(out) + (size_t)b * 2 * 72 * 72 + (oy + 2) * 72 + ox + 2);
+            o[4 * j + t] = (uint16_t)(((uint32_t)q0 & 0xffu) | (((uint32_t)q1 & 0xffu) << 8));
+          }
+        }
+      }
+    }
+    if (OUT != FS_NHWC) {
+      // P8 with CS = 8: chunk 1 is all zero; P16: chunk 1 is all zero; plus the zero halo columns of the band's rows
+      uint4* img = reinterpret_cast<uint4*>(out) + (size_t)b * 2 * 72 * 72;
+      const bool zero_chunk1 = (OUT == FS_P16) || (CS == 8);
+      for (int i = threadIdx.x; i < brow * 72; i += blockDim.x) {
+        const int ly = i / 72, pc = i - ly * 72;
+        const bool halo = pc < 2 || pc >= 71;
+        if (halo) img[(y0 + ly + 2) * 72 + pc] = make_uint4(0, 0, 0, 0);
+        if (halo || zero_chunk1) img[72 * 72 + (y0 + ly + 2) * 72 + pc] = make_uint4(0, 0, 0, 0);
+      }
+    }
+  } else
   for (int idx = threadIdx.x; idx < brow * PW; idx += blockDim.x) {
     const int ly = idx / PW, pc = idx - ly * PW;
     const int oy = y0 + ly;

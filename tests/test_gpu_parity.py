@@ -194,7 +194,10 @@ def test_frames_path_and_chunking(prec, dev):
     # same as transform-then-model
     x = m.ingest(ft, dtype=TDT[prec])
     p2, l2 = m.forward_with_logits(x)
-    assert torch.equal(logits, l2) and torch.equal(probs, p2)
+    if prec == "fp32":
+        assert torch.equal(logits, l2) and torch.equal(probs, p2)
+    else:   # 16-bit frames path runs conv1 on mma.sync with weights rounded to 16 bit; the tensor path keeps fp32 weights
+        assert _rel(logits.double().cpu().numpy(), l2.double().cpu().numpy()) <= 5e-3
     ref = E.forward(sd, I.ingest(frames), arch, dtype=np.float64)
     assert _rel(logits.double().cpu().numpy(), ref["logits"]) <= TOL[prec]
     # ragged chunking (17 = 5+5+5+2) gives bit-identical results; so does B=1
@@ -421,8 +424,8 @@ def test_int8_rejects_redconv_and_needs_calibration(dev):
 @pytest.mark.parametrize("hw", [(240, 240), (161, 300), (480, 640), (100, 120), (372, 350), (720, 1280), (159, 159)])
 @pytest.mark.parametrize("arch,prec", [("squeeze-ernet", "fp32"), ("squeeze-ernet", "bf16"), ("squeeze-redconv", "fp16")])
 def test_fused_transform_conv1_equals_two_kernel_path(hw, arch, prec, dev):
-    """forward_frames() runs transform + conv1 as one kernel; it must agree bit for bit with the standalone
-    (Pillow-exact) transform followed by model(x), for aligned, unaligned, up-scaled and large frames."""
+    """forward_frames() runs transform + conv1 as one kernel; it must agree with the standalone (Pillow-exact)
+    transform followed by model(x) - bit for bit in fp32 - for aligned, unaligned, up-scaled and large frames."""
     H, W = hw
     sd = fixtures.get_state_dict(arch, "w3")
     frames = np.concatenate([fixtures.noise_frames(2, H, W, seed=H + W), fixtures.smooth_frames(1, H, W, seed=H * W)], 0)
@@ -432,7 +435,10 @@ def test_fused_transform_conv1_equals_two_kernel_path(hw, arch, prec, dev):
     l_bgr = m.forward_frames(torch.from_numpy(frames[..., ::-1].copy()).to(dev), bgr=True, return_logits=True)[1]
     x = m.ingest(ft, dtype=TDT[prec])
     l_two = m.forward_with_logits(x)[1]
-    assert torch.equal(l_fused, l_two)
+    if prec == "fp32":
+        assert torch.equal(l_fused, l_two)
+    else:   # conv1 of the 16-bit frames path: mma.sync, weights rounded to 16 bit (tensor path: fp32 weights, FFMA)
+        assert _rel(l_fused.double().cpu().numpy(), l_two.double().cpu().numpy()) <= 5e-3
     assert torch.equal(l_bgr, l_fused)
     # a view into a larger buffer (unaligned start for odd sizes) gives the same answer
     big = torch.zeros(frames.size + 7, dtype=torch.uint8, device=dev)
