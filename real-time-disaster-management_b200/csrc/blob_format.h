@@ -43,6 +43,8 @@ struct ernet_blob_entry {
 #define ERNET_T_TC_BIAS 1       //   [N] fp32: b_f + W_f . cat(b_d)
 #define ERNET_T_TC_DEQ 2        //   [N] fp32, int8 only: per-output-channel weight scale s_w[n] = max|W'_eff[n]|/127
 #define ERNET_T_TC4_WIMG 76     // [3*C4/8][256][8] 16-bit: acff4.fused_conv.weight as the K-major UMMA B operand (tc_tail.cuh)
+#define ERNET_T_TC_RED2_WIMG 77 // [1][12][64][8] 16-bit: conv_red2 (96 -> 48, N padded to 64) as a 1-tap block-kernel image
+#define ERNET_T_TC_RED2_BIAS 78 // [64] fp32 (48 real)
 #define ERNET_T_Q_SCALES 80     // [16+64+96] fp32, int8 only: real value of one int8 step of every channel of the stem /
                                 // pool1 / pool2 tensors (per-channel equalisation of a per-tensor int8 scale; folded into
                                 // the producer's epilogue and the consumer's weights, so the runtime tensor scale is 1)

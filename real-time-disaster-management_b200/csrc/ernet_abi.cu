@@ -42,6 +42,7 @@ struct ernet_handle {
   tc::EpiParams<64> epi1;       // host copies of the per-channel epilogue constants (kernel parameters)
   tc::EpiParams<96> epi2;
   tc::EpiParams<128> epi3;
+  tc::EpiParams<64> epi_r2;     // RedConv conv_red2 (bias only)
   bool has_tail = false;        // blob carries the ACFF4+head tensor-core image
   bool debug_taps = false;      // keep intermediates the fused kernels would not write (acff4)
   tc::TailParams tail;
@@ -69,11 +70,11 @@ struct ernet_handle {
   int c3() const { return red() ? 48 : 96; }           // acff3 input channels
   int c4() const { return red() ? 64 : 128; }          // acff4 input channels
   size_t esize() const { return precision == ERNET_PREC_FP32 ? 4 : 2; }
-  // tensor-core path: 16-bit Squeeze_ErNET (RedConv's chained reductions still run on the CUDA-core path)
+  // tensor-core path: 16-bit handles of both architectures, int8 Squeeze_ErNET
   bool use_tc() const {
     if (precision == ERNET_PREC_INT8) return has_tc && !red();      // int8 exists only as tensor-core kernels
     if (engine == ERNET_ENGINE_SIMT) return false;
-    return has_tc && !red() && (precision == ERNET_PREC_BF16 || precision == ERNET_PREC_FP16);
+    return has_tc && (precision == ERNET_PREC_BF16 || precision == ERNET_PREC_FP16);
   }
   float q_scales[16 + 64 + 96];          // int8: per-channel int8 step of the stem / pool1 / pool2 tensors
   tc::StemInv stem_inv;
@@ -95,6 +96,18 @@ static Plan make_plan(const ernet_handle* h, int n) {
     p.p1 = take(N * 4 * 36 * 36 * 8);          // (B,4,36,36,16)
     p.p2 = take(N * 6 * 18 * 18 * 8 + 6 * 18 * 18 * 8);     // (B,6,18,18,16) + slack
     p.p3 = take(N * 6 * 6 * 128);              // NHWC fp16
+    p.cat4 = take(N * 4 * 4 * 3 * h->c4());
+    p.a4 = take(N * 4 * 4 * 256);
+    p.total = o;
+    return p;
+  }
+  if (p.tc && h->red()) {
+    p.stem = take(N * 2 * 72 * 72 * 8);        // P8 (B,2,72,72,8): 8 real + 8 zero channels
+    p.p1 = take(N * 8 * 36 * 36 * 8);          // P8 (B,8,36,36,8)
+    p.a2 = take(N * 12 * 33 * 33 * 8);         // P8 (B,12,33,33,8): un-pooled acff2 output (conv_red2 input)
+    p.p2 = take(N * 6 * 18 * 18 * 8 + 6 * 18 * 18 * 8);     // P8 (B,6,18,18,8) + one image of slack
+    p.p3 = take(N * 6 * 6 * 128);              // NHWC
+    p.r3 = take(N * 6 * 6 * 64);               // NHWC
     p.cat4 = take(N * 4 * 4 * 3 * h->c4());
     p.a4 = take(N * 4 * 4 * 256);
     p.total = o;
@@ -288,6 +301,38 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
   const float* sw = h->f(ERNET_T_STEM_W);
   const float* sb_ = h->f(ERNET_T_STEM_B);
   const tc::StemInv& s_inv = h->stem_inv;
+  if (h->red()) {
+    if constexpr (KIND != tc::KIND_I8) {
+      // ---- Squeeze_RedConv: conv1+conv_red1 -> P8 (8 real channels), blocks 1-3 with conv_red2 as a 1-tap instance
+      if (frames && tab->fs_max_in_rows > 0 && !h->debug_taps) {
+        StemQ q{};
+        ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem<T, 8, FS_P8>(*tab, frames, n, order == ERNET_BGR, sw, sb_, q, u16(p.stem), s)));
+      } else if (frames) {
+        ERNET_STAGE(ERNET_STAGE_INGEST, launch_ingest<T>(*tab, frames, n, order == ERNET_BGR, buf(p.ingest), 140LL * 140 * 3, 1, 140 * 3, 3, s));
+        StageTimer _t(h, ERNET_STAGE_STEM, s);
+        tc::stem_p8_kernel<T, 8, KIND><<<grid, 128, 0, s>>>(buf(p.ingest), 140LL * 140 * 3, 1, 140 * 3, 3, sw, sb_, u16(p.stem), total, s_inv);
+        ERNET_LAUNCH_CHECK("stem_p8_kernel");
+      } else {
+        long long sb = 3LL * 140 * 140, sc, sy, sx;
+        if (x_layout == ERNET_NCHW) { sc = 140 * 140; sy = 140; sx = 1; }
+        else                        { sc = 1; sy = 140 * 3; sx = 3; }
+        StageTimer _t(h, ERNET_STAGE_STEM, s);
+        if (x_dtype == ERNET_F32) tc::stem_p8_kernel<float, 8, KIND><<<grid, 128, 0, s>>>(static_cast<const float*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total, s_inv);
+        else if (x_dtype == ERNET_F16) tc::stem_p8_kernel<__half, 8, KIND><<<grid, 128, 0, s>>>(static_cast<const __half*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total, s_inv);
+        else tc::stem_p8_kernel<__nv_bfloat16, 8, KIND><<<grid, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total, s_inv);
+        ERNET_LAUNCH_CHECK("stem_p8_kernel");
+      }
+      auto wimgr = [&](int k) { return h->t[ERNET_T_TC_BASE + 4 * k + ERNET_T_TC_WIMG].dev; };
+      ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_block<tc::CfgBlock1, KIND, tc::OUT_P8>(u16(p.stem), wimgr(0), h->epi1, u16(p.p1), n, s)));
+      ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_block<tc::CfgBlock2R, KIND, tc::OUT_P8>(u16(p.p1), wimgr(1), h->epi2, u16(p.a2), n, s)));
+      ERNET_STAGE(ERNET_STAGE_RED2, (tc::launch_acff_block<tc::CfgRed2R, KIND, tc::OUT_P8>(u16(p.a2), h->t[ERNET_T_TC_RED2_WIMG].dev, h->epi_r2, u16(p.p2), n, s)));
+      ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_block<tc::CfgBlock3R, KIND, tc::OUT_NHWC>(u16(p.p2), wimgr(2), h->epi3, u16(p.p3), n, s)));
+      ERNET_STAGE(ERNET_STAGE_RED3, launch_pointwise<T>(buf(p.p3), n, 6, 6, 128, 64, h->f(ERNET_T_RED3_W), h->f(ERNET_T_RED3_B), nullptr, nullptr, 0, 0, buf(p.r3), s));
+      return run_tail<T>(h, buf(p.r3), buf(p.cat4), buf(p.a4), n, probs, logits, s);
+    } else {
+      return fail(ERNET_ERR_UNSUPPORTED, "int8 is implemented for Squeeze_ErNET only");
+    }
+  }
   if (frames && tab->fs_max_in_rows > 0 && !h->debug_taps) {
     StemQ q{};
     for (int i = 0; i < 16; ++i) q.inv[i] = s_inv.v[i];
@@ -365,6 +410,10 @@ static int init_device_attrs() {
   ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__half, 16, FS_P8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__nv_bfloat16, 16, FS_P8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__half, 16, FS_P16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__half, 8, FS_P8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__nv_bfloat16, 8, FS_P8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__half, 8, FS_P8, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__nv_bfloat16, 8, FS_P8, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__half, 16, FS_P8, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__nv_bfloat16, 16, FS_P8, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__half, 16, FS_P16, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -487,9 +536,15 @@ int ernet_load_packed(ernet_handle* h, const void* blob, size_t bytes) {
     const bool q = h->precision == ERNET_PREC_INT8;
     const size_t wimg_bytes[3] = {q ? (size_t)tc::CfgBlock1Q::W_BYTES : (size_t)tc::CfgBlock1::W_BYTES,
                                   q ? (size_t)tc::CfgBlock2Q::W_BYTES : (size_t)tc::CfgBlock2::W_BYTES,
-                                  q ? (size_t)tc::CfgBlock3Q::W_BYTES : (size_t)tc::CfgBlock3::W_BYTES};
+                                  q ? (size_t)tc::CfgBlock3Q::W_BYTES
+                                    : (h->red() ? (size_t)tc::CfgBlock3R::W_BYTES : (size_t)tc::CfgBlock3::W_BYTES)};
     const size_t nout[3] = {64, 96, 128};
-    bool all = !h->red() && h->precision != ERNET_PREC_FP32;
+    bool all = h->precision != ERNET_PREC_FP32 && !(q && h->red());
+    if (h->red()) {
+      const Tensor& wr = h->t[ERNET_T_TC_RED2_WIMG];
+      const Tensor& br = h->t[ERNET_T_TC_RED2_BIAS];
+      all = all && wr.dev && br.dev && wr.nbytes == (size_t)tc::CfgRed2R::W_BYTES && br.nbytes == 64 * sizeof(float);
+    }
     for (int k = 0; k < 3 && all; ++k) {
       const Tensor& w = h->t[ERNET_T_TC_BASE + 4 * k + ERNET_T_TC_WIMG];
       const Tensor& b = h->t[ERNET_T_TC_BASE + 4 * k + ERNET_T_TC_BIAS];
@@ -521,6 +576,10 @@ int ernet_load_packed(ernet_handle* h, const void* blob, size_t bytes) {
       fill(0, h->epi1.bias, h->epi1.scale, h->epi1.shift, h->epi1.deq, h->epi1.out_inv, 64);
       fill(1, h->epi2.bias, h->epi2.scale, h->epi2.shift, h->epi2.deq, h->epi2.out_inv, 96);
       fill(2, h->epi3.bias, h->epi3.scale, h->epi3.shift, h->epi3.deq, h->epi3.out_inv, 128);
+      if (h->red()) {
+        memcpy(h->epi_r2.bias, host_f32(ERNET_T_TC_RED2_BIAS), 64 * sizeof(float));
+        for (int i = 0; i < 64; ++i) { h->epi_r2.scale[i] = 1.f; h->epi_r2.shift[i] = 0.f; h->epi_r2.deq[i] = 1.f; h->epi_r2.out_inv[i] = 1.f; }
+      }
     }
     if (q && !all) {
       memcpy(h->t, old, sizeof(old)); cudaFree(d);
@@ -554,8 +613,8 @@ int ernet_get_chunk(const ernet_handle* h) { return h ? h->chunk : 0; }
 
 int ernet_set_engine(ernet_handle* h, int engine) {
   if (!h || engine < ERNET_ENGINE_AUTO || engine > ERNET_ENGINE_TC) return fail(ERNET_ERR_INVALID_ARG, "bad engine %d", engine);
-  if (engine == ERNET_ENGINE_TC && h->loaded && !(h->has_tc && !h->red() && h->precision != ERNET_PREC_FP32 && h->precision != ERNET_PREC_INT8))
-    return fail(ERNET_ERR_UNSUPPORTED, "tensor-core engine needs a 16-bit Squeeze_ErNET handle");
+  if (engine == ERNET_ENGINE_TC && h->loaded && !(h->has_tc && h->precision != ERNET_PREC_FP32))
+    return fail(ERNET_ERR_UNSUPPORTED, "tensor-core engine needs a 16-bit or int8 handle");
   h->engine = engine;
   return ERNET_OK;
 }
@@ -778,7 +837,7 @@ int ernet_debug_tap(ernet_handle* h, int tap, const void* workspace, int batch, 
   }
   if (p.tc && (tap == ERNET_TAP_STEM || tap == ERNET_TAP_POOL1 || tap == ERNET_TAP_POOL2)) {
     const int Hh = tap == ERNET_TAP_STEM ? 69 : (tap == ERNET_TAP_POOL1 ? 33 : 15);
-    const int NCc = tap == ERNET_TAP_STEM ? 2 : (tap == ERNET_TAP_POOL1 ? 8 : 12);
+    const int NCc = tap == ERNET_TAP_STEM ? 2 : (tap == ERNET_TAP_POOL1 ? 8 : (h->red() ? 6 : 12));
     if (h->precision == ERNET_PREC_BF16) tc::tap_p8_to_nchw_f32<true><<<grid, 256, 0, s>>>(reinterpret_cast<const uint16_t*>(src), NCc, C, Hh, total, out);
     else tc::tap_p8_to_nchw_f32<false><<<grid, 256, 0, s>>>(reinterpret_cast<const uint16_t*>(src), NCc, C, Hh, total, out);
     ERNET_LAUNCH_CHECK("tap_p8_to_nchw_f32");
@@ -854,7 +913,7 @@ int ernet_launches_per_forward(const ernet_handle* h, int batch, int with_ingest
   const int tail_launches = tail ? 1 : 3;
   // frames path: transform + conv1 are one kernel (two with debug taps on); tensor path: conv1 only
   const int front = with_ingest ? (h->debug_taps ? 2 : 1) : 1;
-  const int per = h->use_tc() ? front + 3 + tail_launches : front + 6 + (h->red() ? 2 : 0) + tail_launches;
+  const int per = h->use_tc() ? front + 3 + (h->red() ? 2 : 0) + tail_launches : front + 6 + (h->red() ? 2 : 0) + tail_launches;
   return chunks * per;
 }
 

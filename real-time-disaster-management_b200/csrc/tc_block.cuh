@@ -31,10 +31,17 @@
 namespace ernet {
 namespace tc {
 
-template <int NC_, int N_, int HIN_, int HU_, int IMGS_, int G_, int NBUF_, bool WRES_, int WSTAGES_>
+// POOL_: 2x2 max-pool in the epilogue (else every pixel of the used region is stored).
+// TAPS_: 25 = full ACFF stencil union, 1 = a plain 1x1 convolution (conv_red2, squeeze_ernet_redconv.py:16,33).
+// ACT_:  LeakyReLU + BN affine in the epilogue (else bias only).
+// NREAL_: output channels that exist (N may be padded up to a multiple of 32 with zero weights).
+template <int NC_, int N_, int HIN_, int HU_, int IMGS_, int G_, int NBUF_, bool WRES_, int WSTAGES_,
+          bool POOL_ = true, int TAPS_ = 25, bool ACT_ = true, int NREAL_ = N_>
 struct BlockCfg {
   static constexpr int NC = NC_, N = N_, HIN = HIN_, HU = HU_, IMGS = IMGS_, G = G_, NBUF = NBUF_, WSTAGES = WSTAGES_;
   static constexpr bool WRES = WRES_;
+  static constexpr bool POOL = POOL_, ACT = ACT_;
+  static constexpr int TAPS = TAPS_, NREAL = NREAL_;
   static constexpr int P = HIN + 3;                       // padded pitch: cols -2 .. HIN
   static constexpr int CHUNK_BYTES = P * P * 16;
   static constexpr int IMG_BYTES = NC * CHUNK_BYTES;
@@ -45,17 +52,19 @@ struct BlockCfg {
   static constexpr int NG = (T + G - 1) / G;
   static constexpr int KSTEPS = NC / 2;
   static constexpr int TAP_BYTES = NC * N * 16;
-  static constexpr int W_BYTES = 25 * TAP_BYTES;
+  static constexpr int W_BYTES = TAPS * TAP_BYTES;
   static constexpr int W_SMEM = WRES ? W_BYTES : WSTAGES * TAP_BYTES;
-  static constexpr int OUT_H = HU / 2, OP = OUT_H + 3;
+  static constexpr int OUT_H = POOL ? HU / 2 : HU, OP = OUT_H + 3;
   static constexpr int OFF_W = IN_BYTES;
-  static constexpr int OFF_BAR = OFF_W + W_SMEM;
+  static constexpr int OFF_BAR = (OFF_W + W_SMEM + 15) / 16 * 16;
   static constexpr int SMEM_BYTES = OFF_BAR + 128;
   static_assert(NC % 2 == 0, "K step is 16 channels");
   static_assert(N % 32 == 0 && N <= 256, "N must be a multiple of 32");
   static_assert(G * N * NBUF <= 512, "TMEM has 512 columns");
   static_assert(HU % 2 == 0, "pooling needs an even used size");
-  static_assert(IN_BYTES % 128 == 0 && TAP_BYTES % 128 == 0, "alignment");
+  static_assert(TAPS == 25 || TAPS == 1, "tap set");
+  static_assert(NREAL % 8 == 0 && NREAL <= N, "real output channels");
+  static_assert(IN_BYTES % 16 == 0 && TAP_BYTES % 16 == 0, "bulk copies and un-swizzled descriptors need 16-byte alignment");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
@@ -88,7 +97,9 @@ acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ 
   constexpr bool BF16 = KIND == KIND_BF16;                       // 16-bit output element type
   constexpr uint32_t IDESC = KIND == KIND_I8 ? instr_desc(2u, 1u, 128u, (uint32_t)N)      // s8 x s8 -> s32
                                              : instr_desc(1u, BF16 ? 1u : 0u, 128u, (uint32_t)N);
-  constexpr int OUT_CHUNKS = OUT == OUT_P16 ? N / 16 : N / 8;     // 16-byte chunks per output pixel
+  constexpr int NREAL = Cfg::NREAL;
+  constexpr int OUT_CHUNKS = OUT == OUT_P16 ? NREAL / 16 : NREAL / 8;     // 16-byte chunks per output pixel
+  static_assert(Cfg::POOL || OUT != OUT_P16, "un-pooled int8 output is not needed");
 
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* s_in = smem;
@@ -135,11 +146,11 @@ acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ 
       pdl_wait();
       bulk_g2s(s_in, reinterpret_cast<const uint8_t*>(in) + (size_t)img0 * Cfg::IMG_BYTES, (uint32_t)(nimg * Cfg::IMG_BYTES), bar_in);
       if (!Cfg::WRES) {
-        for (int it = Cfg::WSTAGES; it < NG * 25; ++it) {
+        for (int it = Cfg::WSTAGES; it < NG * Cfg::TAPS; ++it) {
           const int s = it % Cfg::WSTAGES, use = it / Cfg::WSTAGES;
           if (use > 0 && !mbar_wait(&w_empty[s], (use - 1) & 1, abort_flag, 0x100u, it)) break;
           mbar_expect_tx(&w_full[s], Cfg::TAP_BYTES);
-          bulk_g2s(s_w + s * Cfg::TAP_BYTES, reinterpret_cast<const uint8_t*>(wimg) + (size_t)(it % 25) * Cfg::TAP_BYTES,
+          bulk_g2s(s_w + s * Cfg::TAP_BYTES, reinterpret_cast<const uint8_t*>(wimg) + (size_t)(it % Cfg::TAPS) * Cfg::TAP_BYTES,
                    Cfg::TAP_BYTES, &w_full[s]);
         }
       }
@@ -172,7 +183,7 @@ acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ 
       const uint32_t in_addr = smem_u32(s_in), w_addr = smem_u32(s_w);
       constexpr uint32_t A_HI = desc_hi(P * 16), B_HI = desc_hi(128);
       constexpr uint32_t A_KSTEP = (2 * Cfg::CHUNK_BYTES) >> 4, B_KSTEP = (2 * N * 16) >> 4;
-      constexpr int TAP_UNROLL = Cfg::KSTEPS == 1 ? 25 : 1;
+      constexpr int TAP_UNROLL = Cfg::KSTEPS == 1 ? Cfg::TAPS : 1;
       const uint32_t w_lo0 = desc_lo(w_addr, N * 16);
       int ws = 0;                 // weight ring stage and its phase (streamed weights)
       uint32_t wphase = 0;
@@ -191,7 +202,7 @@ acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ 
         }
         const uint32_t d0 = tmem_base + (uint32_t)(buf * G * N);
 #pragma unroll TAP_UNROLL
-        for (int tap = 0; tap < 25; ++tap) {
+        for (int tap = 0; tap < Cfg::TAPS; ++tap) {
           uint32_t b_lo;
           if (Cfg::WRES) {
             b_lo = w_lo0 + (uint32_t)(tap * (Cfg::TAP_BYTES >> 4));
@@ -201,7 +212,7 @@ acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ 
             tc_fence_after();
             b_lo = w_lo0 + (uint32_t)(ws * (Cfg::TAP_BYTES >> 4));
           }
-          const uint32_t toff = (uint32_t)(tap_dy(tap) * P + tap_dx(tap));      // tap shift in 16-byte units
+          const uint32_t toff = Cfg::TAPS == 1 ? 0u : (uint32_t)(tap_dy(tap) * P + tap_dx(tap));   // tap shift in 16-byte units
 #pragma unroll
           for (int tl = 0; tl < G; ++tl) {
             if (tl < ntile) {
@@ -256,8 +267,11 @@ acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ 
             const int n = cb * 32 + j;
             float z = KIND == KIND_I8 ? fmaf(__int2float_rn((int)v[cb & 1][j]), par.deq[n], par.bias[n])
                                       : __uint_as_float(v[cb & 1][j]) + par.bias[n];
-            z = fmaxf(z, 0.01f * z);                           // LeakyReLU(0.01), acff.py:33
-            yv[j] = fmaf(z, par.scale[n], par.shift[n]);       // eval BatchNorm, acff.py:34
+            if (Cfg::ACT) {
+              z = fmaxf(z, 0.01f * z);                         // LeakyReLU(0.01), acff.py:33
+              z = fmaf(z, par.scale[n], par.shift[n]);         // eval BatchNorm, acff.py:34
+            }
+            yv[j] = z;
           }
           // 2x2 max-pool (squeeze_ernet.py:13).  x-neighbour = lane^1, y-neighbour = lane^8.  Each step the
           // lane keeps one half of its channels, ships the other half to the neighbour, and maxes what it
@@ -302,6 +316,25 @@ acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ 
               if (BF16) { __nv_bfloat162 h = __floats2bfloat162_rn(yv[2 * j], yv[2 * j + 1]); pk[j] = *reinterpret_cast<uint32_t*>(&h); }
               else      { __half2 h = __floats2half2_rn(yv[2 * j], yv[2 * j + 1]);            pk[j] = *reinterpret_cast<uint32_t*>(&h); }
             }
+            if (!Cfg::POOL) {                                  // no pooling: the lane stores its own pixel
+              if (valid) {
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                  const int ch = cb * 4 + qq;
+                  if (ch * 8 < NREAL) {
+                    const uint4 o4 = make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
+                    if (OUT == OUT_P8) {
+                      uint4* oimg = reinterpret_cast<uint4*>(out) + (size_t)(img0 + im) * OUT_CHUNKS * OP * OP;
+                      oimg[(ch * OP + y + 2) * OP + x + 2] = o4;
+                    } else {
+                      uint16_t* o = out + ((size_t)((img0 + im) * OUT_H + y) * OUT_H + x) * NREAL + ch * 8;
+                      *reinterpret_cast<uint4*>(o) = o4;
+                    }
+                  }
+                }
+              }
+              continue;
+            }
             uint32_t m1[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -320,14 +353,14 @@ acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ 
               if (BF16) { __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&keep), *reinterpret_cast<const __nv_bfloat162*>(&recv)); m2[j] = *reinterpret_cast<uint32_t*>(&r); }
               else      { __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&keep), *reinterpret_cast<const __half2*>(&recv)); m2[j] = *reinterpret_cast<uint32_t*>(&r); }
             }
-            if (valid) {
+            if (valid && (cb * 4 + qsel) * 8 < NREAL) {
               const uint4 o4 = make_uint4(m2[0], m2[1], m2[2], m2[3]);
               const int ch = cb * 4 + qsel;
               if (OUT == OUT_P8) {
                 uint4* oimg = reinterpret_cast<uint4*>(out) + (size_t)(img0 + im) * OUT_CHUNKS * OP * OP;
                 oimg[(ch * OP + py + 2) * OP + px + 2] = o4;
               } else {
-                uint16_t* o = out + ((size_t)((img0 + im) * OUT_H + py) * OUT_H + px) * N + ch * 8;
+                uint16_t* o = out + ((size_t)((img0 + im) * OUT_H + py) * OUT_H + px) * NREAL + ch * 8;
                 *reinterpret_cast<uint4*>(o) = o4;
               }
             }
@@ -355,6 +388,11 @@ acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ 
 using CfgBlock1 = BlockCfg<2, 64, 69, 66, 1, 4, 2, true, 1>;
 using CfgBlock2 = BlockCfg<8, 96, 33, 30, 1, 4, 1, false, 3>;
 using CfgBlock3 = BlockCfg<12, 128, 15, 12, 2, 4, 1, false, 2>;
+// Squeeze_RedConv (model/squeeze_ernet_redconv.py): block 1 sees 8 real + 8 zero channels; block 2 is split into an
+// un-pooled ACFF2 instance and a 1-tap conv_red2 + pool instance (96 -> 48, N padded to 64); block 3 has 48 inputs.
+using CfgBlock2R = BlockCfg<8, 96, 33, 30, 1, 4, 1, false, 3, /*POOL*/ false>;
+using CfgRed2R = BlockCfg<12, 64, 30, 30, 1, 4, 2, true, 1, /*POOL*/ true, /*TAPS*/ 1, /*ACT*/ false, /*NREAL*/ 48>;
+using CfgBlock3R = BlockCfg<6, 128, 15, 12, 2, 4, 1, false, 3>;
 using CfgBlock1Q = BlockCfg<2, 64, 69, 66, 1, 4, 2, true, 1>;
 using CfgBlock2Q = BlockCfg<4, 96, 33, 30, 1, 4, 1, false, 4>;
 using CfgBlock3Q = BlockCfg<6, 128, 15, 12, 2, 4, 1, false, 3>;
@@ -382,6 +420,12 @@ inline int set_all_block_attrs() {
   if ((rc = set_block_attr<CfgBlock2, KIND_F16, OUT_P8>())) return rc;
   if ((rc = set_block_attr<CfgBlock3, KIND_BF16, OUT_NHWC>())) return rc;
   if ((rc = set_block_attr<CfgBlock3, KIND_F16, OUT_NHWC>())) return rc;
+  if ((rc = set_block_attr<CfgBlock2R, KIND_BF16, OUT_P8>())) return rc;
+  if ((rc = set_block_attr<CfgBlock2R, KIND_F16, OUT_P8>())) return rc;
+  if ((rc = set_block_attr<CfgRed2R, KIND_BF16, OUT_P8>())) return rc;
+  if ((rc = set_block_attr<CfgRed2R, KIND_F16, OUT_P8>())) return rc;
+  if ((rc = set_block_attr<CfgBlock3R, KIND_BF16, OUT_NHWC>())) return rc;
+  if ((rc = set_block_attr<CfgBlock3R, KIND_F16, OUT_NHWC>())) return rc;
   if ((rc = set_block_attr<CfgBlock1Q, KIND_I8, OUT_P16>())) return rc;
   if ((rc = set_block_attr<CfgBlock2Q, KIND_I8, OUT_P16>())) return rc;
   if ((rc = set_block_attr<CfgBlock3Q, KIND_I8, OUT_NHWC>())) return rc;

@@ -17,6 +17,7 @@ T_TC_BASE = 64
 T_TC_WIMG, T_TC_BIAS, T_TC_DEQ = 0, 1, 2   # + 4*k for block k
 T_Q_SCALES = 80
 T_TC4_WIMG = 76
+T_TC_RED2_WIMG, T_TC_RED2_BIAS = 77, 78
 DT_F32, DT_RAW = 0, 16
 
 # offsets from the output coordinate, sorted by (dy, dx); mirrored by kTapDy/kTapDx in csrc/tc_common.cuh
@@ -60,9 +61,9 @@ def fold_block(sd, prefix, c_real, c_pad):
 
 
 def weight_image(weff, precision):
-    """[N][25][C] -> uint16 image [25][C/8][N][8]."""
-    n_out, _, c = weff.shape
-    img = weff.transpose(1, 2, 0).reshape(25, c // 8, 8, n_out).transpose(0, 1, 3, 2)   # [tap][chunk][n][8]
+    """[N][taps][C] -> uint16 image [taps][C/8][N][8]."""
+    n_out, taps, c = weff.shape
+    img = weff.transpose(1, 2, 0).reshape(taps, c // 8, 8, n_out).transpose(0, 1, 3, 2)   # [tap][chunk][n][8]
     return to_bits16(img, precision)
 
 
@@ -143,8 +144,6 @@ def derive_tc(sd, arch, precision, act_scales=None):
         return out
     if precision not in ("fp16", "bf16"):
         return {}
-    if arch != "squeeze-ernet":
-        return {T_TC4_WIMG: (tail_weight_image(sd, precision), DT_RAW)}   # RedConv: tensor-core tail only
     out = {}
     for k, (c, _co) in enumerate(widths(arch)[:3]):
         c_pad = max(16, c)
@@ -153,4 +152,13 @@ def derive_tc(sd, arch, precision, act_scales=None):
         out[base + T_TC_WIMG] = (weight_image(weff, precision), DT_RAW)
         out[base + T_TC_BIAS] = (beff.astype(np.float32), DT_F32)
     out[T_TC4_WIMG] = (tail_weight_image(sd, precision), DT_RAW)
+    if arch == "squeeze-redconv":
+        # conv_red2 (squeeze_ernet_redconv.py:16,33) as a 1-tap instance of the block kernel: 96 -> 48, N padded to 64
+        from .pack import _np64
+        wr = np.zeros((64, 1, 96))
+        wr[:48, 0, :] = _np64(sd, "conv_red2.weight")[:, :, 0, 0]
+        br = np.zeros(64)
+        br[:48] = _np64(sd, "conv_red2.bias")
+        out[T_TC_RED2_WIMG] = (weight_image(wr, precision), DT_RAW)
+        out[T_TC_RED2_BIAS] = (br.astype(np.float32), DT_F32)
     return out

@@ -257,12 +257,12 @@ def test_full_size_properties(dev):
 
 
 # ------------------------------------------------------------------------------------ tensor-core engine
+@pytest.mark.parametrize("arch", fixtures.ARCHS)
 @pytest.mark.parametrize("prec", ["bf16", "fp16"])
 @pytest.mark.parametrize("wset", ["w3neg", "shipped"])
-def test_tc_engine_blocks_match_oracle(prec, wset, dev):
-    """16-bit Squeeze_ErNET runs blocks 1-3 as tcgen05 kernels; check every block boundary against the
-    fp64 oracle and the whole result against the CUDA-core engine on the same device."""
-    arch = "squeeze-ernet"
+def test_tc_engine_blocks_match_oracle(arch, prec, wset, dev):
+    """16-bit models run blocks 1-3 (+ conv_red2 for Squeeze_RedConv) as tcgen05 kernels; check every block
+    boundary against the fp64 oracle and the whole result against the CUDA-core engine on the same device."""
     sd = fixtures.get_state_dict(arch, wset)
     x = fixtures.normal_tensors(3, seed=11)          # odd batch: block 3 packs two images per CTA
     ref = E.forward(sd, x, arch, dtype=np.float64, want_taps=True)
