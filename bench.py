@@ -243,6 +243,18 @@ def gpu_main(args, rank, local_rank, world):
     e2e_value = world * BATCH * e2e_steps / (float(t.item()) * 1e-3)
     assert np.isfinite(ph).all()
 
+    # ---- single-frame latency (BASELINE config 1 flavour: one 240x240 frame -> probabilities), device-resident
+    one = dev_sets[0][:1]
+    for _ in range(10):
+        model.forward_frames(one)
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0.record(stream)
+    for _ in range(200):
+        model.forward_frames(one)
+    l1.record(stream)
+    torch.cuda.synchronize(dev)
+    latency_b1_ms = l0.elapsed_time(l1) / 200
+
     # ---- live per-kernel timing: same steps again with CUDA events around every stage
     barrier()
     model.profile(True)
@@ -304,6 +316,7 @@ def gpu_main(args, rank, local_rank, world):
             "clocks": clocks,
             "roofline": roof,
             "model_flops_frac_of_tensor_peak": value / world * 2 * MACS_PER_IMAGE[ARCH] / 1e12 / peaks["bf16_tflops_sustained"],
+            "latency_b1_ms": latency_b1_ms,
             "cpu_baseline": cpu_info,
         }
         print(json.dumps(line))
