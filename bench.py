@@ -194,6 +194,7 @@ def gpu_main(args, rank, local_rank, world):
     sd = fixtures.get_state_dict(ARCH, "shipped")
     model = rtdm_b200.from_state_dict(ARCH, sd, dev, PRECISION)
     model.prepare_ingest(*FRAME)
+    model.set_persistent(args.schedule == "persistent")
 
     # synthetic inputs: N_INPUT_SETS distinct batches per rank (seeded by rank), rotated so that a step
     # never finds its frames in L2
@@ -332,6 +333,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--schedule", default="persistent", choices=["persistent", "per-image"],
+                    help="tensor-core block kernel schedule (A/B switch; same arithmetic)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

@@ -91,6 +91,9 @@ int ernet_get_chunk(const ernet_handle* h);
 typedef enum ernet_engine { ERNET_ENGINE_AUTO = 0, ERNET_ENGINE_SIMT = 1, ERNET_ENGINE_TC = 2 } ernet_engine;
 int ernet_set_engine(ernet_handle* h, int engine);
 int ernet_get_engine(const ernet_handle* h);   /* the family the next forward will use (SIMT or TC) */
+/* Schedule of the tensor-core block kernels: 1 (default) = persistent CTAs looping over small units fed by
+ * TMA tensor-map box loads (tc_pblock.cuh); 0 = one image per CTA (tc_block.cuh).  Same arithmetic.     */
+int ernet_set_persistent(ernet_handle* h, int on);
 /* Fused kernels keep some intermediates on chip (acff4 inside the ACFF4+head kernel).  With debug taps
  * on they are also written to the workspace so that ernet_debug_tap() can read them (test use).      */
 int ernet_set_debug_taps(ernet_handle* h, int on);
@@ -161,6 +164,9 @@ int ernet_ingest_tables_host(int height, int width, int* meta, int* xmin, int* x
  * pipeline waits that timed out since the last reset (0 in a healthy run), out8[1..3] = tag / block /
  * aux of the first one.  A timed-out kernel terminates normally but its results are invalid.          */
 int ernet_debug_device_status(unsigned int* out8, int reset);
+/* Study builds (-DERNET_TIMELINE) only: per-CTA clock64 stamps of the persistent block kernels, [3 kernels][148][32][8].
+ * Returns ERNET_ERR_UNSUPPORTED in the normal build.                                                    */
+int ernet_debug_timeline(unsigned long long* out, size_t count);
 
 /* Per-stage device timing with CUDA events recorded on the launch stream around every kernel of the
  * forward path (bench.py's live roofline measurement).  Off by default; when on, each forward adds

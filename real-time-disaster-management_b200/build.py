@@ -41,7 +41,8 @@ def build_library(force=False, verbose=False):
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libernet_b200.so (there is no CPU fallback)")
     cus = [s for s in sources() if s.endswith(".cu")]
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", ROOT_INCLUDE, "-o", LIB + ".tmp"] + cus
+    extra = os.environ.get("ERNET_NVCC_EXTRA", "").split()          # study builds, e.g. -DERNET_TIMELINE
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-I", ROOT_INCLUDE, "-o", LIB + ".tmp"] + cus
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode:
         print(r.stdout[-4000:])

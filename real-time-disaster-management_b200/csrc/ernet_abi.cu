@@ -13,6 +13,7 @@
 #include "simt_layers.cuh"
 #include "tc_block.cuh"
 #include "tc_tail.cuh"
+#include "tc_pblock.cuh"
 
 namespace ernet {
 
@@ -45,6 +46,8 @@ struct ernet_handle {
   tc::EpiParams<64> epi_r2;     // RedConv conv_red2 (bias only)
   bool has_tail = false;        // blob carries the ACFF4+head tensor-core image
   bool debug_taps = false;      // keep intermediates the fused kernels would not write (acff4)
+  bool persistent = true;       // persistent TMA-fed block kernels (tc_pblock.cuh) instead of one image per CTA
+  int num_sms = 148;
   tc::TailParams tail;
   void* d_blob = nullptr;
   size_t blob_bytes = 0;
@@ -358,6 +361,11 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
     ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_block<tc::CfgBlock1Q, tc::KIND_I8, tc::OUT_P16>(u16(p.stem), wimg(0), h->epi1, u16(p.p1), n, s)));
     ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_block<tc::CfgBlock2Q, tc::KIND_I8, tc::OUT_P16>(u16(p.p1), wimg(1), h->epi2, u16(p.p2), n, s)));
     ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_block<tc::CfgBlock3Q, tc::KIND_I8, tc::OUT_NHWC>(u16(p.p2), wimg(2), h->epi3, u16(p.p3), n, s)));
+  } else if (h->persistent) {
+    constexpr int K16 = KIND == tc::KIND_I8 ? tc::KIND_F16 : KIND;
+    ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1, K16, tc::OUT_P8>(u16(p.stem), wimg(0), h->epi1, u16(p.p1), n, h->num_sms, s)));
+    ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_pblock<tc::PBlock2, K16, tc::OUT_P8>(u16(p.p1), wimg(1), h->epi2, u16(p.p2), n, h->num_sms, s)));
+    ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_pblock<tc::PBlock3, K16, tc::OUT_NHWC>(u16(p.p2), wimg(2), h->epi3, u16(p.p3), n, h->num_sms, s)));
   } else {
     constexpr int K16 = KIND == tc::KIND_I8 ? tc::KIND_F16 : KIND;
     ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_block<tc::CfgBlock1, K16, tc::OUT_P8>(u16(p.stem), wimg(0), h->epi1, u16(p.p1), n, s)));
@@ -418,6 +426,12 @@ static int init_device_attrs() {
   ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__nv_bfloat16, 16, FS_P8, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__half, 16, FS_P16, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   if ((rc = tc::set_all_block_attrs())) return rc;
+  if ((rc = tc::set_pblock_attr<tc::PBlock1, tc::KIND_BF16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_pblock_attr<tc::PBlock1, tc::KIND_F16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_pblock_attr<tc::PBlock2, tc::KIND_BF16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_pblock_attr<tc::PBlock2, tc::KIND_F16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_pblock_attr<tc::PBlock3, tc::KIND_BF16, tc::OUT_NHWC>())) return rc;
+  if ((rc = tc::set_pblock_attr<tc::PBlock3, tc::KIND_F16, tc::OUT_NHWC>())) return rc;
   if ((rc = tc::set_tail_attrs<tc::TailCfg128>())) return rc;
   if ((rc = tc::set_tail_attrs<tc::TailCfg64>())) return rc;
   return ERNET_OK;
@@ -475,6 +489,7 @@ int ernet_create(ernet_handle** out, int arch, int precision, int device) {
   ernet_handle* h = new (std::nothrow) ernet_handle();
   if (!h) return fail(ERNET_ERR_INVALID_ARG, "out of host memory");
   h->arch = arch; h->precision = precision; h->device = device;
+  h->num_sms = prop.multiProcessorCount;
   *out = h;
   return ERNET_OK;
 }
@@ -616,6 +631,11 @@ int ernet_set_engine(ernet_handle* h, int engine) {
   if (engine == ERNET_ENGINE_TC && h->loaded && !(h->has_tc && h->precision != ERNET_PREC_FP32))
     return fail(ERNET_ERR_UNSUPPORTED, "tensor-core engine needs a 16-bit or int8 handle");
   h->engine = engine;
+  return ERNET_OK;
+}
+int ernet_set_persistent(ernet_handle* h, int on) {
+  if (!h) return fail(ERNET_ERR_INVALID_ARG, "null handle");
+  h->persistent = on != 0;
   return ERNET_OK;
 }
 int ernet_set_debug_taps(ernet_handle* h, int on) {
@@ -880,6 +900,17 @@ int ernet_debug_device_status(unsigned int* out8, int reset) {
     ERNET_CUDA(cudaMemcpyToSymbol(tc::g_tc_status, z, sizeof(z)));
   }
   return ERNET_OK;
+}
+
+int ernet_debug_timeline(unsigned long long* out, size_t count) {
+#ifdef ERNET_TIMELINE
+  if (!out || count > 3 * 148 * 32 * 8) return fail(ERNET_ERR_INVALID_ARG, "bad timeline request");
+  ERNET_CUDA(cudaMemcpyFromSymbol(out, tc::g_timeline, count * sizeof(unsigned long long)));
+  return ERNET_OK;
+#else
+  (void)out; (void)count;
+  return fail(ERNET_ERR_UNSUPPORTED, "library was built without -DERNET_TIMELINE");
+#endif
 }
 
 int ernet_profile_enable(ernet_handle* h, int on) {

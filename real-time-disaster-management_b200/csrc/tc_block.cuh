@@ -87,6 +87,131 @@ enum : int { OUT_P8 = 0,      // 16-bit, (B, N/8, OP, OP, 8) with zero halo: nex
 
 constexpr int kBlockThreads = 320;   // producer + MMA + 8 epilogue warps
 
+// Epilogue of one 16x8 output tile for one warp (32 lanes = 4 rows x 8 cols of the tile): TMEM -> bias
+// [-> LeakyReLU -> BN affine] -> 16-bit / int8 -> [2x2 max-pool via register-half exchange] -> store.
+// `tbase` = TMEM address of the tile's first column for this warp's lane quarter; (y, x) = this lane's output
+// pixel; `img` = global image index.
+template <class Cfg, int KIND, int OUT>
+__device__ __forceinline__ void epilogue_tile(const EpiParams<Cfg::N>& par, uint32_t tbase, int y, int x, bool valid,
+                                        bool xodd, bool yodd, int qsel, uint16_t* __restrict__ out, int img) {
+  constexpr int N = Cfg::N, NREAL = Cfg::NREAL, OP = Cfg::OP, OUT_H = Cfg::OUT_H;
+  constexpr bool BF16 = KIND == KIND_BF16;
+  constexpr int OUT_CHUNKS = OUT == OUT_P16 ? NREAL / 16 : NREAL / 8;
+  const int py = y >> 1, px = x >> 1;
+  const int img0 = img, im = 0;              // (names used by the body below)
+  uint32_t v[2][32];
+  tmem_ld32(tbase, v[0]);
+#pragma unroll
+  for (int cb = 0; cb < N / 32; ++cb) {
+    tmem_ld_wait();                                     // block cb has landed
+    if (cb + 1 < N / 32) tmem_ld32(tbase + (cb + 1) * 32, v[(cb + 1) & 1]);   // prefetch the next 32 columns
+    float yv[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int n = cb * 32 + j;
+      float z = KIND == KIND_I8 ? fmaf(__int2float_rn((int)v[cb & 1][j]), par.deq[n], par.bias[n])
+                                : __uint_as_float(v[cb & 1][j]) + par.bias[n];
+      if (Cfg::ACT) {
+        z = fmaxf(z, 0.01f * z);                         // LeakyReLU(0.01), acff.py:33
+        z = fmaf(z, par.scale[n], par.shift[n]);         // eval BatchNorm, acff.py:34
+      }
+      yv[j] = z;
+    }
+    // 2x2 max-pool (squeeze_ernet.py:13).  x-neighbour = lane^1, y-neighbour = lane^8.  Each step the
+    // lane keeps one half of its channels, ships the other half to the neighbour, and maxes what it
+    // receives, so the lane ends with exactly the 8 channels it stores.  Rounding / quantisation is
+    // monotone, so it commutes with the max and is done first (fewer registers to exchange).
+    if (OUT == OUT_P16) {
+      uint32_t pk[8];                                    // 32 channels as packed int8
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          int q = __float2int_rn(yv[4 * j + e] * par.out_inv[cb * 32 + 4 * j + e]);
+          q = max(-127, min(127, q));
+          w |= ((uint32_t)q & 0xffu) << (8 * e);
+        }
+        pk[j] = w;
+      }
+      uint32_t m1[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t keep = xodd ? pk[j + 4] : pk[j];
+        const uint32_t send = xodd ? pk[j] : pk[j + 4];
+        m1[j] = __vmaxs4(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+      }
+      uint32_t m2[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t keep = yodd ? m1[j + 2] : m1[j];
+        const uint32_t send = yodd ? m1[j] : m1[j + 2];
+        m2[j] = __vmaxs4(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+      }
+      if (valid) {                                       // 8 channels = half of a 16-channel chunk
+        const int ch = cb * 2 + (qsel >> 1);
+        uint2* oimg = reinterpret_cast<uint2*>(out) + ((size_t)(img0 + im) * OUT_CHUNKS * OP * OP) * 2;
+        oimg[((size_t)(ch * OP + py + 2) * OP + px + 2) * 2 + (qsel & 1)] = make_uint2(m2[0], m2[1]);
+      }
+    } else {
+      uint32_t pk[16];                                   // 32 channels as packed bf16x2 / half2
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (BF16) { __nv_bfloat162 h = __floats2bfloat162_rn(yv[2 * j], yv[2 * j + 1]); pk[j] = *reinterpret_cast<uint32_t*>(&h); }
+        else      { __half2 h = __floats2half2_rn(yv[2 * j], yv[2 * j + 1]);            pk[j] = *reinterpret_cast<uint32_t*>(&h); }
+      }
+      if (!Cfg::POOL) {                                  // no pooling: the lane stores its own pixel
+        if (valid) {
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            const int ch = cb * 4 + qq;
+            if (ch * 8 < NREAL) {
+              const uint4 o4 = make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
+              if (OUT == OUT_P8) {
+                uint4* oimg = reinterpret_cast<uint4*>(out) + (size_t)(img0 + im) * OUT_CHUNKS * OP * OP;
+                oimg[(ch * OP + y + 2) * OP + x + 2] = o4;
+              } else {
+                uint16_t* o = out + ((size_t)((img0 + im) * OUT_H + y) * OUT_H + x) * NREAL + ch * 8;
+                *reinterpret_cast<uint4*>(o) = o4;
+              }
+            }
+          }
+        }
+        continue;
+      }
+      uint32_t m1[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t keep = xodd ? pk[j + 8] : pk[j];
+        const uint32_t send = xodd ? pk[j] : pk[j + 8];
+        const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+        if (BF16) { __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&keep), *reinterpret_cast<const __nv_bfloat162*>(&recv)); m1[j] = *reinterpret_cast<uint32_t*>(&r); }
+        else      { __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&keep), *reinterpret_cast<const __half2*>(&recv)); m1[j] = *reinterpret_cast<uint32_t*>(&r); }
+      }
+      uint32_t m2[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t keep = yodd ? m1[j + 4] : m1[j];
+        const uint32_t send = yodd ? m1[j] : m1[j + 4];
+        const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 8);
+        if (BF16) { __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&keep), *reinterpret_cast<const __nv_bfloat162*>(&recv)); m2[j] = *reinterpret_cast<uint32_t*>(&r); }
+        else      { __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&keep), *reinterpret_cast<const __half2*>(&recv)); m2[j] = *reinterpret_cast<uint32_t*>(&r); }
+      }
+      if (valid && (cb * 4 + qsel) * 8 < NREAL) {
+        const uint4 o4 = make_uint4(m2[0], m2[1], m2[2], m2[3]);
+        const int ch = cb * 4 + qsel;
+        if (OUT == OUT_P8) {
+          uint4* oimg = reinterpret_cast<uint4*>(out) + (size_t)(img0 + im) * OUT_CHUNKS * OP * OP;
+          oimg[(ch * OP + py + 2) * OP + px + 2] = o4;
+        } else {
+          uint16_t* o = out + ((size_t)((img0 + im) * OUT_H + py) * OUT_H + px) * NREAL + ch * 8;
+          *reinterpret_cast<uint4*>(o) = o4;
+        }
+      }
+    }
+  }
+      }
+
 // KIND_I8 with a 16-bit output writes fp16 (the int8 engine keeps its non-quantised tensors in fp16).
 template <class Cfg, int KIND, int OUT>
 __global__ void __launch_bounds__(kBlockThreads, 1)
@@ -253,119 +378,8 @@ acff_block_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ 
         const int ty = rem / Cfg::TCOLS, tx = rem - ty * Cfg::TCOLS;
         const int y = ty * 16 + rr, x = tx * 8 + cc;
         const bool valid = (y < Cfg::HU) && (x < Cfg::HU) && (im < nimg);
-        const int py = y >> 1, px = x >> 1;
         const uint32_t tbase = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * G * N + tl * N);
-        uint32_t v[2][32];
-        tmem_ld32(tbase, v[0]);
-#pragma unroll
-        for (int cb = 0; cb < N / 32; ++cb) {
-          tmem_ld_wait();                                     // block cb has landed
-          if (cb + 1 < N / 32) tmem_ld32(tbase + (cb + 1) * 32, v[(cb + 1) & 1]);   // prefetch the next 32 columns
-          float yv[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = cb * 32 + j;
-            float z = KIND == KIND_I8 ? fmaf(__int2float_rn((int)v[cb & 1][j]), par.deq[n], par.bias[n])
-                                      : __uint_as_float(v[cb & 1][j]) + par.bias[n];
-            if (Cfg::ACT) {
-              z = fmaxf(z, 0.01f * z);                         // LeakyReLU(0.01), acff.py:33
-              z = fmaf(z, par.scale[n], par.shift[n]);         // eval BatchNorm, acff.py:34
-            }
-            yv[j] = z;
-          }
-          // 2x2 max-pool (squeeze_ernet.py:13).  x-neighbour = lane^1, y-neighbour = lane^8.  Each step the
-          // lane keeps one half of its channels, ships the other half to the neighbour, and maxes what it
-          // receives, so the lane ends with exactly the 8 channels it stores.  Rounding / quantisation is
-          // monotone, so it commutes with the max and is done first (fewer registers to exchange).
-          if (OUT == OUT_P16) {
-            uint32_t pk[8];                                    // 32 channels as packed int8
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              uint32_t w = 0;
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                int q = __float2int_rn(yv[4 * j + e] * par.out_inv[cb * 32 + 4 * j + e]);
-                q = max(-127, min(127, q));
-                w |= ((uint32_t)q & 0xffu) << (8 * e);
-              }
-              pk[j] = w;
-            }
-            uint32_t m1[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t keep = xodd ? pk[j + 4] : pk[j];
-              const uint32_t send = xodd ? pk[j] : pk[j + 4];
-              m1[j] = __vmaxs4(keep, __shfl_xor_sync(0xffffffffu, send, 1));
-            }
-            uint32_t m2[2];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const uint32_t keep = yodd ? m1[j + 2] : m1[j];
-              const uint32_t send = yodd ? m1[j] : m1[j + 2];
-              m2[j] = __vmaxs4(keep, __shfl_xor_sync(0xffffffffu, send, 8));
-            }
-            if (valid) {                                       // 8 channels = half of a 16-channel chunk
-              const int ch = cb * 2 + (qsel >> 1);
-              uint2* oimg = reinterpret_cast<uint2*>(out) + ((size_t)(img0 + im) * OUT_CHUNKS * OP * OP) * 2;
-              oimg[((size_t)(ch * OP + py + 2) * OP + px + 2) * 2 + (qsel & 1)] = make_uint2(m2[0], m2[1]);
-            }
-          } else {
-            uint32_t pk[16];                                   // 32 channels as packed bf16x2 / half2
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (BF16) { __nv_bfloat162 h = __floats2bfloat162_rn(yv[2 * j], yv[2 * j + 1]); pk[j] = *reinterpret_cast<uint32_t*>(&h); }
-              else      { __half2 h = __floats2half2_rn(yv[2 * j], yv[2 * j + 1]);            pk[j] = *reinterpret_cast<uint32_t*>(&h); }
-            }
-            if (!Cfg::POOL) {                                  // no pooling: the lane stores its own pixel
-              if (valid) {
-#pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
-                  const int ch = cb * 4 + qq;
-                  if (ch * 8 < NREAL) {
-                    const uint4 o4 = make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
-                    if (OUT == OUT_P8) {
-                      uint4* oimg = reinterpret_cast<uint4*>(out) + (size_t)(img0 + im) * OUT_CHUNKS * OP * OP;
-                      oimg[(ch * OP + y + 2) * OP + x + 2] = o4;
-                    } else {
-                      uint16_t* o = out + ((size_t)((img0 + im) * OUT_H + y) * OUT_H + x) * NREAL + ch * 8;
-                      *reinterpret_cast<uint4*>(o) = o4;
-                    }
-                  }
-                }
-              }
-              continue;
-            }
-            uint32_t m1[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint32_t keep = xodd ? pk[j + 8] : pk[j];
-              const uint32_t send = xodd ? pk[j] : pk[j + 8];
-              const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
-              if (BF16) { __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&keep), *reinterpret_cast<const __nv_bfloat162*>(&recv)); m1[j] = *reinterpret_cast<uint32_t*>(&r); }
-              else      { __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&keep), *reinterpret_cast<const __half2*>(&recv)); m1[j] = *reinterpret_cast<uint32_t*>(&r); }
-            }
-            uint32_t m2[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t keep = yodd ? m1[j + 4] : m1[j];
-              const uint32_t send = yodd ? m1[j] : m1[j + 4];
-              const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 8);
-              if (BF16) { __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&keep), *reinterpret_cast<const __nv_bfloat162*>(&recv)); m2[j] = *reinterpret_cast<uint32_t*>(&r); }
-              else      { __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&keep), *reinterpret_cast<const __half2*>(&recv)); m2[j] = *reinterpret_cast<uint32_t*>(&r); }
-            }
-            if (valid && (cb * 4 + qsel) * 8 < NREAL) {
-              const uint4 o4 = make_uint4(m2[0], m2[1], m2[2], m2[3]);
-              const int ch = cb * 4 + qsel;
-              if (OUT == OUT_P8) {
-                uint4* oimg = reinterpret_cast<uint4*>(out) + (size_t)(img0 + im) * OUT_CHUNKS * OP * OP;
-                oimg[(ch * OP + py + 2) * OP + px + 2] = o4;
-              } else {
-                uint16_t* o = out + ((size_t)((img0 + im) * OUT_H + py) * OUT_H + px) * NREAL + ch * 8;
-                *reinterpret_cast<uint4*>(o) = o4;
-              }
-            }
-          }
-        }
+        epilogue_tile<Cfg, KIND, OUT>(par, tbase, y, x, valid, xodd, yodd, qsel, out, img0 + im);
       }
       tc_fence_before();
       __syncwarp();

@@ -42,20 +42,44 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // reads the buffer with ernet_debug_device_status().
 __device__ unsigned int g_tc_status[8];   // [0] = number of timeouts, [1] = first tag, [2] = blockIdx.x, [3] = aux
 
+// Non-blocking phase test.  The waits below poll with it: a suspended mbarrier.try_wait was measured (in-kernel
+// timeline, tools/timeline.py) to resume only at its ~10 us time limit in some producer waits.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile uint32_t* abort_flag, uint32_t tag,
                                           uint32_t aux = 0) {
-  if (mbar_try_wait(bar, parity)) return true;
+  if (mbar_test_wait(bar, parity)) return true;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (*abort_flag) return false;
-    if (clock64() - t0 > 300000000LL) {
-      if (atomicAdd(&g_tc_status[0], 1u) == 0) { g_tc_status[1] = tag; g_tc_status[2] = blockIdx.x; g_tc_status[3] = aux; }
-      *abort_flag = 1u;
-      return false;
+  int spins = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    if ((++spins & 63) == 0) {
+      if (*abort_flag) return false;
+      if (clock64() - t0 > 300000000LL) {
+        if (atomicAdd(&g_tc_status[0], 1u) == 0) { g_tc_status[1] = tag; g_tc_status[2] = blockIdx.x; g_tc_status[3] = aux; }
+        *abort_flag = 1u;
+        return false;
+      }
     }
   }
   return true;
 }
+
+// Optional in-kernel timeline (study builds only: -DERNET_TIMELINE).  Slot layout: [cta < 148][unit < 32][8 stamps].
+#ifdef ERNET_TIMELINE
+__device__ unsigned long long g_timeline[3 * 148 * 32 * 8];
+#define ERNET_TL(k, j) do { if (blockIdx.x < 148 && (k) < 32) g_timeline[((tl_kernel * 148 + blockIdx.x) * 32 + (k)) * 8 + (j)] = (unsigned long long)clock64(); } while (0)
+#else
+#define ERNET_TL(k, j) do { } while (0)
+#endif
 
 // One lane of a converged warp (elect.sync): keeps the surrounding code warp-uniform so that descriptors
 // live in uniform registers instead of going through R2UR + retry loops.

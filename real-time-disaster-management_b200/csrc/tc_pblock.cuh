@@ -1,0 +1,320 @@
+// Persistent version of the fused ACFF block kernel (see tc_block.cuh for the math and the data layouts).
+//
+// What changes is the schedule.  tc_block.cuh runs one image per CTA: nothing overlaps the image load, blocks
+// whose accumulators fill TMEM cannot overlap their epilogue, and a batch of 256 on 148 SMs pays 2 full waves.
+// Here one CTA per SM loops over small UNITS - GX horizontally adjacent 16x8 tiles of one image:
+//   * the unit's input patch, (16+6) x (8*GX+6) pixels x all channel chunks, is fetched by ONE TMA tensor-map
+//     box copy (cp.async.bulk.tensor.5d, SASS UTMALDG) from the padded P8/P16 image into a ring of NSTAGE
+//     buffers - the box lands as [chunk][row][col][16 B], i.e. already the UMMA operand layout with pitch = box
+//     width, and parts of the box outside the tensor are zero-filled by the TMA unit;
+//   * the MMA warp ping-pongs two TMEM accumulator buffers of GX x N columns, so the epilogue of unit k runs
+//     under the MMAs of unit k+1, and the TMA of unit k+2 runs under both;
+//   * weights are loaded once per CTA (block 1, conv_red2) or streamed through the ring per unit;
+//   * units are dealt round-robin to the CTAs: 256 images x 15 units over 148 SMs leaves < 4 % imbalance.
+// Roles: warp 0 input producer, warp 1 MMA issuer, warp 2 weight-ring producer, warps 3-10 epilogue, warp 11 writes the
+// zero halo of the output images (kept off the producer's critical path: ~10 k cycles per image when it was inline).
+#pragma once
+#include <cuda.h>   // CUtensorMap (types only; the encode function is fetched through the runtime)
+
+#include "tc_block.cuh"
+
+namespace ernet {
+namespace tc {
+
+template <int NC_, int N_, int HIN_, int HU_, int GX_, int NSTAGE_, bool WRES_, int WSTAGES_,
+          bool POOL_ = true, int TAPS_ = 25, bool ACT_ = true, int NREAL_ = N_>
+struct PCfg {
+  static constexpr int NC = NC_, N = N_, HIN = HIN_, HU = HU_, GX = GX_, NSTAGE = NSTAGE_, WSTAGES = WSTAGES_;
+  static constexpr bool WRES = WRES_, POOL = POOL_, ACT = ACT_;
+  static constexpr int TAPS = TAPS_, NREAL = NREAL_;
+  static constexpr int WP = HIN + 3;                                   // padded image pitch / height
+  static constexpr int BW = (8 * GX + 6) < WP ? (8 * GX + 6) : WP;     // box width  (pixels)
+  static constexpr int BH = 22 < WP ? 22 : WP;                         // box height (16 output rows + 6)
+  static constexpr int CHUNK_BYTES = BH * BW * 16;
+  static constexpr int STAGE_BYTES = NC * CHUNK_BYTES;
+  static constexpr int TR = (HU + 15) / 16, TCOLS = (HU + 7) / 8;
+  static constexpr int UX = (TCOLS + GX - 1) / GX;                     // units per tile row
+  static constexpr int UNITS_PER_IMG = TR * UX;
+  static constexpr int KSTEPS = NC / 2;
+  static constexpr int TAP_BYTES = NC * N * 16;
+  static constexpr int W_BYTES = TAPS * TAP_BYTES;
+  static constexpr int W_SMEM = WRES ? W_BYTES : WSTAGES * TAP_BYTES;
+  static constexpr int OUT_H = POOL ? HU / 2 : HU, OP = OUT_H + 3;
+  static constexpr int OFF_W = NSTAGE * STAGE_BYTES;
+  static constexpr int OFF_BAR = (OFF_W + W_SMEM + 15) / 16 * 16;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256;
+  static_assert(NC % 2 == 0 && N % 32 == 0 && N <= 256, "operand shape");
+  static_assert(2 * GX * N <= 512, "two TMEM accumulator buffers");
+  static_assert(STAGE_BYTES % 128 == 0, "TMA destination alignment");
+  static_assert(NSTAGE <= 4 && WSTAGES <= 8, "barrier arrays");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+constexpr int kPThreads = 384;   // 12 warps
+
+// cp.async.bulk.tensor.4d: box of the tensor described by `tmap` at coordinates (c0..c3), completion on `bar`.
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+
+template <class Cfg, int KIND, int OUT>
+__global__ void __launch_bounds__(kPThreads, 1)
+acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t* __restrict__ wimg,
+                   const __grid_constant__ EpiParams<Cfg::N> par, uint16_t* __restrict__ out, int batch) {
+  constexpr int N = Cfg::N, GX = Cfg::GX, NSTAGE = Cfg::NSTAGE, BW = Cfg::BW, OP = Cfg::OP;
+  constexpr bool BF16 = KIND == KIND_BF16;
+  constexpr uint32_t IDESC = KIND == KIND_I8 ? instr_desc(2u, 1u, 128u, (uint32_t)N) : instr_desc(1u, BF16 ? 1u : 0u, 128u, (uint32_t)N);
+  constexpr int OUT_CHUNKS = OUT == OUT_P16 ? Cfg::NREAL / 16 : Cfg::NREAL / 8;
+  constexpr int tl_kernel = Cfg::NC == 2 ? 0 : Cfg::NC == 8 ? 1 : 2;   // timeline slot (study builds)
+  (void)tl_kernel;
+
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* s_w = smem + Cfg::OFF_W;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* bar_w = bars;             // [1]  resident weights
+  uint64_t* in_full = bars + 1;       // [4]
+  uint64_t* in_empty = bars + 5;      // [4]
+  uint64_t* w_full = bars + 9;        // [8]
+  uint64_t* w_empty = bars + 17;      // [8]
+  uint64_t* acc_full = bars + 25;     // [2]
+  uint64_t* acc_empty = bars + 27;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
+  volatile uint32_t* abort_flag = tmem_slot + 1;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_units = batch * Cfg::UNITS_PER_IMG;
+
+  if (threadIdx.x == 0) {
+    *abort_flag = 0u;
+    mbar_init(bar_w, 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmap_in);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) ERNET_TL(31, 6);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ input producer (+ halo of the output)
+    if (lane == 0 && Cfg::WRES) {          // constants first: not ordered after the previous kernel (PDL)
+      mbar_expect_tx(bar_w, Cfg::W_BYTES);
+      bulk_g2s(s_w, wimg, Cfg::W_BYTES, bar_w);
+    }
+    pdl_wait();
+    int k = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++k) {
+      const int img = u / Cfg::UNITS_PER_IMG, r = u - img * Cfg::UNITS_PER_IMG;
+      const int ty = r / Cfg::UX, ux = r - ty * Cfg::UX;
+      if (lane == 0) {
+        const int st = k % NSTAGE, use = k / NSTAGE;
+        if (use > 0 && !mbar_wait(&in_empty[st], (use - 1) & 1, abort_flag, 0x500u, k)) break;
+        ERNET_TL(k, 0);
+        mbar_expect_tx(&in_full[st], Cfg::STAGE_BYTES);
+        tma_load_4d(smem + st * Cfg::STAGE_BYTES, &tmap_in, ux * GX * 8 * 4, ty * 16, 0, img, &in_full[st]);
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ weight-ring producer (streamed weights)
+    if (!Cfg::WRES && lane == 0) {
+      int it = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        bool ok = true;
+        for (int tap = 0; tap < Cfg::TAPS && ok; ++tap, ++it) {
+          const int s = it % Cfg::WSTAGES, use = it / Cfg::WSTAGES;
+          if (use > 0) ok = mbar_wait(&w_empty[s], (use - 1) & 1, abort_flag, 0x501u, it);
+          if (!ok) break;
+          mbar_expect_tx(&w_full[s], Cfg::TAP_BYTES);
+          bulk_g2s(s_w + s * Cfg::TAP_BYTES, reinterpret_cast<const uint8_t*>(wimg) + (size_t)tap * Cfg::TAP_BYTES, Cfg::TAP_BYTES, &w_full[s]);
+        }
+        if (!ok) break;
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      bool ok = true;
+      if (Cfg::WRES) ok = mbar_wait(bar_w, 0, abort_flag, 0x502u);
+      const uint32_t in_addr = smem_u32(smem), w_addr = smem_u32(s_w);
+      constexpr uint32_t A_HI = desc_hi(BW * 16), B_HI = desc_hi(128);
+      constexpr uint32_t A_KSTEP = (2 * Cfg::CHUNK_BYTES) >> 4, B_KSTEP = (2 * N * 16) >> 4;
+      constexpr int TAP_UNROLL = Cfg::KSTEPS == 1 ? Cfg::TAPS : 1;
+      const uint32_t w_lo0 = desc_lo(w_addr, N * 16);
+      int ws = 0;
+      uint32_t wphase = 0;
+      int k = 0;
+      for (int u = blockIdx.x; u < total_units && ok; u += gridDim.x, ++k) {
+        const int r = u % Cfg::UNITS_PER_IMG, ux = r % Cfg::UX;
+        const int ntile = min(GX, Cfg::TCOLS - ux * GX);
+        const int st = k % NSTAGE, buf = k & 1, use = k >> 1;
+        ok = mbar_wait(&in_full[st], (k / NSTAGE) & 1, abort_flag, 0x503u, k);
+        ERNET_TL(k, 1);
+        if (ok && use > 0) ok = mbar_wait(&acc_empty[buf], (use - 1) & 1, abort_flag, 0x504u, k);
+        ERNET_TL(k, 2);
+        if (!ok) break;
+        tc_fence_after();
+        // tile tl of the unit: output origin = box origin + (2, 2 + 8*tl)
+        const uint32_t a_lo0 = desc_lo(in_addr + st * Cfg::STAGE_BYTES + (uint32_t)((2 * BW + 2) * 16), Cfg::CHUNK_BYTES);
+        const uint32_t d0 = tmem_base + (uint32_t)(buf * GX * N);
+#pragma unroll TAP_UNROLL
+        for (int tap = 0; tap < Cfg::TAPS; ++tap) {
+          uint32_t b_lo;
+          if (Cfg::WRES) {
+            b_lo = w_lo0 + (uint32_t)(tap * (Cfg::TAP_BYTES >> 4));
+          } else {
+            ok = mbar_wait(&w_full[ws], wphase, abort_flag, 0x505u, k * 32 + tap);
+            if (!ok) break;
+            tc_fence_after();
+            b_lo = w_lo0 + (uint32_t)(ws * (Cfg::TAP_BYTES >> 4));
+          }
+          const uint32_t toff = Cfg::TAPS == 1 ? 0u : (uint32_t)(tap_dy(tap) * BW + tap_dx(tap));
+#pragma unroll
+          for (int tl = 0; tl < GX; ++tl) {
+            if (tl < ntile) {
+#pragma unroll
+              for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+                const uint64_t ad = desc_make(a_lo0 + toff + (uint32_t)(tl * 8) + ks * A_KSTEP, A_HI);
+                const uint64_t bd = desc_make(b_lo + ks * B_KSTEP, B_HI);
+                if (KIND == KIND_I8) mma_i8(d0 + tl * N, ad, bd, IDESC, (tap | ks) != 0 ? 1u : 0u);
+                else                 mma_f16(d0 + tl * N, ad, bd, IDESC, (tap | ks) != 0 ? 1u : 0u);
+              }
+            }
+          }
+          if (!Cfg::WRES) {
+            mma_commit(&w_empty[ws]);
+            if (++ws == Cfg::WSTAGES) { ws = 0; wphase ^= 1; }
+          }
+        }
+        if (ok) { mma_commit(&in_empty[st]); mma_commit(&acc_full[buf]); }
+        ERNET_TL(k, 3);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 11) {
+    // ------------------------------------------------------------------ zero halo of the output images this CTA starts
+    if (OUT != OUT_NHWC) {
+      pdl_wait();
+      constexpr int BORDER = 3 * OP + (OP - 3) * 3;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const int img = u / Cfg::UNITS_PER_IMG;
+        if (u - img * Cfg::UNITS_PER_IMG != 0) continue;
+        uint4* oimg = reinterpret_cast<uint4*>(out) + (size_t)img * OUT_CHUNKS * OP * OP;
+        for (int i = lane; i < OUT_CHUNKS * BORDER; i += 32) {
+          const int ch = i / BORDER, kk = i - ch * BORDER;
+          int rr, cc;
+          if (kk < 3 * OP) { rr = kk / OP; cc = kk - rr * OP; if (rr == 2) rr = OP - 1; }
+          else { const int k2 = kk - 3 * OP; rr = 2 + k2 / 3; cc = k2 % 3; if (cc == 2) cc = OP - 1; }
+          oimg[(ch * OP + rr) * OP + cc] = make_uint4(0, 0, 0, 0);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 3..10)
+    const int q4 = warp & 3;
+    const int ehalf = (warp - 3) >> 2;
+    const int rr = 4 * q4 + (lane >> 3), cc = lane & 7;
+    const bool xodd = (lane & 1) != 0, yodd = ((lane >> 3) & 1) != 0;
+    const int qsel = (xodd ? 2 : 0) + (yodd ? 1 : 0);
+    int k = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++k) {
+      const int img = u / Cfg::UNITS_PER_IMG, r = u - img * Cfg::UNITS_PER_IMG;
+      const int ty = r / Cfg::UX, ux = r - ty * Cfg::UX;
+      const int ntile = min(GX, Cfg::TCOLS - ux * GX);
+      const int buf = k & 1, use = k >> 1;
+      if (!mbar_wait(&acc_full[buf], use & 1, abort_flag, 0x600u + warp, k)) break;
+      if (threadIdx.x == 96) ERNET_TL(k, 4);
+      tc_fence_after();
+      for (int tl = ehalf; tl < ntile; tl += 2) {
+        const int y = ty * 16 + rr, x = (ux * GX + tl) * 8 + cc;
+        const bool valid = (y < Cfg::HU) && (x < Cfg::HU);
+        const uint32_t tbase = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * GX * N + tl * N);
+        epilogue_tile<Cfg, KIND, OUT>(par, tbase, y, x, valid, xodd, yodd, qsel, out, img);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (threadIdx.x == 96) ERNET_TL(k, 5);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) ERNET_TL(31, 7);
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// Tensor map of a padded P8 / P16 activation tensor (batch, NC, WP, WP x 16 bytes): the pixel and byte axes are fused
+// into one inner axis of 32-bit words so that a box row is one contiguous run of BW*16 bytes (a 16-byte inner box
+// makes the TMA unit issue one request per pixel).  Box = (BW*4 words, BH rows, NC chunks, 1 image).
+template <class Cfg>
+inline int make_input_map(CUtensorMap* map, const void* base, int batch) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(ERNET_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[4] = {(cuuint64_t)Cfg::WP * 4, (cuuint64_t)Cfg::WP, (cuuint64_t)Cfg::NC, (cuuint64_t)batch};
+  const cuuint64_t strides[3] = {(cuuint64_t)Cfg::WP * 16, (cuuint64_t)Cfg::WP * Cfg::WP * 16,
+                                 (cuuint64_t)Cfg::NC * Cfg::WP * Cfg::WP * 16};
+  const cuuint32_t box[4] = {(cuuint32_t)Cfg::BW * 4, (cuuint32_t)Cfg::BH, (cuuint32_t)Cfg::NC, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ERNET_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return ERNET_OK;
+}
+
+template <class Cfg, int KIND, int OUT>
+inline int launch_acff_pblock(const void* in, const void* wimg, const EpiParams<Cfg::N>& par, void* out, int batch, int num_sms,
+                              cudaStream_t stream) {
+  CUtensorMap map;
+  int rc = make_input_map<Cfg>(&map, in, batch);
+  if (rc) return rc;
+  const int total = batch * Cfg::UNITS_PER_IMG;
+  const int grid = total < num_sms ? total : num_sms;
+  ERNET_CUDA(launch_pdl(acff_pblock_kernel<Cfg, KIND, OUT>, dim3(grid), dim3(kPThreads), Cfg::SMEM_BYTES, stream, map,
+                        static_cast<const uint16_t*>(wimg), par, static_cast<uint16_t*>(out), batch));
+  return ERNET_OK;
+}
+
+template <class Cfg, int KIND, int OUT>
+inline int set_pblock_attr() {
+  ERNET_CUDA(cudaFuncSetAttribute(acff_pblock_kernel<Cfg, KIND, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  return ERNET_OK;
+}
+
+// Persistent configurations (same math as CfgBlock*): GX tiles per unit, input ring depth, weight residency.
+using PBlock1 = PCfg<2, 64, 69, 66, 3, 3, true, 1>;            // 15 units / image, 21 KB boxes, weights resident
+using PBlock2 = PCfg<8, 96, 33, 30, 2, 2, false, 8>;           //  4 units / image, 62 KB boxes
+using PBlock3 = PCfg<12, 128, 15, 12, 2, 2, false, 4>;         //  1 unit  / image, box = whole padded image
+
+}  // namespace tc
+}  // namespace ernet

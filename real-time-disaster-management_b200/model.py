@@ -217,6 +217,12 @@ class _ErnetB200(nn.Module):
         lib, h, _ = self._ensure_engine()
         return {1: "simt", 2: "tc"}[lib.ernet_get_engine(h)]
 
+    def set_persistent(self, on=True):
+        """Schedule of the tensor-core block kernels: persistent TMA-fed units (default) or one image per CTA."""
+        lib, h, _ = self._ensure_engine()
+        _lib.check(lib.ernet_set_persistent(h, 1 if on else 0))
+        return self
+
     def set_debug_taps(self, on=True):
         """Also write the intermediates that fused kernels keep on chip (needed for tap('acff4'))."""
         lib, h, _ = self._ensure_engine()

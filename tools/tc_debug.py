@@ -31,3 +31,17 @@ for B in [int(a) for a in sys.argv[1:]] or [1, 4]:
     torch.cuda.synchronize()
     err = float(np.abs(l.double().cpu().numpy() - ref).max() / np.abs(ref).max())
     print(f"B={B} rel err {err:.3e} status {status()}", flush=True)
+
+# persistent (TMA-fed units) vs one-image-per-CTA schedule: same arithmetic, must agree bitwise
+if hasattr(m, "set_persistent"):
+    for B in (1, 5, 300):
+        x = torch.from_numpy(fixtures.normal_tensors(B, seed=12)).cuda()
+        m.set_persistent(True)
+        _, l1 = m.forward_with_logits(x)
+        torch.cuda.synchronize()
+        s1 = status()
+        m.set_persistent(False)
+        _, l0 = m.forward_with_logits(x)
+        torch.cuda.synchronize()
+        print(f"persistent vs per-image B={B}: bitwise equal {bool((l1 == l0).all())} max|d| {float((l1 - l0).abs().max()):.3e} status {s1} {status()}", flush=True)
+    m.set_persistent(True)
