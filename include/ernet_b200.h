@@ -91,8 +91,9 @@ int ernet_get_chunk(const ernet_handle* h);
 typedef enum ernet_engine { ERNET_ENGINE_AUTO = 0, ERNET_ENGINE_SIMT = 1, ERNET_ENGINE_TC = 2 } ernet_engine;
 int ernet_set_engine(ernet_handle* h, int engine);
 int ernet_get_engine(const ernet_handle* h);   /* the family the next forward will use (SIMT or TC) */
-/* Schedule of the tensor-core block kernels: 1 (default) = persistent CTAs looping over small units fed by
- * TMA tensor-map box loads (tc_pblock.cuh); 0 = one image per CTA (tc_block.cuh).  Same arithmetic.     */
+/* Schedule of the tensor-core block kernels: 2 (default) = persistent CTAs fed by TMA box loads, with blocks 2 and 3
+ * on CTA pairs (tcgen05 cta_group::2, tc_cblock.cuh); 1 = persistent single CTAs (tc_pblock.cuh); 0 = one image per
+ * CTA (tc_block.cuh).  Same folded weights; 1 and 0 are bit-identical, 2 accumulates the K steps in another order. */
 int ernet_set_persistent(ernet_handle* h, int on);
 /* Fused kernels keep some intermediates on chip (acff4 inside the ACFF4+head kernel).  With debug taps
  * on they are also written to the workspace so that ernet_debug_tap() can read them (test use).      */

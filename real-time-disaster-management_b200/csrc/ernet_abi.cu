@@ -14,6 +14,7 @@
 #include "tc_block.cuh"
 #include "tc_tail.cuh"
 #include "tc_pblock.cuh"
+#include "tc_cblock.cuh"
 
 namespace ernet {
 
@@ -46,7 +47,7 @@ struct ernet_handle {
   tc::EpiParams<64> epi_r2;     // RedConv conv_red2 (bias only)
   bool has_tail = false;        // blob carries the ACFF4+head tensor-core image
   bool debug_taps = false;      // keep intermediates the fused kernels would not write (acff4)
-  bool persistent = true;       // persistent TMA-fed block kernels (tc_pblock.cuh) instead of one image per CTA
+  int persistent = 2;           // block-kernel schedule: 0 one image per CTA, 1 persistent CTAs, 2 persistent + CTA pairs for blocks 2, 3
   int num_sms = 148;
   tc::TailParams tail;
   void* d_blob = nullptr;
@@ -364,8 +365,13 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
   } else if (h->persistent) {
     constexpr int K16 = KIND == tc::KIND_I8 ? tc::KIND_F16 : KIND;
     ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1, K16, tc::OUT_P8>(u16(p.stem), wimg(0), h->epi1, u16(p.p1), n, h->num_sms, s)));
-    ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_pblock<tc::PBlock2, K16, tc::OUT_P8>(u16(p.p1), wimg(1), h->epi2, u16(p.p2), n, h->num_sms, s)));
-    ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_pblock<tc::PBlock3, K16, tc::OUT_NHWC>(u16(p.p2), wimg(2), h->epi3, u16(p.p3), n, h->num_sms, s)));
+    if (h->persistent == 2) {
+      ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_cblock<tc::CBlock2, K16, tc::OUT_P8>(u16(p.p1), wimg(1), h->epi2, u16(p.p2), n, h->num_sms, s)));
+      ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_cblock<tc::CBlock3, K16, tc::OUT_NHWC>(u16(p.p2), wimg(2), h->epi3, u16(p.p3), n, h->num_sms, s)));
+    } else {
+      ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_pblock<tc::PBlock2, K16, tc::OUT_P8>(u16(p.p1), wimg(1), h->epi2, u16(p.p2), n, h->num_sms, s)));
+      ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_pblock<tc::PBlock3, K16, tc::OUT_NHWC>(u16(p.p2), wimg(2), h->epi3, u16(p.p3), n, h->num_sms, s)));
+    }
   } else {
     constexpr int K16 = KIND == tc::KIND_I8 ? tc::KIND_F16 : KIND;
     ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_block<tc::CfgBlock1, K16, tc::OUT_P8>(u16(p.stem), wimg(0), h->epi1, u16(p.p1), n, s)));
@@ -432,6 +438,10 @@ static int init_device_attrs() {
   if ((rc = tc::set_pblock_attr<tc::PBlock2, tc::KIND_F16, tc::OUT_P8>())) return rc;
   if ((rc = tc::set_pblock_attr<tc::PBlock3, tc::KIND_BF16, tc::OUT_NHWC>())) return rc;
   if ((rc = tc::set_pblock_attr<tc::PBlock3, tc::KIND_F16, tc::OUT_NHWC>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::CBlock2, tc::KIND_BF16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::CBlock2, tc::KIND_F16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::CBlock3, tc::KIND_BF16, tc::OUT_NHWC>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::CBlock3, tc::KIND_F16, tc::OUT_NHWC>())) return rc;
   if ((rc = tc::set_tail_attrs<tc::TailCfg128>())) return rc;
   if ((rc = tc::set_tail_attrs<tc::TailCfg64>())) return rc;
   return ERNET_OK;
@@ -635,7 +645,8 @@ int ernet_set_engine(ernet_handle* h, int engine) {
 }
 int ernet_set_persistent(ernet_handle* h, int on) {
   if (!h) return fail(ERNET_ERR_INVALID_ARG, "null handle");
-  h->persistent = on != 0;
+  if (on < 0 || on > 2) return fail(ERNET_ERR_INVALID_ARG, "schedule must be 0, 1 or 2");
+  h->persistent = on;
   return ERNET_OK;
 }
 int ernet_set_debug_taps(ernet_handle* h, int on) {

@@ -218,9 +218,10 @@ class _ErnetB200(nn.Module):
         return {1: "simt", 2: "tc"}[lib.ernet_get_engine(h)]
 
     def set_persistent(self, on=True):
-        """Schedule of the tensor-core block kernels: persistent TMA-fed units (default) or one image per CTA."""
+        """Schedule of the tensor-core block kernels: 2 / True = persistent + CTA pairs (default), 1 = persistent single
+        CTAs, 0 / False = one image per CTA."""
         lib, h, _ = self._ensure_engine()
-        _lib.check(lib.ernet_set_persistent(h, 1 if on else 0))
+        _lib.check(lib.ernet_set_persistent(h, 2 if on is True else int(on)))
         return self
 
     def set_debug_taps(self, on=True):
