@@ -95,6 +95,10 @@ int ernet_get_engine(const ernet_handle* h);   /* the family the next forward wi
  * on CTA pairs (tcgen05 cta_group::2, tc_cblock.cuh); 1 = persistent single CTAs (tc_pblock.cuh); 0 = one image per
  * CTA (tc_block.cuh).  Same folded weights; 1 and 0 are bit-identical, 2 accumulates the K steps in another order. */
 int ernet_set_persistent(ernet_handle* h, int on);
+/* Frames path of the 16-bit tensor-core engines, 5-tap frames (240x240): 1 (default) = word-wide fused transform +
+ * conv1 with ToTensor/Normalize folded into the conv weights (ingest_fast.cuh); 0 = the table-lookup kernel that is
+ * bit-identical to ernet_ingest_u8 followed by ernet_forward.                                              */
+int ernet_set_fast_ingest(ernet_handle* h, int on);
 /* Fused kernels keep some intermediates on chip (acff4 inside the ACFF4+head kernel).  With debug taps
  * on they are also written to the workspace so that ernet_debug_tap() can read them (test use).      */
 int ernet_set_debug_taps(ernet_handle* h, int on);

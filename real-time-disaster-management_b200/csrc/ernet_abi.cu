@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "ingest.cuh"
 #include "simt_layers.cuh"
+#include "ingest_fast.cuh"
 #include "tc_block.cuh"
 #include "tc_tail.cuh"
 #include "tc_pblock.cuh"
@@ -49,6 +50,8 @@ struct ernet_handle {
   bool debug_taps = false;      // keep intermediates the fused kernels would not write (acff4)
   int persistent = 2;           // block-kernel schedule: 0 one image per CTA, 1 persistent CTAs, 2 persistent + CTA pairs for blocks 2, 3
   int num_sms = 148;
+  StemFrag* d_stem_frag = nullptr;   // folded conv1 in mma.sync fragment order (16-bit engines)
+  bool fast_ingest = true;      // word-wide fused transform+conv1 with Normalize folded into conv1 (ingest_fast.cuh)
   tc::TailParams tail;
   void* d_blob = nullptr;
   size_t blob_bytes = 0;
@@ -310,7 +313,12 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
       // ---- Squeeze_RedConv: conv1+conv_red1 -> P8 (8 real channels), blocks 1-3 with conv_red2 as a 1-tap instance
       if (frames && tab->fs_max_in_rows > 0 && !h->debug_taps) {
         StemQ q{};
-        ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem<T, 8, FS_P8>(*tab, frames, n, order == ERNET_BGR, sw, sb_, q, u16(p.stem), s)));
+        FastGeom fg;
+        if (h->fast_ingest && h->d_stem_frag && fast5_geometry(*tab, frames, fg)) {
+          ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem5<T, 8>(*tab, fg, frames, n, order == ERNET_BGR, h->d_stem_frag, u16(p.stem), s)));
+        } else {
+          ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem<T, 8, FS_P8>(*tab, frames, n, order == ERNET_BGR, sw, sb_, q, u16(p.stem), s)));
+        }
       } else if (frames) {
         ERNET_STAGE(ERNET_STAGE_INGEST, launch_ingest<T>(*tab, frames, n, order == ERNET_BGR, buf(p.ingest), 140LL * 140 * 3, 1, 140 * 3, 3, s));
         StageTimer _t(h, ERNET_STAGE_STEM, s);
@@ -341,7 +349,12 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
     StemQ q{};
     for (int i = 0; i < 16; ++i) q.inv[i] = s_inv.v[i];
     constexpr int FSOUT = KIND == tc::KIND_I8 ? FS_P16 : FS_P8;
-    ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem<T, 16, FSOUT>(*tab, frames, n, order == ERNET_BGR, sw, sb_, q, u16(p.stem), s)));
+    FastGeom fg;
+    if (KIND != tc::KIND_I8 && h->fast_ingest && h->d_stem_frag && fast5_geometry(*tab, frames, fg)) {
+      ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem5<T, 16>(*tab, fg, frames, n, order == ERNET_BGR, h->d_stem_frag, u16(p.stem), s)));
+    } else {
+      ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem<T, 16, FSOUT>(*tab, frames, n, order == ERNET_BGR, sw, sb_, q, u16(p.stem), s)));
+    }
   } else if (frames) {
     ERNET_STAGE(ERNET_STAGE_INGEST, launch_ingest<T>(*tab, frames, n, order == ERNET_BGR, buf(p.ingest), 140LL * 140 * 3, 1, 140 * 3, 3, s));
     StageTimer _t(h, ERNET_STAGE_STEM, s);
@@ -431,6 +444,10 @@ static int init_device_attrs() {
   ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__half, 16, FS_P8, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__nv_bfloat16, 16, FS_P8, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__half, 16, FS_P16, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem5_kernel<__nv_bfloat16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem5_kernel<__half, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem5_kernel<__nv_bfloat16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem5_kernel<__half, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   if ((rc = tc::set_all_block_attrs())) return rc;
   if ((rc = tc::set_pblock_attr<tc::PBlock1, tc::KIND_BF16, tc::OUT_P8>())) return rc;
   if ((rc = tc::set_pblock_attr<tc::PBlock1, tc::KIND_F16, tc::OUT_P8>())) return rc;
@@ -508,6 +525,7 @@ void ernet_destroy(ernet_handle* h) {
   if (!h) return;
   DeviceGuard g(h->device);
   if (h->d_blob) cudaFree(h->d_blob);
+  if (h->d_stem_frag) cudaFree(h->d_stem_frag);
   for (auto& kv : h->ingest) if (kv.second.d_base) cudaFree(kv.second.d_base);
   for (int i = 0; i < 2; ++i) {
     if (h->d_frames[i]) cudaFree(h->d_frames[i]);
@@ -583,6 +601,12 @@ int ernet_load_packed(ernet_handle* h, const void* blob, size_t bytes) {
     h->has_tc = all;
     if (all) {
       auto host_f32 = [&](int id) { return reinterpret_cast<const float*>(static_cast<const char*>(blob) + (static_cast<const char*>(h->t[id].dev) - static_cast<const char*>(d))); };
+      {  // conv1 with ToTensor/Normalize folded in, in mma.sync fragment order (ingest_fast.cuh)
+        StemFrag sfh;
+        build_stem_fragments(host_f32(ERNET_T_STEM_W), host_f32(ERNET_T_STEM_B), h->cs(), &sfh);
+        if (!h->d_stem_frag) ERNET_CUDA(cudaMalloc(&h->d_stem_frag, sizeof(StemFrag)));
+        ERNET_CUDA(cudaMemcpy(h->d_stem_frag, &sfh, sizeof(StemFrag), cudaMemcpyHostToDevice));
+      }
       if (q) {
         memcpy(h->q_scales, host_f32(ERNET_T_Q_SCALES), sizeof(h->q_scales));
         for (int i = 0; i < 16; ++i) h->stem_inv.v[i] = 1.f / h->q_scales[i];
@@ -617,6 +641,12 @@ int ernet_load_packed(ernet_handle* h, const void* blob, size_t bytes) {
     h->has_tail = h->precision != ERNET_PREC_FP32 && w4.dev && w4.nbytes == (size_t)3 * h->c4() * 256 * 2;
     if (h->has_tail) {
       auto host_f32 = [&](int id) { return reinterpret_cast<const float*>(static_cast<const char*>(blob) + (static_cast<const char*>(h->t[id].dev) - static_cast<const char*>(d))); };
+      {  // conv1 with ToTensor/Normalize folded in, in mma.sync fragment order (ingest_fast.cuh)
+        StemFrag sfh;
+        build_stem_fragments(host_f32(ERNET_T_STEM_W), host_f32(ERNET_T_STEM_B), h->cs(), &sfh);
+        if (!h->d_stem_frag) ERNET_CUDA(cudaMalloc(&h->d_stem_frag, sizeof(StemFrag)));
+        ERNET_CUDA(cudaMemcpy(h->d_stem_frag, &sfh, sizeof(StemFrag), cudaMemcpyHostToDevice));
+      }
       memcpy(h->tail.bias, host_f32(ERNET_T_BLOCK_BASE + 24 + ERNET_T_PW_B), 256 * sizeof(float));
       memcpy(h->tail.scale, host_f32(ERNET_T_BLOCK_BASE + 24 + ERNET_T_BN_S), 256 * sizeof(float));
       memcpy(h->tail.shift, host_f32(ERNET_T_BLOCK_BASE + 24 + ERNET_T_BN_T), 256 * sizeof(float));
@@ -647,6 +677,11 @@ int ernet_set_persistent(ernet_handle* h, int on) {
   if (!h) return fail(ERNET_ERR_INVALID_ARG, "null handle");
   if (on < 0 || on > 2) return fail(ERNET_ERR_INVALID_ARG, "schedule must be 0, 1 or 2");
   h->persistent = on;
+  return ERNET_OK;
+}
+int ernet_set_fast_ingest(ernet_handle* h, int on) {
+  if (!h) return fail(ERNET_ERR_INVALID_ARG, "null handle");
+  h->fast_ingest = on != 0;
   return ERNET_OK;
 }
 int ernet_set_debug_taps(ernet_handle* h, int on) {

@@ -30,6 +30,7 @@ struct IngestTables {
   // fused transform+stem kernel: bands of kStemBand conv1 rows
   int fs_max_in_rows = 0;        // input rows such a band needs at most
   int fs_stage_raw = 0;          // 1: the raw rows of a band fit in shared memory and are staged with 16-byte loads
+  int fast5_ok = 0;              // 1: 5 non-negative taps per axis, sums within the no-clamp bound of ingest_fast.cuh
   // device arrays (one allocation): per crop column / row
   int* d_base = nullptr;
   int *d_xmin = nullptr, *d_xlen = nullptr, *d_kx = nullptr;
@@ -567,6 +568,19 @@ inline int build_ingest_tables(IngestTables& t, int H, int W) {
     t.fs_max_in_rows = worst;
     t.fs_stage_raw = ((size_t)worst * W * 3 + 64 <= kRawStageBytes) ? 1 : 0;
     if ((size_t)worst * kCrop * 3 > 72 * 1024) t.fs_max_in_rows = 0;      // fused kernel unavailable: fall back to two kernels
+  }
+
+  {  // ingest_fast.cuh keeps 4 * (2^21 + sum k p) in 32 bits and takes the top byte: needs k >= 0 and 1020 * sum k + 2^23 < 2^32
+    bool ok = t.ksx == 5 && t.ksy == 5;
+    auto check = [&](const std::vector<int>& kk, int ks) {
+      for (int i = 0; i < kCrop && ok; ++i) {
+        long long sum = 0;
+        for (int j = 0; j < ks; ++j) { if (kk[(size_t)i * ks + j] < 0) ok = false; sum += kk[(size_t)i * ks + j]; }
+        if (1020LL * sum + (1LL << 23) >= (1LL << 32) || sum < (1LL << 22) - 4096) ok = false;
+      }
+    };
+    if (ok) { check(kx, t.ksx); check(ky, t.ksy); }
+    t.fast5_ok = ok ? 1 : 0;
   }
 
   float lut[256 * 3];

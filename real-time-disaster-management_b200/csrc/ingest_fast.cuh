@@ -1,0 +1,268 @@
+// Fused eval transform + conv1 for the 16-bit tensor-core engines, 5-tap frames (e.g. 240x240 -> 159): word-wide version
+// of ingest_stem_kernel<.., KS = 5> (ingest.cuh).  Same integer resample (bit-exact with Pillow: two passes, 22-bit
+// coefficients, rounding between the passes - dataloaders/aider.py:421-423), different data movement and a different
+// split of the float work:
+//   phase 0  raw rows of the band: ONE bulk copy (cp.async.bulk, TMA engine) of the contiguous bytes into shared memory
+//   phase 1  horizontal pass: 5 aligned word loads + funnel shifts per output pixel, bytes extracted with PRMT, 15 IMAD
+//            on 4x coefficients (the 8-bit result is the top byte: no shift, no clamp), one RGBX word out
+//   phase 2  vertical pass: four pixels per thread (5 x LDS.128), 60 IMAD, packed RGB bytes out [rows][420]
+//   phase 3  conv1 (model/squeeze_ernet.py:11,25) on mma.sync m16n8k16 fp16 straight from those BYTES: ToTensor and
+//            Normalize (aider.py:424-425) are affine per channel, so they are folded into the conv weights and bias
+//            (w' = w / (255 std_c), b' = b - sum w mean_c / std_c); the A fragments are the uint8 pixels themselves,
+//            turned into exact fp16 by PRMT (0x6400 | v = 1024 + v) and one HSUB2.  This removes the 256x3 table
+//            lookup and the rounding of the normalised tensor to 16 bit that the two-kernel path has; the result is
+//            closer to the fp32 reference, not bit-identical to the two-kernel path.
+// K order of the implicit GEMM: k = ky*10 + (kx*3 + c), 9 real + 1 zero column per ky, 30 -> 32.
+#pragma once
+#include "ingest.cuh"
+#include "tc_common.cuh"
+
+namespace ernet {
+
+constexpr int kFastThreads = 448;            // 14 warps, 2 CTAs per SM; phase 1 uses 3 row groups x 140 columns
+
+struct FastGeom {                             // shared-memory carve-up (bytes), computed on the host
+  int off_hbuf, off_vbuf, off_bar, total;
+};
+
+// Folded conv1 constants in mma.sync fragment order, built once per handle (build_stem_fragments below):
+//   frag[order][lane][s][j][hh]  fp16 pairs w'[k][n], w'[k+1][n], k = 16s + 2t + 8hh, n = 8j + g (lane = 4g + t)
+//   then CS floats: folded bias
+struct StemFrag { uint32_t frag[2][32][8]; float bias[16]; };
+
+template <typename T, int CS>
+__global__ void __launch_bounds__(kFastThreads, 2)
+ingest_stem5_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restrict__ frames_end, int H, int W, int bgr,
+                    const int* __restrict__ xmin, const int* __restrict__ kx, const int* __restrict__ ymin, const int* __restrict__ ylen,
+                    const int* __restrict__ ky, const StemFrag* __restrict__ sf, const __grid_constant__ FastGeom geo,
+                    void* __restrict__ out) {
+  extern __shared__ __align__(128) uint8_t fsm[];
+  const uint32_t* raww = reinterpret_cast<const uint32_t*>(fsm);           // [in_rows][W*3] packed RGB bytes (bulk copy)
+  uint32_t* hbuf4 = reinterpret_cast<uint32_t*>(fsm + geo.off_hbuf);       // [in_rows + 5][140] RGBX words
+  uint8_t* vbuf = fsm + geo.off_vbuf;                                      // [2*band + 2][420] RGB bytes
+  uint64_t* bar = reinterpret_cast<uint64_t*>(fsm + geo.off_bar);
+
+  const int b = blockIdx.y;
+  const int y0 = blockIdx.x * kStemBand;
+  const int y1 = min(y0 + kStemBand, 69);
+  const int n0 = 2 * y0, n1 = 2 * (y1 - 1) + 2;
+  const int r0 = __ldg(ymin + n0);
+  const int in_rows = __ldg(ymin + n1) + __ldg(ylen + n1) - r0;
+  const int tid = threadIdx.x;
+  const int rowb = W * 3;                                                  // bytes per raw row
+
+  if (tid == 0) { tc::mbar_init(bar, 1); tc::fence_mbar_init(); }
+  __syncthreads();
+  pdl_wait();                 // frames may come from the previous kernel of the stream; the stem tensor is read by block 1
+  pdl_launch_dependents();
+
+  // ---- phase 0: the raw rows of the band are contiguous: ONE bulk copy (TMA engine), no instructions per byte.  The
+  // copy starts at the 16-byte boundary below the band; `off` is carried into the byte offsets of phase 1.  A band whose
+  // rounded range leaves [frames, frames_end) (first / last band of an unaligned buffer) is copied by the threads instead.
+  const uint8_t* band = frames + ((size_t)b * H + r0) * rowb;
+  const uint8_t* a0 = reinterpret_cast<const uint8_t*>(reinterpret_cast<size_t>(band) & ~(size_t)15);
+  const int off = (int)(band - a0);
+  const uint32_t bytes = (uint32_t)((off + in_rows * rowb + 15) & ~15);
+  const bool bulk = a0 >= frames && a0 + bytes <= frames_end;
+  if (bulk) {
+    if (tid == 0) { tc::mbar_expect_tx(bar, bytes); tc::bulk_g2s(fsm, a0, bytes, bar); }
+  } else {
+    for (int i = tid; i < (int)(bytes >> 4); i += kFastThreads) {
+      const uint8_t* pv = a0 + (size_t)i * 16;
+      if (pv >= frames && pv + 16 <= frames_end) {
+        reinterpret_cast<uint4*>(fsm)[i] = __ldg(reinterpret_cast<const uint4*>(pv));
+      } else {
+        for (int e = 0; e < 16; ++e) fsm[i * 16 + e] = (pv + e >= frames && pv + e < frames_end) ? __ldg(pv + e) : (uint8_t)0;
+      }
+    }
+  }
+  // per-thread constants of phase 1 while the copy is in flight
+  const int ox = tid % kCrop, rg = tid / kCrop;
+  uint32_t kc[5];
+#pragma unroll
+  for (int t = 0; t < 5; ++t) kc[t] = (uint32_t)__ldg(kx + ox * 5 + t) << 2;      // 4k: the result byte is the top byte
+  const int bo = off + 3 * __ldg(xmin + ox);
+  const int sh = (bo & 3) * 8;
+  if (bulk) { while (!tc::mbar_test_wait(bar, 0)) { } }
+  else __syncthreads();
+
+  // ---- phase 1: horizontal pass.  Thread = output column; 5 aligned words cover the 15 bytes of the 5 taps, a funnel
+  // shift aligns them to the pixel, bytes come out with constant PRMT selectors.  acc = 4 * (2^21 + sum k p) < 2^32.
+  if (tid < 3 * kCrop) {
+    const uint32_t* p = raww + rg * (rowb >> 2) + (bo >> 2);
+    uint32_t* h = hbuf4 + rg * kCrop + ox;
+    for (int r = rg; r < in_rows; r += 3, p += 3 * (rowb >> 2), h += 3 * kCrop) {
+      const uint32_t w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3], w4 = p[4];
+      const uint32_t v[4] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh)};
+      uint32_t a[3] = {1u << 23, 1u << 23, 1u << 23};
+#pragma unroll
+      for (int t = 0; t < 5; ++t)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          a[c] += kc[t] * __byte_perm(v[(3 * t + c) >> 2], 0u, 0x4440u + (uint32_t)((3 * t + c) & 3));
+        }
+      *h = __byte_perm(__byte_perm(a[0], a[1], 0x0073), a[2], 0x7710);    // R | G << 8 | B << 16
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: vertical pass, four pixels per task -> packed RGB bytes
+  const int nrows = n1 - n0 + 1;
+  if (tid < (kFastThreads / 35) * 35)
+  for (int rn = tid / 35, g = tid - (tid / 35) * 35; rn < nrows; rn += kFastThreads / 35) {
+    const int oy = n0 + rn;
+    const uint4* hp = reinterpret_cast<const uint4*>(hbuf4 + (__ldg(ymin + oy) - r0) * kCrop) + g;
+    uint32_t acc[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) acc[j] = 1u << 23;
+#pragma unroll
+    for (int t = 0; t < 5; ++t) {
+      const uint32_t c = (uint32_t)__ldg(ky + oy * 5 + t) << 2;
+      const uint4 q = hp[t * (kCrop / 4)];
+      const uint32_t px[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[3 * j + 0] += c * __byte_perm(px[j], 0u, 0x4440);
+        acc[3 * j + 1] += c * __byte_perm(px[j], 0u, 0x4441);
+        acc[3 * j + 2] += c * __byte_perm(px[j], 0u, 0x4442);
+      }
+    }
+    uint32_t* vp = reinterpret_cast<uint32_t*>(vbuf + rn * (kCrop * 3)) + 3 * g;
+#pragma unroll
+    for (int wd = 0; wd < 3; ++wd)
+      vp[wd] = __byte_perm(__byte_perm(acc[4 * wd], acc[4 * wd + 1], 0x0073), __byte_perm(acc[4 * wd + 2], acc[4 * wd + 3], 0x0073), 0x5410);
+  }
+  __syncthreads();
+
+  // ---- phase 3: conv1 3x3 / stride 2 as an implicit GEMM on mma.sync (16 pixels x 8 channels per instruction)
+  {
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    constexpr int NT = CS / 8;
+    int koff[2][2];                                        // byte offset of this lane's k pairs inside a pixel's window
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int k = 16 * s + 2 * t + 8 * hh;
+        koff[s][hh] = (k / 10) * (kCrop * 3) + (k % 10);
+      }
+    uint32_t bfrag[2][2][2];
+    {
+      const uint4* fp = reinterpret_cast<const uint4*>(sf->frag[bgr ? 1 : 0][lane]);
+      const uint4 f0 = __ldg(fp), f1 = __ldg(fp + 1);
+      bfrag[0][0][0] = f0.x; bfrag[0][0][1] = f0.y; bfrag[0][1][0] = f0.z; bfrag[0][1][1] = f0.w;
+      bfrag[1][0][0] = f1.x; bfrag[1][0][1] = f1.y; bfrag[1][1][0] = f1.z; bfrag[1][1][1] = f1.w;
+    }
+    float bia[NT][2];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { bia[j][0] = __ldg(sf->bias + 8 * j + 2 * t); bia[j][1] = __ldg(sf->bias + 8 * j + 2 * t + 1); }
+    const __half2 k1024 = __floats2half2_rn(1024.f, 1024.f);
+    const int brow = y1 - y0;
+    uint4* img = reinterpret_cast<uint4*>(out) + (size_t)b * 2 * 72 * 72;
+    uint32_t* orow = reinterpret_cast<uint32_t*>(img + (y0 + 2) * 72 + 2) + t;     // lane's 4-byte slot of chunk 0, band row 0, pixel 0
+    for (int ly = warp; ly < brow; ly += kFastThreads / 32) {
+      const uint8_t* vrow = vbuf + (2 * ly) * (kCrop * 3);
+      uint32_t* orow_l = orow + ly * (72 * 4);
+#pragma unroll
+      for (int xg = 0; xg < 5; ++xg) {
+        const int ox0 = xg * 16 + g, ox1 = ox0 + 8;
+        const uint8_t* base0 = vrow + 6 * (xg < 4 ? ox0 : min(ox0, 68));
+        const uint8_t* base1 = vrow + 6 * (xg < 4 ? ox1 : min(ox1, 68));
+        uint32_t afrag[2][4];
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const uint32_t u0 = *reinterpret_cast<const uint16_t*>(base0 + koff[s][hh]);
+            const uint32_t u1 = *reinterpret_cast<const uint16_t*>(base1 + koff[s][hh]);
+            uint32_t f0 = __byte_perm(u0, 0x64646464u, 0x4140), f1 = __byte_perm(u1, 0x64646464u, 0x4140);   // (1024 + v) fp16 pairs
+            __half2 h0 = __hsub2(*reinterpret_cast<const __half2*>(&f0), k1024), h1 = __hsub2(*reinterpret_cast<const __half2*>(&f1), k1024);
+            afrag[s][2 * hh + 0] = *reinterpret_cast<const uint32_t*>(&h0);      // row g
+            afrag[s][2 * hh + 1] = *reinterpret_cast<const uint32_t*>(&h1);      // row g + 8
+          }
+        float acc[NT][4];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) { acc[j][0] = acc[j][2] = bia[j][0]; acc[j][1] = acc[j][3] = bia[j][1]; }
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+          for (int j = 0; j < NT; ++j) StemMma<__half>::mma(acc[j], afrag[s], bfrag[s][j]);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int oxx = half ? ox1 : ox0;
+          if (xg == 4 && oxx >= 69) continue;
+#pragma unroll
+          for (int j = 0; j < NT; ++j) orow_l[j * (72 * 72 * 4) + oxx * 4] = StemMma<T>::pack(acc[j][2 * half], acc[j][2 * half + 1]);
+        }
+      }
+    }
+    // zero halo columns of the band's rows (and the all-zero second chunk of an 8-channel stem)
+    for (int i = tid; i < brow * 72; i += kFastThreads) {
+      const int ly = i / 72, pc = i - ly * 72;
+      const bool halo = pc < 2 || pc >= 71;
+      if (halo) img[(y0 + ly + 2) * 72 + pc] = make_uint4(0, 0, 0, 0);
+      if (halo || CS == 8) img[72 * 72 + (y0 + ly + 2) * 72 + pc] = make_uint4(0, 0, 0, 0);
+    }
+    if (blockIdx.x == 0)
+      for (int i = tid; i < 2 * 2 * 72; i += kFastThreads) img[(i / 144) * 72 * 72 + (i % 144)] = make_uint4(0, 0, 0, 0);
+    if (y1 == 69)
+      for (int i = tid; i < 2 * 72; i += kFastThreads) img[(i / 72) * 72 * 72 + 71 * 72 + (i % 72)] = make_uint4(0, 0, 0, 0);
+  }
+}
+
+// Host: fold ToTensor + Normalize (aider.py:424-425) into conv1 and lay the result out as mma.sync B fragments.
+// w = [27][CS] fp32 (k = (ky*3+kx)*3 + c), bias = [CS].
+inline void build_stem_fragments(const float* w, const float* bias, int cs, StemFrag* out) {
+  const double mean[3] = {0.485, 0.456, 0.406}, stdv[3] = {0.229, 0.224, 0.225};
+  memset(out, 0, sizeof(*out));
+  for (int order = 0; order < 2; ++order) {
+    auto wk = [&](int k, int n) -> float {                 // folded weight of GEMM row k (ky*10 + kx*3 + byte), column n
+      const int kyy = k / 10, off = k % 10;
+      if (kyy >= 3 || off >= 9 || n >= cs) return 0.f;
+      const int kxx = off / 3, cb = off % 3;
+      const int c = order ? 2 - cb : cb;                    // model channel of this byte (order 1 = BGR frames)
+      return (float)((double)w[((kyy * 3 + kxx) * 3 + c) * cs + n] / (255.0 * stdv[c]));
+    };
+    for (int lane = 0; lane < 32; ++lane) {
+      const int g = lane >> 2, t = lane & 3;
+      for (int s = 0; s < 2; ++s)
+        for (int j = 0; j < 2; ++j)
+          for (int hh = 0; hh < 2; ++hh) {
+            const int k0 = 16 * s + 2 * t + 8 * hh, n = 8 * j + g;
+            const __half lo = __float2half_rn(wk(k0, n)), hi = __float2half_rn(wk(k0 + 1, n));
+            uint16_t lob, hib;
+            memcpy(&lob, &lo, 2); memcpy(&hib, &hi, 2);
+            out->frag[order][lane][(s * 2 + j) * 2 + hh] = (uint32_t)lob | ((uint32_t)hib << 16);
+          }
+    }
+  }
+  for (int n = 0; n < cs; ++n) {
+    double s = bias[n];
+    for (int k = 0; k < 27; ++k) s -= (double)w[k * cs + n] * mean[k % 3] / stdv[k % 3];
+    out->bias[n] = (float)s;
+  }
+}
+
+// Geometry + eligibility of the fast path: exactly 5 non-negative taps per axis whose sums leave the 8-bit result in
+// the top byte of 4*acc, rows that are whole words, two CTAs per SM.
+inline bool fast5_geometry(const IngestTables& t, const void* frames, FastGeom& g) {
+  (void)frames;
+  if (!t.fast5_ok || t.fs_max_in_rows <= 0 || (t.W % 4) != 0) return false;
+  const int raw = t.fs_max_in_rows * t.W * 3 + 64;
+  g.off_hbuf = (raw + 127) / 128 * 128;
+  g.off_vbuf = g.off_hbuf + (t.fs_max_in_rows + 5) * kCrop * 4;
+  g.off_bar = (g.off_vbuf + (kStemXnRows + 1) * kCrop * 3 + 16 + 15) / 16 * 16;
+  g.total = g.off_bar + 16;
+  return g.total <= 110 * 1024;
+}
+
+template <typename T, int CS>
+inline int launch_ingest_stem5(const IngestTables& t, const FastGeom& g, const uint8_t* frames, int batch, int bgr, const StemFrag* sf,
+                               void* out, cudaStream_t stream) {
+  dim3 grid((69 + kStemBand - 1) / kStemBand, batch);
+  ERNET_CUDA(launch_pdl(ingest_stem5_kernel<T, CS>, grid, dim3(kFastThreads), (size_t)g.total, stream, frames, frames + (size_t)batch * t.H * t.W * 3, t.H, t.W, bgr,
+                        t.d_xmin, t.d_kx, t.d_ymin, t.d_ylen, t.d_ky, sf, g, out));
+  return ERNET_OK;
+}
+
+}  // namespace ernet

@@ -224,6 +224,13 @@ class _ErnetB200(nn.Module):
         _lib.check(lib.ernet_set_persistent(h, 2 if on is True else int(on)))
         return self
 
+    def set_fast_ingest(self, on=True):
+        """Frames path of the 16-bit engines: folded-normalisation fast kernel (default) or the table-lookup kernel that is
+        bit-identical to ingest() followed by forward()."""
+        lib, h, _ = self._ensure_engine()
+        _lib.check(lib.ernet_set_fast_ingest(h, 1 if on else 0))
+        return self
+
     def set_debug_taps(self, on=True):
         """Also write the intermediates that fused kernels keep on chip (needed for tap('acff4'))."""
         lib, h, _ = self._ensure_engine()
