@@ -172,6 +172,9 @@ int ernet_debug_device_status(unsigned int* out8, int reset);
 /* Study builds (-DERNET_TIMELINE) only: per-CTA clock64 stamps of the persistent block kernels, [3 kernels][148][32][8].
  * Returns ERNET_ERR_UNSUPPORTED in the normal build.                                                    */
 int ernet_debug_timeline(unsigned long long* out, size_t count);
+/* Study builds only: global-timer view of the forward chain, [8 kernels][first entry, first PDL-wait return, last exit,
+ * last entry] in ns; reset != 0 re-arms the minima / maxima.                                               */
+int ernet_debug_chain(unsigned long long* out32, int reset);
 
 /* Per-stage device timing with CUDA events recorded on the launch stream around every kernel of the
  * forward path (bench.py's live roofline measurement).  Off by default; when on, each forward adds

@@ -51,6 +51,7 @@ struct ernet_handle {
   int persistent = 2;           // block-kernel schedule: 0 one image per CTA, 1 persistent CTAs, 2 persistent + CTA pairs for blocks 2, 3
   int num_sms = 148;
   StemFrag* d_stem_frag = nullptr;   // folded conv1 in mma.sync fragment order (16-bit engines)
+  bool pair_block1 = false;     // block 1 on the CTA-pair kernel as well (experiment switch: ERNET_PAIR_BLOCK1=0)
   bool fast_ingest = true;      // word-wide fused transform+conv1 with Normalize folded into conv1 (ingest_fast.cuh)
   tc::TailParams tail;
   void* d_blob = nullptr;
@@ -377,7 +378,11 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
     ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_block<tc::CfgBlock3Q, tc::KIND_I8, tc::OUT_NHWC>(u16(p.p2), wimg(2), h->epi3, u16(p.p3), n, s)));
   } else if (h->persistent) {
     constexpr int K16 = KIND == tc::KIND_I8 ? tc::KIND_F16 : KIND;
-    ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1, K16, tc::OUT_P8>(u16(p.stem), wimg(0), h->epi1, u16(p.p1), n, h->num_sms, s)));
+    if (h->persistent == 2 && h->pair_block1) {
+      ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_cblock<tc::CBlock1, K16, tc::OUT_P8>(u16(p.stem), wimg(0), h->epi1, u16(p.p1), n, h->num_sms, s)));
+    } else {
+      ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1, K16, tc::OUT_P8>(u16(p.stem), wimg(0), h->epi1, u16(p.p1), n, h->num_sms, s)));
+    }
     if (h->persistent == 2) {
       ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_cblock<tc::CBlock2, K16, tc::OUT_P8>(u16(p.p1), wimg(1), h->epi2, u16(p.p2), n, h->num_sms, s)));
       ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_cblock<tc::CBlock3, K16, tc::OUT_NHWC>(u16(p.p2), wimg(2), h->epi3, u16(p.p3), n, h->num_sms, s)));
@@ -455,6 +460,8 @@ static int init_device_attrs() {
   if ((rc = tc::set_pblock_attr<tc::PBlock2, tc::KIND_F16, tc::OUT_P8>())) return rc;
   if ((rc = tc::set_pblock_attr<tc::PBlock3, tc::KIND_BF16, tc::OUT_NHWC>())) return rc;
   if ((rc = tc::set_pblock_attr<tc::PBlock3, tc::KIND_F16, tc::OUT_NHWC>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::CBlock1, tc::KIND_BF16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::CBlock1, tc::KIND_F16, tc::OUT_P8>())) return rc;
   if ((rc = tc::set_cblock_attr<tc::CBlock2, tc::KIND_BF16, tc::OUT_P8>())) return rc;
   if ((rc = tc::set_cblock_attr<tc::CBlock2, tc::KIND_F16, tc::OUT_P8>())) return rc;
   if ((rc = tc::set_cblock_attr<tc::CBlock3, tc::KIND_BF16, tc::OUT_NHWC>())) return rc;
@@ -517,6 +524,7 @@ int ernet_create(ernet_handle** out, int arch, int precision, int device) {
   if (!h) return fail(ERNET_ERR_INVALID_ARG, "out of host memory");
   h->arch = arch; h->precision = precision; h->device = device;
   h->num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("ERNET_PAIR_BLOCK1")) h->pair_block1 = atoi(e) != 0;
   *out = h;
   return ERNET_OK;
 }
@@ -955,6 +963,21 @@ int ernet_debug_timeline(unsigned long long* out, size_t count) {
   return ERNET_OK;
 #else
   (void)out; (void)count;
+  return fail(ERNET_ERR_UNSUPPORTED, "library was built without -DERNET_TIMELINE");
+#endif
+}
+
+int ernet_debug_chain(unsigned long long* out32, int reset) {
+#ifdef ERNET_TIMELINE
+  if (out32) ERNET_CUDA(cudaMemcpyFromSymbol(out32, tc::g_chain, 32 * sizeof(unsigned long long)));
+  if (reset) {
+    unsigned long long z[32];
+    for (int k = 0; k < 8; ++k) { z[4 * k] = z[4 * k + 1] = ~0ULL; z[4 * k + 2] = z[4 * k + 3] = 0ULL; }
+    ERNET_CUDA(cudaMemcpyToSymbol(tc::g_chain, z, sizeof(z)));
+  }
+  return ERNET_OK;
+#else
+  (void)out32; (void)reset;
   return fail(ERNET_ERR_UNSUPPORTED, "library was built without -DERNET_TIMELINE");
 #endif
 }

@@ -51,10 +51,12 @@ ingest_stem5_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restric
   const int tid = threadIdx.x;
   const int rowb = W * 3;                                                  // bytes per raw row
 
+  ERNET_CHAIN_ENTRY(0);
   if (tid == 0) { tc::mbar_init(bar, 1); tc::fence_mbar_init(); }
   __syncthreads();
   pdl_wait();                 // frames may come from the previous kernel of the stream; the stem tensor is read by block 1
   pdl_launch_dependents();
+  ERNET_CHAIN_WAITED(0);
 
   // ---- phase 0: the raw rows of the band are contiguous: ONE bulk copy (TMA engine), no instructions per byte.  The
   // copy starts at the 16-byte boundary below the band; `off` is carried into the byte offsets of phase 1.  A band whose
@@ -208,6 +210,7 @@ ingest_stem5_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restric
     if (y1 == 69)
       for (int i = tid; i < 2 * 72; i += kFastThreads) img[(i / 72) * 72 * 72 + 71 * 72 + (i % 72)] = make_uint4(0, 0, 0, 0);
   }
+  ERNET_CHAIN_EXIT(0);
 }
 
 // Host: fold ToTensor + Normalize (aider.py:424-425) into conv1 and lay the result out as mma.sync B fragments.

@@ -26,6 +26,8 @@
 namespace ernet {
 namespace tc {
 
+constexpr int kCThreads = 384;   // 12 warps
+
 template <int NC_, int N_, int HIN_, int HU_, int GX_, int NSLOT_, bool WRES_, int WSTAGES_, bool POOL_ = true,
           bool ACT_ = true, int NREAL_ = N_>
 struct CCfg {
@@ -105,7 +107,7 @@ __device__ __forceinline__ void mma2_commit(uint64_t* bar) {
 }
 
 template <class Cfg, int KIND, int OUT>
-__global__ void __launch_bounds__(kPThreads, 1)
+__global__ void __launch_bounds__(kCThreads, 1)
 acff_cblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
                    const __grid_constant__ EpiParams<Cfg::N> par, uint16_t* __restrict__ out, int batch) {
   constexpr int N = Cfg::N, NH = Cfg::NH, GX = Cfg::GX, NSLOT = Cfg::NSLOT, BW = Cfg::BW, OP = Cfg::OP, KS = Cfg::KS;
@@ -113,7 +115,7 @@ acff_cblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
   static_assert(KIND != KIND_I8, "the CTA-pair kernel is the 16-bit path");
   constexpr uint32_t IDESC = instr_desc(1u, BF16 ? 1u : 0u, 256u, (uint32_t)N);
   constexpr int OUT_CHUNKS = Cfg::NREAL / 8;
-  constexpr int tl_kernel = Cfg::NC == 8 ? 1 : 2;   // timeline slot (study builds)
+  constexpr int tl_kernel = Cfg::NC == 2 ? 0 : Cfg::NC == 8 ? 1 : 2;   // timeline slot (study builds)
   (void)tl_kernel;
 
   extern __shared__ __align__(128) uint8_t smem[];
@@ -139,6 +141,7 @@ acff_cblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
   // unit of this CTA in round k (the last pair-unit may have no second half: that CTA recomputes the last unit, no stores)
   auto unit_of = [&](int k, bool& dup) { const int u = 2 * (k * npairs + pair) + (int)rank; dup = u >= total_units; return dup ? total_units - 1 : u; };
 
+  ERNET_CHAIN_ENTRY(tl_kernel + 1);
   if (threadIdx.x == 0) {
     *abort_flag = 0u;
     for (int i = 0; i < 16; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 1); mbar_init(&w_full[i], 1); }
@@ -160,6 +163,7 @@ acff_cblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
   if (warp == 0) {
     // ------------------------------------------------------------------ input producer: one box per (unit, K step)
     pdl_wait();
+    ERNET_CHAIN_WAITED(tl_kernel + 1);
     if (lane == 0) {
       int q = 0;
       for (int k = 0; k < nk; ++k) {
@@ -310,6 +314,7 @@ acff_cblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                       // the peer's shared memory and barriers stay alive until both CTAs are done
+  ERNET_CHAIN_EXIT(tl_kernel + 1);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc2(tmem_base, 512);
@@ -365,7 +370,7 @@ inline int max_pairs(int num_sms) {
   static int cached = -1;
   if (cached < 0) {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(num_sms / 2 * 2); cfg.blockDim = dim3(kPThreads); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.gridDim = dim3(num_sms / 2 * 2); cfg.blockDim = dim3(kCThreads); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -386,7 +391,7 @@ inline int launch_acff_cblock(const void* in, const void* wimg, const EpiParams<
   if ((rc = make_weight_map<Cfg>(&map_w, wimg))) return rc;
   const int pair_units = (batch * Cfg::UNITS_PER_IMG + 1) / 2;
   const int pairs = pair_units < max_pairs<Cfg, KIND, OUT>(num_sms) ? pair_units : max_pairs<Cfg, KIND, OUT>(num_sms);
-  ERNET_CUDA(launch_pdl_pair(acff_cblock_kernel<Cfg, KIND, OUT>, dim3(2 * pairs), dim3(kPThreads), Cfg::SMEM_BYTES, stream, map_in, map_w, par,
+  ERNET_CUDA(launch_pdl_pair(acff_cblock_kernel<Cfg, KIND, OUT>, dim3(2 * pairs), dim3(kCThreads), Cfg::SMEM_BYTES, stream, map_in, map_w, par,
                              static_cast<uint16_t*>(out), batch));
   return ERNET_OK;
 }
@@ -398,6 +403,7 @@ inline int set_cblock_attr() {
 }
 
 // Pair configurations: GX tiles per CTA per unit, input slots (K steps in flight), weight residency / ring depth (bundles).
+using CBlock1 = CCfg<2, 64, 69, 66, 3, 4, true, 1>;              // 26 KB of weights resident per CTA + 4 x 21 KB slots (one K step per unit)
 using CBlock2 = CCfg<8, 96, 33, 30, 2, 5, true, 1>;             // 154 KB of weights resident per CTA + 5 x 15 KB slots
 using CBlock3 = CCfg<12, 128, 15, 12, 2, 12, false, 9>;         // 12 x 10 KB slots (two units) + 9 x 10 KB weight bundles
 

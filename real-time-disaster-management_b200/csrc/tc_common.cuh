@@ -77,8 +77,17 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volati
 #ifdef ERNET_TIMELINE
 __device__ unsigned long long g_timeline[3 * 148 * 32 * 8];
 #define ERNET_TL(k, j) do { if (blockIdx.x < 148 && (k) < 32) g_timeline[((tl_kernel * 148 + blockIdx.x) * 32 + (k)) * 8 + (j)] = (unsigned long long)clock64(); } while (0)
+// whole-chain view on the global timer: per kernel {first CTA entry, first return from the PDL wait, last CTA exit, last CTA entry}
+__device__ unsigned long long g_chain[8][4];
+__device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define ERNET_CHAIN_ENTRY(kid) do { if (threadIdx.x == 0) { const unsigned long long t_ = ::ernet::tc::gtime_ns(); atomicMin(&::ernet::tc::g_chain[kid][0], t_); atomicMax(&::ernet::tc::g_chain[kid][3], t_); } } while (0)
+#define ERNET_CHAIN_WAITED(kid) do { if (threadIdx.x == 0) atomicMin(&::ernet::tc::g_chain[kid][1], ::ernet::tc::gtime_ns()); } while (0)
+#define ERNET_CHAIN_EXIT(kid) do { if (threadIdx.x == 0) atomicMax(&::ernet::tc::g_chain[kid][2], ::ernet::tc::gtime_ns()); } while (0)
 #else
 #define ERNET_TL(k, j) do { } while (0)
+#define ERNET_CHAIN_ENTRY(kid) do { } while (0)
+#define ERNET_CHAIN_WAITED(kid) do { } while (0)
+#define ERNET_CHAIN_EXIT(kid) do { } while (0)
 #endif
 
 // One lane of a converged warp (elect.sync): keeps the surrounding code warp-uniform so that descriptors

@@ -12,7 +12,11 @@
 //   * weights are loaded once per CTA (block 1, conv_red2) or streamed through the ring per unit;
 //   * units are dealt round-robin to the CTAs: 256 images x 15 units over 148 SMs leaves < 4 % imbalance.
 // Roles: warp 0 input producer, warp 1 MMA issuer, warp 2 weight-ring producer, warps 3-10 epilogue, warp 11 writes the
-// zero halo of the output images (kept off the producer's critical path: ~10 k cycles per image when it was inline).
+// zero halo of the output images (kept off the producer's critical path: ~10 k cycles per image when it was inline), warp 12
+// second MMA issuer (resident-weight configurations).  Anything the issuing thread waits on between two MMAs - an
+// mbarrier test, a shared-memory load, even tcgen05.commit - empties the tensor pipe for 50-200 cycles (tools/
+// mma_commit.cu: 4060 instead of 3744 cycles per unit of 75 MMAs); with even units issued by warp 1 and odd units by
+// warp 12 one thread's boundary stalls sit under the other thread's MMAs (3736 cycles per unit).
 #pragma once
 #include <cuda.h>   // CUtensorMap (types only; the encode function is fetched through the runtime)
 
@@ -50,7 +54,7 @@ struct PCfg {
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-constexpr int kPThreads = 384;   // 12 warps
+constexpr int kPThreads = 416;   // 13 warps
 
 // cp.async.bulk.tensor.4d: box of the tensor described by `tmap` at coordinates (c0..c3), completion on `bar`.
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
@@ -86,12 +90,15 @@ acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t* 
   uint64_t* acc_empty = bars + 27;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
   volatile uint32_t* abort_flag = tmem_slot + 1;
+  volatile uint32_t* turn = tmem_slot + 2;     // units whose MMAs are (nearly) all issued: hand-over between the two issuers
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_units = batch * Cfg::UNITS_PER_IMG;
+  ERNET_CHAIN_ENTRY(1);
 
   if (threadIdx.x == 0) {
     *abort_flag = 0u;
+    *turn = 0u;
     mbar_init(bar_w, 1);
     for (int i = 0; i < 4; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 1); }
     for (int i = 0; i < 8; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
@@ -114,6 +121,7 @@ acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t* 
       bulk_g2s(s_w, wimg, Cfg::W_BYTES, bar_w);
     }
     pdl_wait();
+    ERNET_CHAIN_WAITED(1);
     int k = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++k) {
       const int img = u / Cfg::UNITS_PER_IMG, r = u - img * Cfg::UNITS_PER_IMG;
@@ -142,9 +150,13 @@ acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t* 
         if (!ok) break;
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
+  } else if (warp == 1 || warp == 12) {
+    // ------------------------------------------------------------------ MMA issuers: warp 1 takes units k = 0, 2, .. and warp 12
+    // the odd ones when the weights are resident (each unit has its own TMEM buffer k & 1 and input stage, so the two
+    // streams are independent); with streamed weights the ring is consumed in order by warp 1 alone
+    constexpr int NISSUE = Cfg::WRES ? 2 : 1;
+    const int me = warp == 1 ? 0 : 1;
+    if (me < NISSUE && elect_one()) {
       bool ok = true;
       if (Cfg::WRES) ok = mbar_wait(bar_w, 0, abort_flag, 0x502u);
       const uint32_t in_addr = smem_u32(smem), w_addr = smem_u32(s_w);
@@ -154,8 +166,8 @@ acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t* 
       const uint32_t w_lo0 = desc_lo(w_addr, N * 16);
       int ws = 0;
       uint32_t wphase = 0;
-      int k = 0;
-      for (int u = blockIdx.x; u < total_units && ok; u += gridDim.x, ++k) {
+      int k = me;
+      for (int u = blockIdx.x + me * (int)gridDim.x; u < total_units && ok; u += NISSUE * (int)gridDim.x, k += NISSUE) {
         const int r = u % Cfg::UNITS_PER_IMG, ux = r % Cfg::UX;
         const int ntile = min(GX, Cfg::TCOLS - ux * GX);
         const int st = k % NSTAGE, buf = k & 1, use = k >> 1;
@@ -164,6 +176,10 @@ acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t* 
         if (ok && use > 0) ok = mbar_wait(&acc_empty[buf], (use - 1) & 1, abort_flag, 0x504u, k);
         ERNET_TL(k, 2);
         if (!ok) break;
+        if (NISSUE > 1) {          // start when the other issuer is within a few MMAs of the end of unit k - 1 (timing only:
+          while (*turn < (uint32_t)k) { if (*abort_flag) { ok = false; break; } }   // the two units share no data)
+          if (!ok) break;
+        }
         tc_fence_after();
         // tile tl of the unit: output origin = box origin + (2, 2 + 8*tl)
         const uint32_t a_lo0 = desc_lo(in_addr + st * Cfg::STAGE_BYTES + (uint32_t)((2 * BW + 2) * 16), Cfg::CHUNK_BYTES);
@@ -180,6 +196,7 @@ acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t* 
             b_lo = w_lo0 + (uint32_t)(ws * (Cfg::TAP_BYTES >> 4));
           }
           const uint32_t toff = Cfg::TAPS == 1 ? 0u : (uint32_t)(tap_dy(tap) * BW + tap_dx(tap));
+          if (NISSUE > 1 && tap == Cfg::TAPS - 4) *turn = (uint32_t)(k + 1);
 #pragma unroll
           for (int tl = 0; tl < GX; ++tl) {
             if (tl < ntile) {
@@ -251,6 +268,7 @@ acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t* 
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) ERNET_TL(31, 7);
+  ERNET_CHAIN_EXIT(1);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);

@@ -86,6 +86,7 @@ acff4_head_kernel(const uint16_t* __restrict__ in /*(B,6,6,C4)*/, const float* _
   const int img0 = blockIdx.x * Cfg::IMGS;
   const int nimg = min(Cfg::IMGS, batch - img0);
 
+  ERNET_CHAIN_ENTRY(4);
   if (threadIdx.x == 0) {
     *abort_flag = 0u;
     mbar_init(bar_in, 1);
@@ -112,6 +113,7 @@ acff4_head_kernel(const uint16_t* __restrict__ in /*(B,6,6,C4)*/, const float* _
                Cfg::STAGE_BYTES, &w_full[st]);
     }
     pdl_wait();
+    ERNET_CHAIN_WAITED(4);
     mbar_expect_tx(bar_in, (uint32_t)(nimg * 36 * C4 * 2));
     bulk_g2s(smem, reinterpret_cast<const uint8_t*>(in) + (size_t)img0 * 36 * C4 * 2, (uint32_t)(nimg * 36 * C4 * 2), bar_in);
   }
@@ -246,6 +248,7 @@ acff4_head_kernel(const uint16_t* __restrict__ in /*(B,6,6,C4)*/, const float* _
   }
   tc_fence_before();
   __syncthreads();
+  ERNET_CHAIN_EXIT(4);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
