@@ -336,10 +336,17 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
         ERNET_LAUNCH_CHECK("stem_p8_kernel");
       }
       auto wimgr = [&](int k) { return h->t[ERNET_T_TC_BASE + 4 * k + ERNET_T_TC_WIMG].dev; };
-      ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_block<tc::CfgBlock1, KIND, tc::OUT_P8>(u16(p.stem), wimgr(0), h->epi1, u16(p.p1), n, s)));
-      ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_block<tc::CfgBlock2R, KIND, tc::OUT_P8>(u16(p.p1), wimgr(1), h->epi2, u16(p.a2), n, s)));
-      ERNET_STAGE(ERNET_STAGE_RED2, (tc::launch_acff_block<tc::CfgRed2R, KIND, tc::OUT_P8>(u16(p.a2), h->t[ERNET_T_TC_RED2_WIMG].dev, h->epi_r2, u16(p.p2), n, s)));
-      ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_block<tc::CfgBlock3R, KIND, tc::OUT_NHWC>(u16(p.p2), wimgr(2), h->epi3, u16(p.p3), n, s)));
+      if (h->persistent == 2) {
+        ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1, KIND, tc::OUT_P8>(u16(p.stem), wimgr(0), h->epi1, u16(p.p1), n, h->num_sms, s)));
+        ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_cblock<tc::CBlock2R, KIND, tc::OUT_P8>(u16(p.p1), wimgr(1), h->epi2, u16(p.a2), n, h->num_sms, s)));
+        ERNET_STAGE(ERNET_STAGE_RED2, (tc::launch_acff_pblock<tc::PRed2R, KIND, tc::OUT_P8>(u16(p.a2), h->t[ERNET_T_TC_RED2_WIMG].dev, h->epi_r2, u16(p.p2), n, h->num_sms, s)));
+        ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_cblock<tc::CBlock3R, KIND, tc::OUT_NHWC>(u16(p.p2), wimgr(2), h->epi3, u16(p.p3), n, h->num_sms, s)));
+      } else {
+        ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_block<tc::CfgBlock1, KIND, tc::OUT_P8>(u16(p.stem), wimgr(0), h->epi1, u16(p.p1), n, s)));
+        ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_block<tc::CfgBlock2R, KIND, tc::OUT_P8>(u16(p.p1), wimgr(1), h->epi2, u16(p.a2), n, s)));
+        ERNET_STAGE(ERNET_STAGE_RED2, (tc::launch_acff_block<tc::CfgRed2R, KIND, tc::OUT_P8>(u16(p.a2), h->t[ERNET_T_TC_RED2_WIMG].dev, h->epi_r2, u16(p.p2), n, s)));
+        ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_block<tc::CfgBlock3R, KIND, tc::OUT_NHWC>(u16(p.p2), wimgr(2), h->epi3, u16(p.p3), n, s)));
+      }
       ERNET_STAGE(ERNET_STAGE_RED3, launch_pointwise<T>(buf(p.p3), n, 6, 6, 128, 64, h->f(ERNET_T_RED3_W), h->f(ERNET_T_RED3_B), nullptr, nullptr, 0, 0, buf(p.r3), s));
       return run_tail<T>(h, buf(p.r3), buf(p.cat4), buf(p.a4), n, probs, logits, s);
     } else {
@@ -466,6 +473,12 @@ static int init_device_attrs() {
   if ((rc = tc::set_cblock_attr<tc::CBlock2, tc::KIND_F16, tc::OUT_P8>())) return rc;
   if ((rc = tc::set_cblock_attr<tc::CBlock3, tc::KIND_BF16, tc::OUT_NHWC>())) return rc;
   if ((rc = tc::set_cblock_attr<tc::CBlock3, tc::KIND_F16, tc::OUT_NHWC>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::CBlock2R, tc::KIND_BF16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::CBlock2R, tc::KIND_F16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::CBlock3R, tc::KIND_BF16, tc::OUT_NHWC>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::CBlock3R, tc::KIND_F16, tc::OUT_NHWC>())) return rc;
+  if ((rc = tc::set_pblock_attr<tc::PRed2R, tc::KIND_BF16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_pblock_attr<tc::PRed2R, tc::KIND_F16, tc::OUT_P8>())) return rc;
   if ((rc = tc::set_tail_attrs<tc::TailCfg128>())) return rc;
   if ((rc = tc::set_tail_attrs<tc::TailCfg64>())) return rc;
   return ERNET_OK;

@@ -406,6 +406,9 @@ inline int set_cblock_attr() {
 using CBlock1 = CCfg<2, 64, 69, 66, 3, 4, true, 1>;              // 26 KB of weights resident per CTA + 4 x 21 KB slots (one K step per unit)
 using CBlock2 = CCfg<8, 96, 33, 30, 2, 5, true, 1>;             // 154 KB of weights resident per CTA + 5 x 15 KB slots
 using CBlock3 = CCfg<12, 128, 15, 12, 2, 12, false, 9>;         // 12 x 10 KB slots (two units) + 9 x 10 KB weight bundles
+// Squeeze_RedConv: ACFF2 without the pool (conv_red2 sits between it and pool2), ACFF3 on 48 input channels
+using CBlock2R = CCfg<8, 96, 33, 30, 2, 5, true, 1, /*POOL*/ false>;
+using CBlock3R = CCfg<6, 128, 15, 12, 2, 9, false, 9>;
 
 }  // namespace tc
 }  // namespace ernet

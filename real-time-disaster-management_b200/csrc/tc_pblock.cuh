@@ -32,8 +32,9 @@ struct PCfg {
   static constexpr bool WRES = WRES_, POOL = POOL_, ACT = ACT_;
   static constexpr int TAPS = TAPS_, NREAL = NREAL_;
   static constexpr int WP = HIN + 3;                                   // padded image pitch / height
-  static constexpr int BW = (8 * GX + 6) < WP ? (8 * GX + 6) : WP;     // box width  (pixels)
-  static constexpr int BH = 22 < WP ? 22 : WP;                         // box height (16 output rows + 6)
+  static constexpr int HALO = TAPS == 1 ? 0 : 1;                       // a 1x1 convolution needs no neighbours: the box is the tiles
+  static constexpr int BW = (8 * GX + 6 * HALO) < WP ? (8 * GX + 6 * HALO) : WP;     // box width  (pixels)
+  static constexpr int BH = (16 + 6 * HALO) < WP ? (16 + 6 * HALO) : WP;             // box height (16 output rows + 6)
   static constexpr int CHUNK_BYTES = BH * BW * 16;
   static constexpr int STAGE_BYTES = NC * CHUNK_BYTES;
   static constexpr int TR = (HU + 15) / 16, TCOLS = (HU + 7) / 8;
@@ -131,7 +132,7 @@ acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t* 
         if (use > 0 && !mbar_wait(&in_empty[st], (use - 1) & 1, abort_flag, 0x500u, k)) break;
         ERNET_TL(k, 0);
         mbar_expect_tx(&in_full[st], Cfg::STAGE_BYTES);
-        tma_load_4d(smem + st * Cfg::STAGE_BYTES, &tmap_in, ux * GX * 8 * 4, ty * 16, 0, img, &in_full[st]);
+        tma_load_4d(smem + st * Cfg::STAGE_BYTES, &tmap_in, (ux * GX * 8 + 2 * (1 - Cfg::HALO)) * 4, ty * 16 + 2 * (1 - Cfg::HALO), 0, img, &in_full[st]);
       }
     }
   } else if (warp == 2) {
@@ -182,7 +183,7 @@ acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t* 
         }
         tc_fence_after();
         // tile tl of the unit: output origin = box origin + (2, 2 + 8*tl)
-        const uint32_t a_lo0 = desc_lo(in_addr + st * Cfg::STAGE_BYTES + (uint32_t)((2 * BW + 2) * 16), Cfg::CHUNK_BYTES);
+        const uint32_t a_lo0 = desc_lo(in_addr + st * Cfg::STAGE_BYTES + (uint32_t)(Cfg::HALO * (2 * BW + 2) * 16), Cfg::CHUNK_BYTES);
         const uint32_t d0 = tmem_base + (uint32_t)(buf * GX * N);
 #pragma unroll TAP_UNROLL
         for (int tap = 0; tap < Cfg::TAPS; ++tap) {
@@ -196,7 +197,7 @@ acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t* 
             b_lo = w_lo0 + (uint32_t)(ws * (Cfg::TAP_BYTES >> 4));
           }
           const uint32_t toff = Cfg::TAPS == 1 ? 0u : (uint32_t)(tap_dy(tap) * BW + tap_dx(tap));
-          if (NISSUE > 1 && tap == Cfg::TAPS - 4) *turn = (uint32_t)(k + 1);
+          if (NISSUE > 1 && tap == (Cfg::TAPS > 4 ? Cfg::TAPS - 4 : 0)) *turn = (uint32_t)(k + 1);
 #pragma unroll
           for (int tl = 0; tl < GX; ++tl) {
             if (tl < ntile) {
@@ -333,6 +334,8 @@ inline int set_pblock_attr() {
 using PBlock1 = PCfg<2, 64, 69, 66, 3, 3, true, 1>;            // 15 units / image, 21 KB boxes, weights resident
 using PBlock2 = PCfg<8, 96, 33, 30, 2, 2, false, 8>;           //  4 units / image, 62 KB boxes
 using PBlock3 = PCfg<12, 128, 15, 12, 2, 2, false, 4>;         //  1 unit  / image, box = whole padded image
+// Squeeze_RedConv: conv_red2 (96 -> 48, 1x1, bias only) + 2x2 pool as a 1-tap instance: 2 units / image, 98 KB boxes
+using PRed2R = PCfg<12, 64, 30, 30, 4, 2, true, 1, /*POOL*/ true, /*TAPS*/ 1, /*ACT*/ false, /*NREAL*/ 48>;
 
 }  // namespace tc
 }  // namespace ernet

@@ -445,3 +445,58 @@ def test_fused_transform_conv1_equals_two_kernel_path(hw, arch, prec, dev):
     big[7:] = ft.flatten()
     l_view = m.forward_frames(big[7:].view(ft.shape), return_logits=True)[1]
     assert torch.equal(l_view, l_fused)
+
+
+# ------------------------------------------------------------------------------------ schedules of the tensor-core engine
+@pytest.mark.gpu
+@pytest.mark.parametrize("arch", fixtures.ARCHS)
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_block_kernel_schedules_agree(arch, prec, dev):
+    """The block kernels exist in three schedules (one image per CTA, persistent CTAs, persistent + CTA pairs with
+    tcgen05 cta_group::2).  Same folded weights everywhere: 0 and 1 issue the same MMAs in the same order (bitwise
+    equal for Squeeze_ErNET, where both run blocks 1-3 with the tap-outer order), 2 runs K outer (rounding differs), and
+    every schedule meets the oracle tolerance, for batches that leave CTA pairs with a missing half (odd unit counts)."""
+    sd = fixtures.get_state_dict(arch, "shipped")
+    for B in (1, 3, 37):
+        x = fixtures.normal_tensors(B, seed=100 + B)
+        ref = E.forward(sd, x, arch, dtype=np.float64)["logits"]
+        xt = torch.from_numpy(x).to(dev)
+        m = rtdm_b200.from_state_dict(arch, sd, dev, prec)
+        out = {}
+        for sched in (0, 1, 2):
+            m.set_persistent(sched)
+            out[sched] = m.forward_with_logits(xt)[1].clone()
+            lg = out[sched].double().cpu().numpy()
+            assert _rel(lg, ref) <= TOL[prec], (sched, B)
+            assert _top1_ok(lg, ref, TOL[prec]), (sched, B)
+        if arch == "squeeze-ernet":
+            assert torch.equal(out[0], out[1])
+        assert _rel(out[2].double().cpu().numpy(), out[0].double().cpu().numpy()) <= 1e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("arch,prec", [("squeeze-ernet", "bf16"), ("squeeze-redconv", "fp16")])
+def test_fast_ingest_matches_table_lookup_kernel(arch, prec, dev):
+    """240x240 frames take the word-wide fused transform+conv1 kernel with Normalize folded into conv1; the
+    table-lookup kernel (bit-identical to ingest() + forward()) stays selectable.  Both meet the oracle tolerance, agree
+    with each other to 16-bit rounding, accept BGR frames and unaligned buffers."""
+    sd = fixtures.get_state_dict(arch, "shipped")
+    frames = np.concatenate([fixtures.noise_frames(5, seed=71), fixtures.smooth_frames(4, seed=72)], 0)
+    ref = E.forward(sd, I.ingest(frames), arch, dtype=np.float64)["logits"]
+    ft = torch.from_numpy(frames).to(dev)
+    m = rtdm_b200.from_state_dict(arch, sd, dev, prec)
+    l_fast = m.forward_frames(ft, return_logits=True)[1]
+    m.set_fast_ingest(False)
+    l_slow = m.forward_frames(ft, return_logits=True)[1]
+    m.set_fast_ingest(True)
+    for lg in (l_fast, l_slow):
+        assert _rel(lg.double().cpu().numpy(), ref) <= TOL[prec]
+        assert _top1_ok(lg.double().cpu().numpy(), ref, TOL[prec])
+    assert not torch.equal(l_fast, l_slow)                       # two different kernels really ran
+    assert _rel(l_fast.double().cpu().numpy(), l_slow.double().cpu().numpy()) <= 1e-2
+    l_bgr = m.forward_frames(torch.from_numpy(frames[..., ::-1].copy()).to(dev), bgr=True, return_logits=True)[1]
+    assert torch.equal(l_bgr, l_fast)
+    for shift in (1, 7, 16):                                      # first / last band of an unaligned buffer: guarded copy
+        big = torch.zeros(frames.size + shift, dtype=torch.uint8, device=dev)
+        big[shift:] = ft.flatten()
+        assert torch.equal(m.forward_frames(big[shift:].view(ft.shape), return_logits=True)[1], l_fast)
