@@ -37,3 +37,8 @@ for kern in range(3):
                 break
             r = [int(v - t0) if v else -1 for v in a[k, :6]]
             print(f"  unit {k:2d}: tma {r[0]:7d} landed {r[1]:7d} accfree {r[2]:7d} issued {r[3]:7d} accfull {r[4]:7d} epidone {r[5]:7d}")
+
+print("--- acff4+head (cta 0, 1, 100): cycles from entry: pdl wait returned, input landed, depthwise done, accumulators complete, epilogue done")
+for cta in (0, 1, 100):
+    a = t[2, cta, 20]
+    print(f"  cta {cta}: " + " ".join(str(int(v - a[0])) for v in a[1:6]))
