@@ -46,7 +46,7 @@ MACS_PER_IMAGE = {"squeeze-ernet": 45.48e6, "squeeze-redconv": 38.80e6}      # S
 # algorithmic work per image of each stage: (flops, bytes moved at 16-bit)
 STAGE_WORK = {
     # frames path: transform + conv1 fused (uint8 frame in, stem tensor out; the 140x140 tensor stays on chip)
-    "ingest": (2 * 2.057e6, 240 * 240 * 3 + 69 * 69 * 16 * 2),
+    "ingest": (2 * 2.057e6, 240 * 240 * 3 + 2 * 72 * 72 * 16),
     "stem": (2 * 2.057e6, 140 * 140 * 3 * 2 + 69 * 69 * 16 * 2),
     "dw1": (2 * 1.939e6, 69 * 69 * 16 * 2 + 66 * 66 * 48 * 2),
     "pw1": (2 * 13.790e6 * (66 * 66) / (67 * 67), 66 * 66 * 48 * 2 + 33 * 33 * 64 * 2),
@@ -64,6 +64,22 @@ STAGE_WORK = {
     "tc_block3": (2 * (12 * 12 * 96 * 27 + 12 * 12 * 288 * 128), 12 * 18 * 18 * 16 + 6 * 6 * 128 * 2),
 }
 GEMM_STAGES = {"pw1", "pw2", "pw3", "pw4", "tc_block1", "tc_block2", "tc_block3", "tc_block4"}
+# FLOPs the tensor-core block kernels actually ISSUE per image (25-tap dense form, padded 16x8 tiles): reported next to
+# the algorithmic figure so that the roofline fraction and the tensor-pipe utilisation can both be read off
+ISSUED_FLOPS = {
+    "squeeze-ernet": {"tc_block1": 45 * 25 * 1 * 2 * 128 * 64 * 16, "tc_block2": 8 * 25 * 4 * 2 * 128 * 96 * 16,
+                      "tc_block3": 2 * 25 * 6 * 2 * 128 * 128 * 16, "tc_block4": 24 * 2 * 128 * 256 * 16 // 2},
+    "squeeze-redconv": {"tc_block1": 45 * 25 * 1 * 2 * 128 * 64 * 16, "tc_block2": 8 * 25 * 4 * 2 * 128 * 96 * 16,
+                        "tc_block3": 2 * 25 * 3 * 2 * 128 * 128 * 16, "tc_block4": 12 * 2 * 128 * 256 * 16 // 2},
+}
+
+
+def workload_name(arch, precision, batch):
+    model = {"squeeze-ernet": "Squeeze-ErNet", "squeeze-redconv": "Squeeze-ErNet-RedConv"}[arch]
+    cfg = {("squeeze-ernet", "bf16", 256): "BASELINE.json configs[1]", ("squeeze-redconv", "fp16", 1024): "BASELINE.json configs[2]",
+           ("squeeze-ernet", "int8", 4096): "BASELINE.json configs[3]"}.get((arch, precision, batch), "non-headline configuration")
+    return (f"{model} {precision} batch {batch} per GPU on 1xB200 ({cfg}): 240x240x3 uint8 frames -> eval transform -> "
+            "forward -> probabilities")
 
 
 def load_peaks():
@@ -129,7 +145,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_run(steps, warmup, sample_frames):
+def cpu_reference_run(steps, warmup, sample_frames, ARCH=ARCH):
     """Times the reference's CPU path on a bounded sample per step.  Returns (frames_per_s, info)."""
     import fixtures
     from oracle import ernet_torch as T
@@ -164,8 +180,7 @@ def reference_main(args, rank):
         "impl": "reference", "metric": "images/sec", "value": fps, "unit": "images/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"Squeeze-ErNet bf16 batch {BATCH} per GPU on 1xB200 (BASELINE.json configs[1]): "
-                               "240x240x3 uint8 frames -> eval transform -> forward -> probabilities",
+        "config": {"workload": workload_name(ARCH, PRECISION, BATCH),
                    "arch": ARCH, "reference_arm": f"CPU fp32, bounded sample of {sample} of those frames per step"},
         "cpu_baseline": info,
         "e2e": {"value": fps, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -191,10 +206,15 @@ def gpu_main(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    ARCH, PRECISION, BATCH = args.arch, args.precision, args.batch
     sd = fixtures.get_state_dict(ARCH, "shipped")
     model = rtdm_b200.from_state_dict(ARCH, sd, dev, PRECISION)
+    if PRECISION == "int8":
+        model.calibrate()
+    if PRECISION in ("fp32", "int8") or args.schedule != "pairs":
+        pass                                 # fp32: CUDA-core engine; int8: one image per CTA (schedule switch ignored)
     model.prepare_ingest(*FRAME)
-    model.set_persistent(args.schedule == "persistent")
+    model.set_persistent({"pairs": 2, "persistent": 1, "per-image": 0}[args.schedule])
 
     # synthetic inputs: N_INPUT_SETS distinct batches per rank (seeded by rank), rotated so that a step
     # never finds its frames in L2
@@ -291,20 +311,27 @@ def gpu_main(args, rank, local_rank, world):
         tpath = os.path.join(ROOT, "profiles", "ncu_dram_bytes_per_launch.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            if dom in tj.get("stages", {}) and tj.get("batch") == BATCH:
+            if dom in tj.get("stages", {}) and tj.get("batch") == BATCH and ARCH == "squeeze-ernet" and PRECISION == "bf16":
                 traffic = tj["stages"][dom]        # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full)
+                if dom in tj.get("tensor_pipe_active_pct", {}):
+                    roof["tensor_pipe_active_pct_ncu"] = tj["tensor_pipe_active_pct"][dom]
+        if dom in ISSUED_FLOPS.get(ARCH, {}):
+            # what the tensor pipe really executes for this kernel (the 25-tap dense form) against the same peak
+            issued = ISSUED_FLOPS[ARCH][dom] * BATCH / (per_launch_ms * 1e-3) / 1e12
+            roof.update({"issued_tflops": issued, "issued_frac": issued / peaks["bf16_tflops_sustained"],
+                         "note": "achieved/frac count the reference's MACs (depthwise + 1x1 of the kept region); the kernel "
+                                 "issues the 25-tap dense form, 8-10x more MMA work, which is what issued_* measures"})
         roof.update({"frac": achieved / peak, "traffic": traffic, "kernel": dom, "peak_source": peaks["source"],
                      "launch_ms": per_launch_ms, "share_of_step": dms / total_stage_ms,
                      "stage_ms_per_step": {k: round(v[0] / prof_steps, 5) for k, v in prof.items()},
                      "per_kernel": per_kernel})
         launches = model.launches_per_forward(BATCH, True) * args.steps
-        cpu_fps, _, cpu_info = cpu_reference_run(6, 1, 32)
+        cpu_fps, _, cpu_info = cpu_reference_run(6, 1, 32, ARCH)
         line = {
             "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": PRECISION, "data": "synthetic",
-            "config": {"workload": f"Squeeze-ErNet bf16 batch {BATCH} per GPU on 1xB200 (BASELINE.json configs[1]): "
-                                   "240x240x3 uint8 frames -> eval transform -> forward -> probabilities",
+            "config": {"workload": workload_name(ARCH, PRECISION, BATCH),
                        "arch": ARCH, "batch_per_gpu": BATCH, "global_batch": BATCH * world, "frame": "240x240x3 u8",
                        "weights": "shipped squeeze-ernet-state_dict",
                        "l2": f"inputs rotate over {N_INPUT_SETS} distinct batches "
@@ -333,8 +360,12 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--schedule", default="persistent", choices=["persistent", "per-image"],
-                    help="tensor-core block kernel schedule (A/B switch; same arithmetic)")
+    ap.add_argument("--schedule", default="pairs", choices=["pairs", "persistent", "per-image"],
+                    help="tensor-core block kernel schedule (A/B switch; same folded weights)")
+    ap.add_argument("--arch", default=ARCH, choices=["squeeze-ernet", "squeeze-redconv"],
+                    help="default = BASELINE.json configs[1]; the other configs are parity cases, measured on request")
+    ap.add_argument("--precision", default=PRECISION, choices=["fp32", "bf16", "fp16", "int8"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="frames per GPU per step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

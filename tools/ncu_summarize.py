@@ -8,16 +8,18 @@ rep, tag, batch = sys.argv[1], sys.argv[2], int(sys.argv[3])
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
-keys = ["gpu__time_duration.sum", "sm__cycles_active.avg", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+keys = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "sm__cycles_active.avg", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_shared_mem"]
-stage_of = [("ingest_stem", "ingest"), ("BlockCfg<2, 64", "tc_block1"), ("BlockCfg<8, 96", "tc_block2"),
+stage_of = [("ingest_stem", "ingest"), ("PCfg<2, 64", "tc_block1"), ("CCfg<2, 64", "tc_block1"), ("CCfg<8, 96", "tc_block2"), ("CCfg<12, 128", "tc_block3"),
+            ("PCfg<8, 96", "tc_block2"), ("PCfg<12, 128", "tc_block3"), ("BlockCfg<2, 64", "tc_block1"), ("BlockCfg<8, 96", "tc_block2"),
             ("BlockCfg<12, 128", "tc_block3"), ("acff4_head", "tc_block4"), ("BlockCfg<4, 96", "tc_block2"), ("BlockCfg<6, 128", "tc_block3")]
 lines = [f"# ncu --set full --clock-control none, tools/run_forward.py, batch {batch} ({tag})\n",
          "# per-launch values from cold-cache, serialised replays: compare shares, not absolutes\n"]
 dram = {}
+tpipe = {}
 tot = 0.0
 for r in rows[2:]:
     name = r[hdr.index("Kernel Name")]
@@ -32,8 +34,9 @@ for r in rows[2:]:
         return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
     if st and st not in dram:
         dram[st] = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
+        tpipe[st] = float(r[hdr.index("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")])
     tot += float(r[hdr.index("gpu__time_duration.sum")])
 lines.append(f"\n# sum of kernel durations in this capture: {tot:.1f} us\n")
 open(f"profiles/{tag}_ncu_full.txt", "w").writelines(lines)
-json.dump({"batch": batch, "source": f"profiles/{tag}_ncu_full.txt", "stages": dram}, open("profiles/ncu_dram_bytes_per_launch.json", "w"), indent=1)
+json.dump({"batch": batch, "source": f"profiles/{tag}_ncu_full.txt", "stages": dram, "tensor_pipe_active_pct": tpipe}, open("profiles/ncu_dram_bytes_per_launch.json", "w"), indent=1)
 print("".join(lines[-40:]))
