@@ -62,6 +62,7 @@ STAGE_WORK = {
     "tc_block1": (2 * (66 * 66 * 16 * 27 + 66 * 66 * 48 * 64), 2 * 72 * 72 * 16 + 8 * 36 * 36 * 16),
     "tc_block2": (2 * (30 * 30 * 64 * 27 + 30 * 30 * 192 * 96), 8 * 36 * 36 * 16 + 12 * 18 * 18 * 16),
     "tc_block3": (2 * (12 * 12 * 96 * 27 + 12 * 12 * 288 * 128), 12 * 18 * 18 * 16 + 6 * 6 * 128 * 2),
+    "tc_block4": (2 * (0.055e6 + 1.573e6 + 0.021e6), 6 * 6 * 128 * 2 + 20),          # ACFF4 + head in one kernel
 }
 GEMM_STAGES = {"pw1", "pw2", "pw3", "pw4", "tc_block1", "tc_block2", "tc_block3", "tc_block4"}
 # FLOPs the tensor-core block kernels actually ISSUE per image (25-tap dense form, padded 16x8 tiles): reported next to
