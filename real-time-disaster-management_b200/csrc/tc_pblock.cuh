@@ -56,6 +56,9 @@ struct PCfg {
 };
 
 constexpr int kPThreads = 416;   // 13 warps
+#ifndef ERNET_PBLOCK_MINB
+#define ERNET_PBLOCK_MINB 1
+#endif
 
 // cp.async.bulk.tensor.4d: box of the tensor described by `tmap` at coordinates (c0..c3), completion on `bar`.
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
@@ -69,7 +72,7 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
 }
 
 template <class Cfg, int KIND, int OUT>
-__global__ void __launch_bounds__(kPThreads, 1)
+__global__ void __launch_bounds__(kPThreads, ERNET_PBLOCK_MINB)
 acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t* __restrict__ wimg,
                    const __grid_constant__ EpiParams<Cfg::N> par, uint16_t* __restrict__ out, int batch) {
   constexpr int N = Cfg::N, GX = Cfg::GX, NSTAGE = Cfg::NSTAGE, BW = Cfg::BW, OP = Cfg::OP;

@@ -286,9 +286,10 @@ class _ErnetB200(nn.Module):
         return self._run(x, True)
 
     # ------------------------------------------------------------------ frames -> probabilities
-    def forward_frames(self, frames, *, bgr=False, return_logits=False):
+    def forward_frames(self, frames, *, bgr=False, return_logits=False, stream=None):
         """uint8 (B,H,W,3) device frames -> probabilities: the eval transform
-        (dataloaders/aider.py:421-426) and the model in one call."""
+        (dataloaders/aider.py:421-426) and the model in one call.  ``stream``: a torch.cuda.Stream to enqueue on
+        (default: the current stream); outputs are allocated on it."""
         if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[3] != 3:
             raise ValueError(f"expected uint8 frames of shape (B,H,W,3), got {frames.dtype} {tuple(frames.shape)}")
         lib, h, idx = self._ensure_engine()
@@ -299,7 +300,13 @@ class _ErnetB200(nn.Module):
         ws = self._get_workspace(lib, h, B, frames.device)
         probs = torch.empty((B, 5), dtype=torch.float32, device=frames.device)
         logits = torch.empty((B, 5), dtype=torch.float32, device=frames.device) if return_logits else None
-        stream = torch.cuda.current_stream(frames.device).cuda_stream
+        if stream is None:
+            stream = torch.cuda.current_stream(frames.device).cuda_stream
+        else:
+            probs.record_stream(stream)
+            if logits is not None:
+                logits.record_stream(stream)
+            stream = stream.cuda_stream
         _lib.check(lib.ernet_forward_frames(h, frames.data_ptr(), B, H, W, _lib.BGR if bgr else _lib.RGB,
                                             probs.data_ptr(), logits.data_ptr() if return_logits else None,
                                             ws.data_ptr(), ws.numel(), stream))
