@@ -79,63 +79,100 @@ acff_dw_kernel(const T* __restrict__ x, int H, int W, int C, int out_h, int out_
   const T* xb = x + (size_t)b * H * W * C;
 
   for (int i = threadIdx.x; i < 30 * C; i += blockDim.x) wsm[i] = i < 27 * C ? w[i] : bias[i - 27 * C];
-  for (int i = threadIdx.x; i < hh * hw * cv; i += blockDim.x) {
-    const int v = i % cv;
-    const int p = i / cv;
-    const int px = p % hw, py = p / hw;
-    const int gy = y0 - 2 + py, gx = x0 - 2 + px;
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (gy >= 0 && gy < H && gx >= 0 && gx < W)
-      val = __ldg(reinterpret_cast<const uint4*>(xb + ((size_t)gy * W + gx) * C) + v);
-    tile[i] = val;
+  // halo staging, 8 independent 16-byte loads in flight per thread (one load per iteration left the kernel waiting on
+  // a chain of ~15 dependent HBM latencies per CTA)
+  for (int i0 = threadIdx.x; i0 < hh * hw * cv; i0 += 8 * blockDim.x) {
+    uint4 val[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * blockDim.x;
+      const int v = i % cv;
+      const int p = i / cv;
+      const int px = p % hw, py = p / hw;
+      const int gy = y0 - 2 + py, gx = x0 - 2 + px;
+      val[u] = make_uint4(0, 0, 0, 0);
+      if (i < hh * hw * cv && gy >= 0 && gy < H && gx >= 0 && gx < W)
+        val[u] = __ldg(reinterpret_cast<const uint4*>(xb + ((size_t)gy * W + gx) * C) + v);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < hh * hw * cv) tile[i] = val[u];
+    }
   }
   __syncthreads();
 
-  const int items = th * tw * cv;
+  // Each thread produces a strip of PX consecutive pixels for one channel vector: the PX + 6 columns of a tile row
+  // are loaded once and feed every branch that has taps in that row (dy = -2..4: d3, d2, d1, d1+d2+d3, d1, d2, d3), the
+  // tap's weight vector is loaded once per strip.  24 (fp32) shared-memory vectors per pixel instead of 54: the
+  // kernel was bound by shared-memory bandwidth, not by HBM.
+  constexpr int PX = NV == 4 ? 4 : 2;
+  const int sxn = tw / PX;                     // tw is a multiple of PX (dw_pick_tile)
+  const int items = th * sxn * cv;
   for (int i = threadIdx.x; i < items; i += blockDim.x) {
     const int v = i % cv;
     const int p = i / cv;
-    const int lx = p % tw, ly = p / tw;
-    const int oy = y0 + ly, ox = x0 + lx;
-    if (oy >= out_h || ox >= out_w) continue;
-    float acc[3][NV];
+    const int lx0 = (p % sxn) * PX, ly = p / sxn;
+    const int oy = y0 + ly, ox0 = x0 + lx0;
+    if (oy >= out_h || ox0 >= out_w) continue;
+    float acc[3][PX][NV];
 #pragma unroll
     for (int d = 0; d < 3; ++d)
 #pragma unroll
-      for (int k = 0; k < NV; ++k) acc[d][k] = wsm[27 * C + d * C + v * NV + k];
+      for (int px = 0; px < PX; ++px)
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      const int dil = d + 1;
+        for (int k = 0; k < NV; ++k) acc[d][px][k] = wsm[27 * C + d * C + v * NV + k];
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
+    for (int ry = 0; ry < 7; ++ry) {
+      const int dy = ry - 2;
+      const uint4* rowp = tile + ((size_t)(ly + ry) * hw + lx0) * cv + v;
+      float xr[PX + 6][NV];
+#pragma unroll
+      for (int c = 0; c < PX + 6; ++c) unpack16<T>(rowp[(size_t)c * cv], xr[c]);     // unused columns are dropped by the compiler
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const int dil = d + 1;
+        // branch d has taps in this row when dy = ky*dil - (dil-1) for ky in 0..2
+        const int t = dy + (dil - 1);
+        if (t < 0 || t % dil != 0 || t / dil > 2) continue;
+        const int ky = t / dil;
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          // tap offset from the output coordinate: k*dil - (dil-1); +2 for the halo origin
-          const int ty = ly + 2 + ky * dil - (dil - 1);
-          const int tx = lx + 2 + kx * dil - (dil - 1);
-          float xv[NV];
-          unpack16<T>(tile[((size_t)ty * hw + tx) * cv + v], xv);
           const float* wr = wsm + (d * 9 + ky * 3 + kx) * C + v * NV;
+          float wv[NV];
 #pragma unroll
-          for (int k = 0; k < NV; ++k) acc[d][k] = fmaf(xv[k], wr[k], acc[d][k]);
+          for (int k = 0; k < NV; ++k) wv[k] = wr[k];
+          const int col = 2 + kx * dil - (dil - 1);          // column of pixel 0's tap in xr
+#pragma unroll
+          for (int px = 0; px < PX; ++px)
+#pragma unroll
+            for (int k = 0; k < NV; ++k) acc[d][px][k] = fmaf(xr[px + col][k], wv[k], acc[d][px][k]);
         }
+      }
     }
-    T* o = out + (((size_t)b * out_h + oy) * out_w + ox) * (3 * C) + v * NV;
 #pragma unroll
-    for (int d = 0; d < 3; ++d) *reinterpret_cast<uint4*>(o + d * C) = pack16<T>(acc[d]);
+    for (int px = 0; px < PX; ++px) {
+      if (ox0 + px >= out_w) break;
+      T* o = out + (((size_t)b * out_h + oy) * out_w + ox0 + px) * (3 * C) + v * NV;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) *reinterpret_cast<uint4*>(o + d * C) = pack16<T>(acc[d][px]);
+    }
   }
 }
 
 inline void dw_pick_tile(int C, int esize, int out_h, int out_w, int& th, int& tw, size_t& smem) {
-  // largest square-ish tile whose halo fits in ~96 KB (two CTAs per SM)
-  static const int cand[] = {22, 16, 15, 12, 11, 10, 8, 6, 5, 4, 3, 2, 1};
+  // largest square-ish tile whose halo fits in ~96 KB (two CTAs per SM); the width is a whole number of the strips
+  // a thread computes (4 pixels at fp32, 2 at 16 bit), columns past the image are skipped in the kernel
+  const int px = esize == 4 ? 4 : 2;
+  static const int cand[] = {24, 22, 16, 15, 12, 11, 10, 8, 6, 5, 4, 3, 2, 1};
   for (int t : cand) {
     int tth = t < out_h ? t : out_h, ttw = t < out_w ? t : out_w;
+    ttw = (ttw + px - 1) / px * px;
     size_t s = (size_t)(tth + 6) * (ttw + 6) * C * esize + 30 * (size_t)C * sizeof(float);
     if (s <= 96 * 1024) { th = tth; tw = ttw; smem = s; return; }
   }
-  th = tw = 1;
-  smem = (size_t)49 * C * esize + 30 * (size_t)C * sizeof(float);
+  th = 1; tw = px;
+  smem = (size_t)7 * (px + 6) * C * esize + 30 * (size_t)C * sizeof(float);
 }
 
 template <typename T>
