@@ -50,7 +50,9 @@ struct ernet_handle {
   bool debug_taps = false;      // keep intermediates the fused kernels would not write (acff4)
   int persistent = 2;           // block-kernel schedule: 0 one image per CTA, 1 persistent CTAs, 2 persistent + CTA pairs for blocks 2, 3
   int num_sms = 148;
+  void* d_w1_pair = nullptr;         // block-1 weights regrouped for tap pairing ([13][2][64][16 B], tc_pblock.cuh)
   StemFrag* d_stem_frag = nullptr;   // folded conv1 in mma.sync fragment order (16-bit engines)
+  bool pair_taps = true;        // two taps per MMA in block 1 when its input has one real chunk (ERNET_PAIR_TAPS=0 switches it off)
   bool pair_block1 = false;     // block 1 on the CTA-pair kernel as well (experiment switch: ERNET_PAIR_BLOCK1=0)
   bool fast_ingest = true;      // word-wide fused transform+conv1 with Normalize folded into conv1 (ingest_fast.cuh)
   tc::TailParams tail;
@@ -316,7 +318,7 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
         StemQ q{};
         FastGeom fg;
         if (h->fast_ingest && h->d_stem_frag && fast5_geometry(*tab, frames, fg)) {
-          ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem5<T, 8>(*tab, fg, frames, n, order == ERNET_BGR, h->d_stem_frag, u16(p.stem), s)));
+          ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem5<T, 8>(*tab, fg, frames, n, order == ERNET_BGR, h->d_stem_frag, q, !(h->persistent == 2 && h->d_w1_pair && h->pair_taps), u16(p.stem), s)));
         } else {
           ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem<T, 8, FS_P8>(*tab, frames, n, order == ERNET_BGR, sw, sb_, q, u16(p.stem), s)));
         }
@@ -337,7 +339,11 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
       }
       auto wimgr = [&](int k) { return h->t[ERNET_T_TC_BASE + 4 * k + ERNET_T_TC_WIMG].dev; };
       if (h->persistent == 2) {
-        ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1, KIND, tc::OUT_P8>(u16(p.stem), wimgr(0), h->epi1, u16(p.p1), n, h->num_sms, s)));
+        if (h->d_w1_pair && h->pair_taps) {
+          ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1P, KIND, tc::OUT_P8>(u16(p.stem), h->d_w1_pair, h->epi1, u16(p.p1), n, h->num_sms, s)));
+        } else {
+          ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1, KIND, tc::OUT_P8>(u16(p.stem), wimgr(0), h->epi1, u16(p.p1), n, h->num_sms, s)));
+        }
         ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_cblock<tc::CBlock2R, KIND, tc::OUT_P8>(u16(p.p1), wimgr(1), h->epi2, u16(p.a2), n, h->num_sms, s)));
         ERNET_STAGE(ERNET_STAGE_RED2, (tc::launch_acff_pblock<tc::PRed2R, KIND, tc::OUT_P8>(u16(p.a2), h->t[ERNET_T_TC_RED2_WIMG].dev, h->epi_r2, u16(p.p2), n, h->num_sms, s)));
         ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_cblock<tc::CBlock3R, KIND, tc::OUT_NHWC>(u16(p.p2), wimgr(2), h->epi3, u16(p.p3), n, h->num_sms, s)));
@@ -358,8 +364,9 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
     for (int i = 0; i < 16; ++i) q.inv[i] = s_inv.v[i];
     constexpr int FSOUT = KIND == tc::KIND_I8 ? FS_P16 : FS_P8;
     FastGeom fg;
-    if (KIND != tc::KIND_I8 && h->fast_ingest && h->d_stem_frag && fast5_geometry(*tab, frames, fg)) {
-      ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem5<T, 16>(*tab, fg, frames, n, order == ERNET_BGR, h->d_stem_frag, u16(p.stem), s)));
+    if (h->fast_ingest && h->d_stem_frag && fast5_geometry(*tab, frames, fg)) {
+      const bool zc1 = !(KIND == tc::KIND_I8 && h->persistent == 2 && h->d_w1_pair && h->pair_taps);
+      ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem5<T, 16, FSOUT>(*tab, fg, frames, n, order == ERNET_BGR, h->d_stem_frag, q, zc1, u16(p.stem), s)));
     } else {
       ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem<T, 16, FSOUT>(*tab, frames, n, order == ERNET_BGR, sw, sb_, q, u16(p.stem), s)));
     }
@@ -379,7 +386,15 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
     ERNET_LAUNCH_CHECK("stem_p8_kernel");
   }
   auto wimg = [&](int k) { return h->t[ERNET_T_TC_BASE + 4 * k + ERNET_T_TC_WIMG].dev; };
-  if (KIND == tc::KIND_I8) {
+  if (KIND == tc::KIND_I8 && h->persistent == 2) {
+    if (h->d_w1_pair && h->pair_taps) {
+      ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1P, tc::KIND_I8, tc::OUT_P16>(u16(p.stem), h->d_w1_pair, h->epi1, u16(p.p1), n, h->num_sms, s)));
+    } else {
+      ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1, tc::KIND_I8, tc::OUT_P16>(u16(p.stem), wimg(0), h->epi1, u16(p.p1), n, h->num_sms, s)));
+    }
+    ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_cblock<tc::CBlock2Q, tc::KIND_I8, tc::OUT_P16>(u16(p.p1), wimg(1), h->epi2, u16(p.p2), n, h->num_sms, s)));
+    ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_cblock<tc::CBlock3Q, tc::KIND_I8, tc::OUT_NHWC>(u16(p.p2), wimg(2), h->epi3, u16(p.p3), n, h->num_sms, s)));
+  } else if (KIND == tc::KIND_I8) {
     ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_block<tc::CfgBlock1Q, tc::KIND_I8, tc::OUT_P16>(u16(p.stem), wimg(0), h->epi1, u16(p.p1), n, s)));
     ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_block<tc::CfgBlock2Q, tc::KIND_I8, tc::OUT_P16>(u16(p.p1), wimg(1), h->epi2, u16(p.p2), n, s)));
     ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_block<tc::CfgBlock3Q, tc::KIND_I8, tc::OUT_NHWC>(u16(p.p2), wimg(2), h->epi3, u16(p.p3), n, s)));
@@ -456,6 +471,7 @@ static int init_device_attrs() {
   ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__half, 16, FS_P8, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__nv_bfloat16, 16, FS_P8, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__half, 16, FS_P16, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem5_kernel<__half, 16, FS_P16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   ERNET_CUDA(cudaFuncSetAttribute(ingest_stem5_kernel<__nv_bfloat16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   ERNET_CUDA(cudaFuncSetAttribute(ingest_stem5_kernel<__half, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   ERNET_CUDA(cudaFuncSetAttribute(ingest_stem5_kernel<__nv_bfloat16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
@@ -479,6 +495,12 @@ static int init_device_attrs() {
   if ((rc = tc::set_cblock_attr<tc::CBlock3R, tc::KIND_F16, tc::OUT_NHWC>())) return rc;
   if ((rc = tc::set_pblock_attr<tc::PRed2R, tc::KIND_BF16, tc::OUT_P8>())) return rc;
   if ((rc = tc::set_pblock_attr<tc::PRed2R, tc::KIND_F16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_pblock_attr<tc::PBlock1, tc::KIND_I8, tc::OUT_P16>())) return rc;
+  if ((rc = tc::set_pblock_attr<tc::PBlock1P, tc::KIND_I8, tc::OUT_P16>())) return rc;
+  if ((rc = tc::set_pblock_attr<tc::PBlock1P, tc::KIND_BF16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_pblock_attr<tc::PBlock1P, tc::KIND_F16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::CBlock2Q, tc::KIND_I8, tc::OUT_P16>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::CBlock3Q, tc::KIND_I8, tc::OUT_NHWC>())) return rc;
   if ((rc = tc::set_tail_attrs<tc::TailCfg128>())) return rc;
   if ((rc = tc::set_tail_attrs<tc::TailCfg64>())) return rc;
   return ERNET_OK;
@@ -538,6 +560,7 @@ int ernet_create(ernet_handle** out, int arch, int precision, int device) {
   h->arch = arch; h->precision = precision; h->device = device;
   h->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("ERNET_PAIR_BLOCK1")) h->pair_block1 = atoi(e) != 0;
+  if (const char* e = getenv("ERNET_PAIR_TAPS")) h->pair_taps = atoi(e) != 0;
   *out = h;
   return ERNET_OK;
 }
@@ -547,6 +570,7 @@ void ernet_destroy(ernet_handle* h) {
   DeviceGuard g(h->device);
   if (h->d_blob) cudaFree(h->d_blob);
   if (h->d_stem_frag) cudaFree(h->d_stem_frag);
+  if (h->d_w1_pair) cudaFree(h->d_w1_pair);
   for (auto& kv : h->ingest) if (kv.second.d_base) cudaFree(kv.second.d_base);
   for (int i = 0; i < 2; ++i) {
     if (h->d_frames[i]) cudaFree(h->d_frames[i]);
@@ -622,6 +646,19 @@ int ernet_load_packed(ernet_handle* h, const void* blob, size_t bytes) {
     h->has_tc = all;
     if (all) {
       auto host_f32 = [&](int id) { return reinterpret_cast<const float*>(static_cast<const char*>(blob) + (static_cast<const char*>(h->t[id].dev) - static_cast<const char*>(d))); };
+      if (q || h->red()) {
+        // Block 1 sees one real 16-byte chunk per pixel (16 int8 channels / RedConv's 8 16-bit channels; chunk 1 of the
+        // packed image multiplies zeros): regroup [25 taps][2 chunks][64][16 B] into 13 tap pairs for the PAIR kernel
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(host_f32(ERNET_T_TC_BASE + ERNET_T_TC_WIMG));
+        std::vector<uint8_t> pr(13 * 2 * 64 * 16, 0);
+        for (int p = 0; p < 13; ++p) {
+          const int tapA = p == 0 ? 0 : 2 * p - 1, tapB = p == 0 ? -1 : 2 * p;
+          memcpy(pr.data() + (size_t)(p * 2 + 0) * 1024, src + (size_t)(tapA * 2) * 1024, 1024);
+          if (tapB >= 0) memcpy(pr.data() + (size_t)(p * 2 + 1) * 1024, src + (size_t)(tapB * 2) * 1024, 1024);
+        }
+        if (!h->d_w1_pair) ERNET_CUDA(cudaMalloc(&h->d_w1_pair, pr.size()));
+        ERNET_CUDA(cudaMemcpy(h->d_w1_pair, pr.data(), pr.size(), cudaMemcpyHostToDevice));
+      }
       {  // conv1 with ToTensor/Normalize folded in, in mma.sync fragment order (ingest_fast.cuh)
         StemFrag sfh;
         build_stem_fragments(host_f32(ERNET_T_STEM_W), host_f32(ERNET_T_STEM_B), h->cs(), &sfh);
@@ -662,12 +699,6 @@ int ernet_load_packed(ernet_handle* h, const void* blob, size_t bytes) {
     h->has_tail = h->precision != ERNET_PREC_FP32 && w4.dev && w4.nbytes == (size_t)3 * h->c4() * 256 * 2;
     if (h->has_tail) {
       auto host_f32 = [&](int id) { return reinterpret_cast<const float*>(static_cast<const char*>(blob) + (static_cast<const char*>(h->t[id].dev) - static_cast<const char*>(d))); };
-      {  // conv1 with ToTensor/Normalize folded in, in mma.sync fragment order (ingest_fast.cuh)
-        StemFrag sfh;
-        build_stem_fragments(host_f32(ERNET_T_STEM_W), host_f32(ERNET_T_STEM_B), h->cs(), &sfh);
-        if (!h->d_stem_frag) ERNET_CUDA(cudaMalloc(&h->d_stem_frag, sizeof(StemFrag)));
-        ERNET_CUDA(cudaMemcpy(h->d_stem_frag, &sfh, sizeof(StemFrag), cudaMemcpyHostToDevice));
-      }
       memcpy(h->tail.bias, host_f32(ERNET_T_BLOCK_BASE + 24 + ERNET_T_PW_B), 256 * sizeof(float));
       memcpy(h->tail.scale, host_f32(ERNET_T_BLOCK_BASE + 24 + ERNET_T_BN_S), 256 * sizeof(float));
       memcpy(h->tail.shift, host_f32(ERNET_T_BLOCK_BASE + 24 + ERNET_T_BN_T), 256 * sizeof(float));

@@ -30,12 +30,14 @@ struct FastGeom {                             // shared-memory carve-up (bytes),
 //   then CS floats: folded bias
 struct StemFrag { uint32_t frag[2][32][8]; float bias[16]; };
 
-template <typename T, int CS>
+// OUT = FS_P8: 16-bit stem tensor (B,2,72,72,8); FS_P16: int8 stem tensor (B,2,72,72,16) quantised with q.inv[c] (the
+// int8 engine); zero_chunk1: also write the all-zero second chunk (not needed when block 1 pairs taps and never reads it).
+template <typename T, int CS, int OUT = FS_P8>
 __global__ void __launch_bounds__(kFastThreads, 2)
 ingest_stem5_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restrict__ frames_end, int H, int W, int bgr,
                     const int* __restrict__ xmin, const int* __restrict__ kx, const int* __restrict__ ymin, const int* __restrict__ ylen,
                     const int* __restrict__ ky, const StemFrag* __restrict__ sf, const __grid_constant__ FastGeom geo,
-                    void* __restrict__ out) {
+                    const __grid_constant__ StemQ q, int zero_chunk1, void* __restrict__ out) {
   extern __shared__ __align__(128) uint8_t fsm[];
   const uint32_t* raww = reinterpret_cast<const uint32_t*>(fsm);           // [in_rows][W*3] packed RGB bytes (bulk copy)
   uint32_t* hbuf4 = reinterpret_cast<uint32_t*>(fsm + geo.off_hbuf);       // [in_rows + 5][140] RGBX words
@@ -193,8 +195,18 @@ ingest_stem5_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restric
         for (int half = 0; half < 2; ++half) {
           const int oxx = half ? ox1 : ox0;
           if (xg == 4 && oxx >= 69) continue;
+          if (OUT == FS_P16) {
+            uint16_t* o16 = reinterpret_cast<uint16_t*>(orow_l + oxx * 4 - t) + t;      // pixel's 16 bytes, this lane's channel pairs
 #pragma unroll
-          for (int j = 0; j < NT; ++j) orow_l[j * (72 * 72 * 4) + oxx * 4] = StemMma<T>::pack(acc[j][2 * half], acc[j][2 * half + 1]);
+            for (int j = 0; j < NT; ++j) {
+              int q0 = __float2int_rn(acc[j][2 * half] * q.inv[8 * j + 2 * t]), q1 = __float2int_rn(acc[j][2 * half + 1] * q.inv[8 * j + 2 * t + 1]);
+              q0 = max(-127, min(127, q0)); q1 = max(-127, min(127, q1));
+              o16[4 * j] = (uint16_t)(((uint32_t)q0 & 0xffu) | (((uint32_t)q1 & 0xffu) << 8));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < NT; ++j) orow_l[j * (72 * 72 * 4) + oxx * 4] = StemMma<T>::pack(acc[j][2 * half], acc[j][2 * half + 1]);
+          }
         }
       }
     }
@@ -203,12 +215,13 @@ ingest_stem5_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restric
       const int ly = i / 72, pc = i - ly * 72;
       const bool halo = pc < 2 || pc >= 71;
       if (halo) img[(y0 + ly + 2) * 72 + pc] = make_uint4(0, 0, 0, 0);
-      if (halo || CS == 8) img[72 * 72 + (y0 + ly + 2) * 72 + pc] = make_uint4(0, 0, 0, 0);
+      if (zero_chunk1 ? (halo || CS == 8 || OUT == FS_P16) : (halo && CS == 16 && OUT == FS_P8)) img[72 * 72 + (y0 + ly + 2) * 72 + pc] = make_uint4(0, 0, 0, 0);
     }
+    const int nch = (zero_chunk1 || (CS == 16 && OUT == FS_P8)) ? 2 : 1;         // chunks whose halo rows are written
     if (blockIdx.x == 0)
-      for (int i = tid; i < 2 * 2 * 72; i += kFastThreads) img[(i / 144) * 72 * 72 + (i % 144)] = make_uint4(0, 0, 0, 0);
+      for (int i = tid; i < nch * 2 * 72; i += kFastThreads) img[(i / 144) * 72 * 72 + (i % 144)] = make_uint4(0, 0, 0, 0);
     if (y1 == 69)
-      for (int i = tid; i < 2 * 72; i += kFastThreads) img[(i / 72) * 72 * 72 + 71 * 72 + (i % 72)] = make_uint4(0, 0, 0, 0);
+      for (int i = tid; i < nch * 72; i += kFastThreads) img[(i / 72) * 72 * 72 + 71 * 72 + (i % 72)] = make_uint4(0, 0, 0, 0);
   }
   ERNET_CHAIN_EXIT(0);
 }
@@ -259,12 +272,12 @@ inline bool fast5_geometry(const IngestTables& t, const void* frames, FastGeom& 
   return g.total <= 110 * 1024;
 }
 
-template <typename T, int CS>
+template <typename T, int CS, int OUT = FS_P8>
 inline int launch_ingest_stem5(const IngestTables& t, const FastGeom& g, const uint8_t* frames, int batch, int bgr, const StemFrag* sf,
-                               void* out, cudaStream_t stream) {
+                               const StemQ& q, bool zero_chunk1, void* out, cudaStream_t stream) {
   dim3 grid((69 + kStemBand - 1) / kStemBand, batch);
-  ERNET_CUDA(launch_pdl(ingest_stem5_kernel<T, CS>, grid, dim3(kFastThreads), (size_t)g.total, stream, frames, frames + (size_t)batch * t.H * t.W * 3, t.H, t.W, bgr,
-                        t.d_xmin, t.d_kx, t.d_ymin, t.d_ylen, t.d_ky, sf, g, out));
+  ERNET_CUDA(launch_pdl(ingest_stem5_kernel<T, CS, OUT>, grid, dim3(kFastThreads), (size_t)g.total, stream, frames, frames + (size_t)batch * t.H * t.W * 3, t.H, t.W, bgr,
+                        t.d_xmin, t.d_kx, t.d_ymin, t.d_ylen, t.d_ky, sf, g, q, zero_chunk1 ? 1 : 0, out));
   return ERNET_OK;
 }
 

@@ -100,6 +100,14 @@ __device__ __forceinline__ void mma2_f16(uint32_t d_tmem, uint64_t adesc, uint64
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void mma2_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on the barrier at this offset in BOTH CTAs of the pair when every MMA issued so far has completed
 __device__ __forceinline__ void mma2_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -112,9 +120,9 @@ acff_cblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
                    const __grid_constant__ EpiParams<Cfg::N> par, uint16_t* __restrict__ out, int batch) {
   constexpr int N = Cfg::N, NH = Cfg::NH, GX = Cfg::GX, NSLOT = Cfg::NSLOT, BW = Cfg::BW, OP = Cfg::OP, KS = Cfg::KS;
   constexpr bool BF16 = KIND == KIND_BF16;
-  static_assert(KIND != KIND_I8, "the CTA-pair kernel is the 16-bit path");
-  constexpr uint32_t IDESC = instr_desc(1u, BF16 ? 1u : 0u, 256u, (uint32_t)N);
-  constexpr int OUT_CHUNKS = Cfg::NREAL / 8;
+  // kind::i8: 16 int8 channels per 16-byte chunk, K step 32 = the same two chunks per MMA; s8 x s8 -> s32
+  constexpr uint32_t IDESC = KIND == KIND_I8 ? instr_desc(2u, 1u, 256u, (uint32_t)N) : instr_desc(1u, BF16 ? 1u : 0u, 256u, (uint32_t)N);
+  constexpr int OUT_CHUNKS = OUT == OUT_P16 ? Cfg::NREAL / 16 : Cfg::NREAL / 8;
   constexpr int tl_kernel = Cfg::NC == 2 ? 0 : Cfg::NC == 8 ? 1 : 2;   // timeline slot (study builds)
   (void)tl_kernel;
 
@@ -246,8 +254,10 @@ acff_cblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
               const uint64_t bd = desc_make(b_lo + (uint32_t)(t * (Cfg::TAPW_BYTES >> 4)), B_HI);
 #pragma unroll
               for (int tl = 0; tl < GX; ++tl)
-                if (tl < ntile)
-                  mma2_f16(d0 + tl * N, desc_make(a_lo0 + toff + (uint32_t)(tl * 8), A_HI), bd, IDESC, (ks | tap) != 0 ? 1u : 0u);
+                if (tl < ntile) {
+                  if (KIND == KIND_I8) mma2_i8(d0 + tl * N, desc_make(a_lo0 + toff + (uint32_t)(tl * 8), A_HI), bd, IDESC, (ks | tap) != 0 ? 1u : 0u);
+                  else mma2_f16(d0 + tl * N, desc_make(a_lo0 + toff + (uint32_t)(tl * 8), A_HI), bd, IDESC, (ks | tap) != 0 ? 1u : 0u);
+                }
             }
             if (!Cfg::WRES) {
               mma2_commit(&w_empty[ws]);
@@ -409,6 +419,9 @@ using CBlock3 = CCfg<12, 128, 15, 12, 2, 12, false, 9>;         // 12 x 10 KB sl
 // Squeeze_RedConv: ACFF2 without the pool (conv_red2 sits between it and pool2), ACFF3 on 48 input channels
 using CBlock2R = CCfg<8, 96, 33, 30, 2, 5, true, 1, /*POOL*/ false>;
 using CBlock3R = CCfg<6, 128, 15, 12, 2, 9, false, 9>;
+// int8 engine (chunks of 16 channels): both weight halves are resident (77 KB / 154 KB per CTA)
+using CBlock2Q = CCfg<4, 96, 33, 30, 2, 8, true, 1>;
+using CBlock3Q = CCfg<6, 128, 15, 12, 2, 6, true, 1>;
 
 }  // namespace tc
 }  // namespace ernet

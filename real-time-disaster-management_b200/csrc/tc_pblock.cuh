@@ -11,8 +11,8 @@
 //     under the MMAs of unit k+1, and the TMA of unit k+2 runs under both;
 //   * weights are loaded once per CTA (block 1, conv_red2) or streamed through the ring per unit;
 //   * units are dealt round-robin to the CTAs: 256 images x 15 units over 148 SMs leaves < 4 % imbalance.
-// Roles: warp 0 input producer, warp 1 MMA issuer, warp 2 weight-ring producer, warps 3-10 epilogue, warp 11 writes the
-// zero halo of the output images (kept off the producer's critical path: ~10 k cycles per image when it was inline), warp 12
+// Roles: warp 0 input producer, warp 1 MMA issuer, warp 2 weight-ring producer, 8-12 epilogue warps, then one warp that writes the
+// zero halo of the output images (kept off the producer's critical path: ~10 k cycles per image when it was inline), and the
 // second MMA issuer (resident-weight configurations).  Anything the issuing thread waits on between two MMAs - an
 // mbarrier test, a shared-memory load, even tcgen05.commit - empties the tensor pipe for 50-200 cycles (tools/
 // mma_commit.cu: 4060 instead of 3744 cycles per unit of 75 MMAs); with even units issued by warp 1 and odd units by
@@ -25,9 +25,21 @@
 namespace ernet {
 namespace tc {
 
+// PAIR_: the input has ONE real 16-byte chunk per pixel (16 int8 channels, or the 8 real 16-bit channels of RedConv's
+// stem) where an MMA K step wants two.  Instead of multiplying a zero chunk, the second chunk of the A descriptor is
+// pointed at the SAME staged chunk shifted by another tap (LBO = byte distance between the two taps' windows): one
+// MMA does two taps, 13 instead of 25 per tile.  Weights: [13 pairs][tap A chunk, tap B chunk][N][16 B].
 template <int NC_, int N_, int HIN_, int HU_, int GX_, int NSTAGE_, bool WRES_, int WSTAGES_,
-          bool POOL_ = true, int TAPS_ = 25, bool ACT_ = true, int NREAL_ = N_>
+          bool POOL_ = true, int TAPS_ = 25, bool ACT_ = true, int NREAL_ = N_, bool PAIR_ = false>
 struct PCfg {
+  static constexpr bool PAIR = PAIR_;
+  static constexpr int NPAIR = 13;
+  // epilogue warps per TMEM lane quarter: one per tile of the unit (up to 3), so that with tap pairing (13 MMAs per
+  // tile) the epilogue of a unit still finishes inside the unit's MMA time
+  static constexpr int EPW = GX_ <= 3 ? GX_ : 2;
+  static constexpr int NEPI = 4 * EPW;
+  static constexpr int WARP_HALO = 3 + NEPI, WARP_MMA2 = 4 + NEPI;
+  static constexpr int THREADS = 32 * (5 + NEPI);
   static constexpr int NC = NC_, N = N_, HIN = HIN_, HU = HU_, GX = GX_, NSTAGE = NSTAGE_, WSTAGES = WSTAGES_;
   static constexpr bool WRES = WRES_, POOL = POOL_, ACT = ACT_;
   static constexpr int TAPS = TAPS_, NREAL = NREAL_;
@@ -36,26 +48,27 @@ struct PCfg {
   static constexpr int BW = (8 * GX + 6 * HALO) < WP ? (8 * GX + 6 * HALO) : WP;     // box width  (pixels)
   static constexpr int BH = (16 + 6 * HALO) < WP ? (16 + 6 * HALO) : WP;             // box height (16 output rows + 6)
   static constexpr int CHUNK_BYTES = BH * BW * 16;
-  static constexpr int STAGE_BYTES = NC * CHUNK_BYTES;
+  static constexpr int STAGE_BYTES = (PAIR ? 1 : NC) * CHUNK_BYTES;          // bytes one box delivers
+  static constexpr int STAGE_STRIDE = (STAGE_BYTES + 127) / 128 * 128;      // TMA destinations are 128-byte aligned
   static constexpr int TR = (HU + 15) / 16, TCOLS = (HU + 7) / 8;
   static constexpr int UX = (TCOLS + GX - 1) / GX;                     // units per tile row
   static constexpr int UNITS_PER_IMG = TR * UX;
   static constexpr int KSTEPS = NC / 2;
   static constexpr int TAP_BYTES = NC * N * 16;
-  static constexpr int W_BYTES = TAPS * TAP_BYTES;
+  static constexpr int W_BYTES = (PAIR ? NPAIR : TAPS) * TAP_BYTES;
+  static_assert(!PAIR || (NC == 2 && TAPS == 25 && WRES_), "tap pairing: one real chunk of two, resident weights");
   static constexpr int W_SMEM = WRES ? W_BYTES : WSTAGES * TAP_BYTES;
   static constexpr int OUT_H = POOL ? HU / 2 : HU, OP = OUT_H + 3;
-  static constexpr int OFF_W = NSTAGE * STAGE_BYTES;
+  static constexpr int OFF_W = NSTAGE * STAGE_STRIDE;
   static constexpr int OFF_BAR = (OFF_W + W_SMEM + 15) / 16 * 16;
   static constexpr int SMEM_BYTES = OFF_BAR + 256;
   static_assert(NC % 2 == 0 && N % 32 == 0 && N <= 256, "operand shape");
   static_assert(2 * GX * N <= 512, "two TMEM accumulator buffers");
-  static_assert(STAGE_BYTES % 128 == 0, "TMA destination alignment");
   static_assert(NSTAGE <= 4 && WSTAGES <= 8, "barrier arrays");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-constexpr int kPThreads = 416;   // 13 warps
+constexpr int kPThreads = 544;   // upper bound: 17 warps (Cfg::THREADS is what a configuration launches)
 #ifndef ERNET_PBLOCK_MINB
 #define ERNET_PBLOCK_MINB 1
 #endif
@@ -106,7 +119,7 @@ acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t* 
     mbar_init(bar_w, 1);
     for (int i = 0; i < 4; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 1); }
     for (int i = 0; i < 8; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], Cfg::NEPI); }
     fence_mbar_init();
     tma_prefetch_desc(&tmap_in);
   }
@@ -135,7 +148,7 @@ acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t* 
         if (use > 0 && !mbar_wait(&in_empty[st], (use - 1) & 1, abort_flag, 0x500u, k)) break;
         ERNET_TL(k, 0);
         mbar_expect_tx(&in_full[st], Cfg::STAGE_BYTES);
-        tma_load_4d(smem + st * Cfg::STAGE_BYTES, &tmap_in, (ux * GX * 8 + 2 * (1 - Cfg::HALO)) * 4, ty * 16 + 2 * (1 - Cfg::HALO), 0, img, &in_full[st]);
+        tma_load_4d(smem + st * Cfg::STAGE_STRIDE, &tmap_in, (ux * GX * 8 + 2 * (1 - Cfg::HALO)) * 4, ty * 16 + 2 * (1 - Cfg::HALO), 0, img, &in_full[st]);
       }
     }
   } else if (warp == 2) {
@@ -154,7 +167,7 @@ acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t* 
         if (!ok) break;
       }
     }
-  } else if (warp == 1 || warp == 12) {
+  } else if (warp == 1 || warp == Cfg::WARP_MMA2) {
     // ------------------------------------------------------------------ MMA issuers: warp 1 takes units k = 0, 2, .. and warp 12
     // the odd ones when the weights are resident (each unit has its own TMEM buffer k & 1 and input stage, so the two
     // streams are independent); with streamed weights the ring is consumed in order by warp 1 alone
@@ -186,8 +199,27 @@ acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t* 
         }
         tc_fence_after();
         // tile tl of the unit: output origin = box origin + (2, 2 + 8*tl)
-        const uint32_t a_lo0 = desc_lo(in_addr + st * Cfg::STAGE_BYTES + (uint32_t)(Cfg::HALO * (2 * BW + 2) * 16), Cfg::CHUNK_BYTES);
+        const uint32_t a_lo0 = desc_lo(in_addr + st * Cfg::STAGE_STRIDE + (uint32_t)(Cfg::HALO * (2 * BW + 2) * 16), Cfg::CHUNK_BYTES);
         const uint32_t d0 = tmem_base + (uint32_t)(buf * GX * N);
+        if constexpr (Cfg::PAIR) {
+#pragma unroll
+          for (int pr = 0; pr < Cfg::NPAIR; ++pr) {
+            // pair 0 = tap 0 alone (its partner chunk has zero weights), pair p = taps 2p-1, 2p; windows ascend with the tap index
+            const int tapA = pr == 0 ? 0 : 2 * pr - 1, tapB = pr == 0 ? 1 : 2 * pr;
+            const int offA = tap_dy(tapA) * BW + tap_dx(tapA), offB = tap_dy(tapB) * BW + tap_dx(tapB);
+            const uint32_t a_lo = ((a_lo0 & 0x3FFFu) + (uint32_t)offA) | ((uint32_t)(offB - offA) << 16);
+            const uint32_t b_lo = w_lo0 + (uint32_t)(pr * (Cfg::TAP_BYTES >> 4));
+            if (NISSUE > 1 && pr == Cfg::NPAIR - 2) *turn = (uint32_t)(k + 1);
+#pragma unroll
+            for (int tl = 0; tl < GX; ++tl) {
+              if (tl < ntile) {
+                const uint64_t ad = desc_make(a_lo + (uint32_t)(tl * 8), A_HI), bd = desc_make(b_lo, B_HI);
+                if (KIND == KIND_I8) mma_i8(d0 + tl * N, ad, bd, IDESC, pr != 0 ? 1u : 0u);
+                else                 mma_f16(d0 + tl * N, ad, bd, IDESC, pr != 0 ? 1u : 0u);
+              }
+            }
+          }
+        } else
 #pragma unroll TAP_UNROLL
         for (int tap = 0; tap < Cfg::TAPS; ++tap) {
           uint32_t b_lo;
@@ -223,7 +255,7 @@ acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t* 
       }
     }
     __syncwarp();
-  } else if (warp == 11) {
+  } else if (warp == Cfg::WARP_HALO) {
     // ------------------------------------------------------------------ zero halo of the output images this CTA starts
     if (OUT != OUT_NHWC) {
       pdl_wait();
@@ -244,7 +276,7 @@ acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t* 
   } else {
     // ------------------------------------------------------------------ epilogue (warps 3..10)
     const int q4 = warp & 3;
-    const int ehalf = (warp - 3) >> 2;
+    const int ehalf = (warp - 3) >> 2;           // which tiles of the unit this warp takes: ehalf, ehalf + EPW, ..
     const int rr = 4 * q4 + (lane >> 3), cc = lane & 7;
     const bool xodd = (lane & 1) != 0, yodd = ((lane >> 3) & 1) != 0;
     const int qsel = (xodd ? 2 : 0) + (yodd ? 1 : 0);
@@ -257,7 +289,7 @@ acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t* 
       if (!mbar_wait(&acc_full[buf], use & 1, abort_flag, 0x600u + warp, k)) break;
       if (threadIdx.x == 96) ERNET_TL(k, 4);
       tc_fence_after();
-      for (int tl = ehalf; tl < ntile; tl += 2) {
+      for (int tl = ehalf; tl < ntile; tl += Cfg::EPW) {
         const int y = ty * 16 + rr, x = (ux * GX + tl) * 8 + cc;
         const bool valid = (y < Cfg::HU) && (x < Cfg::HU);
         const uint32_t tbase = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * GX * N + tl * N);
@@ -305,7 +337,7 @@ inline int make_input_map(CUtensorMap* map, const void* base, int batch) {
   const cuuint64_t dims[4] = {(cuuint64_t)Cfg::WP * 4, (cuuint64_t)Cfg::WP, (cuuint64_t)Cfg::NC, (cuuint64_t)batch};
   const cuuint64_t strides[3] = {(cuuint64_t)Cfg::WP * 16, (cuuint64_t)Cfg::WP * Cfg::WP * 16,
                                  (cuuint64_t)Cfg::NC * Cfg::WP * Cfg::WP * 16};
-  const cuuint32_t box[4] = {(cuuint32_t)Cfg::BW * 4, (cuuint32_t)Cfg::BH, (cuuint32_t)Cfg::NC, 1};
+  const cuuint32_t box[4] = {(cuuint32_t)Cfg::BW * 4, (cuuint32_t)Cfg::BH, (cuuint32_t)(Cfg::PAIR ? 1 : Cfg::NC), 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -322,7 +354,7 @@ inline int launch_acff_pblock(const void* in, const void* wimg, const EpiParams<
   if (rc) return rc;
   const int total = batch * Cfg::UNITS_PER_IMG;
   const int grid = total < num_sms ? total : num_sms;
-  ERNET_CUDA(launch_pdl(acff_pblock_kernel<Cfg, KIND, OUT>, dim3(grid), dim3(kPThreads), Cfg::SMEM_BYTES, stream, map,
+  ERNET_CUDA(launch_pdl(acff_pblock_kernel<Cfg, KIND, OUT>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, map,
                         static_cast<const uint16_t*>(wimg), par, static_cast<uint16_t*>(out), batch));
   return ERNET_OK;
 }
@@ -338,6 +370,8 @@ using PBlock1 = PCfg<2, 64, 69, 66, 3, 3, true, 1>;            // 15 units / ima
 using PBlock2 = PCfg<8, 96, 33, 30, 2, 2, false, 8>;           //  4 units / image, 62 KB boxes
 using PBlock3 = PCfg<12, 128, 15, 12, 2, 2, false, 4>;         //  1 unit  / image, box = whole padded image
 // Squeeze_RedConv: conv_red2 (96 -> 48, 1x1, bias only) + 2x2 pool as a 1-tap instance: 2 units / image, 98 KB boxes
+// block 1 with one real input chunk (int8 Squeeze_ErNET, 16-bit Squeeze_RedConv): 13 two-tap MMAs per tile
+using PBlock1P = PCfg<2, 64, 69, 66, 3, 3, true, 1, true, 25, true, 64, /*PAIR*/ true>;
 using PRed2R = PCfg<12, 64, 30, 30, 4, 2, true, 1, /*POOL*/ true, /*TAPS*/ 1, /*ACT*/ false, /*NREAL*/ 48>;
 
 }  // namespace tc
