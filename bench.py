@@ -338,9 +338,10 @@ def gpu_main(args, rank, local_rank, world):
                        "l2": f"inputs rotate over {N_INPUT_SETS} distinct batches "
                              f"({N_INPUT_SETS * BATCH * 172800 / 1e6:.0f} MB > 126 MB L2)",
                        "parallelism": f"dp{world}, no collective on the hot path"},
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": BATCH * FRAME[0] * FRAME[1] * 3,
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": BATCH * model.host_copy_bytes_per_frame(*FRAME),
                     "d2h_bytes_per_step": BATCH * 5 * 4, "steps": e2e_steps,
-                    "api": "Squeeze_ErNET.classify_host -> ernet_classify_frames_host (pinned host buffers)"},
+                    "api": "Squeeze_ErNET.classify_host -> ernet_classify_frames_host (pinned host buffers; only the "
+                           "frame rows the crop window reads are copied)"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roof,

@@ -132,6 +132,9 @@ int ernet_forward_frames(ernet_handle* h, const uint8_t* frames_hwc, int batch, 
                          int channel_order, float* probs_out, float* logits_out,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* Bytes of one height x width frame that ernet_classify_frames_host really sends to the device: only the rows the
+ * crop window of the eval transform reads (240x240: 213 of 240 rows).  0 on error.                         */
+size_t ernet_host_copy_bytes_per_frame(ernet_handle* h, int height, int width);
 /* Same with HOST buffers: `predict()` of aider-predict.py:47-86 / the loop body of
  * evaluate-classification-metrics.py:69-82 for a batch.  Host->device copies of the frames and the
  * device->host copy of the results happen inside, double-buffered against the kernels on internal

@@ -34,6 +34,7 @@ SIGNATURES = {
     "ernet_set_persistent": (_i, [_vp, _i]),
     "ernet_debug_timeline": (_i, [_vp, _sz]),
     "ernet_debug_chain": (_i, [_vp, _i]),
+    "ernet_host_copy_bytes_per_frame": (_sz, [_vp, _i, _i]),
     "ernet_set_fast_ingest": (_i, [_vp, _i]),
     "ernet_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "ernet_ingest_u8": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),

@@ -30,6 +30,8 @@ struct IngestTables {
   // fused transform+stem kernel: bands of kStemBand conv1 rows
   int fs_max_in_rows = 0;        // input rows such a band needs at most
   int fs_stage_raw = 0;          // 1: the raw rows of a band fit in shared memory and are staged with 16-byte loads
+  int col_lo = 0, col_hi = 0;    // same for columns
+  int row_lo = 0, row_hi = 0;    // input rows [row_lo, row_hi) are the only ones the crop window reads
   int fast5_ok = 0;              // 1: 5 non-negative taps per axis, sums within the no-clamp bound of ingest_fast.cuh
   // device arrays (one allocation): per crop column / row
   int* d_base = nullptr;
@@ -544,6 +546,12 @@ inline int build_ingest_tables(IngestTables& t, int H, int W) {
   host_coeffs(W, t.new_w, t.left, kCrop, t.ksx, xmin, xlen, kx);
   host_coeffs(H, t.new_h, t.top, kCrop, t.ksy, ymin, ylen, ky);
   if (t.ksx > kMaxTaps || t.ksy > kMaxTaps) return fail(ERNET_ERR_UNSUPPORTED, "frame %dx%d needs too many taps", H, W);
+  t.col_lo = xmin[0];
+  t.col_hi = xmin[kCrop - 1] + xlen[kCrop - 1];
+  for (int i = 0; i < kCrop; ++i) { if (xmin[i] < t.col_lo) t.col_lo = xmin[i]; if (xmin[i] + xlen[i] > t.col_hi) t.col_hi = xmin[i] + xlen[i]; }
+  t.row_lo = ymin[0];
+  t.row_hi = ymin[kCrop - 1] + ylen[kCrop - 1];
+  for (int i = 0; i < kCrop; ++i) { if (ymin[i] < t.row_lo) t.row_lo = ymin[i]; if (ymin[i] + ylen[i] > t.row_hi) t.row_hi = ymin[i] + ylen[i]; }
   // band size: largest that keeps the uint8 row buffer within 64 KB
   static const int kBands[] = {28, 20, 14, 10, 7, 5, 4, 2, 1};
   t.band_rows = 1;

@@ -374,6 +374,11 @@ class _ErnetB200(nn.Module):
         _lib.check(lib.ernet_profile_read(h, ms, cnt, n))
         return {_lib.STAGES[i]: (ms[i], cnt[i]) for i in range(n) if cnt[i]}
 
+    def host_copy_bytes_per_frame(self, height, width):
+        """Bytes of one frame that classify_host() sends over PCIe (the rows the crop window reads)."""
+        lib, h, _ = self._ensure_engine()
+        return int(lib.ernet_host_copy_bytes_per_frame(h, int(height), int(width)))
+
     def launches_per_forward(self, batch, with_ingest=True):
         lib, h, _ = self._ensure_engine()
         return lib.ernet_launches_per_forward(h, int(batch), 1 if with_ingest else 0)
