@@ -500,3 +500,32 @@ def test_fast_ingest_matches_table_lookup_kernel(arch, prec, dev):
         big = torch.zeros(frames.size + shift, dtype=torch.uint8, device=dev)
         big[shift:] = ft.flatten()
         assert torch.equal(m.forward_frames(big[shift:].view(ft.shape), return_logits=True)[1], l_fast)
+
+
+@pytest.mark.gpu
+def test_config5_full_size_sharding(dev):
+    """BASELINE config 5 size: 8192 frames, bf16.  Sharding rule of the multi-GPU path (contiguous slices, one handle per
+    shard, no collective): the 2-, 4- and 8-way results concatenate to the single-call result bit for bit, on the
+    device and through the host entry point; probabilities are normalised; a sub-sample meets the oracle tolerance."""
+    arch = "squeeze-ernet"
+    sd = fixtures.get_state_dict(arch, "shipped")
+    g = torch.Generator(device="cpu").manual_seed(8192)
+    base = torch.randint(0, 256, (512, 240, 240, 3), dtype=torch.uint8, generator=g)
+    base[256:] = torch.from_numpy(fixtures.smooth_frames(256, seed=77))
+    ft = base.repeat(16, 1, 1, 1).to(dev)                      # 8192 frames (16 copies of 512 distinct ones)
+    ft[3::7] = ft[3::7].flip(2)                                # ... made distinct again by mirroring a subset
+    m = rtdm_b200.from_state_dict(arch, sd, dev, "bf16")
+    p, l = m.forward_frames(ft, return_logits=True)
+    assert p.shape == (8192, 5) and torch.isfinite(l).all()
+    assert torch.allclose(p.sum(1), torch.ones(8192, device=dev), atol=1e-5)
+    for ways in (2, 4, 8):
+        n = 8192 // ways
+        shards = [rtdm_b200.from_state_dict(arch, sd, dev, "bf16").forward_frames(ft[i * n:(i + 1) * n], return_logits=True)[1]
+                  for i in range(ways)]
+        assert torch.equal(torch.cat(shards), l), ways
+    idx = np.arange(5, 8192, 683)
+    ref = E.forward(sd, I.ingest(ft[idx].cpu().numpy()), arch, dtype=np.float64)["logits"]
+    lg = l.double().cpu().numpy()[idx]
+    assert _rel(lg, ref) <= TOL["bf16"] and _top1_ok(lg, ref, TOL["bf16"])
+    ph = m.classify_host(ft[:1024].cpu().numpy())
+    assert np.array_equal(ph, p[:1024].cpu().numpy())
