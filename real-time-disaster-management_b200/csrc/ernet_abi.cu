@@ -16,6 +16,7 @@
 #include "tc_tail.cuh"
 #include "tc_pblock.cuh"
 #include "tc_cblock.cuh"
+#include "tc_dblock.cuh"
 
 namespace ernet {
 
@@ -50,6 +51,11 @@ struct ernet_handle {
   bool debug_taps = false;      // keep intermediates the fused kernels would not write (acff4)
   int persistent = 2;           // block-kernel schedule: 0 one image per CTA, 1 persistent CTAs, 2 persistent + CTA pairs for blocks 2, 3
   int num_sms = 148;
+  tc::DBlock1Consts* d_dblock1 = nullptr;   // fp16 constants of the depthwise + 1x1 block-1 kernel (tc_dblock.cuh)
+  tc::EpiParams<64> epi1d;           // its epilogue constants: bias = fused_conv.bias (the depthwise biases are added on the CUDA cores)
+  bool dw_block1 = false;            // experiment (ERNET_DW_BLOCK1=1): block 1 as depthwise on CUDA cores + 1x1 on tcgen05
+                                     // (tc_dblock.cuh).  Correct, but 94 us against 59 us for the 25-tap form: six depthwise warps
+                                     // are latency-bound (see the header of tc_dblock.cuh)
   void* d_w1_pair = nullptr;         // block-1 weights regrouped for tap pairing ([13][2][64][16 B], tc_pblock.cuh)
   StemFrag* d_stem_frag = nullptr;   // folded conv1 in mma.sync fragment order (16-bit engines)
   bool trim_columns = false;    // host path: also skip the columns outside the crop footprint (ERNET_TRIM_COLUMNS=1).  Off:
@@ -361,32 +367,43 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
       return fail(ERNET_ERR_UNSUPPORTED, "int8 is implemented for Squeeze_ErNET only");
     }
   }
-  if (frames && tab->fs_max_in_rows > 0 && !h->debug_taps) {
-    StemQ q{};
-    for (int i = 0; i < 16; ++i) q.inv[i] = s_inv.v[i];
-    constexpr int FSOUT = KIND == tc::KIND_I8 ? FS_P16 : FS_P8;
-    FastGeom fg;
-    if (h->fast_ingest && h->d_stem_frag && fast5_geometry(*tab, frames, fg)) {
-      const bool zc1 = !(KIND == tc::KIND_I8 && h->persistent == 2 && h->d_w1_pair && h->pair_taps);
-      ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem5<T, 16, FSOUT>(*tab, fg, frames, n, order == ERNET_BGR, h->d_stem_frag, q, zc1, u16(p.stem), s)));
+  // Block 1 on the depthwise + 1x1 kernel (tc_dblock.cuh) wants the stem tensor in fp16 whatever the engine's type:
+  // every stem producer below then runs its fp16 instance (SK = element kind of the stem tensor, ST = its type).
+  const bool use_d1 = KIND != tc::KIND_I8 && h->persistent == 2 && h->dw_block1 && h->d_dblock1 && !h->debug_taps;
+  auto run_stem = [&](auto st_tag, auto sk_tag) -> int {
+    using ST = decltype(st_tag);
+    constexpr int SK = decltype(sk_tag)::value;
+    if (frames && tab->fs_max_in_rows > 0 && !h->debug_taps) {
+      StemQ q{};
+      for (int i = 0; i < 16; ++i) q.inv[i] = s_inv.v[i];
+      constexpr int FSOUT = SK == tc::KIND_I8 ? FS_P16 : FS_P8;
+      FastGeom fg;
+      if (h->fast_ingest && h->d_stem_frag && fast5_geometry(*tab, frames, fg)) {
+        const bool zc1 = !(SK == tc::KIND_I8 && h->persistent == 2 && h->d_w1_pair && h->pair_taps);
+        ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem5<ST, 16, FSOUT>(*tab, fg, frames, n, order == ERNET_BGR, h->d_stem_frag, q, zc1, u16(p.stem), s)));
+      } else {
+        ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem<ST, 16, FSOUT>(*tab, frames, n, order == ERNET_BGR, sw, sb_, q, u16(p.stem), s)));
+      }
+    } else if (frames) {
+      ERNET_STAGE(ERNET_STAGE_INGEST, launch_ingest<T>(*tab, frames, n, order == ERNET_BGR, buf(p.ingest), 140LL * 140 * 3, 1, 140 * 3, 3, s));
+      StageTimer _t(h, ERNET_STAGE_STEM, s);
+      tc::stem_p8_kernel<T, 16, SK><<<grid, 128, 0, s>>>(buf(p.ingest), 140LL * 140 * 3, 1, 140 * 3, 3, sw, sb_, u16(p.stem), total, s_inv);
+      ERNET_LAUNCH_CHECK("stem_p8_kernel");
     } else {
-      ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem<T, 16, FSOUT>(*tab, frames, n, order == ERNET_BGR, sw, sb_, q, u16(p.stem), s)));
+      long long sb = 3LL * 140 * 140, sc, sy, sx;
+      if (x_layout == ERNET_NCHW) { sc = 140 * 140; sy = 140; sx = 1; }
+      else                        { sc = 1; sy = 140 * 3; sx = 3; }
+      StageTimer _t(h, ERNET_STAGE_STEM, s);
+      if (x_dtype == ERNET_F32) tc::stem_p8_kernel<float, 16, SK><<<grid, 128, 0, s>>>(static_cast<const float*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total, s_inv);
+      else if (x_dtype == ERNET_F16) tc::stem_p8_kernel<__half, 16, SK><<<grid, 128, 0, s>>>(static_cast<const __half*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total, s_inv);
+      else tc::stem_p8_kernel<__nv_bfloat16, 16, SK><<<grid, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total, s_inv);
+      ERNET_LAUNCH_CHECK("stem_p8_kernel");
     }
-  } else if (frames) {
-    ERNET_STAGE(ERNET_STAGE_INGEST, launch_ingest<T>(*tab, frames, n, order == ERNET_BGR, buf(p.ingest), 140LL * 140 * 3, 1, 140 * 3, 3, s));
-    StageTimer _t(h, ERNET_STAGE_STEM, s);
-    tc::stem_p8_kernel<T, 16, KIND><<<grid, 128, 0, s>>>(buf(p.ingest), 140LL * 140 * 3, 1, 140 * 3, 3, sw, sb_, u16(p.stem), total, s_inv);
-    ERNET_LAUNCH_CHECK("stem_p8_kernel");
-  } else {
-    long long sb = 3LL * 140 * 140, sc, sy, sx;
-    if (x_layout == ERNET_NCHW) { sc = 140 * 140; sy = 140; sx = 1; }
-    else                        { sc = 1; sy = 140 * 3; sx = 3; }
-    StageTimer _t(h, ERNET_STAGE_STEM, s);
-    if (x_dtype == ERNET_F32) tc::stem_p8_kernel<float, 16, KIND><<<grid, 128, 0, s>>>(static_cast<const float*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total, s_inv);
-    else if (x_dtype == ERNET_F16) tc::stem_p8_kernel<__half, 16, KIND><<<grid, 128, 0, s>>>(static_cast<const __half*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total, s_inv);
-    else tc::stem_p8_kernel<__nv_bfloat16, 16, KIND><<<grid, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total, s_inv);
-    ERNET_LAUNCH_CHECK("stem_p8_kernel");
-  }
+    return ERNET_OK;
+  };
+  if (use_d1) rc = run_stem(__half{}, std::integral_constant<int, tc::KIND_F16>{});
+  else        rc = run_stem(T{}, std::integral_constant<int, KIND>{});
+  if (rc) return rc;
   auto wimg = [&](int k) { return h->t[ERNET_T_TC_BASE + 4 * k + ERNET_T_TC_WIMG].dev; };
   if (KIND == tc::KIND_I8 && h->persistent == 2) {
     if (h->d_w1_pair && h->pair_taps) {
@@ -402,7 +419,9 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
     ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_block<tc::CfgBlock3Q, tc::KIND_I8, tc::OUT_NHWC>(u16(p.p2), wimg(2), h->epi3, u16(p.p3), n, s)));
   } else if (h->persistent) {
     constexpr int K16 = KIND == tc::KIND_I8 ? tc::KIND_F16 : KIND;
-    if (h->persistent == 2 && h->pair_block1) {
+    if (use_d1) {
+      ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_dblock1<K16, tc::OUT_P8>(u16(p.stem), h->d_dblock1, h->epi1d, u16(p.p1), n, h->num_sms, s)));
+    } else if (h->persistent == 2 && h->pair_block1) {
       ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_cblock<tc::CBlock1, K16, tc::OUT_P8>(u16(p.stem), wimg(0), h->epi1, u16(p.p1), n, h->num_sms, s)));
     } else {
       ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1, K16, tc::OUT_P8>(u16(p.stem), wimg(0), h->epi1, u16(p.p1), n, h->num_sms, s)));
@@ -503,6 +522,8 @@ static int init_device_attrs() {
   if ((rc = tc::set_pblock_attr<tc::PBlock1P, tc::KIND_F16, tc::OUT_P8>())) return rc;
   if ((rc = tc::set_cblock_attr<tc::CBlock2Q, tc::KIND_I8, tc::OUT_P16>())) return rc;
   if ((rc = tc::set_cblock_attr<tc::CBlock3Q, tc::KIND_I8, tc::OUT_NHWC>())) return rc;
+  if ((rc = tc::set_dblock1_attr<tc::KIND_BF16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_dblock1_attr<tc::KIND_F16, tc::OUT_P8>())) return rc;
   if ((rc = tc::set_tail_attrs<tc::TailCfg128>())) return rc;
   if ((rc = tc::set_tail_attrs<tc::TailCfg64>())) return rc;
   return ERNET_OK;
@@ -563,6 +584,7 @@ int ernet_create(ernet_handle** out, int arch, int precision, int device) {
   h->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("ERNET_PAIR_BLOCK1")) h->pair_block1 = atoi(e) != 0;
   if (const char* e = getenv("ERNET_PAIR_TAPS")) h->pair_taps = atoi(e) != 0;
+  if (const char* e = getenv("ERNET_DW_BLOCK1")) h->dw_block1 = atoi(e) != 0;
   if (const char* e = getenv("ERNET_TRIM_COLUMNS")) h->trim_columns = atoi(e) != 0;
   *out = h;
   return ERNET_OK;
@@ -574,6 +596,7 @@ void ernet_destroy(ernet_handle* h) {
   if (h->d_blob) cudaFree(h->d_blob);
   if (h->d_stem_frag) cudaFree(h->d_stem_frag);
   if (h->d_w1_pair) cudaFree(h->d_w1_pair);
+  if (h->d_dblock1) cudaFree(h->d_dblock1);
   for (auto& kv : h->ingest) if (kv.second.d_base) cudaFree(kv.second.d_base);
   for (int i = 0; i < 2; ++i) {
     if (h->d_frames[i]) cudaFree(h->d_frames[i]);
@@ -662,6 +685,12 @@ int ernet_load_packed(ernet_handle* h, const void* blob, size_t bytes) {
         if (!h->d_w1_pair) ERNET_CUDA(cudaMalloc(&h->d_w1_pair, pr.size()));
         ERNET_CUDA(cudaMemcpy(h->d_w1_pair, pr.data(), pr.size(), cudaMemcpyHostToDevice));
       }
+      if (!q && !h->red()) {   // depthwise + 1x1 block-1 kernel: fp16 constants from the layer-wise tensors
+        tc::DBlock1Consts dc;
+        tc::build_dblock1(host_f32(ERNET_T_BLOCK_BASE + ERNET_T_PW_W), host_f32(ERNET_T_BLOCK_BASE + ERNET_T_DW_W), host_f32(ERNET_T_BLOCK_BASE + ERNET_T_DW_B), &dc);
+        if (!h->d_dblock1) ERNET_CUDA(cudaMalloc(&h->d_dblock1, sizeof(dc)));
+        ERNET_CUDA(cudaMemcpy(h->d_dblock1, &dc, sizeof(dc), cudaMemcpyHostToDevice));
+      }
       {  // conv1 with ToTensor/Normalize folded in, in mma.sync fragment order (ingest_fast.cuh)
         StemFrag sfh;
         build_stem_fragments(host_f32(ERNET_T_STEM_W), host_f32(ERNET_T_STEM_B), h->cs(), &sfh);
@@ -684,6 +713,8 @@ int ernet_load_packed(ernet_handle* h, const void* blob, size_t bytes) {
         for (int i = 0; i < n; ++i) out_inv[i] = (q && k < 2) ? 1.f / qs[i] : 1.f;
       };
       fill(0, h->epi1.bias, h->epi1.scale, h->epi1.shift, h->epi1.deq, h->epi1.out_inv, 64);
+      h->epi1d = h->epi1;
+      if (!h->red()) memcpy(h->epi1d.bias, host_f32(ERNET_T_BLOCK_BASE + ERNET_T_PW_B), 64 * sizeof(float));
       fill(1, h->epi2.bias, h->epi2.scale, h->epi2.shift, h->epi2.deq, h->epi2.out_inv, 96);
       fill(2, h->epi3.bias, h->epi3.scale, h->epi3.shift, h->epi3.deq, h->epi3.out_inv, 128);
       if (h->red()) {
