@@ -54,8 +54,8 @@ struct ernet_handle {
   tc::DBlock1Consts* d_dblock1 = nullptr;   // fp16 constants of the depthwise + 1x1 block-1 kernel (tc_dblock.cuh)
   tc::EpiParams<64> epi1d;           // its epilogue constants: bias = fused_conv.bias (the depthwise biases are added on the CUDA cores)
   bool dw_block1 = false;            // experiment (ERNET_DW_BLOCK1=1): block 1 as depthwise on CUDA cores + 1x1 on tcgen05
-                                     // (tc_dblock.cuh).  Correct, but 94 us against 59 us for the 25-tap form: six depthwise warps
-                                     // are latency-bound (see the header of tc_dblock.cuh)
+                                     // (tc_dblock.cuh).  Correct, but 82 us against 59 us for the 25-tap form: issue-bound on the
+                                     // CUDA cores (see the header of tc_dblock.cuh)
   void* d_w1_pair = nullptr;         // block-1 weights regrouped for tap pairing ([13][2][64][16 B], tc_pblock.cuh)
   StemFrag* d_stem_frag = nullptr;   // folded conv1 in mma.sync fragment order (16-bit engines)
   bool trim_columns = false;    // host path: also skip the columns outside the crop footprint (ERNET_TRIM_COLUMNS=1).  Off:

@@ -73,6 +73,24 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volati
   return true;
 }
 
+// Same contract, but the wait SUSPENDS in hardware (mbarrier.try_wait) instead of polling: for warps that are not on the
+// critical path of a kernel whose bottleneck is the CUDA cores (tc_dblock.cuh) - a dozen polling epilogue warps were
+// measured to take half of the issue slots there.
+__device__ __forceinline__ bool mbar_wait_suspend(uint64_t* bar, uint32_t parity, volatile uint32_t* abort_flag, uint32_t tag,
+                                                  uint32_t aux = 0) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (*abort_flag) return false;
+    if (clock64() - t0 > 300000000LL) {
+      if (atomicAdd(&g_tc_status[0], 1u) == 0) { g_tc_status[1] = tag; g_tc_status[2] = blockIdx.x; g_tc_status[3] = aux; }
+      *abort_flag = 1u;
+      return false;
+    }
+  }
+  return true;
+}
+
 // Optional in-kernel timeline (study builds only: -DERNET_TIMELINE).  Slot layout: [cta < 148][unit < 32][8 stamps].
 #ifdef ERNET_TIMELINE
 __device__ unsigned long long g_timeline[3 * 148 * 32 * 8];

@@ -7,17 +7,19 @@
 // packed fp16 arithmetic (27 HFMA2 x 4 per pixel and 8-channel chunk), and what is left for the tensor pipe is the
 // real 1x1 convolution: K = 48, three MMAs per tile.  Per unit:
 //   warp 0        TMA box load of the input patch (22 x 30 pixels x 2 chunks of 8 fp16 channels) into a 3-stage ring
-//   warps 2-7     depthwise: one thread = 4 consecutive pixels x 8 channels x 3 dilations; the 10 columns of a patch row
-//                 are loaded once (LDS.128) and feed every branch with taps in that row, tap weights are broadcast
+//   warps 2-13    depthwise (two sets of six, even / odd units): one thread = 4 consecutive pixels x 8 channels, one
+//                 dilation at a time; the columns of a patch row are loaded once per branch (LDS.128), tap weights are broadcast
 //                 loads; results go straight into the UMMA A operand [tile][k-chunk = branch*2 + chunk][128 rows][16 B]
 //                 (the concat of acff.py:46 is the K order), double buffered
 //   warp 1        9 tcgen05.mma (M = 128, N = 64, K = 16) per unit, accumulators double buffered in TMEM
-//   warps 8-19    epilogue as in tc_pblock.cuh: bias, LeakyReLU, BN, 16-bit, 2x2 max-pool by register exchange, P8 store
-//   warp 20       zero halo of the output images
+//   warps 16-27   epilogue as in tc_pblock.cuh: bias, LeakyReLU, BN, 16-bit, 2x2 max-pool by register exchange, P8 store
+//   warp 14       zero halo of the output images (15 idle)
 // STATUS: experiment, off by default (ERNET_DW_BLOCK1=1 enables it).  Results match the oracle to the same tolerance as
-// the 25-tap kernel, but the kernel takes 94 us per 256 images against 59 us: with six depthwise warps (one 4-pixel
-// strip per thread per unit, ~540 instructions, 70 LDS.128) the CUDA-core stage is latency-bound at ~5 k cycles per
-// unit - it needs 2-3x the warps (register budget: 21 warps x 97 registers today) or two units in flight per warp.
+// the 25-tap kernel, but it takes 82 us per 256 images against 59 us.  ncu: the kernel is bound by instruction ISSUE, not
+// by shared memory or latency - 14.6 k warp instructions per unit at ~2.9 per cycle: 2.6 k HFMA2 + ~1 k loads/stores for
+// the depthwise stage, ~5.4 k for the twelve epilogue warps (bias / LeakyReLU / BN / pack / pool exchange: free while the
+// tensor pipe was the bottleneck, not free here), ~2 k of barrier polling.  With the polling gone the floor is ~2.5-3 k
+// cycles per unit against 3.65 k for the 25-tap form: a 20 % gain on this kernel at best, so the MMA-bound form stays.
 // Internally fp16 whatever the engine: the stem tensor is written as fp16 (the transform+conv1 kernel packs to fp16 for
 // this consumer), products and the 9-tap sums stay far inside fp16 range (|x| < 8, |w| < 1), the 1x1 conv runs
 // kind::f16 with fp32 accumulation, and the output is rounded once to the engine's type (bf16 / fp16).
@@ -43,8 +45,10 @@ struct DCfg1 {                                                     // block 1 of
   static constexpr int OFF_DW = OFF_WF + WF_BYTES;
   static constexpr int OFF_BAR = (OFF_DW + DWW_BYTES + DWB_BYTES + 127) / 128 * 128;
   static constexpr int SMEM_BYTES = OFF_BAR + 256;
-  static constexpr int DW_WARPS = 6, EPI_WARPS = 12;
-  static constexpr int WARP_DW0 = 2, WARP_EPI0 = 8, WARP_HALO = 20, THREADS = 32 * 21;
+  // two sets of 6 depthwise warps: set 0 takes the even units, set 1 the odd ones (own A buffer and TMEM buffer each), so
+  // that twice as many warps hide each other's shared-memory latency without loading anything twice
+  static constexpr int DW_SET = 6, DW_WARPS = 2 * DW_SET, EPI_WARPS = 12;
+  static constexpr int WARP_DW0 = 2, WARP_EPI0 = 16, WARP_HALO = 14, THREADS = 32 * 28;
   static_assert(TCOLS % GX == 0, "whole units");
   static_assert(OFF_A % 128 == 0 && A_TILE % 128 == 0, "alignment");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -93,9 +97,9 @@ acff_dblock1_kernel(const __grid_constant__ CUtensorMap tmap_in, const DBlock1Co
 
   if (threadIdx.x == 0) {
     *abort_flag = 0u;
-    for (int i = 0; i < 4; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], Cfg::DW_WARPS); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], Cfg::DW_SET); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], Cfg::DW_WARPS); mbar_init(&a_empty[i], 1);
+      mbar_init(&a_full[i], Cfg::DW_SET); mbar_init(&a_empty[i], 1);
       mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], Cfg::EPI_WARPS);
     }
     fence_mbar_init();
@@ -136,8 +140,8 @@ acff_dblock1_kernel(const __grid_constant__ CUtensorMap tmap_in, const DBlock1Co
       int k = 0;
       for (int u = blockIdx.x; u < total_units && ok; u += gridDim.x, ++k) {
         const int buf = k & 1, use = k >> 1;
-        ok = mbar_wait(&a_full[buf], use & 1, abort_flag, 0x901u, k);
-        if (ok && use > 0) ok = mbar_wait(&acc_empty[buf], (use - 1) & 1, abort_flag, 0x902u, k);
+        ok = mbar_wait_suspend(&a_full[buf], use & 1, abort_flag, 0x901u, k);
+        if (ok && use > 0) ok = mbar_wait_suspend(&acc_empty[buf], (use - 1) & 1, abort_flag, 0x902u, k);
         if (!ok) break;
         tc_fence_after();
 #pragma unroll
@@ -155,55 +159,48 @@ acff_dblock1_kernel(const __grid_constant__ CUtensorMap tmap_in, const DBlock1Co
     __syncwarp();
   } else if (warp >= Cfg::WARP_DW0 && warp < Cfg::WARP_DW0 + Cfg::DW_WARPS) {
     // ------------------------------------------------------------------ depthwise trio on the CUDA cores (fp16)
-    const int dwarp = warp - Cfg::WARP_DW0;
+    const int dwarp = (warp - Cfg::WARP_DW0) % Cfg::DW_SET, set = (warp - Cfg::WARP_DW0) / Cfg::DW_SET;
     const int v = dwarp / 3, tl = dwarp % 3;              // 8-channel chunk (warp-uniform: broadcast weight loads), tile of the unit
     const int ly = lane >> 1, lx0 = (lane & 1) * 4;       // strip of 4 pixels in the 16 x 8 tile
-    int k = 0;
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++k) {
+    int k = set;
+    for (int u = blockIdx.x + set * (int)gridDim.x; u < total_units; u += 2 * (int)gridDim.x, k += 2) {
       const int st = k % NSTAGE, buf = k & 1, use = k >> 1;
-      if (!mbar_wait(&in_full[st], (k / NSTAGE) & 1, abort_flag, 0x903u + dwarp, k)) break;
-      if (use > 0 && !mbar_wait(&a_empty[buf], (use - 1) & 1, abort_flag, 0x910u + dwarp, k)) break;
+      if (!mbar_wait_suspend(&in_full[st], (k / NSTAGE) & 1, abort_flag, 0x903u + dwarp, k)) break;
+      if (use > 0 && !mbar_wait_suspend(&a_empty[buf], (use - 1) & 1, abort_flag, 0x910u + dwarp, k)) break;
       const uint4* patch = reinterpret_cast<const uint4*>(smem + st * Cfg::STAGE_STRIDE + v * Cfg::CHUNK_BYTES) + ly * BW + 8 * tl + lx0;
-      uint32_t acc[3][4][4];
+      uint4* arow = reinterpret_cast<uint4*>(s_a + buf * Cfg::A_BUF + tl * Cfg::A_TILE) + ly * 8 + lx0;
+      // one dilation at a time: 16 accumulators live instead of 48 (the three branches share only the row dy = 1)
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
+        const int dil = d + 1;
+        uint32_t acc[4][4];
         const uint4 b = s_dwb[d * 2 + v];
 #pragma unroll
-        for (int px = 0; px < 4; ++px) { acc[d][px][0] = b.x; acc[d][px][1] = b.y; acc[d][px][2] = b.z; acc[d][px][3] = b.w; }
-      }
+        for (int px = 0; px < 4; ++px) { acc[px][0] = b.x; acc[px][1] = b.y; acc[px][2] = b.z; acc[px][3] = b.w; }
 #pragma unroll
-      for (int ry = 0; ry < 7; ++ry) {
-        const int dy = ry - 2;
-        uint4 xr[10];
+        for (int ky = 0; ky < 3; ++ky) {
+          const int ry = 2 + ky * dil - (dil - 1);          // patch row of this tap row relative to the output row
+          uint4 xr[10];
 #pragma unroll
-        for (int c = 0; c < 10; ++c) xr[c] = patch[ry * BW + c];          // columns no tap of this row uses are dropped by the compiler
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const int dil = d + 1, t = dy + (dil - 1);
-          if (t < 0 || t % dil != 0 || t / dil > 2) continue;
-          const int ky = t / dil;
+          for (int c = 0; c < 10; ++c) xr[c] = patch[ry * BW + c];        // unused columns are dropped by the compiler
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
             const uint4 w = s_dww[(d * 9 + ky * 3 + kx) * 2 + v];
             const int col = 2 + kx * dil - (dil - 1);
 #pragma unroll
             for (int px = 0; px < 4; ++px) {
-              acc[d][px][0] = hfma2_u32(xr[px + col].x, w.x, acc[d][px][0]);
-              acc[d][px][1] = hfma2_u32(xr[px + col].y, w.y, acc[d][px][1]);
-              acc[d][px][2] = hfma2_u32(xr[px + col].z, w.z, acc[d][px][2]);
-              acc[d][px][3] = hfma2_u32(xr[px + col].w, w.w, acc[d][px][3]);
+              acc[px][0] = hfma2_u32(xr[px + col].x, w.x, acc[px][0]);
+              acc[px][1] = hfma2_u32(xr[px + col].y, w.y, acc[px][1]);
+              acc[px][2] = hfma2_u32(xr[px + col].z, w.z, acc[px][2]);
+              acc[px][3] = hfma2_u32(xr[px + col].w, w.w, acc[px][3]);
             }
           }
         }
+#pragma unroll
+        for (int px = 0; px < 4; ++px) arow[(d * 2 + v) * 128 + px] = make_uint4(acc[px][0], acc[px][1], acc[px][2], acc[px][3]);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&in_empty[st]);           // this warp has read everything it needs from the stage
-      uint4* arow = reinterpret_cast<uint4*>(s_a + buf * Cfg::A_BUF + tl * Cfg::A_TILE) + ly * 8 + lx0;
-#pragma unroll
-      for (int d = 0; d < 3; ++d)
-#pragma unroll
-        for (int px = 0; px < 4; ++px)
-          arow[(d * 2 + v) * 128 + px] = make_uint4(acc[d][px][0], acc[d][px][1], acc[d][px][2], acc[d][px][3]);
       fence_proxy_async();                                  // generic-proxy writes of A -> visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[buf]);
@@ -226,8 +223,8 @@ acff_dblock1_kernel(const __grid_constant__ CUtensorMap tmap_in, const DBlock1Co
         }
       }
     }
-  } else {
-    // ------------------------------------------------------------------ epilogue (warps 8..19): one warp per (lane quarter, tile)
+  } else if (warp >= Cfg::WARP_EPI0) {
+    // ------------------------------------------------------------------ epilogue (warps 16..27): one warp per (lane quarter, tile)
     const int q4 = warp & 3;
     const int tl = (warp - Cfg::WARP_EPI0) >> 2;
     const int rr = 4 * q4 + (lane >> 3), cc = lane & 7;
@@ -238,7 +235,7 @@ acff_dblock1_kernel(const __grid_constant__ CUtensorMap tmap_in, const DBlock1Co
       const int img = u / Cfg::UNITS_PER_IMG, r = u - img * Cfg::UNITS_PER_IMG;
       const int ty = r / Cfg::UX, ux = r - ty * Cfg::UX;
       const int buf = k & 1, use = k >> 1;
-      if (!mbar_wait(&acc_full[buf], use & 1, abort_flag, 0xa00u + warp, k)) break;
+      if (!mbar_wait_suspend(&acc_full[buf], use & 1, abort_flag, 0xa00u + warp, k)) break;
       tc_fence_after();
       const int y = ty * 16 + rr, x = (ux * GX + tl) * 8 + cc;
       const bool valid = (y < Cfg::HU) && (x < Cfg::HU);
