@@ -44,7 +44,8 @@ typedef enum ernet_status {
 } ernet_status;
 
 /* `--model {squeeze-ernet,squeeze-redconv}` of aider-predict.py:124-138 / load_model :22-32.        */
-typedef enum ernet_arch { ERNET_ARCH_SQUEEZE = 0, ERNET_ARCH_REDCONV = 1 } ernet_arch;
+typedef enum ernet_arch { ERNET_ARCH_SQUEEZE = 0, ERNET_ARCH_REDCONV = 1,
+                          ERNET_ARCH_ERNET = 2 /* baseline ErNET, (B,3,240,240) inputs, layer-wise CUDA-core kernels */ } ernet_arch;
 
 /* `--quant {fp32,fp16,int8}` of build_tensorrt_model.py:320-330 (+ bf16, new).                      */
 typedef enum ernet_precision {

@@ -118,6 +118,16 @@ def avg_pool_5x5_s1_p1(x):
     return out / x.dtype.type(25)
 
 
+def avg_pool_5x5_s1_p0(x):
+    """nn.AvgPool2d(kernel_size=5, stride=1, padding=0) of ErNET (model/ernet.py:21): (B,C,H,W) -> (B,C,H-4,W-4)."""
+    B, C, H, W = x.shape
+    out = np.zeros((B, C, H - 4, W - 4), dtype=x.dtype)
+    for i in range(5):
+        for j in range(5):
+            out += x[:, :, i:i + H - 4, j:j + W - 4]
+    return out / x.dtype.type(25)
+
+
 def softmax_dim1(z):
     m = z.max(axis=1, keepdims=True)
     e = np.exp(z - m)
@@ -162,6 +172,8 @@ def forward(sd, x, arch, dtype=None, want_taps=False):
     squeeze-ernet, 62 for squeeze-redconv).
     ``x``: (B,3,140,140) NCHW.  A non-140 spatial size is rejected the way the
     reference's ``view(-1, 20)`` effectively does (squeeze_ernet.py:39)."""
+    if arch == "ernet":
+        return forward_ernet(sd, x, dtype, want_taps)
     x = np.asarray(x)
     if dtype is None:
         dtype = x.dtype
@@ -203,6 +215,38 @@ def forward(sd, x, arch, dtype=None, want_taps=False):
     logits = flat @ sd["fc.weight"].T + sd["fc.bias"]             # :40
     probs = softmax_dim1(logits)                                  # :41
     res = {"logits": logits, "probs": probs}
+    if taps is not None:
+        res["taps"] = taps
+    return res
+
+
+ARCH_ERNET = "ernet"
+
+
+def forward_ernet(sd, x, dtype=None, want_taps=False):
+    """Baseline ErNET (model/ernet.py:6-49): conv1 -> ACFF(16,64) pool ACFF(64,96) pool ACFF(96,128) pool
+    ACFF(128,128) ACFF(128,128) ACFF(128,256) -> conv2 1x1 -> AvgPool(5,1,0) -> view(-1,45) -> fc -> softmax.
+    ``x``: (B,3,240,240) NCHW (the only size for which view(-1, 5*3*3) keeps one row per sample, ernet.py:42)."""
+    x = np.asarray(x)
+    dtype = np.dtype(x.dtype if dtype is None else dtype)
+    if x.ndim != 4 or x.shape[1:] != (3, 240, 240):
+        raise ValueError(f"expected (B,3,240,240), got {x.shape}")
+    sd = _cast_sd(sd, dtype)
+    taps = {} if want_taps else None
+    out = conv2d_dense(x.astype(dtype), sd["conv1.weight"], None, stride=2)     # ernet.py:25
+    if taps is not None:
+        taps["stem"] = out
+    for k in (1, 2, 3):
+        out = max_pool_2x2(acff(out, sd, f"acff{k}", taps))                       # :26-31
+        if taps is not None:
+            taps[f"pool{k}"] = out
+    for k in (4, 5, 6):
+        out = acff(out, sd, f"acff{k}", taps)                                     # :32-34
+    out = conv2d_pointwise(out, sd["conv2.weight"], None)                         # :35
+    out = avg_pool_5x5_s1_p0(out)                                                 # :36
+    flat = out.reshape(-1, 5 * 3 * 3)                                             # :42  (c*9 + i*3 + j)
+    logits = flat @ sd["fc.weight"].T + sd["fc.bias"]                             # :43
+    res = {"logits": logits, "probs": softmax_dim1(logits)}
     if taps is not None:
         res["taps"] = taps
     return res

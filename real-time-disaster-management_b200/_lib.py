@@ -12,7 +12,7 @@ OK = 0
 ERR_INVALID_ARG, ERR_BAD_SHAPE, ERR_NOT_LOADED, ERR_BAD_BLOB, ERR_WORKSPACE, ERR_CUDA, ERR_UNSUPPORTED = \
     -1, -2, -3, -4, -5, -6, -7
 
-ARCH = {"squeeze-ernet": 0, "squeeze-redconv": 1}
+ARCH = {"squeeze-ernet": 0, "squeeze-redconv": 1, "ernet": 2}
 PRECISION = {"fp32": 0, "fp16": 1, "bf16": 2, "int8": 3}
 DTYPE_F32, DTYPE_F16, DTYPE_BF16, DTYPE_U8 = 0, 1, 2, 3
 NCHW, NHWC = 0, 1

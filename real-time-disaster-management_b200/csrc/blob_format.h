@@ -48,4 +48,6 @@ struct ernet_blob_entry {
 #define ERNET_T_Q_SCALES 80     // [16+64+96] fp32, int8 only: real value of one int8 step of every channel of the stem /
                                 // pool1 / pool2 tensors (per-channel equalisation of a per-tensor int8 scale; folded into
                                 // the producer's epilogue and the consumer's weights, so the runtime tensor scale is 1)
+#define ERNET_T_EBLOCK_BASE 88  // ErNET (arch 2) blocks 5 and 6: + 8*(k-4), same six tensors as ERNET_T_BLOCK_BASE
+#define ERNET_T_EHEAD_W 104     // ErNET: [5][49][256] conv2 o AvgPool(5,1,0) o view o fc collapsed per pixel (pack.py)
 #define ERNET_T_MAX 128

@@ -30,6 +30,7 @@ struct Tensor {
 
 struct Plan {                 // byte offsets into the caller's workspace for one chunk
   size_t ingest, stem, cat1, p1, cat2, a2, p2, cat3, p3, r3, cat4, a4, total;
+  size_t ecat, ea, eb;        // ErNET: concat buffer and two ping-pong activation buffers
   bool tc;                    // stem/p1/p2 are in the padded P8 layout of tc_block.cuh
 };
 
@@ -84,6 +85,8 @@ struct ernet_handle {
   std::vector<cudaEvent_t> prof_pool;
 
   bool red() const { return arch == ERNET_ARCH_REDCONV; }
+  bool ernet() const { return arch == ERNET_ARCH_ERNET; }
+  int in_hw() const { return ernet() ? 240 : 140; }    // model input size (ErNET is the 240x240-native model)
   int cs() const { return red() ? 8 : 16; }            // stem output channels
   int c3() const { return red() ? 48 : 96; }           // acff3 input channels
   int c4() const { return red() ? 64 : 128; }          // acff4 input channels
@@ -108,6 +111,14 @@ static Plan make_plan(const ernet_handle* h, int n) {
   size_t o = 0;
   auto take = [&](size_t elems) { size_t r = o; o += align_up(elems * e, 256); return r; };
   p.tc = h->use_tc();
+  if (h->ernet()) {                              // layer-wise path, NHWC: sizes of the largest user of each buffer
+    p.stem = take(N * 119 * 119 * 16);
+    p.ecat = take(N * 117 * 117 * 48);           // ACFF1 concat (ACFF2: 56*56*192 is smaller)
+    p.ea = take(N * 58 * 58 * 64);               // pool1 (also pool3 13*13*128, acff5 9*9*128)
+    p.eb = take(N * 28 * 28 * 96);               // pool2 (also acff4 11*11*128, acff6 7*7*256)
+    p.total = o;
+    return p;
+  }
   p.ingest = take(N * 140 * 140 * 3);
   if (p.tc && h->precision == ERNET_PREC_INT8) {   // P16 images: 16 int8 channels per 16-byte chunk (sizes in 2-byte units)
     p.stem = take(N * 2 * 72 * 72 * 8);        // (B,2,72,72,16) int8
@@ -164,8 +175,26 @@ static int check_tensor(const ernet_handle* h, int id, size_t elems) {
   return ERNET_OK;
 }
 
+static const int kErnetCin[6] = {16, 64, 96, 128, 128, 128}, kErnetCout[6] = {64, 96, 128, 128, 128, 256};
+static inline int ernet_block_base(int k) { return k < 4 ? ERNET_T_BLOCK_BASE + 8 * k : ERNET_T_EBLOCK_BASE + 8 * (k - 4); }
+
 static int validate_simt_tensors(const ernet_handle* h) {
   int rc;
+  if (h->ernet()) {
+    if ((rc = check_tensor(h, ERNET_T_STEM_W, 27 * 16))) return rc;
+    if ((rc = check_tensor(h, ERNET_T_STEM_B, 16))) return rc;
+    for (int k = 0; k < 6; ++k) {
+      const int base = ernet_block_base(k), ci = kErnetCin[k], co = kErnetCout[k];
+      if ((rc = check_tensor(h, base + ERNET_T_DW_W, 27 * ci))) return rc;
+      if ((rc = check_tensor(h, base + ERNET_T_DW_B, 3 * ci))) return rc;
+      if ((rc = check_tensor(h, base + ERNET_T_PW_W, (size_t)3 * ci * co))) return rc;
+      if ((rc = check_tensor(h, base + ERNET_T_PW_B, co))) return rc;
+      if ((rc = check_tensor(h, base + ERNET_T_BN_S, co))) return rc;
+      if ((rc = check_tensor(h, base + ERNET_T_BN_T, co))) return rc;
+    }
+    if ((rc = check_tensor(h, ERNET_T_EHEAD_W, 5 * 49 * 256))) return rc;
+    return check_tensor(h, ERNET_T_HEAD_B, 5);
+  }
   const int cs = h->cs();
   if ((rc = check_tensor(h, ERNET_T_STEM_W, 27 * cs))) return rc;
   if ((rc = check_tensor(h, ERNET_T_STEM_B, cs))) return rc;
@@ -442,8 +471,63 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
   return run_tail<T>(h, buf(p.p3), buf(p.cat4), buf(p.a4), n, probs, logits, s);
 }
 
+// Baseline ErNET (model/ernet.py:24-48), one chunk through the layer-wise CUDA-core kernels: conv1, then per ACFF block
+// the depthwise trio + concat and the 1x1 conv with LeakyReLU, BN (and the 2x2 max-pool of blocks 1-3) in its epilogue.
+template <typename T>
+static int run_chunk_ernet(ernet_handle* h, const void* x, int x_dtype, int x_layout, int n, float* probs, float* logits,
+                           char* ws, cudaStream_t s) {
+  const Plan p = make_plan(h, n);
+  auto buf = [&](size_t off) { return reinterpret_cast<T*>(ws + off); };
+  int rc;
+  {
+    long long sb = 3LL * 240 * 240, sc, sy, sx;
+    if (x_layout == ERNET_NCHW) { sc = 240 * 240; sy = 240; sx = 1; }
+    else                        { sc = 1; sy = 240 * 3; sx = 3; }
+    const int total = n * 119 * 119, grid = (total + 127) / 128;
+    const float* w = h->f(ERNET_T_STEM_W); const float* b = h->f(ERNET_T_STEM_B);
+    StageTimer _t(h, ERNET_STAGE_STEM, s);
+    if (x_dtype == ERNET_F32) stem_kernel<float, T, 16><<<grid, 128, 0, s>>>(static_cast<const float*>(x), sb, sc, sy, sx, w, b, buf(p.stem), total, 119);
+    else if (x_dtype == ERNET_F16) stem_kernel<__half, T, 16><<<grid, 128, 0, s>>>(static_cast<const __half*>(x), sb, sc, sy, sx, w, b, buf(p.stem), total, 119);
+    else stem_kernel<__nv_bfloat16, T, 16><<<grid, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(x), sb, sc, sy, sx, w, b, buf(p.stem), total, 119);
+    ERNET_LAUNCH_CHECK("stem_kernel");
+  }
+  // (input size, pooled?) per block: 119 -> 117 -> 58 -> 56 -> 28 -> 26 -> 13 -> 11 -> 9 -> 7
+  const int hin[6] = {119, 58, 28, 13, 11, 9};
+  const int pool[6] = {1, 1, 1, 0, 0, 0};
+  const int st_dw[6] = {ERNET_STAGE_DW1, ERNET_STAGE_DW2, ERNET_STAGE_DW3, ERNET_STAGE_DW4, ERNET_STAGE_DW4, ERNET_STAGE_DW4};   // profiling labels: blocks 4-6 share one
+  const int st_pw[6] = {ERNET_STAGE_PW1, ERNET_STAGE_PW2, ERNET_STAGE_PW3, ERNET_STAGE_PW4, ERNET_STAGE_PW4, ERNET_STAGE_PW4};
+  const T* cur = buf(p.stem);
+  T* pp[2] = {buf(p.ea), buf(p.eb)};
+  for (int k = 0; k < 6; ++k) {
+    const int base = ernet_block_base(k), ci = kErnetCin[k], co = kErnetCout[k];
+    const int H = hin[k], Ho = H - 2;
+    // with a pool only the even-sized region it keeps is computed (58 = floor(117 / 2) needs rows/cols 0..115)
+    const int Hu = pool[k] ? (Ho / 2) * 2 : Ho;
+    ERNET_STAGE(st_dw[k], launch_acff_dw<T>(cur, n, H, H, ci, Hu, Hu, h->f(base + ERNET_T_DW_W), h->f(base + ERNET_T_DW_B), buf(p.ecat), s));
+    T* dst = pp[k & 1];
+    ERNET_STAGE(st_pw[k], launch_pointwise<T>(buf(p.ecat), n, Hu, Hu, 3 * ci, co, h->f(base + ERNET_T_PW_W), h->f(base + ERNET_T_PW_B),
+                                  h->f(base + ERNET_T_BN_S), h->f(base + ERNET_T_BN_T), 1, pool[k], dst, s));
+    cur = dst;
+  }
+  {
+    StageTimer _t(h, ERNET_STAGE_HEAD, s);
+    ernet_head_kernel<T><<<n, 256, 0, s>>>(cur, h->f(ERNET_T_EHEAD_W), h->f(ERNET_T_HEAD_B), probs, logits);
+    ERNET_LAUNCH_CHECK("ernet_head_kernel");
+  }
+  return ERNET_OK;
+}
+
 static int run_chunk(ernet_handle* h, const void* x, int x_dtype, int x_layout, const uint8_t* frames,
                      const IngestTables* tab, int order, int n, float* probs, float* logits, char* ws, cudaStream_t s) {
+  if (h->ernet()) {
+    if (frames) return fail(ERNET_ERR_UNSUPPORTED, "the frames path (fused transform) is not wired for ErNET yet: pass (B,3,240,240) tensors to ernet_forward");
+    switch (h->precision) {
+      case ERNET_PREC_FP32: return run_chunk_ernet<float>(h, x, x_dtype, x_layout, n, probs, logits, ws, s);
+      case ERNET_PREC_FP16: return run_chunk_ernet<__half>(h, x, x_dtype, x_layout, n, probs, logits, ws, s);
+      case ERNET_PREC_BF16: return run_chunk_ernet<__nv_bfloat16>(h, x, x_dtype, x_layout, n, probs, logits, ws, s);
+      default: return fail(ERNET_ERR_UNSUPPORTED, "int8 is implemented for Squeeze_ErNET only");
+    }
+  }
   if (h->use_tc()) {
     if (h->precision == ERNET_PREC_BF16) return run_chunk_tc<__nv_bfloat16, tc::KIND_BF16>(h, x, x_dtype, x_layout, frames, tab, order, n, probs, logits, ws, s);
     if (h->precision == ERNET_PREC_INT8) return run_chunk_tc<__half, tc::KIND_I8>(h, x, x_dtype, x_layout, frames, tab, order, n, probs, logits, ws, s);
@@ -562,8 +646,10 @@ int ernet_abi_version(void) { return ERNET_ABI_VERSION; }
 int ernet_create(ernet_handle** out, int arch, int precision, int device) {
   if (!out) return fail(ERNET_ERR_INVALID_ARG, "ernet_create: out is null");
   *out = nullptr;
-  if (arch != ERNET_ARCH_SQUEEZE && arch != ERNET_ARCH_REDCONV)
+  if (arch != ERNET_ARCH_SQUEEZE && arch != ERNET_ARCH_REDCONV && arch != ERNET_ARCH_ERNET)
     return fail(ERNET_ERR_INVALID_ARG, "Unsupported model: arch=%d", arch);   // aider-predict.py:32
+  if (arch == ERNET_ARCH_ERNET && precision == ERNET_PREC_INT8)
+    return fail(ERNET_ERR_UNSUPPORTED, "int8 is implemented for Squeeze_ErNET only");
   if (precision < ERNET_PREC_FP32 || precision > ERNET_PREC_INT8)
     return fail(ERNET_ERR_INVALID_ARG, "unknown precision %d", precision);
   int ndev = 0;
@@ -802,7 +888,7 @@ static int forward_common(ernet_handle* h, const void* x, int x_dtype, int x_lay
   const IngestTables* tab = nullptr;
   if (frames) { int rc = get_tables(h, H, W, &tab); if (rc) return rc; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const size_t x_img = 3ull * 140 * 140 * dtype_size(x_dtype);
+  const size_t x_img = 3ull * h->in_hw() * h->in_hw() * dtype_size(x_dtype);
   const size_t f_img = (size_t)H * W * 3;
   for (int b0 = 0; b0 < batch; b0 += h->chunk) {
     const int n = batch - b0 < h->chunk ? batch - b0 : h->chunk;
@@ -1109,6 +1195,7 @@ int ernet_profile_read(ernet_handle* h, double* ms_by_stage, int* launches_by_st
 int ernet_launches_per_forward(const ernet_handle* h, int batch, int with_ingest) {
   if (!h || batch < 1) return 0;
   const int chunks = (batch + h->chunk - 1) / h->chunk;
+  if (h->ernet()) return chunks * 14;            // conv1, 6 x (depthwise, 1x1), head
   const bool tail = h->has_tail && h->engine != ERNET_ENGINE_SIMT;
   const int tail_launches = tail ? 1 : 3;
   // frames path: transform + conv1 are one kernel (two with debug taps on); tensor path: conv1 only

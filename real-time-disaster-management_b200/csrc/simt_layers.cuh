@@ -22,15 +22,15 @@ template <typename TI, typename TO, int CS>
 __global__ void __launch_bounds__(128)
 stem_kernel(const TI* __restrict__ x, long long sb, long long sc, long long sy, long long sx,
             const float* __restrict__ w /*[27][CS]*/, const float* __restrict__ bias /*[CS]*/,
-            TO* __restrict__ out /*(B,69,69,CS)*/, int total) {
+            TO* __restrict__ out /*(B,HO,HO,CS)*/, int total, int HO = 69) {
   __shared__ float ws[27 * CS + CS];
   for (int i = threadIdx.x; i < 27 * CS + CS; i += blockDim.x) ws[i] = i < 27 * CS ? w[i] : bias[i - 27 * CS];
   __syncthreads();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int b = idx / (69 * 69);
-  const int r = idx - b * 69 * 69;
-  const int oy = r / 69, ox = r - oy * 69;
+  const int b = idx / (HO * HO);
+  const int r = idx - b * HO * HO;
+  const int oy = r / HO, ox = r - oy * HO;
   float acc[CS];
 #pragma unroll
   for (int o = 0; o < CS; ++o) acc[o] = ws[27 * CS + o];
@@ -409,6 +409,52 @@ __global__ void tap_nhwc_to_nchw_f32(const T* __restrict__ src, int C, int HW, l
   const int c = (int)(bc % C);
   const long long b = bc / C;
   dst[i] = to_f32<T>(src[(b * HW + p) * C + c]);
+}
+
+// ---------------------------------------------------------------------------------- ErNET head
+// conv2 (1x1, 256 -> 5) -> AvgPool2d(5, stride 1) on the 7x7 map -> view(-1, 45) -> fc -> softmax (model/ernet.py:20-23,35-44):
+// everything before the softmax is linear, so the packer collapses it to a position-dependent W_eff[5][49][256]
+// (pack.py) and logits = b + sum_{pixel, channel} W_eff * acff6.  One CTA of 256 threads (= channels) per image.
+template <typename T>
+__global__ void __launch_bounds__(256)
+ernet_head_kernel(const T* __restrict__ a6 /*(B,7,7,256)*/, const float* __restrict__ w_eff /*[5][49][256]*/,
+                  const float* __restrict__ b_fc, float* __restrict__ probs, float* __restrict__ logits) {
+  __shared__ float red[8][5];
+  const int b = blockIdx.x, c = threadIdx.x;
+  const T* p = a6 + (size_t)b * 49 * 256 + c;
+  float part[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int i = 0; i < 49; ++i) {
+    const float v = to_f32<T>(p[i * 256]);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) part[j] = fmaf(v, __ldg(w_eff + (j * 49 + i) * 256 + c), part[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 5; ++j)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part[j] += __shfl_xor_sync(0xffffffffu, part[j], o);
+  if ((c & 31) == 0)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) red[c >> 5][j] = part[j];
+  __syncthreads();
+  if (c == 0) {
+    float z[5], m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      float t = b_fc[j];
+#pragma unroll
+      for (int wv = 0; wv < 8; ++wv) t += red[wv][j];
+      z[j] = t;
+      m = fmaxf(m, t);
+    }
+    float e[5], sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { e[j] = expf(z[j] - m); sum += e[j]; }
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      probs[(size_t)b * 5 + j] = e[j] / sum;
+      if (logits) logits[(size_t)b * 5 + j] = z[j];
+    }
+  }
 }
 
 }  // namespace ernet

@@ -59,6 +59,7 @@ class _ErnetB200(nn.Module):
         arch = self.ARCH
         red = arch == "squeeze-redconv"
         w = widths(arch)
+        self.IN_HW = 240 if arch == "ernet" else 140     # ErNET is the 240x240-native model (model/ernet.py:21-22,42)
         self.conv1 = nn.Conv2d(3, 16, 3, 2, 0, bias=False)
         if red:
             self.conv_red1 = nn.Conv2d(16, 8, 1)
@@ -70,8 +71,11 @@ class _ErnetB200(nn.Module):
         if red:
             self.conv_red3 = nn.Conv2d(128, 64, 1)
         self.acff4 = _ACFFParams(*w[3])
+        if arch == "ernet":
+            self.acff5 = _ACFFParams(*w[4])
+            self.acff6 = _ACFFParams(*w[5])
         self.conv2 = nn.Conv2d(256, 5, 1, bias=False)
-        self.fc = nn.Linear(2 * 2 * 5, 5)
+        self.fc = nn.Linear(3 * 3 * 5 if arch == "ernet" else 2 * 2 * 5, 5)
         if precision is not None and precision not in _lib.PRECISION:
             raise ValueError(f"unknown precision {precision!r}; expected one of {sorted(_lib.PRECISION)}")
         self._precision = precision          # None: follow the parameter dtype (fp32, or fp16 after .half())
@@ -247,9 +251,9 @@ class _ErnetB200(nn.Module):
     def _run(self, x, want_logits):
         if not isinstance(x, torch.Tensor):
             raise TypeError("expected a torch.Tensor")
-        if x.dim() != 4 or tuple(x.shape[1:]) != (3, 140, 140):
-            # the reference fails (or silently mixes images) for any other size, squeeze_ernet.py:39
-            raise ValueError(f"expected input of shape (B,3,140,140), got {tuple(x.shape)}")
+        if x.dim() != 4 or tuple(x.shape[1:]) != (3, self.IN_HW, self.IN_HW):
+            # the reference fails (or silently mixes images) for any other size, squeeze_ernet.py:39 / ernet.py:42
+            raise ValueError(f"expected input of shape (B,3,{self.IN_HW},{self.IN_HW}), got {tuple(x.shape)}")
         if x.dtype not in _DTYPE_CODE:
             raise ValueError(f"unsupported input dtype {x.dtype}")
         lib, h, idx = self._ensure_engine()
@@ -404,12 +408,21 @@ class Squeeze_RedConv(_ErnetB200):
     ARCH = "squeeze-redconv"
 
 
+class ErNET(_ErnetB200):
+    """Baseline ErNET (model/ernet.py:6-49): six ACFF blocks, (B,3,240,240) inputs, fc 45 -> 5; same 82 state_dict keys.
+    First native path: the layer-wise CUDA-core kernels in fp32 / fp16 / bf16 through
+    ``model(x)``; the tensor-core block kernels, the fused frames path and int8 are not wired for it yet."""
+    ARCH = "ernet"
+
+
 def load_model(model_name, weights_path, device, *, precision=None):
     """Mirror of ``load_model`` in aider-predict.py:22-45 / evaluate-classification-metrics.py:24-47."""
     if model_name == "squeeze-ernet":
         model = Squeeze_ErNET(precision=precision)
     elif model_name == "squeeze-redconv":
         model = Squeeze_RedConv(precision=precision)
+    elif model_name == "ernet":                      # aider-predict.py:25
+        model = ErNET(precision=precision)
     else:
         raise ValueError(f"Unsupported model: {model_name}")
     checkpoint = torch.load(weights_path, map_location="cpu", weights_only=True)
@@ -424,7 +437,7 @@ def load_model(model_name, weights_path, device, *, precision=None):
 
 def from_state_dict(arch, sd, device="cuda", precision="fp32"):
     """Build an eval-mode engine from a mapping of numpy arrays / tensors."""
-    cls = {"squeeze-ernet": Squeeze_ErNET, "squeeze-redconv": Squeeze_RedConv}.get(arch)
+    cls = {"squeeze-ernet": Squeeze_ErNET, "squeeze-redconv": Squeeze_RedConv, "ernet": ErNET}.get(arch)
     if cls is None:
         raise ValueError(f"Unsupported model: {arch}")
     m = cls(precision=precision)

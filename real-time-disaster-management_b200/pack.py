@@ -30,14 +30,24 @@ T_RED2_W, T_RED2_B, T_RED3_W, T_RED3_B = 40, 41, 42, 43
 T_HEAD_W, T_HEAD_B = 44, 45
 T_TC_BASE = 64
 
-ARCH_ID = {"squeeze-ernet": 0, "squeeze-redconv": 1}
+T_EBLOCK_BASE = 88          # ErNET blocks 5, 6 (k = 4, 5): 88 + 8*(k-4)
+T_EHEAD_W = 104             # ErNET head: conv2 o AvgPool(5,1,0) o view o fc collapsed to [5][49][256]
+
+ARCH_ID = {"squeeze-ernet": 0, "squeeze-redconv": 1, "ernet": 2}
 PREC_ID = {"fp32": 0, "fp16": 1, "bf16": 2, "int8": 3}
 DT_F32, DT_F16, DT_BF16, DT_U8, DT_RAW = 0, 1, 2, 3, 16
 
 
 def widths(arch):
+    if arch == "ernet":                       # model/ernet.py:11-19
+        return [(16, 64), (64, 96), (96, 128), (128, 128), (128, 128), (128, 256)]
     return [(8, 64), (64, 96), (48, 128), (64, 256)] if arch == "squeeze-redconv" else \
            [(16, 64), (64, 96), (96, 128), (128, 256)]
+
+
+def block_base(k):
+    """blob id base of ACFF block k (0-based)."""
+    return T_BLOCK_BASE + 8 * k if k < 4 else T_EBLOCK_BASE + 8 * (k - 4)
 
 
 def expected_shapes(arch):
@@ -57,7 +67,7 @@ def expected_shapes(arch):
         for n in ("weight", "bias", "running_mean", "running_var"):
             ks[f"{p}.batch_norm.{n}"] = (co,)
         ks[f"{p}.batch_norm.num_batches_tracked"] = ()
-    ks.update({"conv2.weight": (5, 256, 1, 1), "fc.weight": (5, 20), "fc.bias": (5,)})
+    ks.update({"conv2.weight": (5, 256, 1, 1), "fc.weight": (5, 45 if arch == "ernet" else 20), "fc.bias": (5,)})
     return ks
 
 
@@ -95,7 +105,7 @@ def derive_simt(sd, arch):
     out[T_STEM_B] = b1
     for k, (c, co) in enumerate(widths(arch)):
         p = f"acff{k + 1}"
-        base = T_BLOCK_BASE + 8 * k
+        base = block_base(k)
         dw = np.stack([_np64(sd, f"{p}.conv{j}.weight")[:, 0].reshape(c, 9).T for j in (1, 2, 3)], 0)  # [3][9][C]
         db = np.stack([_np64(sd, f"{p}.conv{j}.bias") for j in (1, 2, 3)], 0)                          # [3][C]
         pw = _np64(sd, f"{p}.fused_conv.weight")[:, :, 0, 0].T.copy()                                   # [3C][N]
@@ -111,6 +121,18 @@ def derive_simt(sd, arch):
         out[T_RED3_W] = _np64(sd, "conv_red3.weight")[:, :, 0, 0].T.copy()   # [128][64]
         out[T_RED3_B] = _np64(sd, "conv_red3.bias")
     wc2 = _np64(sd, "conv2.weight")[:, :, 0, 0]                              # (5,256)
+    if arch == "ernet":
+        # conv2 (1x1, no bias) -> AvgPool2d(5, stride 1, no padding) on the 7x7 map -> view(-1, 45) -> fc (ernet.py:35-43):
+        # all linear, so logits = b + sum_{y,x,k} W_eff[o][y][x][k] * acff6[k][y][x] with
+        # W_eff[o][y][x][k] = sum_c conv2[c][k] * (1/25) * sum_{i,j : 0 <= y-i < 5, 0 <= x-j < 5} fc[o][c*9 + i*3 + j]
+        wfc = _np64(sd, "fc.weight").reshape(5, 5, 3, 3)                     # [o][c][i][j]
+        cover = np.zeros((5, 5, 7, 7))
+        for i in range(3):
+            for j in range(3):
+                cover[:, :, i:i + 5, j:j + 5] += wfc[:, :, i, j][:, :, None, None]
+        out[T_EHEAD_W] = np.einsum("ocyx,ck->oyxk", cover, wc2).reshape(5, 49, 256) / 25.0
+        out[T_HEAD_B] = _np64(sd, "fc.bias")
+        return out
     wfc = _np64(sd, "fc.weight").reshape(5, 5, 4).sum(axis=2)                # (5 out, 5 conv2-ch): sum of the 2x2 taps
     out[T_HEAD_W] = (wfc @ wc2) / 25.0                                       # (5,256)
     out[T_HEAD_B] = _np64(sd, "fc.bias")
@@ -147,6 +169,10 @@ def pack_state_dict(sd, arch, precision, act_scales=None):
         raise ValueError(f"unknown precision {precision}")
     validate_state_dict(sd, arch)
     tensors = {i: (v.astype(np.float32), DT_F32) for i, v in derive_simt(sd, arch).items()}
+    if arch == "ernet":
+        if precision == "int8":
+            raise ValueError("int8 is implemented for squeeze-ernet only")
+        return assemble(arch, precision, tensors)          # ErNET runs on the layer-wise CUDA-core kernels (all precisions)
     if precision in ("fp16", "bf16", "int8"):
         from . import pack_tc
         tensors.update(pack_tc.derive_tc(sd, arch, precision, act_scales))

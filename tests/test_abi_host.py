@@ -117,4 +117,4 @@ def test_shim_errors_without_gpu_or_in_train_mode():
     with pytest.raises(ValueError):
         rtdm_b200.Squeeze_ErNET(precision="fp64")
     with pytest.raises(ValueError, match="Unsupported model"):
-        rtdm_b200.load_model("ernet", "/nonexistent", "cpu")
+        rtdm_b200.load_model("yolov3", "/nonexistent", "cpu")       # "ernet" is a supported name since the ErNET path exists

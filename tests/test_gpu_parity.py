@@ -1,6 +1,7 @@
 """GPU parity tests: every call goes through the C ABI (ctypes -> libernet_b200.so) and is compared with
 the CPU oracle / the goldens produced by the real reference.  Run with `pytest -m gpu` on a B200."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -529,3 +530,49 @@ def test_config5_full_size_sharding(dev):
     assert _rel(lg, ref) <= TOL["bf16"] and _top1_ok(lg, ref, TOL["bf16"])
     ph = m.classify_host(ft[:1024].cpu().numpy())
     assert np.array_equal(ph, p[:1024].cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------ ErNET
+@pytest.mark.gpu
+@pytest.mark.parametrize("wset", ["shipped", "w3", "w3neg"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "fp16"])
+def test_ernet_logits_match_reference(wset, prec, dev):
+    """Baseline ErNET on (B,3,240,240) inputs through the C ABI (layer-wise CUDA-core kernels) against the fc output of
+    the real reference class (tests/golden/ernet_golden.npz), same tolerances as the Squeeze models."""
+    g = np.load(os.path.join(fixtures.GOLDEN, "ernet_golden.npz"))
+    sd = fixtures.get_state_dict("ernet", wset)
+    x = fixtures.normal_tensors(3, seed=17, hw=240)
+    ref = g[f"ernet/{wset}/norm/logits64"]
+    m = rtdm_b200.from_state_dict("ernet", sd, dev, prec)
+    probs, logits = m.forward_with_logits(torch.from_numpy(x).to(dev))
+    lg = logits.double().cpu().numpy()
+    assert _rel(lg, ref) <= TOL[prec], _rel(lg, ref)
+    assert _top1_ok(lg, ref, TOL[prec])
+    assert np.abs(probs.double().cpu().numpy().sum(1) - 1).max() < 1e-5
+
+
+@pytest.mark.gpu
+def test_ernet_call_surface_and_batching(dev):
+    """Same plugin surface as the reference class (model/ernet.py): 82 state_dict keys, model(x) -> probabilities of the
+    input's dtype, wrong spatial size raises, chunked batches and NHWC tensors give the same bits, frames path says no."""
+    sd = fixtures.get_state_dict("ernet", "shipped")
+    m = rtdm_b200.ErNET()
+    assert len(m.state_dict()) == 82
+    m.load_state_dict({k: torch.as_tensor(np.asarray(v)) for k, v in sd.items()})
+    m = m.to(dev).eval()
+    x = torch.from_numpy(fixtures.normal_tensors(7, seed=23, hw=240)).to(dev)
+    with torch.no_grad():
+        p = m(x)
+    assert p.shape == (7, 5) and p.dtype == torch.float32
+    ref = E.forward(sd, x.cpu().numpy(), "ernet", dtype=np.float64)
+    assert _rel(m.logits(x).double().cpu().numpy(), ref["logits"]) <= TOL["fp32"]
+    m.set_chunk(3)
+    assert torch.equal(m(x), p)
+    assert torch.equal(m(x[2:3]), p[2:3])
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 3, 140, 140, device=dev))
+    with pytest.raises(RuntimeError):
+        m.forward_frames(torch.zeros(1, 240, 240, 3, dtype=torch.uint8, device=dev))
+    mh = rtdm_b200.from_state_dict("ernet", sd, dev, "fp32").half()
+    ph = mh(x.half())
+    assert ph.dtype == torch.float16 and (ph.float().argmax(1) == p.argmax(1)).all()

@@ -4,6 +4,8 @@ The goldens were produced by tests/golden/make_golden.py, which imports the refe
 own Squeeze_ErNET / Squeeze_RedConv (model/squeeze_ernet.py, model/squeeze_ernet_redconv.py)
 and the torchvision/Pillow eval transform (dataloaders/aider.py:421-426).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -122,3 +124,51 @@ def test_ingest_constants():
     assert I.center_crop_offset(159) == 10          # round(9.5) -> 10 (banker's)
     xmin, xlen, kk = I.resample_coeffs(240, 159)
     assert kk.shape == (159, 5) and int(kk.sum(1).min()) >= (1 << 22) - 3
+
+
+# ------------------------------------------------------------------------------------ ErNET
+@pytest.mark.parametrize("wset", ["shipped", "w3", "w3neg"])
+def test_ernet_oracle_matches_reference_goldens(wset):
+    """oracle/ernet_numpy.forward_ernet against outputs of the real reference class (tests/golden/make_golden_ernet.py):
+    fc output, probabilities and sub-sampled intermediates of every layer, fp64."""
+    import fixtures
+    from oracle import ernet_numpy as E
+    g = np.load(os.path.join(fixtures.GOLDEN, "ernet_golden.npz"))
+    sd = fixtures.get_state_dict("ernet", wset)
+    x = fixtures.normal_tensors(3, seed=17, hw=240)
+    r = E.forward(sd, x, "ernet", dtype=np.float64, want_taps=True)
+    tag = f"ernet/{wset}/norm"
+    ref = g[f"{tag}/logits64"]
+    assert np.abs(r["logits"] - ref).max() <= 1e-9 * np.abs(ref).max()
+    assert np.abs(r["probs"] - g[f"{tag}/probs64"]).max() <= 1e-9
+    for name, v in r["taps"].items():
+        key = f"{tag}/tap/{'conv1' if name == 'stem' else name}"
+        if f"{key}/shape" not in g.files:
+            continue                                   # oracle-internal tap without a reference module of that name
+        assert tuple(g[f"{key}/shape"]) == v.shape, name
+        assert np.abs(v[0, :, ::5, ::5] - g[f"{key}/sub"]).max() <= 1e-9 * max(1.0, np.abs(g[f"{key}/sub"]).max()), name
+    r32 = E.forward(sd, x, "ernet", dtype=np.float32)
+    assert np.abs(r32["logits"] - g[f"{tag}/logits32"]).max() <= 2e-4 * np.abs(ref).max()
+
+
+def test_ernet_packer_head_collapse():
+    """The packer folds conv2 -> AvgPool(5,1,0) -> view -> fc into W_eff[5][49][256]: check it against the oracle's
+    un-collapsed head on random activations, and the blob ids of the six blocks."""
+    import fixtures
+    import rtdm_b200
+    from oracle import ernet_numpy as E
+    from rtdm_b200 import pack as P
+    sd = fixtures.get_state_dict("ernet", "w3")
+    t = P.derive_simt(sd, "ernet")
+    assert t[P.T_EHEAD_W].shape == (5, 49, 256)
+    for k, (c, co) in enumerate(P.widths("ernet")):
+        assert t[P.block_base(k) + P.T_PW_W].shape == (3 * c, co)
+    a6 = np.random.RandomState(3).standard_normal((2, 256, 7, 7))
+    z = E.avg_pool_5x5_s1_p0(E.conv2d_pointwise(a6, np.asarray(sd["conv2.weight"], np.float64), None))
+    want = z.reshape(-1, 45) @ np.asarray(sd["fc.weight"], np.float64).T + np.asarray(sd["fc.bias"], np.float64)
+    got = np.einsum("opk,bkp->bo", t[P.T_EHEAD_W], a6.reshape(2, 256, 49)) + t[P.T_HEAD_B]
+    assert np.abs(got - want).max() <= 1e-10 * np.abs(want).max()
+    blob = rtdm_b200.pack_state_dict(sd, "ernet", "bf16")
+    assert len(blob) > 4 * sum(int(np.prod(v.shape)) for v in t.values())
+    with pytest.raises(ValueError):
+        rtdm_b200.pack_state_dict(sd, "ernet", "int8")
