@@ -50,4 +50,5 @@ struct ernet_blob_entry {
                                 // the producer's epilogue and the consumer's weights, so the runtime tensor scale is 1)
 #define ERNET_T_EBLOCK_BASE 88  // ErNET (arch 2) blocks 5 and 6: + 8*(k-4), same six tensors as ERNET_T_BLOCK_BASE
 #define ERNET_T_EHEAD_W 104     // ErNET: [5][49][256] conv2 o AvgPool(5,1,0) o view o fc collapsed per pixel (pack.py)
+#define ERNET_T_ETC_BASE 106    // ErNET tensor-core images: + 2*k, k = 0..5: [25][C/8][N][8] 16-bit, then [N] fp32 folded bias
 #define ERNET_T_MAX 128

@@ -31,6 +31,7 @@ struct Tensor {
 struct Plan {                 // byte offsets into the caller's workspace for one chunk
   size_t ingest, stem, cat1, p1, cat2, a2, p2, cat3, p3, r3, cat4, a4, total;
   size_t ecat, ea, eb;        // ErNET: concat buffer and two ping-pong activation buffers
+  size_t e4, e5, e6;          // ErNET tensor-core path: outputs of blocks 4-6 (stem / p1 / p2 / p3 hold the first three)
   bool tc;                    // stem/p1/p2 are in the padded P8 layout of tc_block.cuh
 };
 
@@ -48,6 +49,8 @@ struct ernet_handle {
   tc::EpiParams<96> epi2;
   tc::EpiParams<128> epi3;
   tc::EpiParams<64> epi_r2;     // RedConv conv_red2 (bias only)
+  tc::EpiParams<128> ee4, ee5;  // ErNET blocks 4, 5 (blocks 1-3 reuse epi1-3)
+  tc::EpiParams<256> ee6;       // ErNET block 6
   bool has_tail = false;        // blob carries the ACFF4+head tensor-core image
   bool debug_taps = false;      // keep intermediates the fused kernels would not write (acff4)
   int persistent = 2;           // block-kernel schedule: 0 one image per CTA, 1 persistent CTAs, 2 persistent + CTA pairs for blocks 2, 3
@@ -111,6 +114,17 @@ static Plan make_plan(const ernet_handle* h, int n) {
   size_t o = 0;
   auto take = [&](size_t elems) { size_t r = o; o += align_up(elems * e, 256); return r; };
   p.tc = h->use_tc();
+  if (h->ernet() && p.tc) {                      // P8 images between the tensor-core kernels (+ slack for the last pair-unit)
+    p.stem = take(N * 2 * 122 * 122 * 8);        // (B,2,122,122,8)
+    p.p1 = take(N * 8 * 61 * 61 * 8);            // (B,8,61,61,8)
+    p.p2 = take(N * 12 * 31 * 31 * 8);           // (B,12,31,31,8)
+    p.p3 = take(N * 16 * 16 * 16 * 8);           // (B,16,16,16,8)
+    p.e4 = take(N * 16 * 14 * 14 * 8);           // (B,16,14,14,8)
+    p.e5 = take(N * 16 * 12 * 12 * 8);           // (B,16,12,12,8)
+    p.e6 = take(N * 7 * 7 * 256);                // NHWC
+    p.total = o;
+    return p;
+  }
   if (h->ernet()) {                              // layer-wise path, NHWC: sizes of the largest user of each buffer
     p.stem = take(N * 119 * 119 * 16);
     p.ecat = take(N * 117 * 117 * 48);           // ACFF1 concat (ACFF2: 56*56*192 is smaller)
@@ -517,10 +531,49 @@ static int run_chunk_ernet(ernet_handle* h, const void* x, int x_dtype, int x_la
   return ERNET_OK;
 }
 
+// ErNET on the tensor-core block kernels: conv1 -> P8, block 1 on the persistent kernel, blocks 2-6 on CTA pairs
+// (blocks 4-6 without a pool; block 6 with N = 256), head on the CUDA cores.
+template <typename T, int KIND>
+static int run_chunk_ernet_tc(ernet_handle* h, const void* x, int x_dtype, int x_layout, int n, float* probs, float* logits,
+                              char* ws, cudaStream_t s) {
+  const Plan p = make_plan(h, n);
+  auto u16 = [&](size_t off) { return reinterpret_cast<uint16_t*>(ws + off); };
+  auto wimg = [&](int k) { return h->t[ERNET_T_ETC_BASE + 2 * k].dev; };
+  int rc;
+  {
+    long long sb = 3LL * 240 * 240, sc, sy, sx;
+    if (x_layout == ERNET_NCHW) { sc = 240 * 240; sy = 240; sx = 1; }
+    else                        { sc = 1; sy = 240 * 3; sx = 3; }
+    const int total = n * 122 * 122, grid = (total + 127) / 128;
+    const float* w = h->f(ERNET_T_STEM_W); const float* b = h->f(ERNET_T_STEM_B);
+    StageTimer _t(h, ERNET_STAGE_STEM, s);
+    if (x_dtype == ERNET_F32) tc::stem_p8_kernel<float, 16, KIND, 119><<<grid, 128, 0, s>>>(static_cast<const float*>(x), sb, sc, sy, sx, w, b, u16(p.stem), total, h->stem_inv);
+    else if (x_dtype == ERNET_F16) tc::stem_p8_kernel<__half, 16, KIND, 119><<<grid, 128, 0, s>>>(static_cast<const __half*>(x), sb, sc, sy, sx, w, b, u16(p.stem), total, h->stem_inv);
+    else tc::stem_p8_kernel<__nv_bfloat16, 16, KIND, 119><<<grid, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(x), sb, sc, sy, sx, w, b, u16(p.stem), total, h->stem_inv);
+    ERNET_LAUNCH_CHECK("stem_p8_kernel");
+  }
+  ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::EBlock1, KIND, tc::OUT_P8>(u16(p.stem), wimg(0), h->epi1, u16(p.p1), n, h->num_sms, s)));
+  ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_cblock<tc::EBlock2, KIND, tc::OUT_P8>(u16(p.p1), wimg(1), h->epi2, u16(p.p2), n, h->num_sms, s)));
+  ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_cblock<tc::EBlock3, KIND, tc::OUT_P8>(u16(p.p2), wimg(2), h->epi3, u16(p.p3), n, h->num_sms, s)));
+  ERNET_STAGE(ERNET_STAGE_TC_BLOCK4, (tc::launch_acff_cblock<tc::EBlock4, KIND, tc::OUT_P8>(u16(p.p3), wimg(3), h->ee4, u16(p.e4), n, h->num_sms, s)));
+  ERNET_STAGE(ERNET_STAGE_TC_BLOCK4, (tc::launch_acff_cblock<tc::EBlock5, KIND, tc::OUT_P8>(u16(p.e4), wimg(4), h->ee5, u16(p.e5), n, h->num_sms, s)));
+  ERNET_STAGE(ERNET_STAGE_TC_BLOCK4, (tc::launch_acff_cblock<tc::EBlock6, KIND, tc::OUT_NHWC>(u16(p.e5), wimg(5), h->ee6, u16(p.e6), n, h->num_sms, s)));
+  {
+    StageTimer _t(h, ERNET_STAGE_HEAD, s);
+    ernet_head_kernel<T><<<n, 256, 0, s>>>(reinterpret_cast<const T*>(ws + p.e6), h->f(ERNET_T_EHEAD_W), h->f(ERNET_T_HEAD_B), probs, logits);
+    ERNET_LAUNCH_CHECK("ernet_head_kernel");
+  }
+  return ERNET_OK;
+}
+
 static int run_chunk(ernet_handle* h, const void* x, int x_dtype, int x_layout, const uint8_t* frames,
                      const IngestTables* tab, int order, int n, float* probs, float* logits, char* ws, cudaStream_t s) {
   if (h->ernet()) {
     if (frames) return fail(ERNET_ERR_UNSUPPORTED, "the frames path (fused transform) is not wired for ErNET yet: pass (B,3,240,240) tensors to ernet_forward");
+    if (h->use_tc()) {
+      if (h->precision == ERNET_PREC_BF16) return run_chunk_ernet_tc<__nv_bfloat16, tc::KIND_BF16>(h, x, x_dtype, x_layout, n, probs, logits, ws, s);
+      return run_chunk_ernet_tc<__half, tc::KIND_F16>(h, x, x_dtype, x_layout, n, probs, logits, ws, s);
+    }
     switch (h->precision) {
       case ERNET_PREC_FP32: return run_chunk_ernet<float>(h, x, x_dtype, x_layout, n, probs, logits, ws, s);
       case ERNET_PREC_FP16: return run_chunk_ernet<__half>(h, x, x_dtype, x_layout, n, probs, logits, ws, s);
@@ -606,6 +659,18 @@ static int init_device_attrs() {
   if ((rc = tc::set_pblock_attr<tc::PBlock1P, tc::KIND_F16, tc::OUT_P8>())) return rc;
   if ((rc = tc::set_cblock_attr<tc::CBlock2Q, tc::KIND_I8, tc::OUT_P16>())) return rc;
   if ((rc = tc::set_cblock_attr<tc::CBlock3Q, tc::KIND_I8, tc::OUT_NHWC>())) return rc;
+  if ((rc = tc::set_pblock_attr<tc::EBlock1, tc::KIND_BF16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_pblock_attr<tc::EBlock1, tc::KIND_F16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::EBlock2, tc::KIND_BF16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::EBlock2, tc::KIND_F16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::EBlock3, tc::KIND_BF16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::EBlock3, tc::KIND_F16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::EBlock4, tc::KIND_BF16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::EBlock4, tc::KIND_F16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::EBlock5, tc::KIND_BF16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::EBlock5, tc::KIND_F16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::EBlock6, tc::KIND_BF16, tc::OUT_NHWC>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::EBlock6, tc::KIND_F16, tc::OUT_NHWC>())) return rc;
   if ((rc = tc::set_dblock1_attr<tc::KIND_BF16, tc::OUT_P8>())) return rc;
   if ((rc = tc::set_dblock1_attr<tc::KIND_F16, tc::OUT_P8>())) return rc;
   if ((rc = tc::set_tail_attrs<tc::TailCfg128>())) return rc;
@@ -732,7 +797,35 @@ int ernet_load_packed(ernet_handle* h, const void* blob, size_t bytes) {
   }
   int rc = validate_simt_tensors(h);
   if (rc) { memcpy(h->t, old, sizeof(old)); cudaFree(d); return rc; }
-  {
+  if (h->ernet()) {
+    // tensor-core images of the six blocks (16-bit blobs): all present with the sizes the kernel configurations expect?
+    const size_t wb[6] = {(size_t)25 * 2 * 64 * 16, (size_t)25 * 8 * 96 * 16, (size_t)25 * 12 * 128 * 16, (size_t)25 * 16 * 128 * 16,
+                          (size_t)25 * 16 * 128 * 16, (size_t)25 * 16 * 256 * 16};
+    bool all = h->precision == ERNET_PREC_BF16 || h->precision == ERNET_PREC_FP16;
+    for (int k = 0; k < 6 && all; ++k) {
+      const Tensor& w = h->t[ERNET_T_ETC_BASE + 2 * k];
+      const Tensor& b = h->t[ERNET_T_ETC_BASE + 2 * k + 1];
+      all = w.dev && b.dev && w.nbytes == wb[k] && b.nbytes == (size_t)kErnetCout[k] * sizeof(float);
+    }
+    h->has_tc = all;
+    h->has_tail = false;
+    if (all) {
+      auto host_f32 = [&](int id) { return reinterpret_cast<const float*>(static_cast<const char*>(blob) + (static_cast<const char*>(h->t[id].dev) - static_cast<const char*>(d))); };
+      auto fill = [&](int k, float* bias, float* scale, float* shift, float* deq, float* out_inv, int n) {
+        memcpy(bias, host_f32(ERNET_T_ETC_BASE + 2 * k + 1), n * sizeof(float));
+        memcpy(scale, host_f32(ernet_block_base(k) + ERNET_T_BN_S), n * sizeof(float));
+        memcpy(shift, host_f32(ernet_block_base(k) + ERNET_T_BN_T), n * sizeof(float));
+        for (int i = 0; i < n; ++i) { deq[i] = 1.f; out_inv[i] = 1.f; }
+      };
+      fill(0, h->epi1.bias, h->epi1.scale, h->epi1.shift, h->epi1.deq, h->epi1.out_inv, 64);
+      fill(1, h->epi2.bias, h->epi2.scale, h->epi2.shift, h->epi2.deq, h->epi2.out_inv, 96);
+      fill(2, h->epi3.bias, h->epi3.scale, h->epi3.shift, h->epi3.deq, h->epi3.out_inv, 128);
+      fill(3, h->ee4.bias, h->ee4.scale, h->ee4.shift, h->ee4.deq, h->ee4.out_inv, 128);
+      fill(4, h->ee5.bias, h->ee5.scale, h->ee5.shift, h->ee5.deq, h->ee5.out_inv, 128);
+      fill(5, h->ee6.bias, h->ee6.scale, h->ee6.shift, h->ee6.deq, h->ee6.out_inv, 256);
+      for (int i = 0; i < 16; ++i) h->stem_inv.v[i] = 1.f;
+    }
+  } else {
     const bool q = h->precision == ERNET_PREC_INT8;
     const size_t wimg_bytes[3] = {q ? (size_t)tc::CfgBlock1Q::W_BYTES : (size_t)tc::CfgBlock1::W_BYTES,
                                   q ? (size_t)tc::CfgBlock2Q::W_BYTES : (size_t)tc::CfgBlock2::W_BYTES,
@@ -816,7 +909,7 @@ int ernet_load_packed(ernet_handle* h, const void* blob, size_t bytes) {
   }
   {
     const Tensor& w4 = h->t[ERNET_T_TC4_WIMG];
-    h->has_tail = h->precision != ERNET_PREC_FP32 && w4.dev && w4.nbytes == (size_t)3 * h->c4() * 256 * 2;
+    h->has_tail = !h->ernet() && h->precision != ERNET_PREC_FP32 && w4.dev && w4.nbytes == (size_t)3 * h->c4() * 256 * 2;
     if (h->has_tail) {
       auto host_f32 = [&](int id) { return reinterpret_cast<const float*>(static_cast<const char*>(blob) + (static_cast<const char*>(h->t[id].dev) - static_cast<const char*>(d))); };
       memcpy(h->tail.bias, host_f32(ERNET_T_BLOCK_BASE + 24 + ERNET_T_PW_B), 256 * sizeof(float));
@@ -1195,7 +1288,7 @@ int ernet_profile_read(ernet_handle* h, double* ms_by_stage, int* launches_by_st
 int ernet_launches_per_forward(const ernet_handle* h, int batch, int with_ingest) {
   if (!h || batch < 1) return 0;
   const int chunks = (batch + h->chunk - 1) / h->chunk;
-  if (h->ernet()) return chunks * 14;            // conv1, 6 x (depthwise, 1x1), head
+  if (h->ernet()) return chunks * (h->use_tc() ? 8 : 14);   // conv1, 6 fused blocks, head | conv1, 6 x (depthwise, 1x1), head
   const bool tail = h->has_tail && h->engine != ERNET_ENGINE_SIMT;
   const int tail_launches = tail ? 1 : 3;
   // frames path: transform + conv1 are one kernel (two with debug taps on); tensor path: conv1 only

@@ -451,7 +451,7 @@ inline int set_all_block_attrs() {
 // stages: (B, 2 chunks, 72, 72, 8) with the zero halo included.  One thread per padded pixel.
 // KIND_I8: channel c is quantised with out_inv.v[c] (= 1 / its int8 step) into chunk 0 of a P16 image, chunk 1 is zero.
 struct StemInv { float v[16]; };
-template <typename TI, int CS, int KIND>
+template <typename TI, int CS, int KIND, int HS = 69>
 __global__ void __launch_bounds__(128)
 stem_p8_kernel(const TI* __restrict__ x, long long sb, long long sc, long long sy, long long sx,
                const float* __restrict__ w /*[27][CS]*/, const float* __restrict__ bias, uint16_t* __restrict__ out, int total,
@@ -461,13 +461,13 @@ stem_p8_kernel(const TI* __restrict__ x, long long sb, long long sc, long long s
   __syncthreads();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  constexpr int P = 72;
+  constexpr int P = HS + 3;          // HS = conv1 output size: 69 (140x140 inputs), 119 (ErNET, 240x240)
   const int b = idx / (P * P);
   const int r = idx - b * P * P;
   const int pr = r / P, pc = r - pr * P;
   const int oy = pr - 2, ox = pc - 2;
   uint4* o = reinterpret_cast<uint4*>(out) + (size_t)b * 2 * P * P + pr * P + pc;
-  if (oy < 0 || oy >= 69 || ox < 0 || ox >= 69) {
+  if (oy < 0 || oy >= HS || ox < 0 || ox >= HS) {
     o[0] = make_uint4(0, 0, 0, 0);
     o[P * P] = make_uint4(0, 0, 0, 0);
     return;

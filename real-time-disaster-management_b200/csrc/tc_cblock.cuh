@@ -34,9 +34,13 @@ struct CCfg {
   static constexpr int NC = NC_, N = N_, HIN = HIN_, HU = HU_, GX = GX_, NSLOT = NSLOT_, WSTAGES = WSTAGES_;
   static constexpr bool WRES = WRES_, POOL = POOL_, ACT = ACT_;
   static constexpr int TAPS = 25, NREAL = NREAL_, NH = N / 2, TG = 5, NTG = TAPS / TG;
+  static constexpr int WELEM = NH * 4 > 256 ? 8 : 4;                   // element size of the weight tensor map (box rows <= 256 elements)
   static constexpr int WP = HIN + 3;
-  static constexpr int BW = (8 * GX + 6) < WP ? (8 * GX + 6) : WP;
-  static constexpr int BH = 22 < WP ? 22 : WP;
+  // A pooled block uses HU = HIN - 3 rows/cols, so its taps reach at most the ONE halo row/col that P8 stores after the
+  // image and a box may be clamped to the tensor.  An un-pooled block (HU = HIN - 2, ErNET blocks 4-6) reaches one row/col
+  // further: its box keeps the full 22 x (8 GX + 6) footprint and the TMA unit zero-fills what lies outside the tensor.
+  static constexpr int BW = (POOL_ && (8 * GX + 6) >= WP) ? WP : (8 * GX + 6);
+  static constexpr int BH = (POOL_ && 22 >= WP) ? WP : 22;
   static constexpr int CHUNK_BYTES = BH * BW * 16;
   static constexpr int SLOT_BYTES = 2 * CHUNK_BYTES;                   // one K step: 16 channels of the patch
   static constexpr int KS = NC / 2;
@@ -51,7 +55,8 @@ struct CCfg {
   static constexpr int OFF_W = NSLOT * SLOT_BYTES;
   static constexpr int OFF_BAR = (OFF_W + W_SMEM + 15) / 16 * 16;
   static constexpr int SMEM_BYTES = OFF_BAR + 512 + 16;
-  static_assert(TCOLS % GX == 0, "both halves of a pair-unit issue the same number of tiles");
+  // every unit issues GX tiles: a tile past the last tile column only multiplies TMA zero fill and is masked in the
+  // epilogue (x >= HU), so both halves of a pair-unit always issue the same MMAs
   static_assert(NC % 2 == 0 && N % 32 == 0 && N <= 256, "operand shape");
   static_assert(2 * GX * N <= 512, "two TMEM accumulator buffers");
   static_assert(SLOT_BYTES % 128 == 0 && WB_BYTES % 128 == 0, "TMA destination alignment");
@@ -196,7 +201,7 @@ acff_cblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
       if (Cfg::WRES) {
         if (leader) mbar_expect_tx(&w_full[0], 2 * Cfg::NBUNDLE * Cfg::WB_BYTES);
         for (int b = 0; b < Cfg::NBUNDLE; ++b)
-          tma2_load_3d(s_w + b * Cfg::WB_BYTES, &tmap_w, (int)rank * NH * 4, 2 * (b / Cfg::NTG), (b % Cfg::NTG) * Cfg::TG,
+          tma2_load_3d(s_w + b * Cfg::WB_BYTES, &tmap_w, (int)rank * NH * (16 / Cfg::WELEM), 2 * (b / Cfg::NTG), (b % Cfg::NTG) * Cfg::TG,
                        mapa_u32(smem_u32(&w_full[0]), 0));
       } else {
         int it = 0;
@@ -206,7 +211,7 @@ acff_cblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
             const int s = it % Cfg::WSTAGES, use = it / Cfg::WSTAGES;
             if (use > 0 && !mbar_wait(&w_empty[s], (use - 1) & 1, abort_flag, 0x701u, it)) { ok = false; break; }
             if (leader) mbar_expect_tx(&w_full[s], 2 * Cfg::WB_BYTES);
-            tma2_load_3d(s_w + s * Cfg::WB_BYTES, &tmap_w, (int)rank * NH * 4, 2 * (b / Cfg::NTG), (b % Cfg::NTG) * Cfg::TG,
+            tma2_load_3d(s_w + s * Cfg::WB_BYTES, &tmap_w, (int)rank * NH * (16 / Cfg::WELEM), 2 * (b / Cfg::NTG), (b % Cfg::NTG) * Cfg::TG,
                          mapa_u32(smem_u32(&w_full[s]), 0));
           }
       }
@@ -351,11 +356,11 @@ template <class Cfg>
 inline int make_weight_map(CUtensorMap* map, const void* wimg) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(ERNET_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-  const cuuint64_t dims[3] = {(cuuint64_t)Cfg::N * 4, (cuuint64_t)Cfg::NC, (cuuint64_t)Cfg::TAPS};
+  const cuuint64_t dims[3] = {(cuuint64_t)Cfg::N * (16 / Cfg::WELEM), (cuuint64_t)Cfg::NC, (cuuint64_t)Cfg::TAPS};
   const cuuint64_t strides[2] = {(cuuint64_t)Cfg::N * 16, (cuuint64_t)Cfg::NC * Cfg::N * 16};
-  const cuuint32_t box[3] = {(cuuint32_t)Cfg::NH * 4, 2, (cuuint32_t)Cfg::TG};
+  const cuuint32_t box[3] = {(cuuint32_t)Cfg::NH * (16 / Cfg::WELEM), 2, (cuuint32_t)Cfg::TG};
   const cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(wimg), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(map, Cfg::WELEM == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(wimg), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(ERNET_ERR_CUDA, "cuTensorMapEncodeTiled (weights) failed with CUresult %d", (int)r);
   return ERNET_OK;
@@ -420,6 +425,12 @@ using CBlock3 = CCfg<12, 128, 15, 12, 2, 12, false, 9>;         // 12 x 10 KB sl
 using CBlock2R = CCfg<8, 96, 33, 30, 2, 5, true, 1, /*POOL*/ false>;
 using CBlock3R = CCfg<6, 128, 15, 12, 2, 9, false, 9>;
 // int8 engine (chunks of 16 channels): both weight halves are resident (77 KB / 154 KB per CTA)
+// baseline ErNET (240x240 inputs: 119 -> 117/58 -> 56/28 -> 26/13 -> 11 -> 9 -> 7); block 1 runs on tc_pblock.cuh
+using EBlock2 = CCfg<8, 96, 58, 56, 2, 5, true, 1>;
+using EBlock3 = CCfg<12, 128, 28, 26, 2, 6, false, 9>;
+using EBlock4 = CCfg<16, 128, 13, 11, 2, 8, false, 9, /*POOL*/ false>;
+using EBlock5 = CCfg<16, 128, 11, 9, 2, 8, false, 9, /*POOL*/ false>;
+using EBlock6 = CCfg<16, 256, 9, 7, 1, 8, false, 6, /*POOL*/ false>;
 using CBlock2Q = CCfg<4, 96, 33, 30, 2, 8, true, 1>;
 using CBlock3Q = CCfg<6, 128, 15, 12, 2, 6, true, 1>;
 

@@ -372,6 +372,7 @@ using PBlock3 = PCfg<12, 128, 15, 12, 2, 2, false, 4>;         //  1 unit  / ima
 // Squeeze_RedConv: conv_red2 (96 -> 48, 1x1, bias only) + 2x2 pool as a 1-tap instance: 2 units / image, 98 KB boxes
 // block 1 with one real input chunk (int8 Squeeze_ErNET, 16-bit Squeeze_RedConv): 13 two-tap MMAs per tile
 using PBlock1P = PCfg<2, 64, 69, 66, 3, 3, true, 1, true, 25, true, 64, /*PAIR*/ true>;
+using EBlock1 = PCfg<2, 64, 119, 116, 3, 3, true, 1>;          // ErNET block 1: 40 units / image
 using PRed2R = PCfg<12, 64, 30, 30, 4, 2, true, 1, /*POOL*/ true, /*TAPS*/ 1, /*ACT*/ false, /*NREAL*/ 48>;
 
 }  // namespace tc

@@ -410,8 +410,9 @@ class Squeeze_RedConv(_ErnetB200):
 
 class ErNET(_ErnetB200):
     """Baseline ErNET (model/ernet.py:6-49): six ACFF blocks, (B,3,240,240) inputs, fc 45 -> 5; same 82 state_dict keys.
-    First native path: the layer-wise CUDA-core kernels in fp32 / fp16 / bf16 through
-    ``model(x)``; the tensor-core block kernels, the fused frames path and int8 are not wired for it yet."""
+    SURVEY.md section 8f-1.  bf16 / fp16: all six ACFF blocks on the tcgen05 block kernels (block 1 persistent, blocks
+    2-6 on CTA pairs, block 6 with N = 256), conv1 and the collapsed head on CUDA cores; fp32: the layer-wise CUDA-core
+    kernels.  ``model(x)`` on (B,3,240,240) tensors; the fused frames path and int8 are not wired for it yet."""
     ARCH = "ernet"
 
 

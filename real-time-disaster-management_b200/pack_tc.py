@@ -14,6 +14,7 @@ from __future__ import annotations
 import numpy as np
 
 T_TC_BASE = 64
+T_ETC_BASE = 106     # ErNET: + 2*k, k = 0..5 -> (weight image, bias) of acff1..acff6
 T_TC_WIMG, T_TC_BIAS, T_TC_DEQ = 0, 1, 2   # + 4*k for block k
 T_Q_SCALES = 80
 T_TC4_WIMG = 76
@@ -145,6 +146,13 @@ def derive_tc(sd, arch, precision, act_scales=None):
     if precision not in ("fp16", "bf16"):
         return {}
     out = {}
+    if arch == "ernet":
+        # all six ACFF blocks of model/ernet.py:12-19 in the 25-tap dense form; the head stays on the CUDA cores
+        for k, (c, _co) in enumerate(widths(arch)):
+            weff, beff = fold_block(sd, f"acff{k + 1}", c, max(16, c))
+            out[T_ETC_BASE + 2 * k] = (weight_image(weff, precision), DT_RAW)
+            out[T_ETC_BASE + 2 * k + 1] = (beff.astype(np.float32), DT_F32)
+        return out
     for k, (c, _co) in enumerate(widths(arch)[:3]):
         c_pad = max(16, c)
         weff, beff = fold_block(sd, f"acff{k + 1}", c, c_pad)
