@@ -144,6 +144,13 @@ size_t ernet_host_copy_bytes_per_frame(ernet_handle* h, int height, int width);
 int ernet_classify_frames_host(ernet_handle* h, const uint8_t* frames_hwc_host, int batch,
                                int height, int width, int channel_order,
                                float* probs_host, float* logits_host);
+/* The same in two halves, so that a caller can keep ONE call in flight while it submits the next (the copy of batch
+ * i+1 then runs under the kernels of batch i): submit enqueues copies, kernels and the read-back and returns a ticket
+ * (0 / 1, alternating); wait blocks until that call's outputs are in probs_host / logits_host.  Host buffers must
+ * stay valid (and should be pinned) until the wait.  At most two calls may be outstanding.                  */
+int ernet_classify_frames_host_submit(ernet_handle* h, const uint8_t* frames_host, int batch, int height, int width,
+                                      int channel_order, float* probs_host, float* logits_host, int* ticket);
+int ernet_classify_frames_host_wait(ernet_handle* h, int ticket);
 
 /* ---- building blocks exposed for unit tests and micro-benchmarks --------------------------------
  * ACFF depthwise trio (model/acff.py:25-30,46): x (batch,H,W,C) NHWC -> (batch,out_h,out_w,3C)

@@ -35,6 +35,8 @@ SIGNATURES = {
     "ernet_debug_timeline": (_i, [_vp, _sz]),
     "ernet_debug_chain": (_i, [_vp, _i]),
     "ernet_host_copy_bytes_per_frame": (_sz, [_vp, _i, _i]),
+    "ernet_classify_frames_host_submit": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "ernet_classify_frames_host_wait": (_i, [_vp, _i]),
     "ernet_set_fast_ingest": (_i, [_vp, _i]),
     "ernet_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "ernet_ingest_u8": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),

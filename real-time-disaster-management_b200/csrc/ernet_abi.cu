@@ -62,6 +62,7 @@ struct ernet_handle {
                                      // CUDA cores (see the header of tc_dblock.cuh)
   void* d_w1_pair = nullptr;         // block-1 weights regrouped for tap pairing ([13][2][64][16 B], tc_pblock.cuh)
   StemFrag* d_stem_frag = nullptr;   // folded conv1 in mma.sync fragment order (16-bit engines)
+  bool dual_copy = false;       // host path: alternate two copy streams (ERNET_DUAL_COPY=1)
   bool trim_columns = false;    // host path: also skip the columns outside the crop footprint (ERNET_TRIM_COLUMNS=1).  Off:
                                 // measured 78 K img/s against 281 K - a 3-D copy of 639-byte rows runs at ~10 GB/s
   bool pair_taps = true;        // two taps per MMA in block 1 when its input has one real chunk (ERNET_PAIR_TAPS=0 switches it off)
@@ -73,8 +74,9 @@ struct ernet_handle {
   Tensor t[ERNET_T_MAX];
   std::map<std::pair<int, int>, IngestTables> ingest;
   // host-buffer path (ernet_classify_frames_host)
-  cudaStream_t s_copy = nullptr, s_compute = nullptr;
-  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  cudaStream_t s_copy = nullptr, s_copy2 = nullptr, s_compute = nullptr;   // two copy streams: the copies of consecutive sub-chunks overlap
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_call[2] = {nullptr, nullptr};
+  unsigned long long sub_it = 0, calls = 0;   // sub-chunks / calls submitted so far (buffer and ticket alternation)
   uint8_t* d_frames[2] = {nullptr, nullptr};
   size_t d_frames_bytes = 0;
   void* d_ws = nullptr;
@@ -737,6 +739,7 @@ int ernet_create(ernet_handle** out, int arch, int precision, int device) {
   if (const char* e = getenv("ERNET_PAIR_TAPS")) h->pair_taps = atoi(e) != 0;
   if (const char* e = getenv("ERNET_DW_BLOCK1")) h->dw_block1 = atoi(e) != 0;
   if (const char* e = getenv("ERNET_TRIM_COLUMNS")) h->trim_columns = atoi(e) != 0;
+  if (const char* e = getenv("ERNET_DUAL_COPY")) h->dual_copy = atoi(e) != 0;
   *out = h;
   return ERNET_OK;
 }
@@ -753,12 +756,14 @@ void ernet_destroy(ernet_handle* h) {
     if (h->d_frames[i]) cudaFree(h->d_frames[i]);
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+    if (h->ev_call[i]) cudaEventDestroy(h->ev_call[i]);
   }
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : h->prof_pool) cudaEventDestroy(e);
   if (h->d_ws) cudaFree(h->d_ws);
   if (h->d_res) cudaFree(h->d_res);
   if (h->s_copy) cudaStreamDestroy(h->s_copy);
+  if (h->s_copy2) cudaStreamDestroy(h->s_copy2);
   if (h->s_compute) cudaStreamDestroy(h->s_compute);
   delete h;
 }
@@ -1049,9 +1054,9 @@ size_t ernet_host_copy_bytes_per_frame(ernet_handle* h, int height, int width) {
   return (size_t)(tab->row_hi - tab->row_lo) * (h->trim_columns ? (size_t)(tab->col_hi - tab->col_lo) : (size_t)width) * 3;
 }
 
-int ernet_classify_frames_host(ernet_handle* h, const uint8_t* frames_host, int batch, int height, int width,
-                               int channel_order, float* probs_host, float* logits_host) {
-  if (!h || !frames_host || !probs_host) return fail(ERNET_ERR_INVALID_ARG, "ernet_classify_frames_host: null argument");
+int ernet_classify_frames_host_submit(ernet_handle* h, const uint8_t* frames_host, int batch, int height, int width,
+                                      int channel_order, float* probs_host, float* logits_host, int* ticket) {
+  if (!h || !frames_host || !probs_host || !ticket) return fail(ERNET_ERR_INVALID_ARG, "ernet_classify_frames_host: null argument");
   if (!h->loaded) return fail(ERNET_ERR_NOT_LOADED, "no weights loaded (call ernet_load_packed first)");
   if (batch < 1) return fail(ERNET_ERR_INVALID_ARG, "batch must be >= 1, got %d", batch);
   DeviceGuard g(h->device);
@@ -1060,10 +1065,12 @@ int ernet_classify_frames_host(ernet_handle* h, const uint8_t* frames_host, int 
   if (rc) return rc;
   if (!h->s_copy) {
     ERNET_CUDA(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+    ERNET_CUDA(cudaStreamCreateWithFlags(&h->s_copy2, cudaStreamNonBlocking));
     ERNET_CUDA(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
       ERNET_CUDA(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
       ERNET_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+      ERNET_CUDA(cudaEventCreateWithFlags(&h->ev_call[i], cudaEventDisableTiming));
     }
   }
   // sub-chunks so that the H2D copy of one overlaps the kernels of the previous one even inside a single call
@@ -1071,6 +1078,8 @@ int ernet_classify_frames_host(ernet_handle* h, const uint8_t* frames_host, int 
   if (batch >= 128) { const int q = (batch + 3) / 4; chunk = q < chunk ? q : chunk; if (chunk < 32) chunk = 32; }
   const size_t f_img = (size_t)height * width * 3;
   const size_t fbytes = (size_t)chunk * f_img;
+  if (h->d_frames_bytes < fbytes || h->d_ws_bytes < ernet_workspace_bytes(h, chunk) || h->d_res_elems < (size_t)batch * 10)
+    ERNET_CUDA(cudaStreamSynchronize(h->s_compute));        // growing a buffer: nothing may still be using the old one
   if (h->d_frames_bytes < fbytes) {
     for (int i = 0; i < 2; ++i) {
       if (h->d_frames[i]) { cudaFree(h->d_frames[i]); h->d_frames[i] = nullptr; }
@@ -1091,11 +1100,13 @@ int ernet_classify_frames_host(ernet_handle* h, const uint8_t* frames_host, int 
   }
   float* d_probs = h->d_res;
   float* d_logits = h->d_res + (size_t)batch * 5;
-  int it = 0;
-  for (int b0 = 0; b0 < batch; b0 += chunk, ++it) {
+  // the two frame buffers alternate across sub-chunks AND across calls (a submitted call may still be running)
+  for (int b0 = 0; b0 < batch; b0 += chunk, ++h->sub_it) {
     const int n = batch - b0 < chunk ? batch - b0 : chunk;
-    const int s = it & 1;
-    if (it >= 2) ERNET_CUDA(cudaStreamWaitEvent(h->s_copy, h->ev_done[s], 0));   // frame buffer s is free again
+    const unsigned long long it = h->sub_it;
+    const int s = (int)(it & 1);
+    cudaStream_t cs = (h->dual_copy && (it & 1)) ? h->s_copy2 : h->s_copy;
+    if (it >= 2) ERNET_CUDA(cudaStreamWaitEvent(cs, h->ev_done[s], 0));   // frame buffer s is free again
     // only the rows the crop window of the eval transform reads travel over PCIe (240x240: rows 14..226, 89 % of
     // the frame); one strided copy, each "row" of it is the contiguous row range of one frame
     const size_t rowb = (size_t)width * 3, lo = (size_t)tab->row_lo * rowb, span = (size_t)(tab->row_hi - tab->row_lo) * rowb;
@@ -1107,12 +1118,12 @@ int ernet_classify_frames_host(ernet_handle* h, const uint8_t* frames_host, int 
       cp.dstPtr = make_cudaPitchedPtr(h->d_frames[s] + lo + xoff, rowb, rowb, (size_t)height);
       cp.extent = make_cudaExtent(xbytes, (size_t)(tab->row_hi - tab->row_lo), (size_t)n);
       cp.kind = cudaMemcpyHostToDevice;
-      ERNET_CUDA(cudaMemcpy3DAsync(&cp, h->s_copy));
+      ERNET_CUDA(cudaMemcpy3DAsync(&cp, cs));
     } else {
       ERNET_CUDA(cudaMemcpy2DAsync(h->d_frames[s] + lo, f_img, frames_host + (size_t)b0 * f_img + lo, f_img, span, (size_t)n,
-                                   cudaMemcpyHostToDevice, h->s_copy));
+                                   cudaMemcpyHostToDevice, cs));
     }
-    ERNET_CUDA(cudaEventRecord(h->ev_copied[s], h->s_copy));
+    ERNET_CUDA(cudaEventRecord(h->ev_copied[s], cs));
     ERNET_CUDA(cudaStreamWaitEvent(h->s_compute, h->ev_copied[s], 0));
     rc = run_chunk(h, nullptr, 0, 0, h->d_frames[s], tab, channel_order, n, d_probs + (size_t)b0 * 5,
                    d_logits + (size_t)b0 * 5, static_cast<char*>(h->d_ws), h->s_compute);
@@ -1122,8 +1133,25 @@ int ernet_classify_frames_host(ernet_handle* h, const uint8_t* frames_host, int 
   ERNET_CUDA(cudaMemcpyAsync(probs_host, d_probs, (size_t)batch * 5 * sizeof(float), cudaMemcpyDeviceToHost, h->s_compute));
   if (logits_host)
     ERNET_CUDA(cudaMemcpyAsync(logits_host, d_logits, (size_t)batch * 5 * sizeof(float), cudaMemcpyDeviceToHost, h->s_compute));
-  ERNET_CUDA(cudaStreamSynchronize(h->s_compute));
+  const int tk = (int)(h->calls++ & 1);
+  ERNET_CUDA(cudaEventRecord(h->ev_call[tk], h->s_compute));
+  *ticket = tk;
   return ERNET_OK;
+}
+
+int ernet_classify_frames_host_wait(ernet_handle* h, int ticket) {
+  if (!h || ticket < 0 || ticket > 1 || !h->ev_call[ticket]) return fail(ERNET_ERR_INVALID_ARG, "ernet_classify_frames_host_wait: bad ticket");
+  DeviceGuard g(h->device);
+  ERNET_CUDA(cudaEventSynchronize(h->ev_call[ticket]));
+  return ERNET_OK;
+}
+
+int ernet_classify_frames_host(ernet_handle* h, const uint8_t* frames_host, int batch, int height, int width,
+                               int channel_order, float* probs_host, float* logits_host) {
+  int ticket = 0;
+  int rc = ernet_classify_frames_host_submit(h, frames_host, batch, height, width, channel_order, probs_host, logits_host, &ticket);
+  if (rc) return rc;
+  return ernet_classify_frames_host_wait(h, ticket);
 }
 
 int ernet_acff_depthwise(const void* x, int dtype, int batch, int H, int W, int C, int out_h, int out_w,

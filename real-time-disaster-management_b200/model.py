@@ -337,6 +337,30 @@ class _ErnetB200(nn.Module):
                                                   probs.ctypes.data, logits.ctypes.data if return_logits else None))
         return (probs, logits) if return_logits else probs
 
+    def classify_host_submit(self, frames, *, bgr=False, return_logits=False):
+        """Streaming form of classify_host(): enqueue one batch of host frames and return a ticket whose ``result()``
+        blocks for the probabilities.  Keep one ticket outstanding while submitting the next batch and the host->device
+        copy of batch i+1 runs under the kernels of batch i (at most two tickets in flight).  Outputs live in pinned
+        memory; pass pinned frames (``tensor.pin_memory()``) for a truly asynchronous copy."""
+        if isinstance(frames, torch.Tensor):
+            if frames.device.type != "cpu":
+                raise ValueError("classify_host expects host memory; use forward_frames for device tensors")
+            keep = frames.contiguous()
+            ptr, shape, dt = keep.data_ptr(), tuple(keep.shape), keep.dtype == torch.uint8
+        else:
+            keep = np.ascontiguousarray(frames)
+            ptr, shape, dt = keep.ctypes.data, keep.shape, keep.dtype == np.uint8
+        if not dt or len(shape) != 4 or shape[3] != 3:
+            raise ValueError(f"expected uint8 frames of shape (B,H,W,3), got {shape}")
+        lib, h, _ = self._ensure_engine()
+        B, H, W, _c = shape
+        probs = torch.empty((B, 5), dtype=torch.float32).pin_memory()
+        logits = torch.empty((B, 5), dtype=torch.float32).pin_memory() if return_logits else None
+        tk = C.c_int(0)
+        _lib.check(lib.ernet_classify_frames_host_submit(h, ptr, B, H, W, _lib.BGR if bgr else _lib.RGB, probs.data_ptr(),
+                                                         logits.data_ptr() if return_logits else None, C.byref(tk)))
+        return _HostTicket(self, lib, h, tk.value, keep, probs, logits)
+
     def prepare_ingest(self, height, width):
         lib, h, _ = self._ensure_engine()
         _lib.check(lib.ernet_prepare_ingest(h, int(height), int(width)))
@@ -386,6 +410,21 @@ class _ErnetB200(nn.Module):
     def launches_per_forward(self, batch, with_ingest=True):
         lib, h, _ = self._ensure_engine()
         return lib.ernet_launches_per_forward(h, int(batch), 1 if with_ingest else 0)
+
+
+class _HostTicket:
+    """One submitted classify_host call (see classify_host_submit)."""
+
+    def __init__(self, model, lib, handle, ticket, frames, probs, logits):
+        self._model, self._lib, self._h, self._tk = model, lib, handle, ticket
+        self._frames, self._probs, self._logits, self._done = frames, probs, logits, False
+
+    def result(self):
+        if not self._done:
+            _lib.check(self._lib.ernet_classify_frames_host_wait(self._h, self._tk))
+            self._done, self._frames = True, None
+        p = self._probs.numpy()
+        return (p, self._logits.numpy()) if self._logits is not None else p
 
 
 def default_calibration_frames(n=512, seed=99):

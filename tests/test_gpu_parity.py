@@ -576,3 +576,24 @@ def test_ernet_call_surface_and_batching(dev):
     mh = rtdm_b200.from_state_dict("ernet", sd, dev, "fp32").half()
     ph = mh(x.half())
     assert ph.dtype == torch.float16 and (ph.float().argmax(1) == p.argmax(1)).all()
+
+
+@pytest.mark.gpu
+def test_host_submit_wait_matches_blocking_call(dev):
+    """Streaming host API: tickets submitted back to back (one in flight while the next is enqueued, different batch
+    sizes, pinned and pageable inputs) return exactly what the blocking call returns for the same frames."""
+    sd = fixtures.get_state_dict("squeeze-ernet", "shipped")
+    m = rtdm_b200.from_state_dict("squeeze-ernet", sd, dev, "bf16")
+    batches = [np.concatenate([fixtures.noise_frames(n // 2, seed=200 + n), fixtures.smooth_frames(n - n // 2, seed=300 + n)], 0)
+               for n in (150, 64, 257, 1)]
+    want = [m.classify_host(b, return_logits=True) for b in batches]
+    pinned = [torch.from_numpy(b).pin_memory() if i % 2 == 0 else b for i, b in enumerate(batches)]
+    got, pending = [], None
+    for b in pinned:
+        nxt = m.classify_host_submit(b, return_logits=True)
+        if pending is not None:
+            got.append(pending.result())
+        pending = nxt
+    got.append(pending.result())
+    for (p, l), (pw, lw) in zip(got, want):
+        assert np.array_equal(p, pw) and np.array_equal(l, lw)
