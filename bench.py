@@ -301,6 +301,7 @@ def gpu_main(args, rank, local_rank, world):
 
     if rank == 0:
         peaks = load_peaks()
+        depthwise = depthwise_roofline(dev, peaks)
         total_stage_ms = sum(v[0] for v in prof.values())
         dom = max(prof, key=lambda k: prof[k][0])
         dms, dcount = prof[dom]
@@ -360,6 +361,7 @@ def gpu_main(args, rank, local_rank, world):
             "roofline": roof,
             "model_flops_frac_of_tensor_peak": value / world * 2 * MACS_PER_IMAGE[ARCH] / 1e12 / peaks["bf16_tflops_sustained"],
             "latency_b1_ms": latency_b1_ms,
+            "depthwise_hbm": depthwise,
             "cpu_baseline": cpu_info,
         }
         print(json.dumps(line))
@@ -367,6 +369,41 @@ def gpu_main(args, rank, local_rank, world):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def depthwise_roofline(dev, peaks, batch=256, iters=20):
+    """The standalone ACFF depthwise trio (model/acff.py:25-30,46; the fp32 engine's kernel - the 16-bit engines fold it
+    into the tensor-core blocks) through ernet_acff_depthwise on the Squeeze-ErNet block-1 / block-2 shapes: algorithmic
+    bytes = input once + 3x output once, CUDA events on the launching stream, L2 flushed before every launch."""
+    import torch
+    from rtdm_b200 import _lib
+    lib = _lib.load()
+    flush = torch.empty(160 << 20, dtype=torch.float32, device=dev)
+    s = torch.cuda.current_stream(dev)
+    out = {"peak": peaks["hbm_gbs"], "unit": "GB/s", "dtype": "fp32", "batch": batch, "l2": "640 MB written before every launch"}
+    for name, (H, C, oh) in {"block1": (69, 16, 67), "block2": (33, 64, 31)}.items():
+        x = torch.randn(batch, H, H, C, device=dev)
+        w = torch.randn(3, 9, C, device=dev) * 0.3
+        b = torch.randn(3, C, device=dev) * 0.1
+        o = torch.empty(batch, oh, oh, 3 * C, device=dev)
+        nbytes = (x.numel() + o.numel()) * 4
+        best, tot = 1e9, 0.0
+        for it in range(iters + 2):
+            flush.fill_(float(it))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s)
+            _lib.check(lib.ernet_acff_depthwise(x.data_ptr(), 0, batch, H, H, C, oh, oh, w.data_ptr(), b.data_ptr(),
+                                                o.data_ptr(), s.cuda_stream))
+            e1.record(s)
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            if it >= 2:
+                tot += ms
+                best = min(best, ms)
+        gbs = nbytes / (tot / iters * 1e-3) / 1e9
+        out[name] = {"shape": f"({batch},{H},{H},{C}) -> ({batch},{oh},{oh},{3 * C})", "bytes": nbytes,
+                     "us": round(tot / iters * 1e3, 2), "achieved": round(gbs, 1), "frac": round(gbs / peaks["hbm_gbs"], 4)}
+    return out
 
 
 def main():

@@ -159,6 +159,11 @@ int ernet_classify_frames_host_wait(ernet_handle* h, int ticket);
 int ernet_acff_depthwise(const void* x, int dtype, int batch, int H, int W, int C, int out_h, int out_w,
                          const float* w, const float* b, void* out, void* stream);
 
+/* fp32 form of the trio: 1 (default) = register-tile kernel (one channel x 4x4 output patch per thread, tap
+ * weights in registers, no shared memory), 0 = the shared-memory halo kernel (what fp16/bf16 always use).
+ * Process-wide; the two forms are bit-identical.  Returns the previous value.                        */
+int ernet_set_depthwise_form(int form);
+
 /* 1x1 convolution (model/acff.py:31) + bias [+ LeakyReLU(0.01)] [+ per-channel affine = eval BN,
  * acff.py:33-34] [+ 2x2/2 max-pool, squeeze_ernet.py:13].  a: (batch,H,W,K) NHWC; w: [K][N] fp32.   */
 int ernet_pointwise(const void* a, int dtype, int batch, int H, int W, int K, int N,

@@ -1173,6 +1173,12 @@ int ernet_acff_depthwise(const void* x, int dtype, int batch, int H, int W, int 
   return ERNET_OK;
 }
 
+int ernet_set_depthwise_form(int form) {
+  const int prev = g_dw_fp32_form;
+  g_dw_fp32_form = form ? 1 : 0;
+  return prev;
+}
+
 int ernet_pointwise(const void* a, int dtype, int batch, int H, int W, int K, int N, const float* w, const float* bias,
                     const float* bn_scale, const float* bn_shift, int leaky, int pool, void* out, void* stream) {
   if (!a || !w || !out || batch < 1) return fail(ERNET_ERR_INVALID_ARG, "ernet_pointwise: bad argument");

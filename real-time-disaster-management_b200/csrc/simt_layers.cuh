@@ -160,6 +160,138 @@ acff_dw_kernel(const T* __restrict__ x, int H, int W, int C, int out_h, int out_
   }
 }
 
+// fp32 register-tile form (the product path of precision=fp32).  The shared-memory kernel above moves 24 words
+// per output through shared memory (tile data + the tap weights re-read per strip) and that, not HBM, is what
+// bounded it (2.2-2.3 TB/s, l1tex data-pipe wavefronts 76 % busy in ncu).  Here one thread owns ONE channel and a
+// PY x 4 patch of output pixels for all three branches: its 27 tap weights live in registers for the whole patch,
+// every input word of the (PY+6) x 10 footprint is loaded once per thread straight from global memory (lanes =
+// consecutive channels, so a warp load is whole 32-byte sectors; neighbouring patches' overlap is served by L1),
+// i.e. 6.25 words per output at PY = 4 and no weight traffic.  The channel count is a template parameter so that
+// every column / branch offset is an immediate in the load / store instruction (with a run-time C the first
+// version spent 4.7x the useful instruction count on address arithmetic and bounds selects and was issue-bound),
+// and patches whose footprint lies inside the image take a path without bounds checks.  Per accumulator the FMA
+// order is bias, then ky-major / kx-minor - the same as the shared-memory kernel, so the two are bit-identical.
+template <int C, int PY, bool EDGE>
+__device__ __forceinline__ void dw_tile_patch(const float* __restrict__ xb /* image base + channel */, int H, int W,
+                                              int out_h, int out_w, int oy0, int ox0, const float (&wr)[27],
+                                              const float (&bv)[3], float* __restrict__ ob /* image base + channel */) {
+  constexpr int PX = 4;
+  float acc[3][PY][PX];
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+#pragma unroll
+    for (int py = 0; py < PY; ++py)
+#pragma unroll
+      for (int px = 0; px < PX; ++px) acc[d][py][px] = bv[d];
+  const size_t rs = (size_t)W * C;                       // row stride in elements
+  const float* p0 = xb + ((ptrdiff_t)(oy0 - 2) * W + (ox0 - 2)) * C;
+#pragma unroll
+  for (int ry = 0; ry < PY + 6; ++ry) {
+    const float* rp = p0 + ry * rs;
+    float xr[PX + 6];
+    if constexpr (EDGE) {
+      const int iy = oy0 + ry - 2;
+      const bool rowok = iy >= 0 && iy < H;
+#pragma unroll
+      for (int cx = 0; cx < PX + 6; ++cx) {
+        const int ix = ox0 + cx - 2;
+        xr[cx] = 0.f;
+        if (rowok && ix >= 0 && ix < W) xr[cx] = __ldg(rp + cx * C);
+      }
+    } else {
+#pragma unroll
+      for (int cx = 0; cx < PX + 6; ++cx) xr[cx] = __ldg(rp + cx * C);
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const int dil = d + 1;
+#pragma unroll
+      for (int py = 0; py < PY; ++py) {
+        // input row ry is tap row ky of branch d for output row py when ry - 2 - py = ky*dil - (dil-1)
+        const int tt = ry - 2 - py + (dil - 1);
+        if (tt < 0 || tt % dil != 0 || tt / dil > 2) continue;
+        const int ky = tt / dil;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int col = 2 + kx * dil - (dil - 1);
+#pragma unroll
+          for (int px = 0; px < PX; ++px) acc[d][py][px] = fmaf(xr[px + col], wr[d * 9 + ky * 3 + kx], acc[d][py][px]);
+        }
+      }
+    }
+  }
+  const size_t os = (size_t)out_w * (3 * C);
+  float* o0 = ob + ((size_t)oy0 * out_w + ox0) * (3 * C);
+#pragma unroll
+  for (int py = 0; py < PY; ++py) {
+    if (EDGE && oy0 + py >= out_h) break;
+    float* orow = o0 + py * os;
+#pragma unroll
+    for (int px = 0; px < PX; ++px) {
+      if (EDGE && ox0 + px >= out_w) break;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) orow[px * 3 * C + d * C] = acc[d][py][px];
+    }
+  }
+}
+
+template <int C, int PY, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+acff_dw_tile_kernel(const float* __restrict__ x, int H, int W, int out_h, int out_w, int TX, int TY,
+                    long long total, const float* __restrict__ w /*[3][9][C]*/, const float* __restrict__ bias /*[3][C]*/,
+                    float* __restrict__ out /*(B,out_h,out_w,3C)*/) {
+  constexpr int PX = 4;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int c = (int)(gid % C);
+  unsigned t = (unsigned)(gid / C);
+  const int tx = t % TX; t /= TX;
+  const int ty = t % TY;
+  const int b = t / TY;
+  const int ox0 = tx * PX, oy0 = ty * PY;
+  float wr[27], bv[3];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) wr[i] = __ldg(w + i * C + c);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) bv[d] = __ldg(bias + d * C + c);
+  const float* xb = x + (size_t)b * H * W * C + c;
+  float* ob = out + (size_t)b * out_h * out_w * (3 * C) + c;
+  const bool interior = oy0 >= 2 && oy0 + PY + 3 < H && ox0 >= 2 && ox0 + PX + 3 < W && oy0 + PY <= out_h && ox0 + PX <= out_w;
+  if (interior) dw_tile_patch<C, PY, false>(xb, H, W, out_h, out_w, oy0, ox0, wr, bv, ob);
+  else          dw_tile_patch<C, PY, true>(xb, H, W, out_h, out_w, oy0, ox0, wr, bv, ob);
+}
+
+inline int g_dw_fp32_form = 1;    // 1 = register-tile kernel (default), 0 = shared-memory kernel (ernet_set_depthwise_form)
+
+template <int C, int PY = 4, int MINB = 2>
+inline int launch_acff_dw_tile_c(const float* x, int batch, int H, int W, int out_h, int out_w,
+                                 const float* w, const float* bias, float* out, cudaStream_t stream) {
+  const int TX = (out_w + 3) / 4, TY = (out_h + PY - 1) / PY;
+  const long long total = (long long)batch * TY * TX * C;
+  const long long blocks = (total + 255) / 256;
+  if (blocks > 0x7fffffffLL || total / C > 0xffffffffLL) return fail(ERNET_ERR_INVALID_ARG, "depthwise: batch too large for one launch");
+  acff_dw_tile_kernel<C, PY, MINB><<<(unsigned)blocks, 256, 0, stream>>>(x, H, W, out_h, out_w, TX, TY, total, w, bias, out);
+  ERNET_LAUNCH_CHECK("acff_dw_tile_kernel");
+  return ERNET_OK;
+}
+
+// Channel counts of the three architectures (Squeeze_ErNET 16/64/96/128, Squeeze_RedConv 8/64/48/64, ErNET 16..128);
+// returns -1 for any other C (the caller falls back to the shared-memory kernel).
+template <int PY = 4, int MINB = 2>
+inline int launch_acff_dw_tile(const float* x, int batch, int H, int W, int C, int out_h, int out_w,
+                               const float* w, const float* bias, float* out, cudaStream_t stream) {
+  switch (C) {
+    case 8:   return launch_acff_dw_tile_c<8, PY, MINB>(x, batch, H, W, out_h, out_w, w, bias, out, stream);
+    case 16:  return launch_acff_dw_tile_c<16, PY, MINB>(x, batch, H, W, out_h, out_w, w, bias, out, stream);
+    case 32:  return launch_acff_dw_tile_c<32, PY, MINB>(x, batch, H, W, out_h, out_w, w, bias, out, stream);
+    case 48:  return launch_acff_dw_tile_c<48, PY, MINB>(x, batch, H, W, out_h, out_w, w, bias, out, stream);
+    case 64:  return launch_acff_dw_tile_c<64, PY, MINB>(x, batch, H, W, out_h, out_w, w, bias, out, stream);
+    case 96:  return launch_acff_dw_tile_c<96, PY, MINB>(x, batch, H, W, out_h, out_w, w, bias, out, stream);
+    case 128: return launch_acff_dw_tile_c<128, PY, MINB>(x, batch, H, W, out_h, out_w, w, bias, out, stream);
+    default:  return -1;
+  }
+}
+
 inline void dw_pick_tile(int C, int esize, int out_h, int out_w, int& th, int& tw, size_t& smem) {
   // largest square-ish tile whose halo fits in ~96 KB (two CTAs per SM); the width is a whole number of the strips
   // a thread computes (4 pixels at fp32, 2 at 16 bit), columns past the image are skipped in the kernel
@@ -181,6 +313,12 @@ inline int launch_acff_dw(const T* x, int batch, int H, int W, int C, int out_h,
   if (C % Vec16<T>::NV) return fail(ERNET_ERR_INVALID_ARG, "depthwise: C=%d not a multiple of %d", C, Vec16<T>::NV);
   if (out_h > H - 2 || out_w > W - 2 || out_h < 1 || out_w < 1)
     return fail(ERNET_ERR_INVALID_ARG, "depthwise: bad output size %dx%d for input %dx%d", out_h, out_w, H, W);
+  if constexpr (std::is_same<T, float>::value) {
+    if (g_dw_fp32_form) {
+      const int rc = launch_acff_dw_tile(x, batch, H, W, C, out_h, out_w, w, bias, out, stream);
+      if (rc != -1) return rc;
+    }
+  }
   int th, tw;
   size_t smem;
   dw_pick_tile(C, (int)sizeof(T), out_h, out_w, th, tw, smem);

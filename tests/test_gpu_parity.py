@@ -91,6 +91,32 @@ def test_acff_depthwise_kernel(prec, shape, dev):
     assert _rel(got, ref) <= tol
 
 
+@pytest.mark.parametrize("shape", [(3, 69, 69, 16, 67, 67), (2, 69, 69, 8, 66, 66), (2, 33, 33, 64, 31, 31), (3, 15, 15, 96, 13, 13),
+                                   (4, 15, 15, 48, 12, 12), (5, 6, 6, 128, 4, 4), (2, 9, 11, 32, 7, 9), (1, 119, 119, 16, 117, 117),
+                                   (2, 7, 7, 24, 5, 5)])
+def test_acff_depthwise_fp32_forms_bit_identical(shape, dev):
+    """Register-tile kernel (default; compile-time channel counts, C=24 falls back) == shared-memory halo kernel, bitwise."""
+    B, H, W, Cc, out_h, out_w = shape
+    g = torch.Generator(device="cpu").manual_seed(H * 1000 + Cc)
+    x = torch.randn(B, H, W, Cc, generator=g).to(dev)
+    wp = (torch.randn(3, 9, Cc, generator=g) * 0.4).to(dev)
+    bp = (torch.randn(3, Cc, generator=g) * 0.1).to(dev)
+    lib = _lib.load()
+    outs = []
+    for form in (1, 0):
+        prev = lib.ernet_set_depthwise_form(form)
+        try:
+            out = torch.full((B, out_h, out_w, 3 * Cc), float("nan"), device=dev)
+            _lib.check(lib.ernet_acff_depthwise(x.data_ptr(), DCODE["fp32"], B, H, W, Cc, out_h, out_w, wp.data_ptr(),
+                                                bp.data_ptr(), out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+            torch.cuda.synchronize()
+        finally:
+            lib.ernet_set_depthwise_form(prev)
+        outs.append(out.cpu())
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 @pytest.mark.parametrize("cfg", [(2, 66, 66, 48, 64, 1, 1), (2, 30, 30, 192, 96, 1, 1), (3, 12, 12, 288, 128, 1, 1),
                                  (5, 4, 4, 384, 256, 1, 0), (2, 30, 30, 96, 48, 0, 1), (7, 6, 6, 128, 64, 0, 0),
