@@ -164,6 +164,22 @@ int ernet_acff_depthwise(const void* x, int dtype, int batch, int H, int W, int 
  * Process-wide; the two forms are bit-identical.  Returns the previous value.                        */
 int ernet_set_depthwise_form(int form);
 
+/* Depthwise stage of the ADD-fusion ACFF block of the detector half (victim_localization/yolov3/models.py:277-282,302:
+ * out = conv1(x) + conv2(x) + conv3(x), the same three dilated depthwise 3x3 convolutions, summed instead of
+ * concatenated): x (batch,H,W,C) NHWC -> (batch,out_h,out_w,C), out_h<=H-2, out_w<=W-2.  fp32 only (dtype must be
+ * ERNET_F32), any C >= 1.  Followed by ernet_pointwise (fused_conv + LeakyReLU + BN, models.py:307-309) it is the whole
+ * block.  `w` is [3][9][C] fp32, `b` is [3][C] fp32.                                                                */
+int ernet_acff_add_depthwise(const void* x, int dtype, int batch, int H, int W, int C, int out_h, int out_w,
+                             const float* w, const float* b, void* out, void* stream);
+
+/* Evaluation bookkeeping on the device (evaluate-classification-metrics.py:81-87): prediction = argmax over the
+ * `num_classes` scores of each image (lowest index on ties), cm[target][prediction] += 1.  `scores` (batch,num_classes)
+ * fp32, `targets` (batch) int64, `cm` [num_classes][num_classes] int64 accumulated in place; `pred_out` (batch) int64
+ * and `bad` (count of targets outside [0,num_classes)) are optional.  `targets` and `cm` may both be NULL when only
+ * predictions are wanted.  All pointers are device pointers.                                                         */
+int ernet_confusion_update(const float* scores, const long long* targets, int batch, int num_classes,
+                           long long* cm, long long* pred_out, unsigned long long* bad, void* stream);
+
 /* 1x1 convolution (model/acff.py:31) + bias [+ LeakyReLU(0.01)] [+ per-channel affine = eval BN,
  * acff.py:33-34] [+ 2x2/2 max-pool, squeeze_ernet.py:13].  a: (batch,H,W,K) NHWC; w: [K][N] fp32.   */
 int ernet_pointwise(const void* a, int dtype, int batch, int H, int W, int K, int N,

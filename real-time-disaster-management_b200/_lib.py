@@ -45,6 +45,8 @@ SIGNATURES = {
     "ernet_classify_frames_host": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "ernet_acff_depthwise": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "ernet_set_depthwise_form": (_i, [_i]),
+    "ernet_acff_add_depthwise": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "ernet_confusion_update": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "ernet_pointwise": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "ernet_debug_tap": (_i, [_vp, _i, _vp, _i, _vp, _sz, _vp]),
     "ernet_ingest_tables_host": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

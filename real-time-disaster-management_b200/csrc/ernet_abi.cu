@@ -2,6 +2,7 @@
 // reference interfaces each entry point replaces).
 #include <stdarg.h>
 
+#include <algorithm>
 #include <map>
 #include <type_traits>
 #include <new>
@@ -1170,6 +1171,34 @@ int ernet_acff_depthwise(const void* x, int dtype, int batch, int H, int W, int 
     else return fail(ERNET_ERR_INVALID_ARG, "bad dtype %d", dtype);
     if (rc) return rc;
   }
+  return ERNET_OK;
+}
+
+int ernet_acff_add_depthwise(const void* x, int dtype, int batch, int H, int W, int C, int out_h, int out_w,
+                             const float* w, const float* b, void* out, void* stream) {
+  if (!x || !w || !b || !out || batch < 1 || C < 1) return fail(ERNET_ERR_INVALID_ARG, "ernet_acff_add_depthwise: bad argument");
+  if (dtype != ERNET_F32) return fail(ERNET_ERR_INVALID_ARG, "ernet_acff_add_depthwise: fp32 only (dtype %d)", dtype);
+  if (out_h > H - 2 || out_w > W - 2 || out_h < 1 || out_w < 1)
+    return fail(ERNET_ERR_INVALID_ARG, "add-fusion depthwise: bad output size %dx%d for input %dx%d", out_h, out_w, H, W);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long per_img = (long long)((out_h + 3) / 4) * ((out_w + 3) / 4) * C;
+  const int step = (int)std::max<long long>(1, std::min<long long>(batch, 0x60000000LL / per_img));   // one launch = < 2^31 threads
+  for (int b0 = 0; b0 < batch; b0 += step) {
+    const int n = batch - b0 < step ? batch - b0 : step;
+    const size_t xi = (size_t)b0 * H * W * C, oi = (size_t)b0 * out_h * out_w * C;
+    int rc = launch_acff_dw_tile<4, 2, true>(static_cast<const float*>(x) + xi, n, H, W, C, out_h, out_w, w, b,
+                                             static_cast<float*>(out) + oi, s, true);
+    if (rc) return rc;
+  }
+  return ERNET_OK;
+}
+
+int ernet_confusion_update(const float* scores, const long long* targets, int batch, int num_classes,
+                           long long* cm, long long* pred_out, unsigned long long* bad, void* stream) {
+  if (!scores || batch < 1 || num_classes < 1 || (!cm != !targets) || (!cm && !pred_out))
+    return fail(ERNET_ERR_INVALID_ARG, "ernet_confusion_update: bad argument");
+  confusion_update_kernel<<<(batch + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(scores, targets, batch, num_classes, cm, pred_out, bad);
+  ERNET_LAUNCH_CHECK("confusion_update_kernel");
   return ERNET_OK;
 }
 

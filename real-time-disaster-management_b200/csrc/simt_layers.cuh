@@ -171,11 +171,15 @@ acff_dw_kernel(const T* __restrict__ x, int H, int W, int C, int out_h, int out_
 // version spent 4.7x the useful instruction count on address arithmetic and bounds selects and was issue-bound),
 // and patches whose footprint lies inside the image take a path without bounds checks.  Per accumulator the FMA
 // order is bias, then ky-major / kx-minor - the same as the shared-memory kernel, so the two are bit-identical.
-template <int C, int PY, bool EDGE>
-__device__ __forceinline__ void dw_tile_patch(const float* __restrict__ xb /* image base + channel */, int H, int W,
+// ADD = the add-fusion flavour of the block (victim_localization/yolov3/models.py:302: conv1(x) + conv2(x) + conv3(x)):
+// the three branch sums are added, (b1+S1) + (b2+S2) + (b3+S3) in that order, and C channels are stored instead of 3C.
+// C = 0 selects the run-time channel count `c_rt` (channel counts outside the instantiated list).
+template <int C, int PY, bool EDGE, bool ADD>
+__device__ __forceinline__ void dw_tile_patch(const float* __restrict__ xb /* image base + channel */, int H, int W, int c_rt,
                                               int out_h, int out_w, int oy0, int ox0, const float (&wr)[27],
                                               const float (&bv)[3], float* __restrict__ ob /* image base + channel */) {
   constexpr int PX = 4;
+  const int Cc = C > 0 ? C : c_rt;
   float acc[3][PY][PX];
 #pragma unroll
   for (int d = 0; d < 3; ++d)
@@ -183,8 +187,8 @@ __device__ __forceinline__ void dw_tile_patch(const float* __restrict__ xb /* im
     for (int py = 0; py < PY; ++py)
 #pragma unroll
       for (int px = 0; px < PX; ++px) acc[d][py][px] = bv[d];
-  const size_t rs = (size_t)W * C;                       // row stride in elements
-  const float* p0 = xb + ((ptrdiff_t)(oy0 - 2) * W + (ox0 - 2)) * C;
+  const size_t rs = (size_t)W * Cc;                      // row stride in elements
+  const float* p0 = xb + ((ptrdiff_t)(oy0 - 2) * W + (ox0 - 2)) * Cc;
 #pragma unroll
   for (int ry = 0; ry < PY + 6; ++ry) {
     const float* rp = p0 + ry * rs;
@@ -196,11 +200,11 @@ __device__ __forceinline__ void dw_tile_patch(const float* __restrict__ xb /* im
       for (int cx = 0; cx < PX + 6; ++cx) {
         const int ix = ox0 + cx - 2;
         xr[cx] = 0.f;
-        if (rowok && ix >= 0 && ix < W) xr[cx] = __ldg(rp + cx * C);
+        if (rowok && ix >= 0 && ix < W) xr[cx] = __ldg(rp + cx * Cc);
       }
     } else {
 #pragma unroll
-      for (int cx = 0; cx < PX + 6; ++cx) xr[cx] = __ldg(rp + cx * C);
+      for (int cx = 0; cx < PX + 6; ++cx) xr[cx] = __ldg(rp + cx * Cc);
     }
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -220,8 +224,9 @@ __device__ __forceinline__ void dw_tile_patch(const float* __restrict__ xb /* im
       }
     }
   }
-  const size_t os = (size_t)out_w * (3 * C);
-  float* o0 = ob + ((size_t)oy0 * out_w + ox0) * (3 * C);
+  const int OC = ADD ? Cc : 3 * Cc;
+  const size_t os = (size_t)out_w * OC;
+  float* o0 = ob + ((size_t)oy0 * out_w + ox0) * OC;
 #pragma unroll
   for (int py = 0; py < PY; ++py) {
     if (EDGE && oy0 + py >= out_h) break;
@@ -229,66 +234,100 @@ __device__ __forceinline__ void dw_tile_patch(const float* __restrict__ xb /* im
 #pragma unroll
     for (int px = 0; px < PX; ++px) {
       if (EDGE && ox0 + px >= out_w) break;
+      if constexpr (ADD) {
+        orow[px * OC] = (acc[0][py][px] + acc[1][py][px]) + acc[2][py][px];
+      } else {
 #pragma unroll
-      for (int d = 0; d < 3; ++d) orow[px * 3 * C + d * C] = acc[d][py][px];
+        for (int d = 0; d < 3; ++d) orow[px * OC + d * Cc] = acc[d][py][px];
+      }
     }
   }
 }
 
-template <int C, int PY, int MINB>
+template <int C, int PY, int MINB, bool ADD>
 __global__ void __launch_bounds__(256, MINB)
-acff_dw_tile_kernel(const float* __restrict__ x, int H, int W, int out_h, int out_w, int TX, int TY,
+acff_dw_tile_kernel(const float* __restrict__ x, int H, int W, int c_rt, int out_h, int out_w, int TX, int TY,
                     long long total, const float* __restrict__ w /*[3][9][C]*/, const float* __restrict__ bias /*[3][C]*/,
-                    float* __restrict__ out /*(B,out_h,out_w,3C)*/) {
+                    float* __restrict__ out /*(B,out_h,out_w,3C) or (B,out_h,out_w,C) with ADD*/) {
   constexpr int PX = 4;
+  const int Cc = C > 0 ? C : c_rt;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
-  const int c = (int)(gid % C);
-  unsigned t = (unsigned)(gid / C);
+  const int c = (int)(gid % Cc);
+  unsigned t = (unsigned)(gid / Cc);
   const int tx = t % TX; t /= TX;
   const int ty = t % TY;
   const int b = t / TY;
   const int ox0 = tx * PX, oy0 = ty * PY;
   float wr[27], bv[3];
 #pragma unroll
-  for (int i = 0; i < 27; ++i) wr[i] = __ldg(w + i * C + c);
+  for (int i = 0; i < 27; ++i) wr[i] = __ldg(w + i * Cc + c);
 #pragma unroll
-  for (int d = 0; d < 3; ++d) bv[d] = __ldg(bias + d * C + c);
-  const float* xb = x + (size_t)b * H * W * C + c;
-  float* ob = out + (size_t)b * out_h * out_w * (3 * C) + c;
+  for (int d = 0; d < 3; ++d) bv[d] = __ldg(bias + d * Cc + c);
+  const float* xb = x + (size_t)b * H * W * Cc + c;
+  float* ob = out + (size_t)b * out_h * out_w * (ADD ? Cc : 3 * Cc) + c;
   const bool interior = oy0 >= 2 && oy0 + PY + 3 < H && ox0 >= 2 && ox0 + PX + 3 < W && oy0 + PY <= out_h && ox0 + PX <= out_w;
-  if (interior) dw_tile_patch<C, PY, false>(xb, H, W, out_h, out_w, oy0, ox0, wr, bv, ob);
-  else          dw_tile_patch<C, PY, true>(xb, H, W, out_h, out_w, oy0, ox0, wr, bv, ob);
+  if (interior) dw_tile_patch<C, PY, false, ADD>(xb, H, W, c_rt, out_h, out_w, oy0, ox0, wr, bv, ob);
+  else          dw_tile_patch<C, PY, true, ADD>(xb, H, W, c_rt, out_h, out_w, oy0, ox0, wr, bv, ob);
 }
 
 inline int g_dw_fp32_form = 1;    // 1 = register-tile kernel (default), 0 = shared-memory kernel (ernet_set_depthwise_form)
 
-template <int C, int PY = 4, int MINB = 2>
-inline int launch_acff_dw_tile_c(const float* x, int batch, int H, int W, int out_h, int out_w,
+template <int C, int PY = 4, int MINB = 2, bool ADD = false>
+inline int launch_acff_dw_tile_c(const float* x, int batch, int H, int W, int c_rt, int out_h, int out_w,
                                  const float* w, const float* bias, float* out, cudaStream_t stream) {
+  const int Cc = C > 0 ? C : c_rt;
   const int TX = (out_w + 3) / 4, TY = (out_h + PY - 1) / PY;
-  const long long total = (long long)batch * TY * TX * C;
+  const long long total = (long long)batch * TY * TX * Cc;
   const long long blocks = (total + 255) / 256;
-  if (blocks > 0x7fffffffLL || total / C > 0xffffffffLL) return fail(ERNET_ERR_INVALID_ARG, "depthwise: batch too large for one launch");
-  acff_dw_tile_kernel<C, PY, MINB><<<(unsigned)blocks, 256, 0, stream>>>(x, H, W, out_h, out_w, TX, TY, total, w, bias, out);
+  if (blocks > 0x7fffffffLL || total / Cc > 0xffffffffLL) return fail(ERNET_ERR_INVALID_ARG, "depthwise: batch too large for one launch");
+  acff_dw_tile_kernel<C, PY, MINB, ADD><<<(unsigned)blocks, 256, 0, stream>>>(x, H, W, c_rt, out_h, out_w, TX, TY, total, w, bias, out);
   ERNET_LAUNCH_CHECK("acff_dw_tile_kernel");
   return ERNET_OK;
 }
 
-// Channel counts of the three architectures (Squeeze_ErNET 16/64/96/128, Squeeze_RedConv 8/64/48/64, ErNET 16..128);
-// returns -1 for any other C (the caller falls back to the shared-memory kernel).
-template <int PY = 4, int MINB = 2>
+// Channel counts of the three classifier architectures (Squeeze_ErNET 16/64/96/128, Squeeze_RedConv 8/64/48/64, ErNET
+// 16..128) and of the detector's add-fusion blocks (128/256) are compiled in; with `generic` any other C runs the
+// run-time-C instantiation, without it -1 is returned (the concat caller falls back to the shared-memory kernel).
+template <int PY = 4, int MINB = 2, bool ADD = false>
 inline int launch_acff_dw_tile(const float* x, int batch, int H, int W, int C, int out_h, int out_w,
-                               const float* w, const float* bias, float* out, cudaStream_t stream) {
+                               const float* w, const float* bias, float* out, cudaStream_t stream, bool generic = false) {
   switch (C) {
-    case 8:   return launch_acff_dw_tile_c<8, PY, MINB>(x, batch, H, W, out_h, out_w, w, bias, out, stream);
-    case 16:  return launch_acff_dw_tile_c<16, PY, MINB>(x, batch, H, W, out_h, out_w, w, bias, out, stream);
-    case 32:  return launch_acff_dw_tile_c<32, PY, MINB>(x, batch, H, W, out_h, out_w, w, bias, out, stream);
-    case 48:  return launch_acff_dw_tile_c<48, PY, MINB>(x, batch, H, W, out_h, out_w, w, bias, out, stream);
-    case 64:  return launch_acff_dw_tile_c<64, PY, MINB>(x, batch, H, W, out_h, out_w, w, bias, out, stream);
-    case 96:  return launch_acff_dw_tile_c<96, PY, MINB>(x, batch, H, W, out_h, out_w, w, bias, out, stream);
-    case 128: return launch_acff_dw_tile_c<128, PY, MINB>(x, batch, H, W, out_h, out_w, w, bias, out, stream);
-    default:  return -1;
+    case 8:   return launch_acff_dw_tile_c<8, PY, MINB, ADD>(x, batch, H, W, C, out_h, out_w, w, bias, out, stream);
+    case 16:  return launch_acff_dw_tile_c<16, PY, MINB, ADD>(x, batch, H, W, C, out_h, out_w, w, bias, out, stream);
+    case 32:  return launch_acff_dw_tile_c<32, PY, MINB, ADD>(x, batch, H, W, C, out_h, out_w, w, bias, out, stream);
+    case 48:  return launch_acff_dw_tile_c<48, PY, MINB, ADD>(x, batch, H, W, C, out_h, out_w, w, bias, out, stream);
+    case 64:  return launch_acff_dw_tile_c<64, PY, MINB, ADD>(x, batch, H, W, C, out_h, out_w, w, bias, out, stream);
+    case 96:  return launch_acff_dw_tile_c<96, PY, MINB, ADD>(x, batch, H, W, C, out_h, out_w, w, bias, out, stream);
+    case 128: return launch_acff_dw_tile_c<128, PY, MINB, ADD>(x, batch, H, W, C, out_h, out_w, w, bias, out, stream);
+    case 256: return launch_acff_dw_tile_c<256, PY, MINB, ADD>(x, batch, H, W, C, out_h, out_w, w, bias, out, stream);
+    default:
+      if (generic) return launch_acff_dw_tile_c<0, PY, MINB, ADD>(x, batch, H, W, C, out_h, out_w, w, bias, out, stream);
+      return -1;
+  }
+}
+
+// ---------------------------------------------------------------------------------- evaluation bookkeeping
+// argmax over the class scores of each image + confusion-matrix update, cm[target][prediction] += 1 (what
+// evaluate-classification-metrics.py:81-87 does with output.argmax(dim=1) and torchmetrics' ConfusionMatrix).
+// Ties resolve to the lowest class index, NaN scores never win.  Targets outside [0, nc) are counted in *bad.
+__global__ void confusion_update_kernel(const float* __restrict__ scores, const long long* __restrict__ targets, int batch,
+                                        int nc, long long* __restrict__ cm, long long* __restrict__ pred_out,
+                                        unsigned long long* __restrict__ bad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch) return;
+  const float* s = scores + (size_t)i * nc;
+  int best = 0;
+  float bv = s[0];
+  for (int k = 1; k < nc; ++k) {
+    const float v = s[k];
+    if (v > bv || (bv != bv && v == v)) { bv = v; best = k; }
+  }
+  if (pred_out) pred_out[i] = best;
+  if (targets && cm) {
+    const long long t = targets[i];
+    if (t < 0 || t >= nc) { if (bad) atomicAdd(bad, 1ull); return; }
+    atomicAdd(reinterpret_cast<unsigned long long*>(cm) + t * nc + best, 1ull);
   }
 }
 

@@ -1,0 +1,215 @@
+"""Batched evaluation loop with the fused device ingest.
+
+Mirror of ``code/disaster_detection/evaluate-classification-metrics.py``: ``load_model`` (:24-47, re-exported from
+``model.py``), ``evaluate_model`` (:49-105), ``compute_per_class_metrics`` (:107-132) and the CLI (:134-201), with the
+DataLoader-side PIL transforms (``dataloaders/aider.py:421-426``) replaced by the uint8 ingest kernel: the loader
+(``frame_batches``) only decodes JPEGs to uint8 HWC frames on host threads into pinned memory; resize, centre crop,
+ToTensor and Normalize run on the GPU inside ``model.forward_frames``.  The per-batch bookkeeping of the reference
+(``output.argmax(dim=1)`` + five torchmetrics objects, :81-87) is one kernel, ``ernet_confusion_update``, that
+accumulates the 5x5 confusion matrix on the device; it is read back once at the end.
+
+torchmetrics' ``Accuracy/F1Score/Precision/Recall(task="multiclass", num_classes=5)`` default to micro averaging, so
+with one label per image all four equal trace(cm)/sum(cm); the per-class values come from the confusion matrix exactly
+as in the reference.
+"""
+from __future__ import annotations
+
+import argparse
+import csv
+import logging
+import os
+import time
+from concurrent.futures import ThreadPoolExecutor
+from typing import Dict, Iterable, Iterator, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .model import load_model  # noqa: F401  (evaluate-classification-metrics.py:24-47)
+
+logger = logging.getLogger(__name__)
+CLASSES = ['collapsed building', 'fire', 'flooded areas', 'normal', 'traffic incident']    # :110
+NUM_CLASSES = 5
+
+
+class DeviceConfusion:
+    """5x5 int64 confusion matrix (rows = target, columns = prediction) kept on the GPU."""
+
+    def __init__(self, device, num_classes=NUM_CLASSES):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("the evaluation bookkeeping kernel runs on a CUDA device (no CPU fallback)")
+        self.nc = num_classes
+        self.cm = torch.zeros((num_classes, num_classes), dtype=torch.int64, device=self.device)
+        self.bad = torch.zeros(1, dtype=torch.int64, device=self.device)
+
+    def update(self, scores, target, want_pred=False):
+        """scores (B,nc) float on the device, target (B) integer labels (host or device)."""
+        if scores.dim() != 2 or scores.shape[1] != self.nc:
+            raise ValueError(f"expected scores of shape (B,{self.nc}), got {tuple(scores.shape)}")
+        scores = scores.to(device=self.device, dtype=torch.float32).contiguous()
+        target = torch.as_tensor(target).to(device=self.device, dtype=torch.int64, non_blocking=True).contiguous()
+        if target.shape != (scores.shape[0],):
+            raise ValueError("one target per image expected")
+        pred = torch.empty(scores.shape[0], dtype=torch.int64, device=self.device) if want_pred else None
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.load().ernet_confusion_update(scores.data_ptr(), target.data_ptr(), scores.shape[0], self.nc,
+                                                      self.cm.data_ptr(), pred.data_ptr() if want_pred else None,
+                                                      self.bad.data_ptr(), stream))
+        return pred
+
+    def compute(self):
+        bad = int(self.bad.item())
+        if bad:
+            raise ValueError(f"{bad} target label(s) outside [0, {self.nc})")
+        return self.cm.cpu()
+
+
+def compute_per_class_metrics(confusion_matrix) -> Dict[str, float]:
+    """Per-class precision / recall / F1 from the confusion matrix (evaluate-classification-metrics.py:107-132)."""
+    cm = torch.as_tensor(confusion_matrix)
+    metrics = {}
+    for i, class_name in enumerate(CLASSES):
+        tp = cm[i, i].item()
+        fp = cm[:, i].sum().item() - tp
+        fn = cm[i, :].sum().item() - tp
+        precision = tp / (tp + fp) if (tp + fp) > 0 else 0
+        recall = tp / (tp + fn) if (tp + fn) > 0 else 0
+        f1 = 2 * (precision * recall) / (precision + recall) if (precision + recall) > 0 else 0
+        metrics.update({f'{class_name}_precision': precision, f'{class_name}_recall': recall, f'{class_name}_f1': f1})
+    return metrics
+
+
+def evaluate_model(model, test_loader: Iterable, device, use_trt: bool = False, quant: str = 'fp16') -> Dict[str, float]:
+    """Evaluate ``model`` on ``test_loader`` (evaluate-classification-metrics.py:49-105).
+
+    ``test_loader`` yields ``(data, target)``.  ``data`` is either what the reference's DataLoader yields - a float
+    (B,3,H,W) tensor, run through ``model(data)`` - or uint8 (B,H,W,3) frames (host, preferably pinned, or device), run
+    through ``model.forward_frames`` so the eval transform happens on the GPU.  Returns the reference's dictionary:
+    accuracy, f1_score, precision, recall, avg_inference_time, fps (= 1 / mean seconds per batch, as in the reference)
+    and the 15 per-class entries, plus images_per_second and the confusion matrix."""
+    device = torch.device(device)
+    conf = DeviceConfusion(device)
+    inference_times = []
+    n_images = 0
+    with torch.no_grad():
+        for data, target in test_loader:
+            data = torch.as_tensor(data)
+            data = data.to(device, non_blocking=True)
+            if use_trt and quant == 'fp16' and data.is_floating_point():
+                data = data.half()                                           # :74-75
+            start_time = time.time()
+            output = model.forward_frames(data) if data.dtype == torch.uint8 else model(data)
+            torch.cuda.synchronize(device)                                   # :79
+            inference_times.append(time.time() - start_time)
+            conf.update(output, target)                                      # :82-87, on the device
+            n_images += data.shape[0]
+    if not inference_times:
+        raise ValueError("empty test set")
+    cm = conf.compute()
+    total = int(cm.sum())
+    acc = float(torch.diagonal(cm).sum()) / total
+    metrics = {
+        'accuracy': acc, 'f1_score': acc, 'precision': acc, 'recall': acc,      # micro averages, see module docstring
+        'avg_inference_time': float(np.mean(inference_times)),
+        'fps': 1.0 / float(np.mean(inference_times)),
+        'images_per_second': n_images / float(np.sum(inference_times)),
+        'confusion_matrix': cm.numpy(),
+    }
+    metrics.update(compute_per_class_metrics(cm))
+    return metrics
+
+
+# ----------------------------------------------------------------------------------------- frame loader
+def read_split(csv_file, root_dir):
+    """[(absolute image path, label)] from a header-less ``path,label`` CSV (dataloaders/aider.py:106, aider_test.csv)."""
+    if not os.path.exists(csv_file):
+        raise FileNotFoundError(f"CSV file not found: {csv_file}")
+    out = []
+    with open(csv_file, newline="") as f:
+        for row in csv.reader(f):
+            if len(row) >= 2 and row[0]:
+                out.append((os.path.join(str(root_dir), row[0]), int(row[1])))
+    return out
+
+
+def decode_frame(path):
+    """JPEG/PNG -> uint8 (H,W,3) RGB array; a blank 240x240 frame when the file cannot be read, like
+    ``cached_image_loader`` (dataloaders/aider.py:44-56)."""
+    from PIL import Image
+    try:
+        with open(path, 'rb') as f:
+            return np.asarray(Image.open(f).convert('RGB'))
+    except Exception as e:                                                   # noqa: BLE001  (mirrors the reference)
+        logger.error(f"Error loading image {path}: {e}")
+        return np.zeros((240, 240, 3), dtype=np.uint8)
+
+
+def frame_batches(samples, batch_size=64, num_workers=4, pin_memory=True) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
+    """Decode ``samples`` ([(path, label)]) on ``num_workers`` host threads and yield ``(frames, target)`` batches:
+    frames uint8 (B,H,W,3) in pinned memory, target int64 (B).  Frames of different sizes cannot share a batch (the
+    resize tables are per size), so images are bucketed by (H,W); a bucket is emitted when it holds ``batch_size``
+    frames and the partial buckets at the end.  Every sample is yielded exactly once."""
+    if batch_size < 1:
+        raise ValueError("batch_size must be positive")
+    buckets = {}
+
+    def emit(key):
+        frames, labels = buckets.pop(key)
+        t = torch.from_numpy(np.stack(frames, 0))
+        if pin_memory and torch.cuda.is_available():
+            t = t.pin_memory()
+        return t, torch.tensor(labels, dtype=torch.int64)
+
+    with ThreadPoolExecutor(max_workers=max(1, num_workers)) as pool:
+        window = max(2 * batch_size, 4 * num_workers)
+        for i0 in range(0, len(samples), window):
+            chunk = samples[i0:i0 + window]
+            for (path, label), frame in zip(chunk, pool.map(decode_frame, [p for p, _ in chunk])):
+                key = frame.shape[:2]
+                fr, lb = buckets.setdefault(key, ([], []))
+                fr.append(frame)
+                lb.append(label)
+                if len(fr) == batch_size:
+                    yield emit(key)
+    for key in sorted(buckets):
+        yield emit(key)
+
+
+def main(argv=None):
+    """CLI with the reference's flags (evaluate-classification-metrics.py:134-201); ``--quant`` selects the engine
+    precision (the reference's ``--trt --quant`` pair), ``int8`` included."""
+    parser = argparse.ArgumentParser(description='Evaluate model on test set (B200 engine)')
+    parser.add_argument('--model', type=str, default='squeeze-ernet', choices=['ernet', 'squeeze-ernet', 'squeeze-redconv'])
+    parser.add_argument('--weights', type=str, required=True)
+    parser.add_argument('--test-split', type=str, default='dataloaders/aider_test.csv')
+    parser.add_argument('--root-dir', type=str, default='data/AIDER')
+    parser.add_argument('--batch-size', type=int, default=64)
+    parser.add_argument('--num-workers', type=int, default=4)
+    parser.add_argument('--trt', action='store_true', help='accepted for compatibility: the B200 engine is always used')
+    parser.add_argument('--quant', type=str, default='fp16', choices=['fp16', 'bf16', 'fp32', 'int8'])
+    args = parser.parse_args(argv)
+    logging.basicConfig(level=logging.INFO, format='%(asctime)s - %(name)s - %(levelname)s - %(message)s')
+    if not torch.cuda.is_available():
+        raise RuntimeError('CUDA is not available: the B200 engine has no CPU path')
+    device = torch.device('cuda')
+    model = load_model(args.model, args.weights, device, precision=args.quant)
+    samples = read_split(args.test_split, args.root_dir)
+    metrics = evaluate_model(model, frame_batches(samples, args.batch_size, args.num_workers), device)
+    logger.info("\nEvaluation Results:")
+    for k, label in (('accuracy', 'Accuracy'), ('f1_score', 'F1 Score'), ('precision', 'Precision'), ('recall', 'Recall')):
+        logger.info(f"{label}: {metrics[k]:.4f}")
+    logger.info(f"Average Inference Time: {metrics['avg_inference_time']:.4f} seconds")
+    logger.info(f"FPS: {metrics['fps']:.2f}")
+    logger.info("\nPer-class Metrics:")
+    for class_name in CLASSES:
+        logger.info(f"\n{class_name}:")
+        logger.info(f"  Precision: {metrics[f'{class_name}_precision']:.4f}")
+        logger.info(f"  Recall: {metrics[f'{class_name}_recall']:.4f}")
+        logger.info(f"  F1 Score: {metrics[f'{class_name}_f1']:.4f}")
+    return metrics
+
+
+if __name__ == '__main__':
+    main()

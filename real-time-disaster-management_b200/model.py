@@ -51,163 +51,17 @@ class _ACFFParams(nn.Module):
         raise RuntimeError("parameter container: compute happens in libernet_b200.so")
 
 
-class _ErnetB200(nn.Module):
-    ARCH = None
-
-    def __init__(self, *, precision=None, device=None):
-        super().__init__()
-        arch = self.ARCH
-        red = arch == "squeeze-redconv"
-        w = widths(arch)
-        self.IN_HW = 240 if arch == "ernet" else 140     # ErNET is the 240x240-native model (model/ernet.py:21-22,42)
-        self.conv1 = nn.Conv2d(3, 16, 3, 2, 0, bias=False)
-        if red:
-            self.conv_red1 = nn.Conv2d(16, 8, 1)
-        self.acff1 = _ACFFParams(*w[0])
-        self.acff2 = _ACFFParams(*w[1])
-        if red:
-            self.conv_red2 = nn.Conv2d(96, 48, 1)
-        self.acff3 = _ACFFParams(*w[2])
-        if red:
-            self.conv_red3 = nn.Conv2d(128, 64, 1)
-        self.acff4 = _ACFFParams(*w[3])
-        if arch == "ernet":
-            self.acff5 = _ACFFParams(*w[4])
-            self.acff6 = _ACFFParams(*w[5])
-        self.conv2 = nn.Conv2d(256, 5, 1, bias=False)
-        self.fc = nn.Linear(3 * 3 * 5 if arch == "ernet" else 2 * 2 * 5, 5)
-        if precision is not None and precision not in _lib.PRECISION:
-            raise ValueError(f"unknown precision {precision!r}; expected one of {sorted(_lib.PRECISION)}")
-        self._precision = precision          # None: follow the parameter dtype (fp32, or fp16 after .half())
-        self._engine = None                  # (handle, device_index, precision)
-        self._fingerprint = None
-        self._workspace = None
-        self._last_batch = 0
-        self._act_scales = None              # int8: calibrated per-tensor activation scales (stem, pool1, pool2)
-        if device is not None:
-            self.to(device)
-
-    # ------------------------------------------------------------------ precision / engine
-    @property
-    def precision(self):
-        if self._precision is not None:
-            return self._precision
-        return _PREC_OF_DTYPE.get(self.conv1.weight.dtype, "fp32")
-
-    def set_precision(self, precision):
-        if precision not in _lib.PRECISION:
-            raise ValueError(f"unknown precision {precision!r}")
-        self._precision = precision
-        return self
-
-    def _weights_fingerprint(self):
-        fp = []
-        for t in list(self.parameters()) + list(self.buffers()):
-            fp.append((t.data_ptr(), t._version))
-        return tuple(fp)
-
-    def _release(self):
-        if self._engine is not None:
-            _lib.load().ernet_destroy(self._engine[0])
-            self._engine = None
-            self._fingerprint = None
-
-    def __del__(self):
-        try:
-            self._release()
-        except Exception:
-            pass
-
-    def _ensure_engine(self):
-        dev = self.conv1.weight.device
-        if dev.type != "cuda":
-            raise RuntimeError("this model runs only on a CUDA device (B200, sm_100a); call .to('cuda') first — "
-                               "there is no CPU fallback")
-        if self.training:
-            raise RuntimeError("inference-only engine: call model.eval() first (train mode would need dropout and "
-                               "batch statistics, acff.py:34-35)")
-        lib = _lib.load()
-        idx = dev.index if dev.index is not None else torch.cuda.current_device()
-        prec = self.precision
-        if self._engine is None or self._engine[1:] != (idx, prec):
-            self._release()
-            h = C.c_void_p()
-            _lib.check(lib.ernet_create(C.byref(h), _lib.ARCH[self.ARCH], _lib.PRECISION[prec], idx))
-            self._engine = (h, idx, prec)
-        if prec == "int8" and self._act_scales is None:
-            self.calibrate()                 # default synthetic calibration set (SURVEY.md 8d, config 4)
-        fp = (self._weights_fingerprint(), self._act_scales)
-        if fp != self._fingerprint:
-            blob = pack_state_dict(self.state_dict(), self.ARCH, prec, self._act_scales)
-            buf = (C.c_char * len(blob)).from_buffer_copy(blob)
-            _lib.check(lib.ernet_load_packed(self._engine[0], buf, len(blob)))
-            self._fingerprint = fp
-        return lib, self._engine[0], idx
+class _EngineRuntime:
+    """Everything that drives a loaded engine handle through the C ABI: ``model(x)``, the frames path, the host entry
+    points, schedule switches and introspection.  Shared by the weight-holding model classes below (which pack their
+    state_dict on demand) and by ``build_engine.TRTModule`` (which loads a previously packed engine).  A subclass
+    provides ``ARCH``, ``IN_HW``, ``_workspace``, ``_last_batch`` and ``_ensure_engine() -> (lib, handle, device_index)``."""
 
     def _get_workspace(self, lib, h, batch, device):
         need = lib.ernet_workspace_bytes(h, batch)
         if self._workspace is None or self._workspace.numel() < need or self._workspace.device != device:
             self._workspace = torch.empty(need, dtype=torch.uint8, device=device)
         return self._workspace
-
-    # ------------------------------------------------------------------ int8 calibration
-    def calibrate(self, frames=None, *, percentile=100.0, per_channel=True, batch=128):
-        """Activation scales for the int8 engine (the TensorRT scheme behind the reference's int8 artefacts:
-        symmetric int8, activation scales from a calibration set, per-output-channel weight scale
-        max|W|/127, int32 accumulate, fp32 dequant + bias; SURVEY.md section 0.4).
-
-        ``frames``: uint8 (N,H,W,3) calibration frames (numpy / tensor); default = 512 synthetic 240x240
-        frames, seed 99 (half uniform noise, half smooth).  An fp32 twin of this model runs them through the
-        CUDA-core engine; at the three quantised tensors (stem, pool1, pool2 outputs) the ``percentile`` of
-        |activation| becomes 127 int8 steps - per channel when ``per_channel`` (cross-layer equalisation:
-        the per-channel factors are folded into the producer's epilogue constants and the consumer's weights
-        at pack time, the runtime tensor keeps one scale), else per tensor.  Returns the three scale arrays."""
-        dev = self.conv1.weight.device
-        if dev.type != "cuda":
-            raise RuntimeError("calibration runs on the GPU; call .to('cuda') first")
-        if frames is None:
-            frames = default_calibration_frames()
-        frames = torch.as_tensor(np.asarray(frames) if not isinstance(frames, torch.Tensor) else frames)
-        twin = type(self)(precision="fp32")
-        twin.load_state_dict({k: v.detach().float() if v.is_floating_point() else v.detach()
-                              for k, v in self.state_dict().items()})
-        twin = twin.to(dev)
-        twin.eval()
-        names = ("stem", "pool1", "pool2")
-        amax = {n: None for n in names}
-        samples = {n: [] for n in names}
-        for i in range(0, frames.shape[0], batch):
-            twin.forward_frames(frames[i:i + batch].to(dev))
-            for n in names:
-                t = twin.tap(n).abs()                                     # (b,C,H,W)
-                tc_ = t.permute(1, 0, 2, 3).reshape(t.shape[1], -1)       # (C, b*H*W)
-                m = tc_.max(dim=1).values
-                amax[n] = m if amax[n] is None else torch.maximum(amax[n], m)
-                if percentile < 100:
-                    step = max(1, tc_.shape[1] // 20_000)
-                    samples[n].append(tc_[:, ::step].clone())
-        scales = []
-        for n in names:
-            if percentile < 100:
-                v = torch.cat(samples[n], dim=1).double()
-                r = torch.quantile(v, percentile / 100.0, dim=1) if per_channel else \
-                    torch.quantile(v.flatten()[: 16_000_000], percentile / 100.0).expand(v.shape[0])
-            else:
-                r = amax[n].double() if per_channel else amax[n].double().max().expand(amax[n].shape[0])
-            floor = float(amax[n].max()) * 1e-6 + 1e-30                   # dead channels: keep the step finite
-            scales.append(tuple((torch.clamp(r, min=floor) / 127.0).cpu().tolist()))
-        twin._release()
-        self._act_scales = tuple(scales)
-        return self._act_scales
-
-    @property
-    def act_scales(self):
-        return self._act_scales
-
-    def set_act_scales(self, scales):
-        from .pack_tc import normalize_act_scales
-        self._act_scales = tuple(tuple(float(x) for x in a) for a in normalize_act_scales(scales))
-        return self
 
     def set_engine(self, engine):
         """'auto' (default), 'simt' (CUDA-core kernels) or 'tc' (tcgen05 block kernels)."""
@@ -410,6 +264,159 @@ class _ErnetB200(nn.Module):
     def launches_per_forward(self, batch, with_ingest=True):
         lib, h, _ = self._ensure_engine()
         return lib.ernet_launches_per_forward(h, int(batch), 1 if with_ingest else 0)
+
+
+class _ErnetB200(_EngineRuntime, nn.Module):
+    ARCH = None
+
+    def __init__(self, *, precision=None, device=None):
+        super().__init__()
+        arch = self.ARCH
+        red = arch == "squeeze-redconv"
+        w = widths(arch)
+        self.IN_HW = 240 if arch == "ernet" else 140     # ErNET is the 240x240-native model (model/ernet.py:21-22,42)
+        self.conv1 = nn.Conv2d(3, 16, 3, 2, 0, bias=False)
+        if red:
+            self.conv_red1 = nn.Conv2d(16, 8, 1)
+        self.acff1 = _ACFFParams(*w[0])
+        self.acff2 = _ACFFParams(*w[1])
+        if red:
+            self.conv_red2 = nn.Conv2d(96, 48, 1)
+        self.acff3 = _ACFFParams(*w[2])
+        if red:
+            self.conv_red3 = nn.Conv2d(128, 64, 1)
+        self.acff4 = _ACFFParams(*w[3])
+        if arch == "ernet":
+            self.acff5 = _ACFFParams(*w[4])
+            self.acff6 = _ACFFParams(*w[5])
+        self.conv2 = nn.Conv2d(256, 5, 1, bias=False)
+        self.fc = nn.Linear(3 * 3 * 5 if arch == "ernet" else 2 * 2 * 5, 5)
+        if precision is not None and precision not in _lib.PRECISION:
+            raise ValueError(f"unknown precision {precision!r}; expected one of {sorted(_lib.PRECISION)}")
+        self._precision = precision          # None: follow the parameter dtype (fp32, or fp16 after .half())
+        self._engine = None                  # (handle, device_index, precision)
+        self._fingerprint = None
+        self._workspace = None
+        self._last_batch = 0
+        self._act_scales = None              # int8: calibrated per-tensor activation scales (stem, pool1, pool2)
+        if device is not None:
+            self.to(device)
+
+    # ------------------------------------------------------------------ precision / engine
+    @property
+    def precision(self):
+        if self._precision is not None:
+            return self._precision
+        return _PREC_OF_DTYPE.get(self.conv1.weight.dtype, "fp32")
+
+    def set_precision(self, precision):
+        if precision not in _lib.PRECISION:
+            raise ValueError(f"unknown precision {precision!r}")
+        self._precision = precision
+        return self
+
+    def _weights_fingerprint(self):
+        fp = []
+        for t in list(self.parameters()) + list(self.buffers()):
+            fp.append((t.data_ptr(), t._version))
+        return tuple(fp)
+
+    def _release(self):
+        if self._engine is not None:
+            _lib.load().ernet_destroy(self._engine[0])
+            self._engine = None
+            self._fingerprint = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _ensure_engine(self):
+        dev = self.conv1.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("this model runs only on a CUDA device (B200, sm_100a); call .to('cuda') first — "
+                               "there is no CPU fallback")
+        if self.training:
+            raise RuntimeError("inference-only engine: call model.eval() first (train mode would need dropout and "
+                               "batch statistics, acff.py:34-35)")
+        lib = _lib.load()
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        prec = self.precision
+        if self._engine is None or self._engine[1:] != (idx, prec):
+            self._release()
+            h = C.c_void_p()
+            _lib.check(lib.ernet_create(C.byref(h), _lib.ARCH[self.ARCH], _lib.PRECISION[prec], idx))
+            self._engine = (h, idx, prec)
+        if prec == "int8" and self._act_scales is None:
+            self.calibrate()                 # default synthetic calibration set (SURVEY.md 8d, config 4)
+        fp = (self._weights_fingerprint(), self._act_scales)
+        if fp != self._fingerprint:
+            blob = pack_state_dict(self.state_dict(), self.ARCH, prec, self._act_scales)
+            buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+            _lib.check(lib.ernet_load_packed(self._engine[0], buf, len(blob)))
+            self._fingerprint = fp
+        return lib, self._engine[0], idx
+
+    # ------------------------------------------------------------------ int8 calibration
+    def calibrate(self, frames=None, *, percentile=100.0, per_channel=True, batch=128):
+        """Activation scales for the int8 engine (the TensorRT scheme behind the reference's int8 artefacts:
+        symmetric int8, activation scales from a calibration set, per-output-channel weight scale
+        max|W|/127, int32 accumulate, fp32 dequant + bias; SURVEY.md section 0.4).
+
+        ``frames``: uint8 (N,H,W,3) calibration frames (numpy / tensor); default = 512 synthetic 240x240
+        frames, seed 99 (half uniform noise, half smooth).  An fp32 twin of this model runs them through the
+        CUDA-core engine; at the three quantised tensors (stem, pool1, pool2 outputs) the ``percentile`` of
+        |activation| becomes 127 int8 steps - per channel when ``per_channel`` (cross-layer equalisation:
+        the per-channel factors are folded into the producer's epilogue constants and the consumer's weights
+        at pack time, the runtime tensor keeps one scale), else per tensor.  Returns the three scale arrays."""
+        dev = self.conv1.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("calibration runs on the GPU; call .to('cuda') first")
+        if frames is None:
+            frames = default_calibration_frames()
+        frames = torch.as_tensor(np.asarray(frames) if not isinstance(frames, torch.Tensor) else frames)
+        twin = type(self)(precision="fp32")
+        twin.load_state_dict({k: v.detach().float() if v.is_floating_point() else v.detach()
+                              for k, v in self.state_dict().items()})
+        twin = twin.to(dev)
+        twin.eval()
+        names = ("stem", "pool1", "pool2")
+        amax = {n: None for n in names}
+        samples = {n: [] for n in names}
+        for i in range(0, frames.shape[0], batch):
+            twin.forward_frames(frames[i:i + batch].to(dev))
+            for n in names:
+                t = twin.tap(n).abs()                                     # (b,C,H,W)
+                tc_ = t.permute(1, 0, 2, 3).reshape(t.shape[1], -1)       # (C, b*H*W)
+                m = tc_.max(dim=1).values
+                amax[n] = m if amax[n] is None else torch.maximum(amax[n], m)
+                if percentile < 100:
+                    step = max(1, tc_.shape[1] // 20_000)
+                    samples[n].append(tc_[:, ::step].clone())
+        scales = []
+        for n in names:
+            if percentile < 100:
+                v = torch.cat(samples[n], dim=1).double()
+                r = torch.quantile(v, percentile / 100.0, dim=1) if per_channel else \
+                    torch.quantile(v.flatten()[: 16_000_000], percentile / 100.0).expand(v.shape[0])
+            else:
+                r = amax[n].double() if per_channel else amax[n].double().max().expand(amax[n].shape[0])
+            floor = float(amax[n].max()) * 1e-6 + 1e-30                   # dead channels: keep the step finite
+            scales.append(tuple((torch.clamp(r, min=floor) / 127.0).cpu().tolist()))
+        twin._release()
+        self._act_scales = tuple(scales)
+        return self._act_scales
+
+    @property
+    def act_scales(self):
+        return self._act_scales
+
+    def set_act_scales(self, scales):
+        from .pack_tc import normalize_act_scales
+        self._act_scales = tuple(tuple(float(x) for x in a) for a in normalize_act_scales(scales))
+        return self
 
 
 class _HostTicket:

@@ -12,6 +12,7 @@ using namespace ernet;
 
 #define CK(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { printf("%s: %s\n", #e, cudaGetErrorString(_e)); return 1; } } while (0)
 
+template <int PY, int MINB> static int tile(const float* x, int b, int H, int W, int C, int oh, int ow, const float* w, const float* bi, float* o, cudaStream_t s) { return launch_acff_dw_tile<PY, MINB, false>(x, b, H, W, C, oh, ow, w, bi, o, s); }
 typedef int (*launch_fn)(const float*, int, int, int, int, int, int, const float*, const float*, float*, cudaStream_t);
 static int launch_smem(const float* x, int b, int H, int W, int C, int oh, int ow, const float* w, const float* bi, float* o, cudaStream_t s) {
   g_dw_fp32_form = 0; int rc = launch_acff_dw<float>(x, b, H, W, C, oh, ow, w, bi, o, s); g_dw_fp32_form = 1; return rc;
@@ -23,9 +24,9 @@ int main(int argc, char** argv) {
   struct Shape { int H, C, oh; } shapes[] = {{69, 16, 67}, {69, 16, 66}, {33, 64, 31}, {15, 96, 13}, {6, 128, 4}, {69, 8, 67}};
   struct Var { const char* name; launch_fn fn; } vars[] = {
       {"smem", launch_smem},
-      {"tile py4 occ2", launch_acff_dw_tile<4, 2>}, {"tile py4 occ3", launch_acff_dw_tile<4, 3>},
-      {"tile py2 occ3", launch_acff_dw_tile<2, 3>}, {"tile py2 occ4", launch_acff_dw_tile<2, 4>},
-      {"tile py3 occ3", launch_acff_dw_tile<3, 3>}, {"tile py6 occ2", launch_acff_dw_tile<6, 2>}};
+      {"tile py4 occ2", tile<4, 2>}, {"tile py4 occ3", tile<4, 3>},
+      {"tile py2 occ3", tile<2, 3>}, {"tile py2 occ4", tile<2, 4>},
+      {"tile py3 occ3", tile<3, 3>}, {"tile py6 occ2", tile<6, 2>}};
   float* flush; const size_t flush_n = 160u << 20;   // 640 MB > L2
   CK(cudaMalloc(&flush, flush_n * 4));
   {   // what a pure write stream and a copy reach on this GPU (context for the 74 %-write depthwise traffic)
