@@ -114,18 +114,21 @@ def resize_u8(frame, out_h, out_w):
     return _resample_axis(tmp, out_h, axis=0)
 
 
-def crop_u8(frame):
-    """Resize(159) + CenterCrop(140) on an (H,W,3) uint8 frame -> (140,140,3) uint8."""
+def crop_u8(frame, image_size=CROP):
+    """Resize(int(image_size*1.14)) + CenterCrop(image_size) on an (H,W,3) uint8 frame -> (image_size,image_size,3) uint8
+    (get_val_torchvision_transforms, aider.py:412-426: image_size 140 -> Resize(159) for the Squeeze models, 240 ->
+    Resize(273) for ErNET, aider.py:430-431)."""
     frame = np.asarray(frame)
     if frame.ndim != 3 or frame.shape[2] != 3 or frame.dtype != np.uint8:
         raise ValueError("expected (H,W,3) uint8")
-    nh, nw = resized_size(frame.shape[0], frame.shape[1])
-    if nh < CROP or nw < CROP:
+    short = int(image_size * 1.14)                                # aider.py:422
+    nh, nw = resized_size(frame.shape[0], frame.shape[1], short)
+    if nh < image_size or nw < image_size:
         raise ValueError("resized frame smaller than the crop")
     r = resize_u8(frame, nh, nw)
-    top = center_crop_offset(nh)
-    left = center_crop_offset(nw)
-    return r[top:top + CROP, left:left + CROP, :]
+    top = center_crop_offset(nh, image_size)
+    left = center_crop_offset(nw, image_size)
+    return r[top:top + image_size, left:left + image_size, :]
 
 
 def normalise_lut():
@@ -137,12 +140,12 @@ def normalise_lut():
     return ((v - mean) / std).astype(np.float32)
 
 
-def ingest(frames):
-    """frames: (B,H,W,3) uint8 (or a list of (H,W,3) of one size) -> (B,3,140,140) fp32 NCHW."""
+def ingest(frames, image_size=CROP):
+    """frames: (B,H,W,3) uint8 (or a list of (H,W,3) of one size) -> (B,3,image_size,image_size) fp32 NCHW."""
     lut = normalise_lut()
     outs = []
     for f in frames:
-        c = crop_u8(f)                                           # (140,140,3)
+        c = crop_u8(f, image_size)                               # (S,S,3)
         t = np.stack([lut[c[:, :, ch], ch] for ch in range(3)], axis=0)
         outs.append(t)
     return np.stack(outs, axis=0).astype(np.float32)

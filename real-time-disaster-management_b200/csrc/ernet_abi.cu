@@ -118,6 +118,7 @@ static Plan make_plan(const ernet_handle* h, int n) {
   auto take = [&](size_t elems) { size_t r = o; o += align_up(elems * e, 256); return r; };
   p.tc = h->use_tc();
   if (h->ernet() && p.tc) {                      // P8 images between the tensor-core kernels (+ slack for the last pair-unit)
+    p.ingest = take(N * 240 * 240 * 3);          // frames path: the transformed tensor, NHWC
     p.stem = take(N * 2 * 122 * 122 * 8);        // (B,2,122,122,8)
     p.p1 = take(N * 8 * 61 * 61 * 8);            // (B,8,61,61,8)
     p.p2 = take(N * 12 * 31 * 31 * 8);           // (B,12,31,31,8)
@@ -129,6 +130,7 @@ static Plan make_plan(const ernet_handle* h, int n) {
     return p;
   }
   if (h->ernet()) {                              // layer-wise path, NHWC: sizes of the largest user of each buffer
+    p.ingest = take(N * 240 * 240 * 3);
     p.stem = take(N * 119 * 119 * 16);
     p.ecat = take(N * 117 * 117 * 48);           // ACFF1 concat (ACFF2: 56*56*192 is smaller)
     p.ea = take(N * 58 * 58 * 64);               // pool1 (also pool3 13*13*128, acff5 9*9*128)
@@ -572,7 +574,22 @@ static int run_chunk_ernet_tc(ernet_handle* h, const void* x, int x_dtype, int x
 static int run_chunk(ernet_handle* h, const void* x, int x_dtype, int x_layout, const uint8_t* frames,
                      const IngestTables* tab, int order, int n, float* probs, float* logits, char* ws, cudaStream_t s) {
   if (h->ernet()) {
-    if (frames) return fail(ERNET_ERR_UNSUPPORTED, "the frames path (fused transform) is not wired for ErNET yet: pass (B,3,240,240) tensors to ernet_forward");
+    if (frames) {
+      // aider_transforms (aider.py:430: Resize(273) -> CenterCrop(240) -> ToTensor -> Normalize) on the table-driven kernel
+      // into the workspace (NHWC, the engine's type), then the same chain as for tensors
+      const Plan p = make_plan(h, n);
+      int rc;
+      const long long sb = 3LL * 240 * 240;
+      switch (h->precision) {
+        case ERNET_PREC_FP32: rc = launch_ingest<float>(*tab, frames, n, order == ERNET_BGR, reinterpret_cast<float*>(ws + p.ingest), sb, 1, 240 * 3, 3, s); x_dtype = ERNET_F32; break;
+        case ERNET_PREC_FP16: rc = launch_ingest<__half>(*tab, frames, n, order == ERNET_BGR, reinterpret_cast<__half*>(ws + p.ingest), sb, 1, 240 * 3, 3, s); x_dtype = ERNET_F16; break;
+        case ERNET_PREC_BF16: rc = launch_ingest<__nv_bfloat16>(*tab, frames, n, order == ERNET_BGR, reinterpret_cast<__nv_bfloat16*>(ws + p.ingest), sb, 1, 240 * 3, 3, s); x_dtype = ERNET_BF16; break;
+        default: return fail(ERNET_ERR_UNSUPPORTED, "int8 is implemented for Squeeze_ErNET only");
+      }
+      if (rc) return rc;
+      x = ws + p.ingest;
+      x_layout = ERNET_NHWC;
+    }
     if (h->use_tc()) {
       if (h->precision == ERNET_PREC_BF16) return run_chunk_ernet_tc<__nv_bfloat16, tc::KIND_BF16>(h, x, x_dtype, x_layout, n, probs, logits, ws, s);
       return run_chunk_ernet_tc<__half, tc::KIND_F16>(h, x, x_dtype, x_layout, n, probs, logits, ws, s);
@@ -686,7 +703,7 @@ static int get_tables(ernet_handle* h, int H, int W, const IngestTables** out) {
   auto it = h->ingest.find(key);
   if (it == h->ingest.end()) {
     IngestTables t;
-    int rc = build_ingest_tables(t, H, W);
+    int rc = build_ingest_tables(t, H, W, h->in_hw(), h->ernet() ? 273 : 159);   // int(image_size * 1.14), aider.py:422
     if (rc) return rc;
     it = h->ingest.emplace(key, t).first;
   }
@@ -1028,9 +1045,10 @@ int ernet_ingest_u8(ernet_handle* h, const uint8_t* frames, int batch, int heigh
   const IngestTables* tab;
   int rc = get_tables(h, height, width, &tab);
   if (rc) return rc;
-  long long sb = 3LL * 140 * 140, sc, sy, sx;
-  if (out_layout == ERNET_NCHW) { sc = 140 * 140; sy = 140; sx = 1; }
-  else if (out_layout == ERNET_NHWC) { sc = 1; sy = 140 * 3; sx = 3; }
+  const long long S = h->in_hw();
+  long long sb = 3LL * S * S, sc, sy, sx;
+  if (out_layout == ERNET_NCHW) { sc = S * S; sy = S; sx = 1; }
+  else if (out_layout == ERNET_NHWC) { sc = 1; sy = S * 3; sx = 3; }
   else return fail(ERNET_ERR_INVALID_ARG, "bad out_layout %d", out_layout);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool bgr = channel_order == ERNET_BGR;

@@ -24,6 +24,7 @@ constexpr size_t kRawStageBytes = 48 * 1024;
 
 struct IngestTables {
   int H = 0, W = 0, new_h = 0, new_w = 0, top = 0, left = 0;
+  int crop = 140, resize = 159;  // CenterCrop / Resize of this handle's transform: 140 / 159 (squeeze_transforms), 240 / 273 (aider_transforms, ErNET)
   int ksx = 0, ksy = 0;          // taps per output column / row (padded table width)
   int band_rows = 0;             // output rows per CTA
   int max_in_rows = 0;           // input rows a band needs at most
@@ -101,19 +102,19 @@ __global__ void __launch_bounds__(256)
 ingest_kernel(const uint8_t* __restrict__ frames, int H, int W, int bgr,
               const int* __restrict__ xmin, const int* __restrict__ xlen, const int* __restrict__ kx, int ksx,
               const int* __restrict__ ymin, const int* __restrict__ ylen, const int* __restrict__ ky, int ksy,
-              const float* __restrict__ lut, int band_rows,
+              const float* __restrict__ lut, int band_rows, int crop,
               TO* __restrict__ out, long long out_sb, long long out_sc, long long out_sy, long long out_sx) {
-  extern __shared__ uint8_t hbuf[];  // [in_rows][140*3]
+  extern __shared__ uint8_t hbuf[];  // [in_rows][crop*3]
   const int b = blockIdx.y;
   const int oy0 = blockIdx.x * band_rows;
-  const int oy1 = min(oy0 + band_rows, kCrop);
+  const int oy1 = min(oy0 + band_rows, crop);
   const int r0 = ymin[oy0];
   const int r1 = ymin[oy1 - 1] + ylen[oy1 - 1];
   const int in_rows = r1 - r0;
   const uint8_t* src = frames + (size_t)b * H * W * 3;
 
-  for (int idx = threadIdx.x; idx < in_rows * kCrop; idx += blockDim.x) {
-    const int r = idx / kCrop, ox = idx - r * kCrop;
+  for (int idx = threadIdx.x; idx < in_rows * crop; idx += blockDim.x) {
+    const int r = idx / crop, ox = idx - r * crop;
     const int x0 = xmin[ox], n = xlen[ox];
     const uint8_t* p = src + ((size_t)(r0 + r) * W + x0) * 3;
     const int* k = kx + ox * ksx;
@@ -132,15 +133,15 @@ ingest_kernel(const uint8_t* __restrict__ frames, int H, int W, int bgr,
   __syncthreads();
 
   const int rows = oy1 - oy0;
-  for (int idx = threadIdx.x; idx < rows * kCrop; idx += blockDim.x) {
-    const int ry = idx / kCrop, ox = idx - ry * kCrop;
+  for (int idx = threadIdx.x; idx < rows * crop; idx += blockDim.x) {
+    const int ry = idx / crop, ox = idx - ry * crop;
     const int oy = oy0 + ry;
     const int y0 = ymin[oy] - r0, n = ylen[oy];
     const int* k = ky + oy * ksy;
     int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
     for (int t = 0; t < n; ++t) {
       const int c = __ldg(k + t);
-      const uint8_t* h = hbuf + ((size_t)(y0 + t) * kCrop + ox) * 3;
+      const uint8_t* h = hbuf + ((size_t)(y0 + t) * crop + ox) * 3;
       a0 += c * (int)h[0];
       a1 += c * (int)h[1];
       a2 += c * (int)h[2];
@@ -534,38 +535,38 @@ inline void host_lut(float* lut) {
     }
 }
 
-inline int build_ingest_tables(IngestTables& t, int H, int W) {
+inline int build_ingest_tables(IngestTables& t, int H, int W, int crop = kCrop, int resize = kResizeShort) {
   if (H < 1 || W < 1) return fail(ERNET_ERR_INVALID_ARG, "bad frame size %dx%d", H, W);
-  t.H = H; t.W = W;
-  if (W <= H) { t.new_w = kResizeShort; t.new_h = (int)((double)kResizeShort * H / W); }
-  else        { t.new_h = kResizeShort; t.new_w = (int)((double)kResizeShort * W / H); }
-  if (t.new_h < kCrop || t.new_w < kCrop) return fail(ERNET_ERR_BAD_SHAPE, "resized frame smaller than crop");
-  t.top = py_round_half_even((t.new_h - kCrop) / 2.0);
-  t.left = py_round_half_even((t.new_w - kCrop) / 2.0);
+  t.H = H; t.W = W; t.crop = crop; t.resize = resize;
+  if (W <= H) { t.new_w = resize; t.new_h = (int)((double)resize * H / W); }
+  else        { t.new_h = resize; t.new_w = (int)((double)resize * W / H); }
+  if (t.new_h < crop || t.new_w < crop) return fail(ERNET_ERR_BAD_SHAPE, "resized frame smaller than crop");
+  t.top = py_round_half_even((t.new_h - crop) / 2.0);
+  t.left = py_round_half_even((t.new_w - crop) / 2.0);
   std::vector<int> xmin, xlen, kx, ymin, ylen, ky;
-  host_coeffs(W, t.new_w, t.left, kCrop, t.ksx, xmin, xlen, kx);
-  host_coeffs(H, t.new_h, t.top, kCrop, t.ksy, ymin, ylen, ky);
+  host_coeffs(W, t.new_w, t.left, crop, t.ksx, xmin, xlen, kx);
+  host_coeffs(H, t.new_h, t.top, crop, t.ksy, ymin, ylen, ky);
   if (t.ksx > kMaxTaps || t.ksy > kMaxTaps) return fail(ERNET_ERR_UNSUPPORTED, "frame %dx%d needs too many taps", H, W);
   t.col_lo = xmin[0];
-  t.col_hi = xmin[kCrop - 1] + xlen[kCrop - 1];
-  for (int i = 0; i < kCrop; ++i) { if (xmin[i] < t.col_lo) t.col_lo = xmin[i]; if (xmin[i] + xlen[i] > t.col_hi) t.col_hi = xmin[i] + xlen[i]; }
+  t.col_hi = xmin[crop - 1] + xlen[crop - 1];
+  for (int i = 0; i < crop; ++i) { if (xmin[i] < t.col_lo) t.col_lo = xmin[i]; if (xmin[i] + xlen[i] > t.col_hi) t.col_hi = xmin[i] + xlen[i]; }
   t.row_lo = ymin[0];
-  t.row_hi = ymin[kCrop - 1] + ylen[kCrop - 1];
-  for (int i = 0; i < kCrop; ++i) { if (ymin[i] < t.row_lo) t.row_lo = ymin[i]; if (ymin[i] + ylen[i] > t.row_hi) t.row_hi = ymin[i] + ylen[i]; }
+  t.row_hi = ymin[crop - 1] + ylen[crop - 1];
+  for (int i = 0; i < crop; ++i) { if (ymin[i] < t.row_lo) t.row_lo = ymin[i]; if (ymin[i] + ylen[i] > t.row_hi) t.row_hi = ymin[i] + ylen[i]; }
   // band size: largest that keeps the uint8 row buffer within 64 KB
   static const int kBands[] = {28, 20, 14, 10, 7, 5, 4, 2, 1};
   t.band_rows = 1;
   for (int br : kBands) {
     int worst = 0;
-    for (int oy0 = 0; oy0 < kCrop; oy0 += br) {
-      int oy1 = oy0 + br < kCrop ? oy0 + br : kCrop;
+    for (int oy0 = 0; oy0 < crop; oy0 += br) {
+      int oy1 = oy0 + br < crop ? oy0 + br : crop;
       int rows = ymin[oy1 - 1] + ylen[oy1 - 1] - ymin[oy0];
       if (rows > worst) worst = rows;
     }
-    if ((size_t)worst * kCrop * 3 <= 64 * 1024) { t.band_rows = br; t.max_in_rows = worst; break; }
+    if ((size_t)worst * crop * 3 <= 64 * 1024) { t.band_rows = br; t.max_in_rows = worst; break; }
   }
   if (t.max_in_rows == 0) return fail(ERNET_ERR_UNSUPPORTED, "frame %dx%d too large for the ingest row buffer", H, W);
-  {  // geometry of the fused transform+stem bands (kStemBand conv1 rows -> 2*band+1 transform rows)
+  if (crop == kCrop) {  // geometry of the fused transform+stem bands (kStemBand conv1 rows -> 2*band+1 transform rows)
     int worst = 0;
     for (int y0 = 0; y0 < 69; y0 += kStemBand) {
       const int y1 = y0 + kStemBand < 69 ? y0 + kStemBand : 69;
@@ -575,13 +576,13 @@ inline int build_ingest_tables(IngestTables& t, int H, int W) {
     }
     t.fs_max_in_rows = worst;
     t.fs_stage_raw = ((size_t)worst * W * 3 + 64 <= kRawStageBytes) ? 1 : 0;
-    if ((size_t)worst * kCrop * 3 > 72 * 1024) t.fs_max_in_rows = 0;      // fused kernel unavailable: fall back to two kernels
+    if ((size_t)worst * crop * 3 > 72 * 1024) t.fs_max_in_rows = 0;      // fused kernel unavailable: fall back to two kernels
   }
 
   {  // ingest_fast.cuh keeps 4 * (2^21 + sum k p) in 32 bits and takes the top byte: needs k >= 0 and 1020 * sum k + 2^23 < 2^32
-    bool ok = t.ksx == 5 && t.ksy == 5;
+    bool ok = t.ksx == 5 && t.ksy == 5 && crop == kCrop;     // the fast kernel is written for the 140-crop
     auto check = [&](const std::vector<int>& kk, int ks) {
-      for (int i = 0; i < kCrop && ok; ++i) {
+      for (int i = 0; i < crop && ok; ++i) {
         long long sum = 0;
         for (int j = 0; j < ks; ++j) { if (kk[(size_t)i * ks + j] < 0) ok = false; sum += kk[(size_t)i * ks + j]; }
         if (1020LL * sum + (1LL << 23) >= (1LL << 32) || sum < (1LL << 22) - 4096) ok = false;
@@ -594,7 +595,7 @@ inline int build_ingest_tables(IngestTables& t, int H, int W) {
   float lut[256 * 3];
   host_lut(lut);
 
-  const size_t n_int = (size_t)kCrop * (2 + t.ksx) + (size_t)kCrop * (2 + t.ksy);
+  const size_t n_int = (size_t)crop * (2 + t.ksx) + (size_t)crop * (2 + t.ksy);
   const size_t bytes = n_int * sizeof(int) + sizeof(lut);
   ERNET_CUDA(cudaMalloc(&t.d_base, bytes));
   std::vector<int> host(n_int);
@@ -615,10 +616,10 @@ inline int build_ingest_tables(IngestTables& t, int H, int W) {
 template <typename TO>
 inline int launch_ingest(const IngestTables& t, const uint8_t* frames, int batch, int bgr, TO* out,
                          long long sb, long long sc, long long sy, long long sx, cudaStream_t stream) {
-  const size_t smem = (size_t)t.max_in_rows * kCrop * 3;
-  dim3 grid((kCrop + t.band_rows - 1) / t.band_rows, batch);
+  const size_t smem = (size_t)t.max_in_rows * t.crop * 3;
+  dim3 grid((t.crop + t.band_rows - 1) / t.band_rows, batch);
   ingest_kernel<TO><<<grid, 256, smem, stream>>>(frames, t.H, t.W, bgr, t.d_xmin, t.d_xlen, t.d_kx, t.ksx,
-                                                 t.d_ymin, t.d_ylen, t.d_ky, t.ksy, t.d_lut, t.band_rows,
+                                                 t.d_ymin, t.d_ylen, t.d_ky, t.ksy, t.d_lut, t.band_rows, t.crop,
                                                  out, sb, sc, sy, sx);
   ERNET_LAUNCH_CHECK("ingest_kernel");
   return ERNET_OK;

@@ -19,7 +19,6 @@ import csv
 import logging
 import os
 import time
-from concurrent.futures import ThreadPoolExecutor
 from typing import Dict, Iterable, Iterator, Tuple
 
 import numpy as np
@@ -146,35 +145,57 @@ def decode_frame(path):
         return np.zeros((240, 240, 3), dtype=np.uint8)
 
 
+def _decode_chunk(chunk):
+    """Decode one chunk of samples and stack them per frame size: [(frames uint8 array (k,H,W,3), labels)]."""
+    buckets = {}
+    for path, label in chunk:
+        frame = decode_frame(path)
+        fr, lb = buckets.setdefault(frame.shape[:2], ([], []))
+        fr.append(frame)
+        lb.append(label)
+    return [(np.stack(fr, 0), lb) for _, (fr, lb) in sorted(buckets.items())]
+
+
 def frame_batches(samples, batch_size=64, num_workers=4, pin_memory=True) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
-    """Decode ``samples`` ([(path, label)]) on ``num_workers`` host threads and yield ``(frames, target)`` batches:
-    frames uint8 (B,H,W,3) in pinned memory, target int64 (B).  Frames of different sizes cannot share a batch (the
-    resize tables are per size), so images are bucketed by (H,W); a bucket is emitted when it holds ``batch_size``
-    frames and the partial buckets at the end.  Every sample is yielded exactly once."""
+    """Decode ``samples`` ([(path, label)]) on ``num_workers`` host threads (0 = in the calling thread), ``num_workers``
+    chunks of ``batch_size`` consecutive samples ahead of the consumer, and yield ``(frames, target)`` batches: frames
+    uint8 (B,H,W,3), pinned when ``pin_memory``, target int64 (B).  Frames of different sizes cannot share a batch (the
+    resize tables are per size), so a chunk with mixed sizes comes back as one batch per size.  Every sample is yielded
+    exactly once, B <= ``batch_size``.  Threads, not processes: the GPU side is asynchronous, so decoding overlaps it, but
+    PIL holds the GIL for much of a small JPEG's decode and the loop is decode-bound; worker
+    processes would have to be forked from a process that already owns a CUDA context."""
     if batch_size < 1:
         raise ValueError("batch_size must be positive")
-    buckets = {}
+    samples = list(samples)
+    chunks = [samples[i:i + batch_size] for i in range(0, len(samples), batch_size)]
+    pin = pin_memory and torch.cuda.is_available()
 
-    def emit(key):
-        frames, labels = buckets.pop(key)
-        t = torch.from_numpy(np.stack(frames, 0))
-        if pin_memory and torch.cuda.is_available():
-            t = t.pin_memory()
+    def to_batch(arr, labels):
+        t = torch.empty(arr.shape, dtype=torch.uint8, pin_memory=pin)
+        t.numpy()[...] = arr
         return t, torch.tensor(labels, dtype=torch.int64)
 
-    with ThreadPoolExecutor(max_workers=max(1, num_workers)) as pool:
-        window = max(2 * batch_size, 4 * num_workers)
-        for i0 in range(0, len(samples), window):
-            chunk = samples[i0:i0 + window]
-            for (path, label), frame in zip(chunk, pool.map(decode_frame, [p for p, _ in chunk])):
-                key = frame.shape[:2]
-                fr, lb = buckets.setdefault(key, ([], []))
-                fr.append(frame)
-                lb.append(label)
-                if len(fr) == batch_size:
-                    yield emit(key)
-    for key in sorted(buckets):
-        yield emit(key)
+    if num_workers <= 0 or len(chunks) <= 1:
+        for chunk in chunks:
+            for arr, labels in _decode_chunk(chunk):
+                yield to_batch(arr, labels)
+        return
+    from collections import deque
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=num_workers) as pool:
+        pending = deque()
+        it = iter(chunks)
+        for chunk in it:
+            pending.append(pool.submit(_decode_chunk, chunk))
+            if len(pending) >= 2 * num_workers:
+                break
+        while pending:
+            parts = pending.popleft().result()
+            nxt = next(it, None)
+            if nxt is not None:
+                pending.append(pool.submit(_decode_chunk, nxt))
+            for arr, labels in parts:
+                yield to_batch(arr, labels)
 
 
 def main(argv=None):

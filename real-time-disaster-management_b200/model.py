@@ -220,11 +220,12 @@ class _EngineRuntime:
         _lib.check(lib.ernet_prepare_ingest(h, int(height), int(width)))
 
     def ingest(self, frames, *, bgr=False, dtype=torch.float32):
-        """The eval transform alone: uint8 (B,H,W,3) device frames -> (B,3,140,140) tensor."""
+        """The eval transform alone: uint8 (B,H,W,3) device frames -> (B,3,140,140) tensor ((B,3,240,240) for ErNET:
+        ``aider_transforms``, dataloaders/aider.py:430)."""
         lib, h, _ = self._ensure_engine()
         frames = frames.contiguous()
         B, H, W, _c = frames.shape
-        out = torch.empty((B, 3, 140, 140), dtype=dtype, device=frames.device)
+        out = torch.empty((B, 3, self.IN_HW, self.IN_HW), dtype=dtype, device=frames.device)
         stream = torch.cuda.current_stream(frames.device).cuda_stream
         _lib.check(lib.ernet_ingest_u8(h, frames.data_ptr(), B, H, W, _lib.BGR if bgr else _lib.RGB,
                                        out.data_ptr(), _DTYPE_CODE[dtype], _lib.NCHW, stream))
@@ -458,7 +459,9 @@ class ErNET(_ErnetB200):
     """Baseline ErNET (model/ernet.py:6-49): six ACFF blocks, (B,3,240,240) inputs, fc 45 -> 5; same 82 state_dict keys.
     SURVEY.md section 8f-1.  bf16 / fp16: all six ACFF blocks on the tcgen05 block kernels (block 1 persistent, blocks
     2-6 on CTA pairs, block 6 with N = 256), conv1 and the collapsed head on CUDA cores; fp32: the layer-wise CUDA-core
-    kernels.  ``model(x)`` on (B,3,240,240) tensors; the fused frames path and int8 are not wired for it yet."""
+    kernels.  ``model(x)`` on (B,3,240,240) tensors; ``forward_frames`` / ``classify_host`` run ``aider_transforms`` (Resize(273) ->
+    CenterCrop(240) -> ToTensor -> Normalize, dataloaders/aider.py:430) on the table-driven ingest kernel first (not fused
+    into conv1 as for the Squeeze models).  int8 is not wired for it."""
     ARCH = "ernet"
 
 

@@ -623,3 +623,50 @@ def test_host_submit_wait_matches_blocking_call(dev):
     got.append(pending.result())
     for (p, l), (pw, lw) in zip(got, want):
         assert np.array_equal(p, pw) and np.array_equal(l, lw)
+
+
+# ------------------------------------------------------------------------------------ ErNET frames path
+from test_oracle_golden import INGEST240_CASES, ingest240_frame  # noqa: E402
+
+
+@pytest.mark.parametrize("case", INGEST240_CASES, ids=[c[0] for c in INGEST240_CASES])
+def test_ernet_ingest_bit_exact(case, dev):
+    name, kind, h, w, seed = case
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ingest240_golden.npz"))
+    f = ingest240_frame(kind, h, w, seed)
+    m = rtdm_b200.from_state_dict("ernet", fixtures.get_state_dict("ernet", "w3"), dev, "fp32")
+    out = m.ingest(torch.from_numpy(f[None]).to(dev)).cpu().numpy()[0]
+    assert out.shape == (3, 240, 240)
+    lut = I.normalise_lut()
+    crop = g[f"{name}/crop_u8"]
+    want = np.stack([lut[crop[:, :, ch], ch] for ch in range(3)], 0)
+    assert np.array_equal(out, want), name
+    if name == "noise240x240":
+        assert np.array_equal(out, g["noise240x240/tensor"])
+        o16 = m.ingest(torch.from_numpy(f[None]).to(dev), dtype=torch.bfloat16).float().cpu().numpy()[0]
+        assert np.array_equal(o16, torch.from_numpy(want).to(torch.bfloat16).float().numpy())
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "fp16"])
+def test_ernet_frames_path_matches_oracle(prec, dev):
+    frames = np.concatenate([fixtures.noise_frames(3, seed=41), fixtures.smooth_frames(4, seed=42)], 0)      # 240x240x3
+    sd = fixtures.get_state_dict("ernet", "shipped")
+    x = I.ingest(frames, 240)
+    ref = E.forward_ernet(sd, x, dtype=np.float64)["logits"]
+    m = rtdm_b200.from_state_dict("ernet", sd, dev, prec)
+    probs, logits = m.forward_frames(torch.from_numpy(frames).to(dev), return_logits=True)
+    lg = logits.double().cpu().numpy()
+    assert _rel(lg, ref) <= TOL[prec], (prec, _rel(lg, ref))
+    assert _top1_ok(lg, ref, TOL[prec])
+    # frames path == transform, then model(x): same kernels, same bits
+    xin = m.ingest(torch.from_numpy(frames).to(dev), dtype=TDT[prec])
+    assert torch.equal(m.logits(xin), logits)
+    # host entry points (blocking and streaming) give the same numbers; other frame size through the general resize
+    ph, lh = m.classify_host(frames, return_logits=True)
+    assert np.array_equal(lh, logits.cpu().numpy()) and np.array_equal(ph, probs.cpu().numpy())
+    tk = m.classify_host_submit(torch.from_numpy(frames).pin_memory(), return_logits=True)
+    assert np.array_equal(tk.result()[1], lh)
+    big = fixtures.smooth_frames(2, 300, 420, seed=43)
+    ref2 = E.forward_ernet(sd, I.ingest(big, 240), dtype=np.float64)["logits"]
+    lg2 = m.forward_frames(torch.from_numpy(big).to(dev), return_logits=True)[1].double().cpu().numpy()
+    assert _rel(lg2, ref2) <= TOL[prec]

@@ -172,3 +172,27 @@ def test_ernet_packer_head_collapse():
     assert len(blob) > 4 * sum(int(np.prod(v.shape)) for v in t.values())
     with pytest.raises(ValueError):
         rtdm_b200.pack_state_dict(sd, "ernet", "int8")
+
+
+# ------------------------------------------------------------------------------------ ErNET's transform (240 crop)
+INGEST240_CASES = [("noise240x240", "noise", 240, 240, 31), ("smooth480x640", "smooth", 480, 640, 32), ("noise300x280", "noise", 300, 280, 33),
+                   ("noise273x273_id", "noise", 273, 273, 34), ("smooth260x420", "smooth", 260, 420, 35)]
+
+
+def ingest240_frame(kind, h, w, seed):
+    return (fixtures.noise_frames if kind == "noise" else fixtures.smooth_frames)(1, h, w, seed)[0]
+
+
+@pytest.fixture(scope="module")
+def ingest240_golden():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ingest240_golden.npz"))
+
+
+@pytest.mark.parametrize("case", INGEST240_CASES, ids=[c[0] for c in INGEST240_CASES])
+def test_ingest240_oracle_bit_exact_with_torchvision(case, ingest240_golden):
+    """aider_transforms = Resize(273) -> CenterCrop(240) -> ToTensor -> Normalize (dataloaders/aider.py:412-426,430)."""
+    name, kind, h, w, seed = case
+    f = ingest240_frame(kind, h, w, seed)
+    assert np.array_equal(I.crop_u8(f, 240), ingest240_golden[f"{name}/crop_u8"])
+    if name == "noise240x240":
+        assert np.array_equal(I.ingest(f[None], 240)[0], ingest240_golden["noise240x240/tensor"])
