@@ -159,9 +159,10 @@ int ernet_classify_frames_host_wait(ernet_handle* h, int ticket);
 int ernet_acff_depthwise(const void* x, int dtype, int batch, int H, int W, int C, int out_h, int out_w,
                          const float* w, const float* b, void* out, void* stream);
 
-/* fp32 form of the trio: 1 (default) = register-tile kernel (one channel x 4x4 output patch per thread, tap
- * weights in registers, no shared memory), 0 = the shared-memory halo kernel (what fp16/bf16 always use).
- * Process-wide; the two forms are bit-identical.  Returns the previous value.                        */
+/* fp32 form of the trio: 2 (default) = TMA-staged tiles (one box copy per 24x24 / 8x8 output tile, zero fill = the conv
+ * padding) for C = 8 / 16 / 64, register-tile kernel otherwise; 1 = register-tile kernel (one channel x 4x4 output patch
+ * per thread, tap weights in registers, no shared memory); 0 = the shared-memory halo kernel (what fp16/bf16 always use).
+ * Process-wide; the three forms are bit-identical.  Returns the previous value.                        */
 int ernet_set_depthwise_form(int form);
 
 /* Depthwise stage of the ADD-fusion ACFF block of the detector half (victim_localization/yolov3/models.py:277-282,302:

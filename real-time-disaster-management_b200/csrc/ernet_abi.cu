@@ -18,6 +18,7 @@
 #include "tc_pblock.cuh"
 #include "tc_cblock.cuh"
 #include "tc_dblock.cuh"
+#include "dw_tma.cuh"
 
 namespace ernet {
 
@@ -1222,7 +1223,7 @@ int ernet_confusion_update(const float* scores, const long long* targets, int ba
 
 int ernet_set_depthwise_form(int form) {
   const int prev = g_dw_fp32_form;
-  g_dw_fp32_form = form ? 1 : 0;
+  g_dw_fp32_form = form < 0 ? 0 : (form > 2 ? 2 : form);
   return prev;
 }
 

@@ -93,9 +93,11 @@ def test_acff_depthwise_kernel(prec, shape, dev):
 
 @pytest.mark.parametrize("shape", [(3, 69, 69, 16, 67, 67), (2, 69, 69, 8, 66, 66), (2, 33, 33, 64, 31, 31), (3, 15, 15, 96, 13, 13),
                                    (4, 15, 15, 48, 12, 12), (5, 6, 6, 128, 4, 4), (2, 9, 11, 32, 7, 9), (1, 119, 119, 16, 117, 117),
-                                   (2, 7, 7, 24, 5, 5)])
+                                   (2, 7, 7, 24, 5, 5), (2, 58, 58, 64, 56, 56), (1, 69, 69, 16, 66, 61), (3, 40, 33, 8, 38, 31),
+                                   (2, 26, 30, 16, 24, 28)])
 def test_acff_depthwise_fp32_forms_bit_identical(shape, dev):
-    """Register-tile kernel (default; compile-time channel counts, C=24 falls back) == shared-memory halo kernel, bitwise."""
+    """TMA-staged kernel (default for C = 8 / 16 / 64 on maps of at least one tile) == register-tile kernel (compile-time channel
+    counts, C=24 falls back) == shared-memory halo kernel, bitwise; odd sizes exercise the zero-filled box edges."""
     B, H, W, Cc, out_h, out_w = shape
     g = torch.Generator(device="cpu").manual_seed(H * 1000 + Cc)
     x = torch.randn(B, H, W, Cc, generator=g).to(dev)
@@ -103,7 +105,7 @@ def test_acff_depthwise_fp32_forms_bit_identical(shape, dev):
     bp = (torch.randn(3, Cc, generator=g) * 0.1).to(dev)
     lib = _lib.load()
     outs = []
-    for form in (1, 0):
+    for form in (2, 1, 0):
         prev = lib.ernet_set_depthwise_form(form)
         try:
             out = torch.full((B, out_h, out_w, 3 * Cc), float("nan"), device=dev)
@@ -114,7 +116,7 @@ def test_acff_depthwise_fp32_forms_bit_identical(shape, dev):
             lib.ernet_set_depthwise_form(prev)
         outs.append(out.cpu())
     assert torch.isfinite(outs[0]).all()
-    assert torch.equal(outs[0], outs[1])
+    assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[2])
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
@@ -580,7 +582,7 @@ def test_ernet_logits_match_reference(wset, prec, dev):
 @pytest.mark.gpu
 def test_ernet_call_surface_and_batching(dev):
     """Same plugin surface as the reference class (model/ernet.py): 82 state_dict keys, model(x) -> probabilities of the
-    input's dtype, wrong spatial size raises, chunked batches and NHWC tensors give the same bits, frames path says no."""
+    input's dtype, wrong spatial size raises, chunked batches and NHWC tensors give the same bits, frames path answers."""
     sd = fixtures.get_state_dict("ernet", "shipped")
     m = rtdm_b200.ErNET()
     assert len(m.state_dict()) == 82
@@ -597,8 +599,10 @@ def test_ernet_call_surface_and_batching(dev):
     assert torch.equal(m(x[2:3]), p[2:3])
     with pytest.raises(ValueError):
         m(torch.zeros(1, 3, 140, 140, device=dev))
-    with pytest.raises(RuntimeError):
-        m.forward_frames(torch.zeros(1, 240, 240, 3, dtype=torch.uint8, device=dev))
+    pf = m.forward_frames(torch.zeros(2, 240, 240, 3, dtype=torch.uint8, device=dev))    # frames path: test_ernet_frames_path_matches_oracle
+    assert pf.shape == (2, 5) and torch.equal(pf[0], pf[1])
+    with pytest.raises(ValueError):
+        m.forward_frames(torch.zeros(1, 240, 240, 4, dtype=torch.uint8, device=dev))    # RGB frames only
     mh = rtdm_b200.from_state_dict("ernet", sd, dev, "fp32").half()
     ph = mh(x.half())
     assert ph.dtype == torch.float16 and (ph.float().argmax(1) == p.argmax(1)).all()

@@ -6,13 +6,30 @@
 #include <type_traits>
 #include <vector>
 #include <cstdlib>
-#include "../real-time-disaster-management_b200/csrc/simt_layers.cuh"
+#include "../real-time-disaster-management_b200/csrc/dw_tma.cuh"
 namespace ernet { thread_local char g_err[512]; }
 using namespace ernet;
 
 #define CK(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { printf("%s: %s\n", #e, cudaGetErrorString(_e)); return 1; } } while (0)
 
 template <int PY, int MINB> static int tile(const float* x, int b, int H, int W, int C, int oh, int ow, const float* w, const float* bi, float* o, cudaStream_t s) { return launch_acff_dw_tile<PY, MINB, false>(x, b, H, W, C, oh, ow, w, bi, o, s); }
+template <int PX, int TH, int MINB> static int ring(const float* x, int b, int H, int W, int C, int oh, int ow, const float* w, const float* bi, float* o, cudaStream_t s) {
+  switch (C) {
+    case 8: return launch_acff_dw_ring_c<8, PX, TH, MINB>(x, b, H, W, oh, ow, w, bi, o, s);
+    case 16: return launch_acff_dw_ring_c<16, PX, TH, MINB>(x, b, H, W, oh, ow, w, bi, o, s);
+    case 64: return launch_acff_dw_ring_c<64, PX, TH, MINB>(x, b, H, W, oh, ow, w, bi, o, s);
+    case 96: return launch_acff_dw_ring_c<96, PX, TH, MINB>(x, b, H, W, oh, ow, w, bi, o, s);
+    case 128: return launch_acff_dw_ring_c<128, PX, TH, MINB>(x, b, H, W, oh, ow, w, bi, o, s);
+    default: return fail(ERNET_ERR_INVALID_ARG, "ring: C=%d not instantiated", C);
+  }
+}
+template <int MINB, int NT, int TS> static int tma(const float* x, int b, int H, int W, int C, int oh, int ow, const float* w, const float* bi, float* o, cudaStream_t s) {
+  if (oh < TS) return -1;
+  if (C == 16 && TS == 24) return launch_acff_dw_tma_c<16, false, MINB, NT, 24>(x, b, H, W, oh, ow, w, bi, o, s);
+  if (C == 8 && TS == 24) return launch_acff_dw_tma_c<8, false, MINB, NT, 24>(x, b, H, W, oh, ow, w, bi, o, s);
+  if (C == 64 && TS <= 12) return launch_acff_dw_tma_c<64, false, MINB, NT, TS>(x, b, H, W, oh, ow, w, bi, o, s);
+  return -1;
+}
 typedef int (*launch_fn)(const float*, int, int, int, int, int, int, const float*, const float*, float*, cudaStream_t);
 static int launch_smem(const float* x, int b, int H, int W, int C, int oh, int ow, const float* w, const float* bi, float* o, cudaStream_t s) {
   g_dw_fp32_form = 0; int rc = launch_acff_dw<float>(x, b, H, W, C, oh, ow, w, bi, o, s); g_dw_fp32_form = 1; return rc;
@@ -21,12 +38,10 @@ static int launch_smem(const float* x, int b, int H, int W, int C, int oh, int o
 int main(int argc, char** argv) {
   const int B = argc > 1 ? atoi(argv[1]) : 256;
   CK(cudaFuncSetAttribute(acff_dw_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-  struct Shape { int H, C, oh; } shapes[] = {{69, 16, 67}, {69, 16, 66}, {33, 64, 31}, {15, 96, 13}, {6, 128, 4}, {69, 8, 67}};
+  struct Shape { int H, C, oh; } shapes[] = {{69, 16, 67}, {33, 64, 31}, {69, 8, 67}, {119, 16, 117}, {69, 16, 66}, {15, 96, 13}, {6, 128, 4}};
   struct Var { const char* name; launch_fn fn; } vars[] = {
       {"smem", launch_smem},
-      {"tile py4 occ2", tile<4, 2>}, {"tile py4 occ3", tile<4, 3>},
-      {"tile py2 occ3", tile<2, 3>}, {"tile py2 occ4", tile<2, 4>},
-      {"tile py3 occ3", tile<3, 3>}, {"tile py6 occ2", tile<6, 2>}};
+      {"tile py4 occ2", tile<4, 2>}, {"tma (default)", launch_acff_dw_tma}, {"tma24 nt144 occ3", tma<3, 144, 24>}, {"tma12 nt192 occ2", tma<2, 192, 12>}, {"tma8 nt256 occ3", tma<3, 256, 8>}};
   float* flush; const size_t flush_n = 160u << 20;   // 640 MB > L2
   CK(cudaMalloc(&flush, flush_n * 4));
   {   // what a pure write stream and a copy reach on this GPU (context for the 74 %-write depthwise traffic)
@@ -44,7 +59,7 @@ int main(int argc, char** argv) {
     }
     cudaFree(src);
   }
-  const int nshapes = getenv("DW_SHAPES") ? atoi(getenv("DW_SHAPES")) : 6;
+  const int nshapes = getenv("DW_SHAPES") ? atoi(getenv("DW_SHAPES")) : 7;
   const int iters = getenv("DW_ITERS") ? atoi(getenv("DW_ITERS")) : 10;
   const char* only = getenv("DW_VARS");     // e.g. "01" = variants 0 and 1
   int si = 0;
@@ -70,7 +85,7 @@ int main(int argc, char** argv) {
       if (only && &v != &vars[0] && !strchr(only, '0' + (int)(&v - vars))) continue;
       float* dst = (&v == &vars[0]) ? oref : o;
       CK(cudaMemset(dst, 0xff, nout * 4));
-      if (v.fn(x, B, H, H, C, oh, oh, w, bi, dst, 0)) { printf("  %s: launch failed: %s\n", v.name, g_err); continue; }
+      if (int rc_ = v.fn(x, B, H, H, C, oh, oh, w, bi, dst, 0)) { if (rc_ == -1) { printf("  %s: not served\n", v.name); continue; } printf("  %s: launch failed: %s\n", v.name, g_err); continue; }
       CK(cudaDeviceSynchronize());
       bool same = true;
       if (&v == &vars[0]) CK(cudaMemcpy(ref.data(), dst, nout * 4, cudaMemcpyDeviceToHost));
@@ -86,7 +101,7 @@ int main(int argc, char** argv) {
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         if (it >= 2) { best = ms < best ? ms : best; sum += ms; }
       }
-      printf("  %-14s %8.1f us avg %8.1f us best  %7.1f GB/s avg  %s\n", v.name, sum / iters * 1e3, best * 1e3,
+      printf("  %-17s %8.1f us avg %8.1f us best  %7.1f GB/s avg  %s\n", v.name, sum / iters * 1e3, best * 1e3,
              bytes / (sum / iters * 1e-3) / 1e9, same ? "bit-identical" : "MISMATCH");
     }
     cudaFree(x); cudaFree(w); cudaFree(bi); cudaFree(o); cudaFree(oref);
