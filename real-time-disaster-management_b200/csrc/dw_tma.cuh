@@ -14,6 +14,8 @@
 
 namespace ernet {
 
+// C here is the number of channels ONE CTA stages (the whole pixel for C <= 64, a 64- or 32-channel chunk of it for the
+// wide maps of the detector's add-fusion blocks and of block 3: the box is then {CC, BW, BH, 1} at channel offset chunk*CC).
 template <int C, int TS = 24>
 struct DwTmaCfg {
   static constexpr int TH = TS, TW = TS, PX = 4, PY = 4;
@@ -25,18 +27,20 @@ struct DwTmaCfg {
   static constexpr size_t SMEM = BOX_BYTES + 128;                // + alignment slack
 };
 
-template <int C, bool ADD, int MINB, int NT, int TS>
+template <int CT /*channels of the tensor*/, int C /*channels per CTA*/, bool ADD, int MINB, int NT, int TS>
 __global__ void __launch_bounds__(NT, MINB)
 acff_dw_tma_kernel(const __grid_constant__ CUtensorMap tmap, int out_h, int out_w, int tiles_x, int tiles_y,
                    const float* __restrict__ w /*[3][9][C]*/, const float* __restrict__ bias /*[3][C]*/,
                    float* __restrict__ out) {
   using Cfg = DwTmaCfg<C, TS>;
   constexpr int PX = Cfg::PX, PY = Cfg::PY, BW = Cfg::BW;
-  constexpr int OC = ADD ? C : 3 * C;
+  constexpr int OC = ADD ? CT : 3 * CT;
+  constexpr int CHUNKS = CT / C;
   extern __shared__ uint8_t dwt_smem_raw[];
   float* tile = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(dwt_smem_raw) + 127) & ~(uintptr_t)127);   // [BH][BW][C]
   __shared__ __align__(8) uint64_t full;
   int t = blockIdx.x;
+  const int chunk = t % CHUNKS; t /= CHUNKS;
   const int tx = t % tiles_x; t /= tiles_x;
   const int ty = t % tiles_y;
   const int b = t / tiles_y;
@@ -45,18 +49,19 @@ acff_dw_tma_kernel(const __grid_constant__ CUtensorMap tmap, int out_h, int out_
     tc::mbar_init(&full, 1);
     tc::fence_mbar_init();
     tc::mbar_expect_tx(&full, Cfg::BOX_BYTES);
-    tc::tma_load_4d(tile, &tmap, 0, x0 - 2, y0 - 2, b, &full);
+    tc::tma_load_4d(tile, &tmap, chunk * C, x0 - 2, y0 - 2, b, &full);
   }
-  const int c = threadIdx.x % C;
+  const int c = threadIdx.x % C;                     // channel within the staged chunk
+  const int cg = chunk * C + c;                      // channel of the tensor
   float wr[27], bv[3];
 #pragma unroll
-  for (int i = 0; i < 27; ++i) wr[i] = __ldg(w + i * C + c);
+  for (int i = 0; i < 27; ++i) wr[i] = __ldg(w + i * CT + cg);
 #pragma unroll
-  for (int d = 0; d < 3; ++d) bv[d] = __ldg(bias + d * C + c);
+  for (int d = 0; d < 3; ++d) bv[d] = __ldg(bias + d * CT + cg);
   __syncthreads();                                   // the barrier initialisation is visible to every waiter
   while (!tc::mbar_try_wait(&full, 0)) {}
 
-  float* ob = out + (size_t)b * out_h * out_w * OC + c;
+  float* ob = out + (size_t)b * out_h * out_w * OC + cg;
   for (int item = threadIdx.x; item < Cfg::ITEMS; item += NT) {
     const int patch = item / C;
     const int lx0 = (patch % (Cfg::TW / PX)) * PX, ly0 = (patch / (Cfg::TW / PX)) * PY;
@@ -105,14 +110,14 @@ acff_dw_tma_kernel(const __grid_constant__ CUtensorMap tmap, int out_h, int out_
           orow[px * OC] = (acc[0][py][px] + acc[1][py][px]) + acc[2][py][px];
         } else {
 #pragma unroll
-          for (int d = 0; d < 3; ++d) orow[px * OC + d * C] = acc[d][py][px];
+          for (int d = 0; d < 3; ++d) orow[px * OC + d * CT] = acc[d][py][px];
         }
       }
     }
   }
 }
 
-template <int C, bool ADD, int MINB = 3, int NT = 192, int TS = 24>
+template <int CT, bool ADD, int MINB = 3, int NT = 192, int TS = 24, int C = CT>
 inline int launch_acff_dw_tma_c(const float* x, int batch, int H, int W, int out_h, int out_w, const float* w,
                                 const float* bias, float* out, cudaStream_t stream) {
   using Cfg = DwTmaCfg<C, TS>;
@@ -120,8 +125,9 @@ inline int launch_acff_dw_tma_c(const float* x, int batch, int H, int W, int out
   if (!enc) return fail(ERNET_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   if (reinterpret_cast<uintptr_t>(x) & 15) return -1;                      // TMA needs a 16-byte aligned base: use the other kernel
   CUtensorMap map;
-  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)batch};
-  const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  static_assert(CT % C == 0 && NT % C == 0, "chunking");
+  const cuuint64_t dims[4] = {(cuuint64_t)CT, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)batch};
+  const cuuint64_t strides[3] = {(cuuint64_t)CT * 4, (cuuint64_t)W * CT * 4, (cuuint64_t)H * W * CT * 4};
   const cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)Cfg::BW, (cuuint32_t)Cfg::BH, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
@@ -129,11 +135,11 @@ inline int launch_acff_dw_tma_c(const float* x, int batch, int H, int W, int out
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(ERNET_ERR_CUDA, "cuTensorMapEncodeTiled (depthwise input) failed with CUresult %d", (int)r);
   // per device and cheap: set on every launch rather than tracking which devices have seen it
-  ERNET_CUDA(cudaFuncSetAttribute(acff_dw_tma_kernel<C, ADD, MINB, NT, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+  ERNET_CUDA(cudaFuncSetAttribute(acff_dw_tma_kernel<CT, C, ADD, MINB, NT, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
   const int tiles_x = (out_w + Cfg::TW - 1) / Cfg::TW, tiles_y = (out_h + Cfg::TH - 1) / Cfg::TH;
-  const long long grid = (long long)batch * tiles_x * tiles_y;
+  const long long grid = (long long)batch * tiles_x * tiles_y * (CT / C);
   if (grid > 0x7fffffffLL) return fail(ERNET_ERR_INVALID_ARG, "depthwise: batch too large for one launch");
-  acff_dw_tma_kernel<C, ADD, MINB, NT, TS><<<(unsigned)grid, NT, Cfg::SMEM, stream>>>(map, out_h, out_w, tiles_x, tiles_y, w, bias, out);
+  acff_dw_tma_kernel<CT, C, ADD, MINB, NT, TS><<<(unsigned)grid, NT, Cfg::SMEM, stream>>>(map, out_h, out_w, tiles_x, tiles_y, w, bias, out);
   ERNET_LAUNCH_CHECK("acff_dw_tma_kernel");
   return ERNET_OK;
 }
@@ -149,6 +155,16 @@ inline int launch_acff_dw_tma(const float* x, int batch, int H, int W, int C, in
   if (C == 16 && out_h >= 24 && out_w >= 24) return launch_acff_dw_tma_c<16, false, 3, 192, 24>(x, batch, H, W, out_h, out_w, w, bias, out, stream);
   if (C == 8 && out_h >= 24 && out_w >= 24) return launch_acff_dw_tma_c<8, false, 3, 144, 24>(x, batch, H, W, out_h, out_w, w, bias, out, stream);
   if (C == 64 && out_h >= 16 && out_w >= 16) return launch_acff_dw_tma_c<64, false, 4, 128, 8>(x, batch, H, W, out_h, out_w, w, bias, out, stream);
+  return -1;
+}
+
+// Add-fusion flavour (detector, yolov3/models.py:302): 64-channel chunks of the 128- / 256-channel maps, 8x8 tiles.
+inline int launch_acff_add_dw_tma(const float* x, int batch, int H, int W, int C, int out_h, int out_w, const float* w,
+                                  const float* bias, float* out, cudaStream_t stream) {
+  if (out_h < 16 || out_w < 16) return -1;
+  if (C == 64) return launch_acff_dw_tma_c<64, true, 4, 128, 8, 64>(x, batch, H, W, out_h, out_w, w, bias, out, stream);
+  if (C == 128) return launch_acff_dw_tma_c<128, true, 4, 128, 8, 64>(x, batch, H, W, out_h, out_w, w, bias, out, stream);
+  if (C == 256) return launch_acff_dw_tma_c<256, true, 4, 128, 8, 64>(x, batch, H, W, out_h, out_w, w, bias, out, stream);
   return -1;
 }
 

@@ -1205,8 +1205,11 @@ int ernet_acff_add_depthwise(const void* x, int dtype, int batch, int H, int W, 
   for (int b0 = 0; b0 < batch; b0 += step) {
     const int n = batch - b0 < step ? batch - b0 : step;
     const size_t xi = (size_t)b0 * H * W * C, oi = (size_t)b0 * out_h * out_w * C;
-    int rc = launch_acff_dw_tile<4, 2, true>(static_cast<const float*>(x) + xi, n, H, W, C, out_h, out_w, w, b,
-                                             static_cast<float*>(out) + oi, s, true);
+    int rc = g_dw_fp32_form == 2 ? launch_acff_add_dw_tma(static_cast<const float*>(x) + xi, n, H, W, C, out_h, out_w, w, b,
+                                                          static_cast<float*>(out) + oi, s) : -1;
+    if (rc == -1)
+      rc = launch_acff_dw_tile<4, 2, true>(static_cast<const float*>(x) + xi, n, H, W, C, out_h, out_w, w, b,
+                                           static_cast<float*>(out) + oi, s, true);
     if (rc) return rc;
   }
   return ERNET_OK;

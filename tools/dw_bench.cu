@@ -23,13 +23,6 @@ template <int PX, int TH, int MINB> static int ring(const float* x, int b, int H
     default: return fail(ERNET_ERR_INVALID_ARG, "ring: C=%d not instantiated", C);
   }
 }
-template <int MINB, int NT, int TS> static int tma(const float* x, int b, int H, int W, int C, int oh, int ow, const float* w, const float* bi, float* o, cudaStream_t s) {
-  if (oh < TS) return -1;
-  if (C == 16 && TS == 24) return launch_acff_dw_tma_c<16, false, MINB, NT, 24>(x, b, H, W, oh, ow, w, bi, o, s);
-  if (C == 8 && TS == 24) return launch_acff_dw_tma_c<8, false, MINB, NT, 24>(x, b, H, W, oh, ow, w, bi, o, s);
-  if (C == 64 && TS <= 12) return launch_acff_dw_tma_c<64, false, MINB, NT, TS>(x, b, H, W, oh, ow, w, bi, o, s);
-  return -1;
-}
 typedef int (*launch_fn)(const float*, int, int, int, int, int, int, const float*, const float*, float*, cudaStream_t);
 static int launch_smem(const float* x, int b, int H, int W, int C, int oh, int ow, const float* w, const float* bi, float* o, cudaStream_t s) {
   g_dw_fp32_form = 0; int rc = launch_acff_dw<float>(x, b, H, W, C, oh, ow, w, bi, o, s); g_dw_fp32_form = 1; return rc;
@@ -41,7 +34,7 @@ int main(int argc, char** argv) {
   struct Shape { int H, C, oh; } shapes[] = {{69, 16, 67}, {33, 64, 31}, {69, 8, 67}, {119, 16, 117}, {69, 16, 66}, {15, 96, 13}, {6, 128, 4}};
   struct Var { const char* name; launch_fn fn; } vars[] = {
       {"smem", launch_smem},
-      {"tile py4 occ2", tile<4, 2>}, {"tma (default)", launch_acff_dw_tma}, {"tma24 nt144 occ3", tma<3, 144, 24>}, {"tma12 nt192 occ2", tma<2, 192, 12>}, {"tma8 nt256 occ3", tma<3, 256, 8>}};
+      {"tile py4 occ2", tile<4, 2>}, {"tma (default)", launch_acff_dw_tma}};
   float* flush; const size_t flush_n = 160u << 20;   // 640 MB > L2
   CK(cudaMalloc(&flush, flush_n * 4));
   {   // what a pure write stream and a copy reach on this GPU (context for the 74 %-write depthwise traffic)
