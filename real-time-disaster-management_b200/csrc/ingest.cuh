@@ -438,6 +438,10 @@ ingest_stem_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restrict
       o[72 * 72] = make_uint4(0, 0, 0, 0);
       continue;
     }
+    // keep the 27*CS tap weights in shared memory: without this barrier the compiler hoists all of them out of the pixel
+    // loop and, under the 64-register cap of this kernel, parks them in local memory (fp32 instance: 1768 bytes of stack,
+    // 0.67 ms per 256 frames instead of the 16-bit instances' 0.05)
+    asm volatile("" ::: "memory");
     float acc[16];
 #pragma unroll
     for (int c = 0; c < 16; ++c) acc[c] = c < CS ? ws[27 * CS + c] : 0.f;
