@@ -535,32 +535,60 @@ pointwise_kernel(const T* __restrict__ A, int K, int N, const float* __restrict_
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < K; k0 += BK) {
-    for (int i = tid; i < BM * 2; i += NT) {
-      const int r = i >> 1, kh = (i & 1) * 4;
-      const long long off = rowoff[r];
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      if (off >= 0) {
-        const T* p = A + off + k0 + kh;
-        if constexpr (sizeof(T) == 4) {
-          const float4 f = __ldg(reinterpret_cast<const float4*>(p));
-          v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
-        } else {
-          const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
-          const T* e = reinterpret_cast<const T*>(&raw);
+  // Software pipeline over K: the global loads of tile k+1 are issued into registers before the FMAs of tile k (the
+  // kernel used to load, sync, compute, sync - every 8-deep K step paid a full global-memory latency with nothing else
+  // in flight).  Per thread: at most 2 A vectors (BM*2 = 256 of them per tile) and 1 B vector (BK*BN/4 <= NT).
+  constexpr int A_ITEMS = (BM * 2 + NT - 1) / NT;
+  static_assert(BK * BN / 4 <= NT && A_ITEMS <= 2, "prefetch registers sized for these tiles");
+  float pa[A_ITEMS][4];
+  float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto gload = [&](int k0) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) v[j] = to_f32<T>(e[j]);
+    for (int u = 0; u < A_ITEMS; ++u) {
+      const int i = tid + u * NT;
+      pa[u][0] = pa[u][1] = pa[u][2] = pa[u][3] = 0.f;
+      if (i < BM * 2) {
+        const int r = i >> 1, kh = (i & 1) * 4;
+        const long long off = rowoff[r];
+        if (off >= 0) {
+          const T* p = A + off + k0 + kh;
+          if constexpr (sizeof(T) == 4) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(p));
+            pa[u][0] = f.x; pa[u][1] = f.y; pa[u][2] = f.z; pa[u][3] = f.w;
+          } else {
+            const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
+            const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pa[u][j] = to_f32<T>(e[j]);
+          }
         }
       }
+    }
+    if (tid < BK * BN / 4) {
+      const int kk = tid / (BN / 4), c4 = tid % (BN / 4);
+      pb = __ldg(reinterpret_cast<const float4*>(Wt + (size_t)(k0 + kk) * N + n0) + c4);
+    }
+  };
+  auto sstore = [&]() {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) As[kh + j][r] = v[j];
+    for (int u = 0; u < A_ITEMS; ++u) {
+      const int i = tid + u * NT;
+      if (i < BM * 2) {
+        const int r = i >> 1, kh = (i & 1) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) As[kh + j][r] = pa[u][j];
+      }
     }
-    for (int i = tid; i < BK * BN / 4; i += NT) {
-      const int kk = i / (BN / 4), c4 = i % (BN / 4);
-      const float4 f = __ldg(reinterpret_cast<const float4*>(Wt + (size_t)(k0 + kk) * N + n0) + c4);
-      *reinterpret_cast<float4*>(&Bs[kk][c4 * 4]) = f;
+    if (tid < BK * BN / 4) {
+      const int kk = tid / (BN / 4), c4 = tid % (BN / 4);
+      *reinterpret_cast<float4*>(&Bs[kk][c4 * 4]) = pb;
     }
+  };
+  gload(0);
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    sstore();
     __syncthreads();
+    if (k0 + BK < K) gload(k0 + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][tr * 8]);

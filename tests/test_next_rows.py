@@ -294,3 +294,35 @@ def test_build_trt_model_saves_and_reloads(arch, quant, tmp_path, dev):
     assert np.abs(got - ref).max() / np.abs(ref).max() <= tol
     if quant != "int8":
         assert (got.argmax(1) == ref.argmax(1)).all()
+
+
+# ------------------------------------------------------------------------------------ GPU: aider-predict.py mirror
+@pytest.mark.gpu
+@pytest.mark.parametrize("arch", ["squeeze-ernet", "ernet"])
+def test_predict_matches_oracle(arch, tmp_path, dev):
+    """predict(): class name and the reference's second-softmax confidence (aider-predict.py:76-84) from an image file."""
+    from PIL import Image
+    from rtdm_b200 import predict as P
+    sd = fixtures.get_state_dict(arch, "w3")
+    model = rtdm_b200.from_state_dict(arch, sd, dev, "fp32")
+    size = 240 if arch == "ernet" else 140
+    for i, (h, w) in enumerate([(240, 240), (300, 420)]):
+        fr = fixtures.smooth_frames(1, h, w, seed=90 + i)[0]
+        path = os.path.join(str(tmp_path), f"img{i}.png")
+        Image.fromarray(fr).save(path)                                  # RGB on disk; cv2.imread returns it as BGR
+        name, conf = P.predict(model, path, None, dev)
+        x = I.ingest(fr[None], size)
+        ref = (E.forward_ernet(sd, x, dtype=np.float64) if arch == "ernet" else E.forward(sd, x, arch, dtype=np.float64))["probs"][0]
+        z = np.exp(ref - ref.max())
+        second = z / z.sum()
+        assert name == P.CLASSES[int(ref.argmax())]
+        assert conf == pytest.approx(float(second[ref.argmax()]) * 100, rel=1e-4)
+        # the reference's own sequence (PIL transform on the host, then model(data)) gives the same answer
+        from oracle import ernet_torch as T
+        from torchvision import transforms
+        tf = transforms.Compose([transforms.Resize(int(size * 1.14)), transforms.CenterCrop(size), transforms.ToTensor(),
+                                 transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+        name2, conf2 = P.predict(model, path, tf, dev)
+        assert name2 == name and conf2 == pytest.approx(conf, rel=1e-5)
+    with pytest.raises(ValueError):
+        P.predict(model, os.path.join(str(tmp_path), "missing.png"), None, dev)
