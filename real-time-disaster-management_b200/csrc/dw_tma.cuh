@@ -16,23 +16,23 @@ namespace ernet {
 
 // C here is the number of channels ONE CTA stages (the whole pixel for C <= 64, a 64- or 32-channel chunk of it for the
 // wide maps of the detector's add-fusion blocks and of block 3: the box is then {CC, BW, BH, 1} at channel offset chunk*CC).
-template <int C, int TS = 24>
+template <int C, int TS = 24, int PXW = 4>
 struct DwTmaCfg {
-  static constexpr int TH = TS, TW = TS, PX = 4, PY = 4;
+  static constexpr int TH = TS, TW = TS, PX = PXW, PY = 4;
   static constexpr int BH = TH + 6, BW = TW + 6;
-  static constexpr int PATCHES = (TH / PY) * (TW / PX);          // 36
-  static constexpr int ITEMS = PATCHES * C;                      // 576 (C = 16), 288 (C = 8)
+  static constexpr int PATCHES = (TH / PY) * (TW / PX);          // 36 (4-wide patches), 48 (3-wide)
+  static constexpr int ITEMS = PATCHES * C;                      // a thread takes items tid, tid + NT, ...: same channel each time
   static constexpr int NT = 192;                                 // a multiple of C: a thread keeps its channel
   static constexpr uint32_t BOX_BYTES = BH * BW * C * 4;         // 57,600 / 28,800
   static constexpr size_t SMEM = BOX_BYTES + 128;                // + alignment slack
 };
 
-template <int CT /*channels of the tensor*/, int C /*channels per CTA*/, bool ADD, int MINB, int NT, int TS>
+template <int CT /*channels of the tensor*/, int C /*channels per CTA*/, bool ADD, int MINB, int NT, int TS, int PXW>
 __global__ void __launch_bounds__(NT, MINB)
 acff_dw_tma_kernel(const __grid_constant__ CUtensorMap tmap, int out_h, int out_w, int tiles_x, int tiles_y,
                    const float* __restrict__ w /*[3][9][C]*/, const float* __restrict__ bias /*[3][C]*/,
                    float* __restrict__ out) {
-  using Cfg = DwTmaCfg<C, TS>;
+  using Cfg = DwTmaCfg<C, TS, PXW>;
   constexpr int PX = Cfg::PX, PY = Cfg::PY, BW = Cfg::BW;
   constexpr int OC = ADD ? CT : 3 * CT;
   constexpr int CHUNKS = CT / C;
@@ -117,10 +117,11 @@ acff_dw_tma_kernel(const __grid_constant__ CUtensorMap tmap, int out_h, int out_
   }
 }
 
-template <int CT, bool ADD, int MINB = 3, int NT = 192, int TS = 24, int C = CT>
+template <int CT, bool ADD, int MINB = 3, int NT = 192, int TS = 24, int C = CT, int PXW = 4>
 inline int launch_acff_dw_tma_c(const float* x, int batch, int H, int W, int out_h, int out_w, const float* w,
                                 const float* bias, float* out, cudaStream_t stream) {
-  using Cfg = DwTmaCfg<C, TS>;
+  using Cfg = DwTmaCfg<C, TS, PXW>;
+  static_assert(TS % PXW == 0, "tile width is a whole number of patches");
   tc::EncodeTiledFn enc = tc::get_encode_fn();
   if (!enc) return fail(ERNET_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   if (reinterpret_cast<uintptr_t>(x) & 15) return -1;                      // TMA needs a 16-byte aligned base: use the other kernel
@@ -135,25 +136,27 @@ inline int launch_acff_dw_tma_c(const float* x, int batch, int H, int W, int out
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(ERNET_ERR_CUDA, "cuTensorMapEncodeTiled (depthwise input) failed with CUresult %d", (int)r);
   // per device and cheap: set on every launch rather than tracking which devices have seen it
-  ERNET_CUDA(cudaFuncSetAttribute(acff_dw_tma_kernel<CT, C, ADD, MINB, NT, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+  ERNET_CUDA(cudaFuncSetAttribute(acff_dw_tma_kernel<CT, C, ADD, MINB, NT, TS, PXW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
   const int tiles_x = (out_w + Cfg::TW - 1) / Cfg::TW, tiles_y = (out_h + Cfg::TH - 1) / Cfg::TH;
   const long long grid = (long long)batch * tiles_x * tiles_y * (CT / C);
   if (grid > 0x7fffffffLL) return fail(ERNET_ERR_INVALID_ARG, "depthwise: batch too large for one launch");
-  acff_dw_tma_kernel<CT, C, ADD, MINB, NT, TS><<<(unsigned)grid, NT, Cfg::SMEM, stream>>>(map, out_h, out_w, tiles_x, tiles_y, w, bias, out);
+  acff_dw_tma_kernel<CT, C, ADD, MINB, NT, TS, PXW><<<(unsigned)grid, NT, Cfg::SMEM, stream>>>(map, out_h, out_w, tiles_x, tiles_y, w, bias, out);
   ERNET_LAUNCH_CHECK("acff_dw_tma_kernel");
   return ERNET_OK;
 }
 
 // -1: this shape is not served by the TMA kernel (channel counts other than 8 / 16 / 64, or a map smaller than one tile).
 // Measured on B200 (tools/dw_bench, B = 256, L2 flushed; fraction of the measured 6.55 TB/s copy peak):
-//   C=16 69->67  (Squeeze_ErNET block 1)  24x24 tiles, 192 threads x 3 CTAs/SM   60 us  4.98 TB/s  76 %   (register tile 83 us)
-//   C=16 119->117 (ErNET block 1)         same                                   156 us  5.80 TB/s  89 %   (238 us)
+//   C=16 69->67  (Squeeze_ErNET block 1)  24x24 tiles, 192 threads x 3 CTAs/SM   59 us  5.07 TB/s  77 %   (register tile 83 us)
+//   C=16 119->117 (ErNET block 1)         same                                   149 us  6.09 TB/s  93 %   (238 us)
 //   C=64 33->31  (block 2)                8x8 tiles, 128 threads x 4 CTAs/SM      49 us  5.28 TB/s  81 %   (64 us)
-//   C=8  69->67  (Squeeze_RedConv block 1) 24x24 tiles, 144 threads x 3 CTAs/SM   50 us  2.98 TB/s  45 %   (63 us; 32-byte pixels)
+//   C=8  69->67  (Squeeze_RedConv block 1) 24x24 tiles, 192 threads x 3 CTAs/SM   38 us  3.95 TB/s  60 %   (63 us; 32-byte pixels)
 inline int launch_acff_dw_tma(const float* x, int batch, int H, int W, int C, int out_h, int out_w, const float* w,
                               const float* bias, float* out, cudaStream_t stream) {
-  if (C == 16 && out_h >= 24 && out_w >= 24) return launch_acff_dw_tma_c<16, false, 3, 192, 24>(x, batch, H, W, out_h, out_w, w, bias, out, stream);
-  if (C == 8 && out_h >= 24 && out_w >= 24) return launch_acff_dw_tma_c<8, false, 3, 144, 24>(x, batch, H, W, out_h, out_w, w, bias, out, stream);
+  // 3-pixel-wide patches at C = 8 / 16: the half- (quarter-) warps that share a load instruction then sit 48 (24) floats
+  // apart instead of 64 (32) and hit disjoint banks (4-wide patches: 2-way / 4-way conflicts on every tile read)
+  if (C == 16 && out_h >= 24 && out_w >= 24) return launch_acff_dw_tma_c<16, false, 3, 192, 24, 16, 3>(x, batch, H, W, out_h, out_w, w, bias, out, stream);
+  if (C == 8 && out_h >= 24 && out_w >= 24) return launch_acff_dw_tma_c<8, false, 3, 192, 24, 8, 3>(x, batch, H, W, out_h, out_w, w, bias, out, stream);
   if (C == 64 && out_h >= 16 && out_w >= 16) return launch_acff_dw_tma_c<64, false, 4, 128, 8>(x, batch, H, W, out_h, out_w, w, bias, out, stream);
   return -1;
 }

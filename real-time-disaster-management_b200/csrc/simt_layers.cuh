@@ -311,116 +311,6 @@ inline int launch_acff_dw_tile(const float* x, int batch, int H, int W, int C, i
   }
 }
 
-// Row-streaming variant of the register-tile kernel: a thread owns one channel and a PX-wide column strip and walks
-// down TH output rows.  The seven input rows an output row needs (dy = -2..4) live in a register ring of 7 x (PX+6)
-// values; each step loads ONE new input row (PX+6 words for PX outputs x 3 branches: 2.5 words per output at PX = 4
-// instead of 6.25) and is issued before the 108 FMAs of the step, of which only the last 12 (branch 3, tap row 2) depend
-// on it.  The row loop is unrolled by 7 so every ring slot is a compile-time register.  Same FMA order per accumulator
-// as the other two kernels (bias, ky-major, kx-minor): bit-identical.
-template <int C, int PX, int TH, int MINB, bool ADD, bool EDGE_X>
-__device__ __forceinline__ void dw_ring_strip(const float* __restrict__ xb, int H, int W, int out_h, int out_w, int oy0, int ox0,
-                                              const float (&wr)[27], const float (&bv)[3], float* __restrict__ ob) {
-  constexpr int NX = PX + 6;
-  constexpr int OC = ADD ? C : 3 * C;
-  float ring[7][NX];
-  bool colok[NX];
-#pragma unroll
-  for (int cx = 0; cx < NX; ++cx) { const int ix = ox0 + cx - 2; colok[cx] = !EDGE_X || (ix >= 0 && ix < W); }
-  const size_t rs = (size_t)W * C;
-  const float* p0 = xb + ((ptrdiff_t)(oy0 - 2) * W + (ox0 - 2)) * C;       // row oy0-2, column ox0-2
-  auto load_row = [&](float (&dst)[NX], int r /* row index relative to oy0-2 */) {
-    const int iy = oy0 - 2 + r;
-    const bool rowok = iy >= 0 && iy < H;
-    const float* rp = p0 + (size_t)(rowok ? r : 0) * rs;
-#pragma unroll
-    for (int cx = 0; cx < NX; ++cx) {
-      dst[cx] = 0.f;
-      if (rowok && colok[cx]) dst[cx] = __ldg(rp + cx * C);
-    }
-  };
-#pragma unroll
-  for (int r = 0; r < 6; ++r) load_row(ring[r], r);
-  const int rows = min(TH, out_h - oy0);
-  float* orow = ob + ((size_t)oy0 * out_w + ox0) * OC;
-  const size_t os = (size_t)out_w * OC;
-  for (int s0 = 0; s0 < rows; s0 += 7) {
-#pragma unroll
-    for (int u = 0; u < 7; ++u) {
-      const int sidx = s0 + u;
-      if (sidx < rows) {
-        load_row(ring[(u + 6) % 7], sidx + 6);                // input row dy = +4 of this output row
-        float acc[3][PX];
-#pragma unroll
-        for (int d = 0; d < 3; ++d)
-#pragma unroll
-          for (int px = 0; px < PX; ++px) acc[d][px] = bv[d];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const int dil = d + 1;
-#pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
-            const int dy = ky * dil - (dil - 1);               // -2..4
-            const float (&row)[NX] = ring[(u + dy + 2) % 7];
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              const int col = 2 + kx * dil - (dil - 1);
-#pragma unroll
-              for (int px = 0; px < PX; ++px) acc[d][px] = fmaf(row[px + col], wr[d * 9 + ky * 3 + kx], acc[d][px]);
-            }
-          }
-        }
-#pragma unroll
-        for (int px = 0; px < PX; ++px) {
-          if (EDGE_X && ox0 + px >= out_w) break;
-          if constexpr (ADD) {
-            orow[px * OC] = (acc[0][px] + acc[1][px]) + acc[2][px];
-          } else {
-#pragma unroll
-            for (int d = 0; d < 3; ++d) orow[px * OC + d * C] = acc[d][px];
-          }
-        }
-        orow += os;
-      }
-    }
-  }
-}
-
-template <int C, int PX, int TH, int MINB, bool ADD>
-__global__ void __launch_bounds__(256, MINB)
-acff_dw_ring_kernel(const float* __restrict__ x, int H, int W, int out_h, int out_w, int TX, int TY, long long total,
-                    const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= total) return;
-  const int c = (int)(gid % C);
-  unsigned t = (unsigned)(gid / C);
-  const int tx = t % TX; t /= TX;
-  const int ty = t % TY;
-  const int b = t / TY;
-  const int ox0 = tx * PX, oy0 = ty * TH;
-  float wr[27], bv[3];
-#pragma unroll
-  for (int i = 0; i < 27; ++i) wr[i] = __ldg(w + i * C + c);
-#pragma unroll
-  for (int d = 0; d < 3; ++d) bv[d] = __ldg(bias + d * C + c);
-  const float* xb = x + (size_t)b * H * W * C + c;
-  float* ob = out + (size_t)b * out_h * out_w * (ADD ? C : 3 * C) + c;
-  const bool interior_x = ox0 >= 2 && ox0 + PX + 3 < W && ox0 + PX <= out_w;
-  if (interior_x) dw_ring_strip<C, PX, TH, MINB, ADD, false>(xb, H, W, out_h, out_w, oy0, ox0, wr, bv, ob);
-  else            dw_ring_strip<C, PX, TH, MINB, ADD, true>(xb, H, W, out_h, out_w, oy0, ox0, wr, bv, ob);
-}
-
-template <int C, int PX, int TH, int MINB, bool ADD = false>
-inline int launch_acff_dw_ring_c(const float* x, int batch, int H, int W, int out_h, int out_w,
-                                 const float* w, const float* bias, float* out, cudaStream_t stream) {
-  const int TX = (out_w + PX - 1) / PX, TY = (out_h + TH - 1) / TH;
-  const long long total = (long long)batch * TY * TX * C;
-  const long long blocks = (total + 255) / 256;
-  if (blocks > 0x7fffffffLL || total / C > 0xffffffffLL) return fail(ERNET_ERR_INVALID_ARG, "depthwise: batch too large for one launch");
-  acff_dw_ring_kernel<C, PX, TH, MINB, ADD><<<(unsigned)blocks, 256, 0, stream>>>(x, H, W, out_h, out_w, TX, TY, total, w, bias, out);
-  ERNET_LAUNCH_CHECK("acff_dw_ring_kernel");
-  return ERNET_OK;
-}
-
 // ---------------------------------------------------------------------------------- evaluation bookkeeping
 // argmax over the class scores of each image + confusion-matrix update, cm[target][prediction] += 1 (what
 // evaluate-classification-metrics.py:81-87 does with output.argmax(dim=1) and torchmetrics' ConfusionMatrix).

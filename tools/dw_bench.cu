@@ -13,15 +13,9 @@ using namespace ernet;
 #define CK(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { printf("%s: %s\n", #e, cudaGetErrorString(_e)); return 1; } } while (0)
 
 template <int PY, int MINB> static int tile(const float* x, int b, int H, int W, int C, int oh, int ow, const float* w, const float* bi, float* o, cudaStream_t s) { return launch_acff_dw_tile<PY, MINB, false>(x, b, H, W, C, oh, ow, w, bi, o, s); }
-template <int PX, int TH, int MINB> static int ring(const float* x, int b, int H, int W, int C, int oh, int ow, const float* w, const float* bi, float* o, cudaStream_t s) {
-  switch (C) {
-    case 8: return launch_acff_dw_ring_c<8, PX, TH, MINB>(x, b, H, W, oh, ow, w, bi, o, s);
-    case 16: return launch_acff_dw_ring_c<16, PX, TH, MINB>(x, b, H, W, oh, ow, w, bi, o, s);
-    case 64: return launch_acff_dw_ring_c<64, PX, TH, MINB>(x, b, H, W, oh, ow, w, bi, o, s);
-    case 96: return launch_acff_dw_ring_c<96, PX, TH, MINB>(x, b, H, W, oh, ow, w, bi, o, s);
-    case 128: return launch_acff_dw_ring_c<128, PX, TH, MINB>(x, b, H, W, oh, ow, w, bi, o, s);
-    default: return fail(ERNET_ERR_INVALID_ARG, "ring: C=%d not instantiated", C);
-  }
+template <int MINB, int NT, int PXW> static int tma16(const float* x, int b, int H, int W, int C, int oh, int ow, const float* w, const float* bi, float* o, cudaStream_t s) {
+  if (C != 16 || oh < 24) return -1;
+  return launch_acff_dw_tma_c<16, false, MINB, NT, 24, 16, PXW>(x, b, H, W, oh, ow, w, bi, o, s);
 }
 typedef int (*launch_fn)(const float*, int, int, int, int, int, int, const float*, const float*, float*, cudaStream_t);
 static int launch_smem(const float* x, int b, int H, int W, int C, int oh, int ow, const float* w, const float* bi, float* o, cudaStream_t s) {
@@ -34,7 +28,7 @@ int main(int argc, char** argv) {
   struct Shape { int H, C, oh; } shapes[] = {{69, 16, 67}, {33, 64, 31}, {69, 8, 67}, {119, 16, 117}, {69, 16, 66}, {15, 96, 13}, {6, 128, 4}};
   struct Var { const char* name; launch_fn fn; } vars[] = {
       {"smem", launch_smem},
-      {"tile py4 occ2", tile<4, 2>}, {"tma (default)", launch_acff_dw_tma}};
+      {"tile py4 occ2", tile<4, 2>}, {"tma (default)", launch_acff_dw_tma}, {"tma16 px4 nt192 o3", tma16<3, 192, 4>}};
   float* flush; const size_t flush_n = 160u << 20;   // 640 MB > L2
   CK(cudaMalloc(&flush, flush_n * 4));
   {   // what a pure write stream and a copy reach on this GPU (context for the 74 %-write depthwise traffic)
