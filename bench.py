@@ -288,6 +288,16 @@ def gpu_main(args, rank, local_rank, world):
     l1.record(stream)
     torch.cuda.synchronize(dev)
     latency_b1_ms = l0.elapsed_time(l1) / 200
+    # the same through one CUDA-graph launch per frame (model.graph_frames: the captured chain keeps its PDL edges)
+    runner = model.graph_frames(one.clone())
+    for _ in range(10):
+        runner()
+    l0.record(stream)
+    for _ in range(200):
+        runner()
+    l1.record(stream)
+    torch.cuda.synchronize(dev)
+    latency_b1_graph_ms = l0.elapsed_time(l1) / 200
 
     # ---- live per-kernel timing: same steps again with CUDA events around every stage
     barrier()
@@ -361,6 +371,7 @@ def gpu_main(args, rank, local_rank, world):
             "roofline": roof,
             "model_flops_frac_of_tensor_peak": value / world * 2 * MACS_PER_IMAGE[ARCH] / 1e12 / peaks["bf16_tflops_sustained"],
             "latency_b1_ms": latency_b1_ms,
+            "latency_b1_graph_ms": latency_b1_graph_ms,
             "depthwise_hbm": depthwise,
             "cpu_baseline": cpu_info,
         }

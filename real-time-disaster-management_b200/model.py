@@ -171,6 +171,26 @@ class _EngineRuntime:
         self._last_batch = B
         return (probs, logits) if return_logits else probs
 
+    def graph_frames(self, frames, *, bgr=False, return_logits=False):
+        """Capture ``forward_frames(frames)`` into a CUDA graph and return a zero-argument callable that replays it.
+        ``frames`` is the static input buffer: write the next batch into it (``frames.copy_(...)``) and call the runner; it
+        returns the same output tensor(s) every time (clone them to keep a result).  The whole chain - transform + conv1,
+        the block kernels with their programmatic-dependent-launch edges, the head - becomes one graph launch, which is
+        what a single-frame caller (aider-predict.py:76, real-time-inference.py:97) pays per frame."""
+        lib, h, idx = self._ensure_engine()
+        for _ in range(2):                                   # builds the resize tables and sizes the workspace outside the capture
+            self.forward_frames(frames, bgr=bgr, return_logits=return_logits)
+        torch.cuda.synchronize(frames.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self.forward_frames(frames, bgr=bgr, return_logits=return_logits)
+
+        def run():
+            graph.replay()
+            return out
+        run.graph, run.frames, run.out = graph, frames, out
+        return run
+
     def classify_host(self, frames, *, bgr=False, return_logits=False):
         """Host uint8 frames (numpy array or CPU tensor, (B,H,W,3)) -> numpy probabilities.  Copies in
         and out happen inside the library, overlapped with the kernels (``predict()`` of

@@ -674,3 +674,25 @@ def test_ernet_frames_path_matches_oracle(prec, dev):
     ref2 = E.forward_ernet(sd, I.ingest(big, 240), dtype=np.float64)["logits"]
     lg2 = m.forward_frames(torch.from_numpy(big).to(dev), return_logits=True)[1].double().cpu().numpy()
     assert _rel(lg2, ref2) <= TOL[prec]
+
+
+@pytest.mark.parametrize("arch,prec", [("squeeze-ernet", "bf16"), ("squeeze-redconv", "fp16"), ("squeeze-ernet", "fp32"), ("squeeze-ernet", "int8"),
+                                       ("ernet", "bf16")])
+def test_graph_frames_replay_bit_identical(arch, prec, dev):
+    """model.graph_frames: the frames path captured into a CUDA graph replays to exactly the eager result, also after the
+    static input buffer has been overwritten with new frames."""
+    sd = fixtures.get_state_dict(arch, "shipped")
+    m = rtdm_b200.from_state_dict(arch, sd, dev, prec)
+    for B in (1, 5):
+        buf = torch.from_numpy(np.concatenate([fixtures.noise_frames(B, seed=60 + B), ][0:1], 0)).to(dev)
+        eager_p, eager_l = m.forward_frames(buf, return_logits=True)
+        eager_p, eager_l = eager_p.clone(), eager_l.clone()
+        run = m.graph_frames(buf, return_logits=True)
+        p, l = run()
+        torch.cuda.synchronize()
+        assert torch.equal(p, eager_p) and torch.equal(l, eager_l)
+        nxt = torch.from_numpy(fixtures.smooth_frames(B, seed=70 + B)).to(dev)
+        buf.copy_(nxt)
+        p2, l2 = run()
+        want_p, want_l = m.forward_frames(nxt, return_logits=True)
+        assert torch.equal(l2, want_l) and torch.equal(p2, want_p)
