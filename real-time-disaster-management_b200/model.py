@@ -178,17 +178,24 @@ class _EngineRuntime:
         the block kernels with their programmatic-dependent-launch edges, the head - becomes one graph launch, which is
         what a single-frame caller (aider-predict.py:76, real-time-inference.py:97) pays per frame."""
         lib, h, idx = self._ensure_engine()
-        for _ in range(2):                                   # builds the resize tables and sizes the workspace outside the capture
-            self.forward_frames(frames, bgr=bgr, return_logits=return_logits)
-        torch.cuda.synchronize(frames.device)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            out = self.forward_frames(frames, bgr=bgr, return_logits=return_logits)
+        # the graph bakes in device pointers: give it a workspace of its own (the shared one is re-allocated when a larger
+        # batch comes along) and keep it alive with the runner.  Re-capture after loading new weights.
+        own_ws = torch.empty(max(1, lib.ernet_workspace_bytes(h, frames.shape[0])), dtype=torch.uint8, device=frames.device)
+        shared_ws, self._workspace = self._workspace, own_ws
+        try:
+            for _ in range(2):                               # builds the resize tables outside the capture
+                self.forward_frames(frames, bgr=bgr, return_logits=return_logits)
+            torch.cuda.synchronize(frames.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.forward_frames(frames, bgr=bgr, return_logits=return_logits)
+        finally:
+            self._workspace = shared_ws
 
         def run():
             graph.replay()
             return out
-        run.graph, run.frames, run.out = graph, frames, out
+        run.graph, run.frames, run.out, run.workspace = graph, frames, out, own_ws
         return run
 
     def classify_host(self, frames, *, bgr=False, return_logits=False):

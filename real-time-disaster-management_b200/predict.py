@@ -1,5 +1,6 @@
-"""Single-image prediction (BASELINE.json configs[0] flavour): mirror of ``predict`` / ``main`` in
-``code/disaster_detection/aider-predict.py:47-86,127-180``.
+"""Single-image and per-frame prediction (BASELINE.json configs[0] flavour): mirror of ``predict`` / ``main`` in
+``code/disaster_detection/aider-predict.py:47-86,127-180`` and of ``run_inference`` in ``real-time-inference.py:80-108``
+(``FrameClassifier``: pinned staging + CUDA-graph replay for a video stream).
 
 ``predict(model, image_path, transform, device)`` keeps the reference's signature and return value
 ``(class name, confidence in percent)``, including its quirk that the confidence is a *second* softmax over the model's
@@ -46,6 +47,75 @@ def predict(model, image_path: str, transform=None, device=None, use_trt: bool =
         predicted_class = output.data.max(1, keepdim=True)[1]
         confidence = torch.nn.functional.softmax(output.float(), dim=1)[0][predicted_class].item() * 100
     return CLASSES[predicted_class.item()], confidence
+
+
+class FrameClassifier:
+    """Per-frame classification of a video stream (the loop body of real-time-inference.py:80-108) with everything
+    preallocated: a pinned host staging frame, a device frame, the frames path captured into a CUDA graph
+    (``model.graph_frames``) and a pinned result.  ``clf(frame)`` = one host->device copy of the frame, one graph launch,
+    one 20-byte read-back.  ``frame``: uint8 (H,W,3) as OpenCV delivers it (BGR) unless ``bgr=False``."""
+
+    def __init__(self, model, height, width, *, bgr=True, device=None):
+        self.device = torch.device(device) if device is not None else next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("FrameClassifier needs the model on a CUDA device (no CPU fallback)")
+        self.shape = (int(height), int(width), 3)
+        self._host = torch.empty((1,) + self.shape, dtype=torch.uint8).pin_memory()
+        self._dev = torch.zeros((1,) + self.shape, dtype=torch.uint8, device=self.device)
+        self._probs_host = torch.empty((1, 5), dtype=torch.float32).pin_memory()
+        self._stream = torch.cuda.Stream(self.device)
+        with torch.cuda.stream(self._stream):
+            self._run = model.graph_frames(self._dev, bgr=bgr)
+        self._stream.synchronize()
+
+    def probabilities(self, frame):
+        """(5,) float32 numpy array of the model's softmax output for one frame."""
+        arr = np.asarray(frame)
+        if arr.dtype != np.uint8 or arr.shape != self.shape:
+            raise ValueError(f"expected a uint8 frame of shape {self.shape}, got {arr.dtype} {arr.shape}")
+        self._host.numpy()[0] = arr
+        with torch.cuda.stream(self._stream):
+            self._dev.copy_(self._host, non_blocking=True)
+            out = self._run()
+            self._probs_host.copy_(out, non_blocking=True)
+        self._stream.synchronize()
+        return self._probs_host.numpy()[0].copy()
+
+    def __call__(self, frame) -> Tuple[str, float]:
+        p = self.probabilities(frame)
+        k = int(p.argmax())                                           # output.data.max(1)[1], real-time-inference.py:97-98
+        z = np.exp(p - p.max(), dtype=np.float32)
+        confidence = float(z[k] / z.sum()) * 100                      # the second softmax, real-time-inference.py:101
+        return CLASSES[k], confidence
+
+
+_classifiers = {}
+
+
+def run_inference(model, frame, transform=None, input_shape=None, device=None, use_trt: bool = False, quant: str = 'fp16') -> Tuple[str, float]:
+    """Run inference on a single BGR frame (real-time-inference.py:80-108; same arguments).  ``transform=None`` (the fast
+    path) classifies through a cached ``FrameClassifier`` for this model and frame size."""
+    if transform is not None:
+        import cv2
+        from PIL import Image
+        hw = getattr(model, "IN_HW", 140)
+        device = torch.device(device) if device is not None else next(model.parameters()).device
+        tensor = transform(Image.fromarray(cv2.cvtColor(frame, cv2.COLOR_BGR2RGB)))
+        tensor = torch.reshape(tensor, input_shape or (1, 3, hw, hw)).to(device)        # real-time-inference.py:76-77
+        with torch.no_grad():
+            if use_trt and quant == 'fp16':
+                tensor = tensor.half()
+            output = model(tensor)
+            predicted_class = output.data.max(1, keepdim=True)[1]
+            confidence = torch.nn.functional.softmax(output.float(), dim=1)[0][predicted_class].item() * 100
+        return CLASSES[predicted_class.item()], confidence
+    key = (id(model), tuple(np.asarray(frame).shape))
+    clf = _classifiers.get(key)
+    if clf is None:
+        if len(_classifiers) > 8:
+            _classifiers.clear()
+        clf = _classifiers[key] = FrameClassifier(model, frame.shape[0], frame.shape[1], bgr=True, device=device)
+    return clf(frame)
 
 
 def main(argv=None):

@@ -696,3 +696,7 @@ def test_graph_frames_replay_bit_identical(arch, prec, dev):
         p2, l2 = run()
         want_p, want_l = m.forward_frames(nxt, return_logits=True)
         assert torch.equal(l2, want_l) and torch.equal(p2, want_p)
+        # a larger eager batch re-allocates the shared workspace; the graph owns its own and still replays correctly
+        m.forward_frames(torch.from_numpy(fixtures.noise_frames(40, seed=5)).to(dev))
+        p3, l3 = run()
+        assert torch.equal(l3, want_l)

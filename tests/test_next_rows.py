@@ -326,3 +326,24 @@ def test_predict_matches_oracle(arch, tmp_path, dev):
         assert name2 == name and conf2 == pytest.approx(conf, rel=1e-5)
     with pytest.raises(ValueError):
         P.predict(model, os.path.join(str(tmp_path), "missing.png"), None, dev)
+
+
+@pytest.mark.gpu
+def test_run_inference_stream_matches_batch_path(dev):
+    """real-time-inference.py's per-frame call: FrameClassifier (pinned staging + graph replay) == forward_frames on the same
+    BGR frames, frame after frame; the confidence is the reference's second softmax."""
+    from rtdm_b200 import predict as P
+    sd = fixtures.get_state_dict("squeeze-ernet", "w3")
+    model = rtdm_b200.from_state_dict("squeeze-ernet", sd, dev, "bf16")
+    frames = np.concatenate([fixtures.smooth_frames(5, 240, 240, seed=120), fixtures.noise_frames(2, seed=121)], 0)
+    want = model.forward_frames(torch.from_numpy(frames).to(dev), bgr=True).cpu().numpy()
+    clf = P.FrameClassifier(model, 240, 240)
+    for i, fr in enumerate(frames):
+        p = clf.probabilities(fr)
+        assert np.array_equal(p, want[i])
+        name, conf = P.run_inference(model, fr)
+        z = np.exp(want[i] - want[i].max())
+        assert name == P.CLASSES[int(want[i].argmax())]
+        assert conf == pytest.approx(float(z[want[i].argmax()] / z.sum()) * 100, rel=1e-5)
+    with pytest.raises(ValueError):
+        clf(np.zeros((100, 100, 3), np.uint8))

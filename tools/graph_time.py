@@ -44,3 +44,19 @@ for prec in ("bf16", "fp32"):
         ms_g = timed(runner)
         print(json.dumps({"precision": prec, "batch": B, "eager_ms": round(ms_e, 4), "graph_ms": round(ms_g, 4),
                           "eager_img_s": round(B / ms_e * 1e3), "graph_img_s": round(B / ms_g * 1e3), "bit_identical": same and same2}))
+
+# per-frame latency from HOST memory (real-time-inference.py's loop body): pinned staging copy + graph replay + 20-byte read-back
+import time  # noqa: E402
+
+import numpy as np  # noqa: E402
+from rtdm_b200 import predict as P  # noqa: E402
+m = rtdm_b200.from_state_dict("squeeze-ernet", sd, dev, "bf16")
+clf = P.FrameClassifier(m, 240, 240)
+fr = np.random.RandomState(0).randint(0, 256, (64, 240, 240, 3)).astype(np.uint8)
+for i in range(20):
+    clf(fr[i % 64])
+t0 = time.perf_counter()
+for i in range(500):
+    clf(fr[i % 64])
+dt = (time.perf_counter() - t0) / 500
+print(json.dumps({"row": "single frame from host memory (FrameClassifier)", "precision": "bf16", "ms_per_frame": round(dt * 1e3, 4), "fps": round(1 / dt)}))
