@@ -80,7 +80,8 @@ def compute_per_class_metrics(confusion_matrix) -> Dict[str, float]:
     return metrics
 
 
-def evaluate_model(model, test_loader: Iterable, device, use_trt: bool = False, quant: str = 'fp16') -> Dict[str, float]:
+def evaluate_model(model, test_loader: Iterable, device, use_trt: bool = False, quant: str = 'fp16', *,
+                   allow_empty: bool = False) -> Dict[str, float]:
     """Evaluate ``model`` on ``test_loader`` (evaluate-classification-metrics.py:49-105).
 
     ``test_loader`` yields ``(data, target)``.  ``data`` is either what the reference's DataLoader yields - a float
@@ -104,16 +105,23 @@ def evaluate_model(model, test_loader: Iterable, device, use_trt: bool = False, 
             inference_times.append(time.time() - start_time)
             conf.update(output, target)                                      # :82-87, on the device
             n_images += data.shape[0]
-    if not inference_times:
+    if not inference_times and not allow_empty:
         raise ValueError("empty test set")
-    cm = conf.compute()
+    return metrics_from_confusion(conf.compute(), inference_times, n_images)
+
+
+def metrics_from_confusion(cm, inference_times=(), n_images=0) -> Dict[str, float]:
+    """The reference's result dictionary (evaluate-classification-metrics.py:89-103) from a confusion matrix (rows = target,
+    columns = prediction) and the per-batch times."""
+    cm = torch.as_tensor(cm).to(torch.int64).cpu()
     total = int(cm.sum())
-    acc = float(torch.diagonal(cm).sum()) / total
+    acc = float(torch.diagonal(cm).sum()) / total if total else 0.0
+    mean_t = float(np.mean(inference_times)) if len(inference_times) else float("nan")
     metrics = {
         'accuracy': acc, 'f1_score': acc, 'precision': acc, 'recall': acc,      # micro averages, see module docstring
-        'avg_inference_time': float(np.mean(inference_times)),
-        'fps': 1.0 / float(np.mean(inference_times)),
-        'images_per_second': n_images / float(np.sum(inference_times)),
+        'avg_inference_time': mean_t,
+        'fps': 1.0 / mean_t if len(inference_times) else float("nan"),
+        'images_per_second': n_images / float(np.sum(inference_times)) if len(inference_times) else float("nan"),
         'confusion_matrix': cm.numpy(),
     }
     metrics.update(compute_per_class_metrics(cm))

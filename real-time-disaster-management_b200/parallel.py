@@ -57,3 +57,29 @@ def classify_sharded(classify, frames, gather=True, group=None):
     if not gather or world == 1:
         return local if gather else (local, (lo, hi))
     return gather_rows(local, shard_sizes(n, world), group)
+
+
+def reduce_confusion(cm, group=None):
+    """Sum the per-rank confusion matrices (int64 (nc,nc), on the rank's device) over the process group: the one collective
+    of a sharded evaluation, 200 bytes (NCCL all-reduce on GPUs, gloo in the CPU tests).  No-op without a process group."""
+    cm = torch.as_tensor(cm).to(torch.int64).clone()
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(cm, op=dist.ReduceOp.SUM, group=group)
+    return cm
+
+
+def evaluate_sharded(model, samples, device, batch_size=64, num_workers=4, group=None):
+    """Evaluation of ``samples`` ([(path, label)], the same list on every rank) split into contiguous shards: every rank
+    decodes and classifies its shard with its own engine (evaluate.evaluate_model), the 5x5 confusion matrices are
+    all-reduced, and every rank returns the metrics of the WHOLE set (evaluate-classification-metrics.py:89-103).  The
+    timing entries describe this rank's shard."""
+    from .evaluate import evaluate_model, frame_batches, metrics_from_confusion
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = shard_bounds(len(samples), world, rank)
+    local = evaluate_model(model, frame_batches(samples[lo:hi], batch_size, num_workers), device, allow_empty=True)
+    cm = reduce_confusion(torch.as_tensor(local["confusion_matrix"]).to(device), group)
+    out = metrics_from_confusion(cm.cpu())
+    for k in ("avg_inference_time", "fps", "images_per_second"):
+        out[k] = local[k]
+    return out

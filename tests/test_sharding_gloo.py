@@ -65,3 +65,45 @@ def test_two_rank_sharded_classify_equals_single_process(n):
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=10) == 1.0
+
+
+def _cm_worker(rank, world, port, n, out):
+    """Sharded evaluation bookkeeping: each rank builds the confusion matrix of its shard, the matrices are all-reduced and
+    every rank derives the metrics of the whole set."""
+    from oracle import metrics_numpy as M
+    from rtdm_b200 import evaluate as EV
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rs = np.random.RandomState(17)
+        pred, targ = rs.randint(0, 5, n), rs.randint(0, 5, n)
+        lo, hi = parallel.shard_bounds(n, world, rank)
+        cm_local = torch.from_numpy(M.confusion_matrix(pred[lo:hi], targ[lo:hi]))
+        got = EV.metrics_from_confusion(parallel.reduce_confusion(cm_local))
+        cm_full = M.confusion_matrix(pred, targ)
+        want = {**M.micro_metrics(cm_full), **M.per_class_metrics(cm_full)}
+        ok = np.array_equal(got["confusion_matrix"], cm_full) and all(abs(got[k] - v) < 1e-12 for k, v in want.items())
+        t = torch.tensor([1.0 if ok else 0.0])
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            out.put(float(t.item()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [101, 1])
+def test_two_rank_confusion_reduce_equals_single_process(n):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_cm_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) == 1.0
