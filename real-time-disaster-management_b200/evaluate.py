@@ -66,17 +66,21 @@ class DeviceConfusion:
 
 
 def compute_per_class_metrics(confusion_matrix) -> Dict[str, float]:
-    """Per-class precision / recall / F1 from the confusion matrix (evaluate-classification-metrics.py:107-132)."""
-    cm = torch.as_tensor(confusion_matrix)
+    """Per-class precision / recall / F1 from the confusion matrix, keyed ``'<class>_precision'`` etc. like the reference's
+    function of the same name (evaluate-classification-metrics.py:107-132): precision = diag / column sum, recall = diag / row
+    sum, 0 where the denominator is 0."""
+    cm = np.asarray(torch.as_tensor(confusion_matrix).cpu(), dtype=np.float64)
+    tp = np.diag(cm)
+    predicted, actual = cm.sum(axis=0), cm.sum(axis=1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        precision = np.where(predicted > 0, tp / predicted, 0.0)
+        recall = np.where(actual > 0, tp / actual, 0.0)
+        f1 = np.where(precision + recall > 0, 2 * precision * recall / (precision + recall), 0.0)
     metrics = {}
-    for i, class_name in enumerate(CLASSES):
-        tp = cm[i, i].item()
-        fp = cm[:, i].sum().item() - tp
-        fn = cm[i, :].sum().item() - tp
-        precision = tp / (tp + fp) if (tp + fp) > 0 else 0
-        recall = tp / (tp + fn) if (tp + fn) > 0 else 0
-        f1 = 2 * (precision * recall) / (precision + recall) if (precision + recall) > 0 else 0
-        metrics.update({f'{class_name}_precision': precision, f'{class_name}_recall': recall, f'{class_name}_f1': f1})
+    for i, name in enumerate(CLASSES):
+        metrics[f'{name}_precision'] = float(precision[i])
+        metrics[f'{name}_recall'] = float(recall[i])
+        metrics[f'{name}_f1'] = float(f1[i])
     return metrics
 
 
