@@ -118,3 +118,22 @@ def test_shim_errors_without_gpu_or_in_train_mode():
         rtdm_b200.Squeeze_ErNET(precision="fp64")
     with pytest.raises(ValueError, match="Unsupported model"):
         rtdm_b200.load_model("yolov3", "/nonexistent", "cpu")       # "ernet" is a supported name since the ErNET path exists
+
+
+@pytest.mark.parametrize("arch", ["squeeze-ernet", "squeeze-redconv", "ernet"])
+@pytest.mark.parametrize("wrapped", [False, True])
+def test_load_model_reads_real_checkpoints(arch, wrapped, tmp_path):
+    """load_model success path (aider-predict.py:35-41): a plain state_dict .pt file and a training checkpoint of the
+    form {'model_state_dict': ..., 'epoch': ...} both load, strictly, into an eval-mode model on the asked device."""
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in fixtures.shipped_state_dict(arch).items()}
+    path = tmp_path / f"{arch}.pt"
+    torch.save({"model_state_dict": sd, "epoch": 45, "optimizer_state_dict": {}} if wrapped else sd, path)
+    m = rtdm_b200.load_model(arch, str(path), "cpu")
+    assert not m.training and type(m).ARCH == arch
+    got = m.state_dict()
+    assert list(got.keys()) == list(sd.keys())
+    for k in sd:
+        assert torch.equal(got[k], sd[k]), k
+    with pytest.raises(RuntimeError):                   # a checkpoint of another architecture must not load silently
+        other = "squeeze-redconv" if arch != "squeeze-redconv" else "squeeze-ernet"
+        rtdm_b200.load_model(other, str(path), "cpu")

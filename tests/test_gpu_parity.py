@@ -31,13 +31,23 @@ def _rel(a, ref):
     return float(np.abs(a - ref).max() / max(np.abs(ref).max(), 1e-30))
 
 
-def _top1_ok(logits, ref_logits, rel_err_budget):
-    """Top-1 must match unless the reference's own top-2 margin is inside the error budget."""
+def _flips(logits, ref_logits):
+    """(number of top-1 disagreements, their reference top-2 margins relative to |logit|max)."""
     got, want = logits.argmax(1), ref_logits.argmax(1)
     srt = np.sort(ref_logits, axis=1)
     margin = (srt[:, -1] - srt[:, -2]) / np.abs(ref_logits).max()
-    bad = (got != want) & (margin > 2 * rel_err_budget)
-    return not bad.any()
+    flip = got != want
+    return int(flip.sum()), margin[flip]
+
+
+def _top1_ok(logits, ref_logits, rel_err_budget, max_flips=0):
+    """north_star: "identical top-1".  At most `max_flips` disagreements (default none), and any that is allowed must be
+    a near-tie of the reference itself: its own top-2 margin within the measured logit error of this run."""
+    n, margins = _flips(logits, ref_logits)
+    if n > max_flips:
+        return False
+    err = float(np.abs(logits - ref_logits).max() / max(np.abs(ref_logits).max(), 1e-30))
+    return bool((margins <= 2 * min(err, rel_err_budget)).all())
 
 
 # ------------------------------------------------------------------------------------ ingest
@@ -240,6 +250,24 @@ def test_frames_path_and_chunking(prec, dev):
     assert np.array_equal(lh, logits.cpu().numpy()) and np.array_equal(ph, probs.cpu().numpy())
 
 
+@pytest.mark.parametrize("arch", fixtures.ARCHS)
+@pytest.mark.parametrize("wrapped", [False, True])
+def test_load_model_from_checkpoint_file(arch, wrapped, tmp_path, model_golden, dev):
+    """load_model (aider-predict.py:22-45) on a real .pt file - plain state_dict and {'model_state_dict': ...} - gives a
+    CUDA eval-mode model whose logits match the reference's for the shipped checkpoint."""
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in fixtures.shipped_state_dict(arch).items()}
+    path = tmp_path / "ckpt.pt"
+    torch.save({"model_state_dict": sd, "epoch": 3} if wrapped else sd, path)
+    m = rtdm_b200.load_model(arch, str(path), dev)
+    assert not m.training and next(m.parameters()).device.type == "cuda"
+    x = torch.from_numpy(fixtures.normal_tensors(4, seed=7)).to(dev)
+    ref = model_golden[f"{arch}/shipped/norm/logits64"]
+    assert _rel(m.logits(x).double().cpu().numpy(), ref) <= TOL["fp32"]
+    mh = rtdm_b200.load_model(arch, str(path), dev, precision="bf16")
+    lg = mh.logits(x).double().cpu().numpy()
+    assert _rel(lg, ref) <= TOL["bf16"] and _top1_ok(lg, ref, TOL["bf16"])
+
+
 def test_abi_error_paths(dev):
     lib = _lib.load()
     h = C.c_void_p()
@@ -277,12 +305,60 @@ def test_full_size_properties(dev):
     la = m.forward_frames(ft[:128], return_logits=True)[1]
     lb = m.forward_frames(ft[128:], return_logits=True)[1]
     assert torch.equal(torch.cat([la, lb]), l)
-    idx = np.arange(0, 256, 16)
-    ref = E.forward(sd, I.ingest(frames[idx]), arch, dtype=np.float64)
-    lg = l.double().cpu().numpy()[idx]
-    assert _rel(lg, ref["logits"]) <= TOL["bf16"]
-    assert _top1_ok(lg, ref["logits"], TOL["bf16"])
+    ref_l = _torch_ref_logits(sd, frames, arch)               # all 256 frames against the fp64 reference graph
+    lg = l.double().cpu().numpy()
+    nflip, margins = _flips(lg, ref_l)
+    print(f"config 2 (bf16, B=256, shipped): rel logit err {_rel(lg, ref_l):.3e}, top-1 flips {nflip}/256 {np.round(margins, 5).tolist()}")
+    assert _rel(lg, ref_l) <= TOL["bf16"]
+    assert _top1_ok(lg, ref_l, TOL["bf16"], max_flips=CONFIG_FLIP_BUDGET["config2"])
     assert torch.allclose(p.sum(1), torch.ones(256, device=dev), atol=1e-5)
+
+
+def _torch_ref_logits(sd, frames, arch, chunk=256):
+    """fp64 logits of the reference graph (oracle/ernet_torch, pinned to the real classes in test_oracle_golden) on the
+    bit-exact transformed frames: fast enough for full-size configurations."""
+    from oracle import ernet_torch as T
+    tsd = T.to_torch_sd(sd, torch.float64)
+    out = []
+    for i in range(0, len(frames), chunk):
+        x = torch.from_numpy(I.ingest(np.asarray(frames[i:i + chunk]))).double()
+        out.append(T.forward(tsd, x, arch)[1].numpy())
+    return np.concatenate(out, 0)
+
+
+# Top-1 flips allowed at configuration size.  north_star says "identical top-1": the budget is ZERO wherever the
+# reference's own top-2 margin leaves room for the precision's rounding; the synthetic uniform-noise frames with the
+# shipped checkpoint contain exact near-ties (reference margin < 1e-3 of |logit|max for ~1 % of the frames, see
+# profiles/r02_int8_study4_squeeze_ernet.txt), so those configurations get a small counted budget and every flip must
+# still be a near-tie (margin <= 2 x the measured logit error).  The counts are printed and also reported by bench.py.
+CONFIG_FLIP_BUDGET = {"config2": 2, "config3": 4, "config5": 2}
+
+
+def test_config3_full_size(dev):
+    """BASELINE config 3: Squeeze_RedConv fp16, batch 1024, every frame against the fp64 reference graph; determinism
+    and shard equivalence at size."""
+    arch = "squeeze-redconv"
+    sd = fixtures.get_state_dict(arch, "shipped")
+    frames = np.concatenate([fixtures.noise_frames(512, seed=141), fixtures.smooth_frames(512, seed=142)], 0)
+    ft = torch.from_numpy(frames).to(dev)
+    m = rtdm_b200.from_state_dict(arch, sd, dev, "fp16")
+    p, l = m.forward_frames(ft, return_logits=True)
+    assert torch.equal(l, m.forward_frames(ft, return_logits=True)[1])
+    quarters = torch.cat([m.forward_frames(ft[i:i + 256], return_logits=True)[1] for i in range(0, 1024, 256)])
+    assert torch.equal(quarters, l)
+    ref_l = _torch_ref_logits(sd, frames, arch)
+    lg = l.double().cpu().numpy()
+    nflip, margins = _flips(lg, ref_l)
+    print(f"config 3 (RedConv fp16, B=1024, shipped): rel logit err {_rel(lg, ref_l):.3e}, top-1 flips {nflip}/1024 {np.round(margins, 5).tolist()}")
+    assert _rel(lg, ref_l) <= TOL["fp16"]
+    assert _top1_ok(lg, ref_l, TOL["fp16"], max_flips=CONFIG_FLIP_BUDGET["config3"])
+    assert torch.allclose(p.sum(1), torch.ones(1024, device=dev), atol=1e-5)
+    # trained-like random weights: margins are wide, top-1 must be identical on every frame
+    sd3 = fixtures.get_state_dict(arch, "w3")
+    m3 = rtdm_b200.from_state_dict(arch, sd3, dev, "fp16")
+    l3 = m3.forward_frames(ft, return_logits=True)[1].double().cpu().numpy()
+    ref3 = _torch_ref_logits(sd3, frames, arch)
+    assert _rel(l3, ref3) <= TOL["fp16"] and _flips(l3, ref3)[0] == 0
 
 
 # ------------------------------------------------------------------------------------ tensor-core engine
@@ -552,10 +628,12 @@ def test_config5_full_size_sharding(dev):
         shards = [rtdm_b200.from_state_dict(arch, sd, dev, "bf16").forward_frames(ft[i * n:(i + 1) * n], return_logits=True)[1]
                   for i in range(ways)]
         assert torch.equal(torch.cat(shards), l), ways
-    idx = np.arange(5, 8192, 683)
-    ref = E.forward(sd, I.ingest(ft[idx].cpu().numpy()), arch, dtype=np.float64)["logits"]
+    idx = np.concatenate([np.arange(0, 512), np.arange(517, 8192, 683)])      # the 512 distinct frames + a spread of the rest
+    ref = _torch_ref_logits(sd, ft[idx].cpu().numpy(), arch)
     lg = l.double().cpu().numpy()[idx]
-    assert _rel(lg, ref) <= TOL["bf16"] and _top1_ok(lg, ref, TOL["bf16"])
+    nflip, margins = _flips(lg, ref)
+    print(f"config 5 (bf16, 8192 frames, shipped): rel logit err {_rel(lg, ref):.3e}, top-1 flips {nflip}/{len(idx)} {np.round(margins, 5).tolist()}")
+    assert _rel(lg, ref) <= TOL["bf16"] and _top1_ok(lg, ref, TOL["bf16"], max_flips=CONFIG_FLIP_BUDGET["config5"])
     ph = m.classify_host(ft[:1024].cpu().numpy())
     assert np.array_equal(ph, p[:1024].cpu().numpy())
 

@@ -196,3 +196,27 @@ def test_ingest240_oracle_bit_exact_with_torchvision(case, ingest240_golden):
     assert np.array_equal(I.crop_u8(f, 240), ingest240_golden[f"{name}/crop_u8"])
     if name == "noise240x240":
         assert np.array_equal(I.ingest(f[None], 240)[0], ingest240_golden["noise240x240/tensor"])
+
+
+@pytest.mark.parametrize("arch", fixtures.ARCHS)
+@pytest.mark.parametrize("wset", WSETS)
+def test_torch_restatement_matches_reference(arch, wset, model_golden):
+    """oracle/ernet_torch.forward is the timed CPU arm of bench.py and the fp32 reference of the int8 agreement tests:
+    pin it to the outputs of the real reference classes too (logits64 for every weight set; the fp32 run of the shipped
+    checkpoint must reproduce the reference's own fp32 logits to fp32 rounding)."""
+    import torch
+    from oracle import ernet_torch as T
+    sd_np = fixtures.get_state_dict(arch, wset)
+    for iname, x in (("norm", fixtures.normal_tensors(4, seed=7)), ("frames", model_golden["x_frames"])):
+        tag = f"{arch}/{wset}/{iname}"
+        ref = model_golden[f"{tag}/logits64"]
+        p64, l64 = T.forward(T.to_torch_sd(sd_np, torch.float64), torch.from_numpy(x).double(), arch)
+        assert np.abs(l64.numpy() - ref).max() <= 1e-9 * np.abs(ref).max(), tag
+        assert np.abs(p64.numpy() - model_golden[f"{tag}/probs64"]).max() <= 1e-9
+        p32, l32 = T.forward(T.to_torch_sd(sd_np), torch.from_numpy(x), arch)
+        assert l32.dtype == torch.float32
+        assert np.abs(l32.double().numpy() - ref).max() <= 2e-5 * np.abs(ref).max(), tag
+        assert (p32.argmax(1).numpy() == model_golden[f"{tag}/probs64"].argmax(1)).all()
+    ref32 = model_golden[f"{arch}/shipped/norm/logits32"]
+    _, l32 = T.forward(T.to_torch_sd(fixtures.get_state_dict(arch, "shipped")), torch.from_numpy(fixtures.normal_tensors(4, seed=7)), arch)
+    assert np.abs(l32.numpy() - ref32).max() <= 2e-6 * np.abs(ref32).max()
