@@ -202,6 +202,11 @@ int ernet_ingest_tables_host(int height, int width, int* meta, int* xmin, int* x
  * pipeline waits that timed out since the last reset (0 in a healthy run), out8[1..3] = tag / block /
  * aux of the first one.  A timed-out kernel terminates normally but its results are invalid.          */
 int ernet_debug_device_status(unsigned int* out8, int reset);
+/* Call after synchronising with work enqueued by ernet_forward / ernet_forward_frames (the reference's own
+ * sync point is evaluate-classification-metrics.py:79, torch.cuda.synchronize()): ERNET_ERR_CUDA (and the record
+ * is cleared) when a kernel's watchdog fired since the last check, else ERNET_OK.  Reads one word of mapped
+ * host memory: no device round trip.  ernet_classify_frames_host_wait and every forward call check it too.   */
+int ernet_check_watchdog(void);
 /* Study builds (-DERNET_TIMELINE) only: per-CTA clock64 stamps of the persistent block kernels, [3 kernels][148][32][8].
  * Returns ERNET_ERR_UNSUPPORTED in the normal build.                                                    */
 int ernet_debug_timeline(unsigned long long* out, size_t count);

@@ -703,12 +703,48 @@ static int get_tables(ernet_handle* h, int H, int W, const IngestTables** out) {
   auto key = std::make_pair(H, W);
   auto it = h->ingest.find(key);
   if (it == h->ingest.end()) {
+    if (h->ingest.size() >= 64) {                          // bounded cache: a long evaluation over many frame sizes must not grow
+      cudaDeviceSynchronize();                             // device memory without limit; nothing may still be reading a table
+      for (auto& kv : h->ingest) if (kv.second.d_base) cudaFree(kv.second.d_base);
+      h->ingest.clear();
+    }
     IngestTables t;
     int rc = build_ingest_tables(t, H, W, h->in_hw(), h->ernet() ? 273 : 159);   // int(image_size * 1.14), aider.py:422
     if (rc) return rc;
     it = h->ingest.emplace(key, t).first;
   }
   *out = &it->second;
+  return ERNET_OK;
+}
+
+// The mbarrier watchdog of the tensor-core kernels (tc_common.cuh) ends a stuck CTA with partial output instead of
+// hanging the device; it also raises a word in mapped pinned host memory, which the synchronising entry points read
+// (no device round trip) and turn into an error instead of returning wrong probabilities.
+static volatile unsigned int* g_watchdog_host = nullptr;
+static int init_watchdog_flag() {
+  if (g_watchdog_host) return ERNET_OK;
+  unsigned int* hp = nullptr;
+  ERNET_CUDA(cudaHostAlloc(&hp, sizeof(unsigned int), cudaHostAllocMapped | cudaHostAllocPortable));
+  *hp = 0u;
+  g_watchdog_host = hp;
+  return ERNET_OK;
+}
+static int publish_watchdog_flag() {                       // per device: the device-side pointer to the host word
+  unsigned int* dp = nullptr;
+  ERNET_CUDA(cudaHostGetDevicePointer(&dp, const_cast<unsigned int*>(g_watchdog_host), 0));
+  ERNET_CUDA(cudaMemcpyToSymbol(tc::g_tc_host_flag, &dp, sizeof(dp)));
+  return ERNET_OK;
+}
+static int check_watchdog(const char* where) {
+  if (g_watchdog_host && *g_watchdog_host) {
+    unsigned int st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyFromSymbol(st, tc::g_tc_status, sizeof(st));
+    *g_watchdog_host = 0u;
+    unsigned int z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(tc::g_tc_status, z, sizeof(z));
+    return fail(ERNET_ERR_CUDA, "%s: a tensor-core kernel timed out in an mbarrier wait (tag 0x%x, block %u, aux %u, %u waits): results are invalid",
+                where, st[1], st[2], st[3], st[0]);
+  }
   return ERNET_OK;
 }
 
@@ -750,6 +786,7 @@ int ernet_create(ernet_handle** out, int arch, int precision, int device) {
   if (!g.ok) return fail(ERNET_ERR_CUDA, "cudaSetDevice(%d) failed", device);
   int rc = init_device_attrs();
   if (rc) return rc;
+  if ((rc = init_watchdog_flag()) || (rc = publish_watchdog_flag())) return rc;
   ernet_handle* h = new (std::nothrow) ernet_handle();
   if (!h) return fail(ERNET_ERR_INVALID_ARG, "out of host memory");
   h->arch = arch; h->precision = precision; h->device = device;
@@ -999,6 +1036,7 @@ static int forward_common(ernet_handle* h, const void* x, int x_dtype, int x_lay
   } else if (order != ERNET_RGB && order != ERNET_BGR) {
     return fail(ERNET_ERR_INVALID_ARG, "bad channel_order %d", order);
   }
+  { int wrc = check_watchdog("an earlier forward call"); if (wrc) return wrc; }
   const size_t need = ernet_workspace_bytes(h, batch);
   if (!ws || ws_bytes < need) return fail(ERNET_ERR_WORKSPACE, "workspace of %zu bytes needed, %zu given", need, ws ? ws_bytes : 0);
   DeviceGuard g(h->device);
@@ -1095,7 +1133,11 @@ int ernet_classify_frames_host_submit(ernet_handle* h, const uint8_t* frames_hos
   }
   // sub-chunks so that the H2D copy of one overlaps the kernels of the previous one even inside a single call
   int chunk = batch < h->chunk ? batch : h->chunk;
-  if (batch >= 128) { const int q = (batch + 3) / 4; chunk = q < chunk ? q : chunk; if (chunk < 32) chunk = 32; }
+  if (batch >= 128) {                                      // quarter batches, but never below 32 frames nor above the caller's chunk
+    int q = (batch + 3) / 4;
+    if (q < 32) q = 32;
+    if (q < chunk) chunk = q;
+  }
   const size_t f_img = (size_t)height * width * 3;
   const size_t fbytes = (size_t)chunk * f_img;
   if (h->d_frames_bytes < fbytes || h->d_ws_bytes < ernet_workspace_bytes(h, chunk) || h->d_res_elems < (size_t)batch * 10)
@@ -1163,7 +1205,7 @@ int ernet_classify_frames_host_wait(ernet_handle* h, int ticket) {
   if (!h || ticket < 0 || ticket > 1 || !h->ev_call[ticket]) return fail(ERNET_ERR_INVALID_ARG, "ernet_classify_frames_host_wait: bad ticket");
   DeviceGuard g(h->device);
   ERNET_CUDA(cudaEventSynchronize(h->ev_call[ticket]));
-  return ERNET_OK;
+  return check_watchdog("ernet_classify_frames_host_wait");
 }
 
 int ernet_classify_frames_host(ernet_handle* h, const uint8_t* frames_host, int batch, int height, int width,
@@ -1319,6 +1361,8 @@ int ernet_debug_device_status(unsigned int* out8, int reset) {
   }
   return ERNET_OK;
 }
+
+int ernet_check_watchdog(void) { return check_watchdog("ernet_check_watchdog"); }
 
 int ernet_debug_timeline(unsigned long long* out, size_t count) {
 #ifdef ERNET_TIMELINE

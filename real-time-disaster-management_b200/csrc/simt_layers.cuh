@@ -314,7 +314,8 @@ inline int launch_acff_dw_tile(const float* x, int batch, int H, int W, int C, i
 // ---------------------------------------------------------------------------------- evaluation bookkeeping
 // argmax over the class scores of each image + confusion-matrix update, cm[target][prediction] += 1 (what
 // evaluate-classification-metrics.py:81-87 does with output.argmax(dim=1) and torchmetrics' ConfusionMatrix).
-// Ties resolve to the lowest class index, NaN scores never win.  Targets outside [0, nc) are counted in *bad.
+// Ties resolve to the lowest class index; a NaN score wins (first one), exactly like torch.argmax, so a broken forward
+// shows up in the confusion matrix instead of being masked.  Targets outside [0, nc) are counted in *bad.
 __global__ void confusion_update_kernel(const float* __restrict__ scores, const long long* __restrict__ targets, int batch,
                                         int nc, long long* __restrict__ cm, long long* __restrict__ pred_out,
                                         unsigned long long* __restrict__ bad) {
@@ -325,7 +326,7 @@ __global__ void confusion_update_kernel(const float* __restrict__ scores, const 
   float bv = s[0];
   for (int k = 1; k < nc; ++k) {
     const float v = s[k];
-    if (v > bv || (bv != bv && v == v)) { bv = v; best = k; }
+    if (v > bv || (v != v && bv == bv)) { bv = v; best = k; }      // a NaN beats every number, the first NaN stays: torch.argmax
   }
   if (pred_out) pred_out[i] = best;
   if (targets && cm) {

@@ -41,6 +41,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // normally (a __trap() here was observed to wedge the process instead of surfacing an error).  The host
 // reads the buffer with ernet_debug_device_status().
 __device__ unsigned int g_tc_status[8];   // [0] = number of timeouts, [1] = first tag, [2] = blockIdx.x, [3] = aux
+__device__ unsigned int* g_tc_host_flag;  // mapped pinned host word (ernet_abi.cu): raised on a timeout so that the host's
+                                          // synchronising entry points report an error instead of wrong probabilities
+__device__ __forceinline__ void tc_raise_timeout(uint32_t tag, uint32_t aux) {
+  if (atomicAdd(&g_tc_status[0], 1u) == 0) { g_tc_status[1] = tag; g_tc_status[2] = blockIdx.x; g_tc_status[3] = aux; }
+  unsigned int* hp = g_tc_host_flag;
+  if (hp) { *reinterpret_cast<volatile unsigned int*>(hp) = 1u; __threadfence_system(); }
+}
 
 // Non-blocking phase test.  The waits below poll with it: a suspended mbarrier.try_wait was measured (in-kernel
 // timeline, tools/timeline.py) to resume only at its ~10 us time limit in some producer waits.
@@ -64,7 +71,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volati
     if ((++spins & 63) == 0) {
       if (*abort_flag) return false;
       if (clock64() - t0 > 300000000LL) {
-        if (atomicAdd(&g_tc_status[0], 1u) == 0) { g_tc_status[1] = tag; g_tc_status[2] = blockIdx.x; g_tc_status[3] = aux; }
+        tc_raise_timeout(tag, aux);
         *abort_flag = 1u;
         return false;
       }
@@ -83,7 +90,7 @@ __device__ __forceinline__ bool mbar_wait_suspend(uint64_t* bar, uint32_t parity
   while (!mbar_try_wait(bar, parity)) {
     if (*abort_flag) return false;
     if (clock64() - t0 > 300000000LL) {
-      if (atomicAdd(&g_tc_status[0], 1u) == 0) { g_tc_status[1] = tag; g_tc_status[2] = blockIdx.x; g_tc_status[3] = aux; }
+      tc_raise_timeout(tag, aux);
       *abort_flag = 1u;
       return false;
     }

@@ -107,6 +107,7 @@ def evaluate_model(model, test_loader: Iterable, device, use_trt: bool = False, 
             output = model.forward_frames(data) if data.dtype == torch.uint8 else model(data)
             torch.cuda.synchronize(device)                                   # :79
             inference_times.append(time.time() - start_time)
+            _lib.check(_lib.load().ernet_check_watchdog())                   # a timed-out kernel must fail the run, not skew the metrics
             conf.update(output, target)                                      # :82-87, on the device
             n_images += data.shape[0]
     if not inference_times and not allow_empty:

@@ -60,19 +60,32 @@ class FrameClassifier:
         if self.device.type != "cuda":
             raise RuntimeError("FrameClassifier needs the model on a CUDA device (no CPU fallback)")
         self.shape = (int(height), int(width), 3)
+        self._model, self._bgr = model, bgr              # strong reference: the captured graph points into the model's engine
         self._host = torch.empty((1,) + self.shape, dtype=torch.uint8).pin_memory()
         self._dev = torch.zeros((1,) + self.shape, dtype=torch.uint8, device=self.device)
         self._probs_host = torch.empty((1, 5), dtype=torch.float32).pin_memory()
         self._stream = torch.cuda.Stream(self.device)
+        self._capture()
+
+    def _token(self):
+        """Identity of what the captured graph points at: the engine handle and the packed-weights fingerprint.
+        ``_ensure_engine`` re-packs first when the weights, the precision or the device changed."""
+        _lib_, h, _idx = self._model._ensure_engine()
+        return (getattr(h, "value", h), getattr(self._model, "_fingerprint", None), getattr(self._model, "_loaded_version", None))
+
+    def _capture(self):
         with torch.cuda.stream(self._stream):
-            self._run = model.graph_frames(self._dev, bgr=bgr)
+            self._run = self._model.graph_frames(self._dev, bgr=self._bgr)
         self._stream.synchronize()
+        self._tok = self._token()
 
     def probabilities(self, frame):
         """(5,) float32 numpy array of the model's softmax output for one frame."""
         arr = np.asarray(frame)
         if arr.dtype != np.uint8 or arr.shape != self.shape:
             raise ValueError(f"expected a uint8 frame of shape {self.shape}, got {arr.dtype} {arr.shape}")
+        if self._token() != self._tok:                    # load_state_dict / .half() / set_precision since the capture:
+            self._capture()                               # the old graph would replay against freed device memory
         self._host.numpy()[0] = arr
         with torch.cuda.stream(self._stream):
             self._dev.copy_(self._host, non_blocking=True)
@@ -88,8 +101,6 @@ class FrameClassifier:
         confidence = float(z[k] / z.sum()) * 100                      # the second softmax, real-time-inference.py:101
         return CLASSES[k], confidence
 
-
-_classifiers = {}
 
 
 def run_inference(model, frame, transform=None, input_shape=None, device=None, use_trt: bool = False, quant: str = 'fp16') -> Tuple[str, float]:
@@ -109,12 +120,15 @@ def run_inference(model, frame, transform=None, input_shape=None, device=None, u
             predicted_class = output.data.max(1, keepdim=True)[1]
             confidence = torch.nn.functional.softmax(output.float(), dim=1)[0][predicted_class].item() * 100
         return CLASSES[predicted_class.item()], confidence
-    key = (id(model), tuple(np.asarray(frame).shape))
-    clf = _classifiers.get(key)
+    # one runner per (model, frame size), stored ON the model: it lives exactly as long as the model does, and the runner
+    # itself re-captures when the model's weights / precision change (FrameClassifier._token)
+    cache = model.__dict__.setdefault("_frame_classifiers", {})
+    key = tuple(np.asarray(frame).shape)
+    clf = cache.get(key)
     if clf is None:
-        if len(_classifiers) > 8:
-            _classifiers.clear()
-        clf = _classifiers[key] = FrameClassifier(model, frame.shape[0], frame.shape[1], bgr=True, device=device)
+        if len(cache) > 8:
+            cache.clear()
+        clf = cache[key] = FrameClassifier(model, frame.shape[0], frame.shape[1], bgr=True, device=device)
     return clf(frame)
 
 

@@ -778,3 +778,26 @@ def test_graph_frames_replay_bit_identical(arch, prec, dev):
         m.forward_frames(torch.from_numpy(fixtures.noise_frames(40, seed=5)).to(dev))
         p3, l3 = run()
         assert torch.equal(l3, want_l)
+
+
+def test_host_path_small_chunk_large_batch(dev):
+    """A caller-set chunk below 32 with a host batch >= 128 (the sub-chunk floor of the host path must not exceed the chunk
+    the workspace was sized for): results equal the default-chunk call bit for bit."""
+    sd = fixtures.get_state_dict("squeeze-ernet", "shipped")
+    frames = np.concatenate([fixtures.noise_frames(70, seed=401), fixtures.smooth_frames(70, seed=402)], 0)     # 140 frames
+    m = rtdm_b200.from_state_dict("squeeze-ernet", sd, dev, "bf16")
+    want_p, want_l = m.classify_host(frames, return_logits=True)
+    m2 = rtdm_b200.from_state_dict("squeeze-ernet", sd, dev, "bf16").set_chunk(5)
+    got_p, got_l = m2.classify_host(frames, return_logits=True)
+    assert np.array_equal(got_l, want_l) and np.array_equal(got_p, want_p)
+    assert _lib.load().ernet_check_watchdog() == 0
+
+
+def test_confusion_update_nan_matches_torch_argmax(dev):
+    """A NaN score wins the arg-max (first NaN), as in torch.argmax (evaluate-classification-metrics.py:81)."""
+    sc = torch.tensor([[0.1, float("nan"), 0.7, 0.0, 0.2], [0.5, 0.2, 0.1, 0.1, 0.1], [float("nan")] * 5,
+                       [0.2, 0.2, 0.2, 0.2, 0.2], [0.0, 0.1, float("nan"), float("nan"), 0.9]], device=dev)
+    pred = torch.empty(5, dtype=torch.int64, device=dev)
+    _lib.check(_lib.load().ernet_confusion_update(sc.data_ptr(), None, 5, 5, None, pred.data_ptr(), None,
+                                                  torch.cuda.current_stream().cuda_stream))
+    assert torch.equal(pred, sc.argmax(1))

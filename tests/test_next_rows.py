@@ -214,10 +214,10 @@ def test_confusion_update_matches_oracle(dev):
         scores = rs.standard_normal((n, 5)).astype(np.float32)
         scores[::5, 1] = scores[::5, 3] = 9.0                               # ties -> lowest index (torch.argmax on CPU too)
         if n > 5:
-            scores[3, 0] = np.nan                                            # NaN never wins
+            scores[3, 0] = np.nan                                            # a NaN wins (first one), as in torch.argmax
         t = rs.randint(0, 5, n)
         p = conf.update(torch.from_numpy(scores).to(dev), torch.from_numpy(t), want_pred=True).cpu().numpy()
-        ref_p = np.array([int(np.nanargmax(r)) for r in scores])
+        ref_p = torch.from_numpy(scores).argmax(1).numpy()          # evaluate-classification-metrics.py:81 output.argmax(dim=1)
         assert np.array_equal(p, ref_p)
         preds.append(ref_p)
         targs.append(t)

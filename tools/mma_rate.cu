@@ -3,6 +3,8 @@
 //   mode 0: cta_group::1                 (A 4 KB + B N*32 B of shared memory per MMA)
 //   mode 1: cta_group::2 (CTA pair)      (A 4 KB + B N*16 B per CTA per MMA, M = 256 per instruction)
 //   mode 2: cta_group::1 .ws, B operand kept in the collector buffer over runs of `reuse` MMAs
+//   mode 3: cta_group::1 kind::i8 (s8 x s8 -> s32, K = 32 per instruction: the same two 16-byte chunks per row as a
+//           16-bit K = 16 MMA, i.e. twice the operations for the same operand bytes) - the int8 peak denominator
 // Prints cycles per MMA for each N.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -o tools/mma_rate tools/mma_rate.cu
 #include <cooperative_groups.h>
 #include <cstdint>
@@ -14,8 +16,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
-__host__ __device__ constexpr uint32_t instr_desc(uint32_t M, uint32_t N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+__host__ __device__ constexpr uint32_t instr_desc(uint32_t M, uint32_t N, bool i8 = false) {
+  return ((i8 ? 2u : 1u) << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 template <int MODE>
@@ -24,6 +26,8 @@ __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
   else if (MODE == 1)
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+  else if (MODE == 3)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
   else {
     if (cstate == 0)
       asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::fill [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
@@ -68,7 +72,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(long long* out, int iters)
   long long cyc = 0;
   if (threadIdx.x == 0 && rank == 0) {
     constexpr int NB = MODE == 1 ? N / 2 : N;            // B rows held by this CTA
-    constexpr uint32_t IDESC = instr_desc(MODE == 1 ? 256 : 128, N);
+    constexpr uint32_t IDESC = instr_desc(MODE == 1 ? 256 : 128, N, MODE == 3);
     const uint32_t a0 = smem_u32(s_a) + (2 * P + 2) * 16, b0 = smem_u32(s_b);
     constexpr int G = 512 / N < 4 ? 512 / N : 4;         // accumulator tiles in flight (TMEM columns)
     const long long t0 = clock64();
@@ -148,6 +152,7 @@ int main() {
     const int g2 = grid == 1 ? 2 : 148;
     run<0, 64>("cta_group::1", 1, grid); run<0, 96>("cta_group::1", 1, grid); run<0, 128>("cta_group::1", 1, grid); run<0, 256>("cta_group::1", 1, grid);
     run<1, 64>("cta_group::2", 1, g2); run<1, 96>("cta_group::2", 1, g2); run<1, 128>("cta_group::2", 1, g2); run<1, 256>("cta_group::2", 1, g2);
+    run<3, 64>("cta_group::1 kind::i8", 1, grid); run<3, 96>("cta_group::1 kind::i8", 1, grid); run<3, 128>("cta_group::1 kind::i8", 1, grid); run<3, 256>("cta_group::1 kind::i8", 1, grid);
     run<2, 64, 4>("cta_group::1 .ws", 4, grid); run<2, 128, 4>("cta_group::1 .ws", 4, grid); run<2, 64, 1>("cta_group::1 .ws", 1, grid);
   }
   return 0;
