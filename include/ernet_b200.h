@@ -207,6 +207,8 @@ int ernet_debug_device_status(unsigned int* out8, int reset);
  * is cleared) when a kernel's watchdog fired since the last check, else ERNET_OK.  Reads one word of mapped
  * host memory: no device round trip.  ernet_classify_frames_host_wait and every forward call check it too.   */
 int ernet_check_watchdog(void);
+/* sha256 of the sources this library was compiled from (set by build.py; "unknown" for a hand build).           */
+const char* ernet_source_hash(void);
 /* Study builds (-DERNET_TIMELINE) only: per-CTA clock64 stamps of the persistent block kernels, [3 kernels][148][32][8].
  * Returns ERNET_ERR_UNSUPPORTED in the normal build.                                                    */
 int ernet_debug_timeline(unsigned long long* out, size_t count);

@@ -52,6 +52,7 @@ SIGNATURES = {
     "ernet_ingest_tables_host": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ernet_debug_device_status": (_i, [_vp, _i]),
     "ernet_check_watchdog": (_i, []),
+    "ernet_source_hash": (C.c_char_p, []),
     "ernet_profile_enable": (_i, [_vp, _i]),
     "ernet_profile_read": (_i, [_vp, _vp, _vp, _i]),
     "ernet_launches_per_forward": (_i, [_vp, _i, _i]),

@@ -26,11 +26,37 @@ def sources():
     return out
 
 
+def source_hash():
+    """sha256 over the names and contents of every source the library is built from."""
+    import hashlib
+    h = hashlib.sha256()
+    for path in sources():
+        h.update(os.path.basename(path).encode() + b"\0")
+        with open(path, "rb") as f:
+            h.update(f.read())
+        h.update(b"\0")
+    return h.hexdigest()
+
+
+def embedded_hash(lib=LIB):
+    """The source hash the library was compiled from (ernet_source_hash() of the C ABI), read from the file itself - no
+    dlopen, so it also works where the library cannot be loaded."""
+    marker = b"ERNET_SOURCE_HASH="
+    try:
+        with open(lib, "rb") as f:
+            data = f.read()
+    except OSError:
+        return None
+    i = data.find(marker)
+    if i < 0:
+        return None
+    return data[i + len(marker):i + len(marker) + 64].decode("ascii", "replace")
+
+
 def needs_build():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(s) > t for s in sources())
+    """True unless the library on disk was compiled from exactly the sources on disk (hash embedded at compile time;
+    file times are not trusted: a shipped prebuilt library must not be reused silently after the sources changed)."""
+    return embedded_hash() != source_hash()
 
 
 def build_library(force=False, verbose=False):
@@ -42,7 +68,7 @@ def build_library(force=False, verbose=False):
         raise RuntimeError("nvcc not found: cannot build libernet_b200.so (there is no CPU fallback)")
     cus = [s for s in sources() if s.endswith(".cu")]
     extra = os.environ.get("ERNET_NVCC_EXTRA", "").split()          # study builds, e.g. -DERNET_TIMELINE
-    cmd = [nvcc] + NVCC_FLAGS + extra + ["-I", ROOT_INCLUDE, "-o", LIB + ".tmp"] + cus
+    cmd = [nvcc] + NVCC_FLAGS + extra + [f'-DERNET_SOURCE_HASH="{source_hash()}"', "-I", ROOT_INCLUDE, "-o", LIB + ".tmp"] + cus
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode:
         print(r.stdout[-4000:])

@@ -17,7 +17,7 @@
 #include "tc_tail.cuh"
 #include "tc_pblock.cuh"
 #include "tc_cblock.cuh"
-#include "tc_dblock.cuh"
+#include "tc_fblock.cuh"
 #include "dw_tma.cuh"
 
 namespace ernet {
@@ -41,6 +41,8 @@ struct Plan {                 // byte offsets into the caller's workspace for on
 
 using namespace ernet;
 
+constexpr int kSyncImages = 65536;     // >= the largest chunk (ernet_set_chunk)
+
 struct ernet_handle {
   int arch = 0, precision = 0, device = 0;
   int chunk = 1024;
@@ -57,11 +59,10 @@ struct ernet_handle {
   bool debug_taps = false;      // keep intermediates the fused kernels would not write (acff4)
   int persistent = 2;           // block-kernel schedule: 0 one image per CTA, 1 persistent CTAs, 2 persistent + CTA pairs for blocks 2, 3
   int num_sms = 148;
-  tc::DBlock1Consts* d_dblock1 = nullptr;   // fp16 constants of the depthwise + 1x1 block-1 kernel (tc_dblock.cuh)
-  tc::EpiParams<64> epi1d;           // its epilogue constants: bias = fused_conv.bias (the depthwise biases are added on the CUDA cores)
-  bool dw_block1 = false;            // experiment (ERNET_DW_BLOCK1=1): block 1 as depthwise on CUDA cores + 1x1 on tcgen05
-                                     // (tc_dblock.cuh).  Correct, but 82 us against 59 us for the 25-tap form: issue-bound on the
-                                     // CUDA cores (see the header of tc_dblock.cuh)
+  // fused transform + conv1 + block 1 (tc_fblock.cuh): per-image band counters, re-armed by the kernel itself
+  uint32_t* d_sync = nullptr;        // [2][kSyncImages]: ready, taken
+  bool fuse_ingest = false;          // ERNET_FUSE_INGEST=1: transform + conv1 under block 1 in one kernel (tc_fblock.cuh; off until it beats the two kernels)
+  bool last_fused = false;           // the most recent frames chunk took the fused kernel (ernet_launches_per_forward)
   void* d_w1_pair = nullptr;         // block-1 weights regrouped for tap pairing ([13][2][64][16 B], tc_pblock.cuh)
   StemFrag* d_stem_frag = nullptr;   // folded conv1 in mma.sync fragment order (16-bit engines)
   bool dual_copy = false;       // host path: alternate two copy streams (ERNET_DUAL_COPY=1)
@@ -100,7 +101,7 @@ struct ernet_handle {
   size_t esize() const { return precision == ERNET_PREC_FP32 ? 4 : 2; }
   // tensor-core path: 16-bit handles of both architectures, int8 Squeeze_ErNET
   bool use_tc() const {
-    if (precision == ERNET_PREC_INT8) return has_tc && !red();      // int8 exists only as tensor-core kernels
+    if (precision == ERNET_PREC_INT8) return has_tc;                // int8 exists only as tensor-core kernels
     if (engine == ERNET_ENGINE_SIMT) return false;
     return has_tc && (precision == ERNET_PREC_BF16 || precision == ERNET_PREC_FP16);
   }
@@ -140,6 +141,18 @@ static Plan make_plan(const ernet_handle* h, int n) {
     return p;
   }
   p.ingest = take(N * 140 * 140 * 3);
+  if (p.tc && h->precision == ERNET_PREC_INT8 && h->red()) {   // int8 Squeeze_RedConv (sizes in 2-byte units)
+    p.stem = take(N * 2 * 72 * 72 * 8);        // P16 (B,2,72,72,16) int8: 8 real channels in chunk 0
+    p.p1 = take(N * 4 * 36 * 36 * 8);          // P16 (B,4,36,36,16)
+    p.a2 = take(N * 12 * 33 * 33 * 8);         // P8 fp16 (B,12,33,33,8): un-pooled acff2 output (conv_red2 input)
+    p.p2 = take(N * 4 * 18 * 18 * 8 + 4 * 18 * 18 * 8);     // P16 (B,4,18,18,16): 48 real + 16 zero channels, + slack
+    p.p3 = take(N * 6 * 6 * 128);              // NHWC fp16
+    p.r3 = take(N * 6 * 6 * 64);               // NHWC fp16
+    p.cat4 = take(N * 4 * 4 * 3 * h->c4());
+    p.a4 = take(N * 4 * 4 * 256);
+    p.total = o;
+    return p;
+  }
   if (p.tc && h->precision == ERNET_PREC_INT8) {   // P16 images: 16 int8 channels per 16-byte chunk (sizes in 2-byte units)
     p.stem = take(N * 2 * 72 * 72 * 8);        // (B,2,72,72,16) int8
     p.p1 = take(N * 4 * 36 * 36 * 8);          // (B,4,36,36,16)
@@ -371,11 +384,18 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
   if (h->red()) {
     if constexpr (KIND != tc::KIND_I8) {
       // ---- Squeeze_RedConv: conv1+conv_red1 -> P8 (8 real channels), blocks 1-3 with conv_red2 as a 1-tap instance
+      bool fused1 = false;
       if (frames && tab->fs_max_in_rows > 0 && !h->debug_taps) {
         StemQ q{};
         FastGeom fg;
         if (h->fast_ingest && h->d_stem_frag && fast5_geometry(*tab, frames, fg)) {
-          ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem5<T, 8>(*tab, fg, frames, n, order == ERNET_BGR, h->d_stem_frag, q, !(h->persistent == 2 && h->d_w1_pair && h->pair_taps), u16(p.stem), s)));
+          if (h->fuse_ingest && h->persistent == 2 && h->d_w1_pair && h->pair_taps && tc::fused_fits<tc::PBlock1P>(fg) && n <= kSyncImages) {
+            fused1 = h->last_fused = true;     // transform + conv1 run under block 1 in ONE kernel (tc_fblock.cuh)
+            ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_ingest_block1<tc::PBlock1P, KIND, tc::OUT_P8, T, 8, FS_P8>(*tab, fg, frames, n, order == ERNET_BGR, h->d_stem_frag, q, false,
+                        u16(p.stem), h->d_w1_pair, h->epi1, u16(p.p1), h->num_sms, h->d_sync, h->d_sync + kSyncImages, s)));
+          } else {
+            ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem5<T, 8>(*tab, fg, frames, n, order == ERNET_BGR, h->d_stem_frag, q, !(h->persistent == 2 && h->d_w1_pair && h->pair_taps), u16(p.stem), s)));
+          }
         } else {
           ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem<T, 8, FS_P8>(*tab, frames, n, order == ERNET_BGR, sw, sb_, q, u16(p.stem), s)));
         }
@@ -396,7 +416,8 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
       }
       auto wimgr = [&](int k) { return h->t[ERNET_T_TC_BASE + 4 * k + ERNET_T_TC_WIMG].dev; };
       if (h->persistent == 2) {
-        if (h->d_w1_pair && h->pair_taps) {
+        if (fused1) {
+        } else if (h->d_w1_pair && h->pair_taps) {
           ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1P, KIND, tc::OUT_P8>(u16(p.stem), h->d_w1_pair, h->epi1, u16(p.p1), n, h->num_sms, s)));
         } else {
           ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1, KIND, tc::OUT_P8>(u16(p.stem), wimgr(0), h->epi1, u16(p.p1), n, h->num_sms, s)));
@@ -413,12 +434,57 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
       ERNET_STAGE(ERNET_STAGE_RED3, launch_pointwise<T>(buf(p.p3), n, 6, 6, 128, 64, h->f(ERNET_T_RED3_W), h->f(ERNET_T_RED3_B), nullptr, nullptr, 0, 0, buf(p.r3), s));
       return run_tail<T>(h, buf(p.r3), buf(p.cat4), buf(p.a4), n, probs, logits, s);
     } else {
-      return fail(ERNET_ERR_UNSUPPORTED, "int8 is implemented for Squeeze_ErNET only");
+      // ---- int8 Squeeze_RedConv (persistent kernels only): conv1+conv_red1 -> int8 P16 (8 real channels), ACFF1 int8 with
+      // tap pairing, ACFF2 int8 -> fp16 un-pooled, conv_red2 as a 16-bit 1-tap instance writing the int8 pool2 tensor,
+      // ACFF3 int8 -> fp16 NHWC, conv_red3 + ACFF4 + head in fp16 (first conv and head in >= fp16)
+      bool fused1 = false;
+      StemQ q{};
+      for (int i = 0; i < 16; ++i) q.inv[i] = s_inv.v[i];
+      const bool paired = h->d_w1_pair && h->pair_taps;
+      auto wimgq = [&](int k) { return h->t[ERNET_T_TC_BASE + 4 * k + ERNET_T_TC_WIMG].dev; };
+      if (frames && tab->fs_max_in_rows > 0 && !h->debug_taps) {
+        FastGeom fg;
+        if (h->fast_ingest && h->d_stem_frag && fast5_geometry(*tab, frames, fg)) {
+          if (h->fuse_ingest && paired && tc::fused_fits<tc::PBlock1P>(fg) && n <= kSyncImages) {
+            fused1 = h->last_fused = true;
+            ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_ingest_block1<tc::PBlock1P, tc::KIND_I8, tc::OUT_P16, T, 8, FS_P16>(*tab, fg, frames, n, order == ERNET_BGR, h->d_stem_frag, q, false,
+                        u16(p.stem), h->d_w1_pair, h->epi1, u16(p.p1), h->num_sms, h->d_sync, h->d_sync + kSyncImages, s)));
+          } else {
+            ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem5<T, 8, FS_P16>(*tab, fg, frames, n, order == ERNET_BGR, h->d_stem_frag, q, !paired, u16(p.stem), s)));
+          }
+        } else {
+          ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem<T, 8, FS_P16>(*tab, frames, n, order == ERNET_BGR, sw, sb_, q, u16(p.stem), s)));
+        }
+      } else if (frames) {
+        ERNET_STAGE(ERNET_STAGE_INGEST, launch_ingest<T>(*tab, frames, n, order == ERNET_BGR, buf(p.ingest), 140LL * 140 * 3, 1, 140 * 3, 3, s));
+        StageTimer _t(h, ERNET_STAGE_STEM, s);
+        tc::stem_p8_kernel<T, 8, tc::KIND_I8><<<grid, 128, 0, s>>>(buf(p.ingest), 140LL * 140 * 3, 1, 140 * 3, 3, sw, sb_, u16(p.stem), total, s_inv);
+        ERNET_LAUNCH_CHECK("stem_p8_kernel");
+      } else {
+        long long sb = 3LL * 140 * 140, sc, sy, sx;
+        if (x_layout == ERNET_NCHW) { sc = 140 * 140; sy = 140; sx = 1; }
+        else                        { sc = 1; sy = 140 * 3; sx = 3; }
+        StageTimer _t(h, ERNET_STAGE_STEM, s);
+        if (x_dtype == ERNET_F32) tc::stem_p8_kernel<float, 8, tc::KIND_I8><<<grid, 128, 0, s>>>(static_cast<const float*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total, s_inv);
+        else if (x_dtype == ERNET_F16) tc::stem_p8_kernel<__half, 8, tc::KIND_I8><<<grid, 128, 0, s>>>(static_cast<const __half*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total, s_inv);
+        else tc::stem_p8_kernel<__nv_bfloat16, 8, tc::KIND_I8><<<grid, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total, s_inv);
+        ERNET_LAUNCH_CHECK("stem_p8_kernel");
+      }
+      if (fused1) {
+      } else if (paired) {
+        ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1P, tc::KIND_I8, tc::OUT_P16>(u16(p.stem), h->d_w1_pair, h->epi1, u16(p.p1), n, h->num_sms, s)));
+      } else {
+        ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1, tc::KIND_I8, tc::OUT_P16>(u16(p.stem), wimgq(0), h->epi1, u16(p.p1), n, h->num_sms, s)));
+      }
+      ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_cblock<tc::CBlock2RQ, tc::KIND_I8, tc::OUT_P8>(u16(p.p1), wimgq(1), h->epi2, u16(p.a2), n, h->num_sms, s)));
+      ERNET_STAGE(ERNET_STAGE_RED2, (tc::launch_acff_pblock<tc::PRed2RQ, tc::KIND_F16, tc::OUT_P16>(u16(p.a2), h->t[ERNET_T_TC_RED2_WIMG].dev, h->epi_r2, u16(p.p2), n, h->num_sms, s)));
+      ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_cblock<tc::CBlock3RQ, tc::KIND_I8, tc::OUT_NHWC>(u16(p.p2), wimgq(2), h->epi3, u16(p.p3), n, h->num_sms, s)));
+      ERNET_STAGE(ERNET_STAGE_RED3, launch_pointwise<T>(buf(p.p3), n, 6, 6, 128, 64, h->f(ERNET_T_RED3_W), h->f(ERNET_T_RED3_B), nullptr, nullptr, 0, 0, buf(p.r3), s));
+      return run_tail<T>(h, buf(p.r3), buf(p.cat4), buf(p.a4), n, probs, logits, s);
     }
   }
-  // Block 1 on the depthwise + 1x1 kernel (tc_dblock.cuh) wants the stem tensor in fp16 whatever the engine's type:
-  // every stem producer below then runs its fp16 instance (SK = element kind of the stem tensor, ST = its type).
-  const bool use_d1 = KIND != tc::KIND_I8 && h->persistent == 2 && h->dw_block1 && h->d_dblock1 && !h->debug_taps;
+  // SK = element kind of the stem tensor, ST = its type
+  bool fused1 = false;
   auto run_stem = [&](auto st_tag, auto sk_tag) -> int {
     using ST = decltype(st_tag);
     constexpr int SK = decltype(sk_tag)::value;
@@ -429,7 +495,20 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
       FastGeom fg;
       if (h->fast_ingest && h->d_stem_frag && fast5_geometry(*tab, frames, fg)) {
         const bool zc1 = !(SK == tc::KIND_I8 && h->persistent == 2 && h->d_w1_pair && h->pair_taps);
-        ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem5<ST, 16, FSOUT>(*tab, fg, frames, n, order == ERNET_BGR, h->d_stem_frag, q, zc1, u16(p.stem), s)));
+        const bool can_fuse = h->fuse_ingest && h->persistent >= 1 && !(h->persistent == 2 && h->pair_block1) && n <= kSyncImages;
+        if (can_fuse && SK == tc::KIND_I8 && h->persistent == 2 && !zc1 && tc::fused_fits<tc::PBlock1P>(fg)) {
+          fused1 = h->last_fused = true;
+          if constexpr (SK == tc::KIND_I8)
+            ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_ingest_block1<tc::PBlock1P, tc::KIND_I8, tc::OUT_P16, ST, 16, FS_P16>(*tab, fg, frames, n, order == ERNET_BGR, h->d_stem_frag, q, false,
+                        u16(p.stem), h->d_w1_pair, h->epi1, u16(p.p1), h->num_sms, h->d_sync, h->d_sync + kSyncImages, s)));
+        } else if (can_fuse && SK != tc::KIND_I8 && tc::fused_fits<tc::PBlock1>(fg)) {
+          fused1 = h->last_fused = true;     // transform + conv1 run under block 1 in ONE kernel (tc_fblock.cuh)
+          if constexpr (SK != tc::KIND_I8)
+            ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_ingest_block1<tc::PBlock1, SK, tc::OUT_P8, ST, 16, FS_P8>(*tab, fg, frames, n, order == ERNET_BGR, h->d_stem_frag, q, true,
+                        u16(p.stem), h->t[ERNET_T_TC_BASE + ERNET_T_TC_WIMG].dev, h->epi1, u16(p.p1), h->num_sms, h->d_sync, h->d_sync + kSyncImages, s)));
+        } else {
+          ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem5<ST, 16, FSOUT>(*tab, fg, frames, n, order == ERNET_BGR, h->d_stem_frag, q, zc1, u16(p.stem), s)));
+        }
       } else {
         ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem<ST, 16, FSOUT>(*tab, frames, n, order == ERNET_BGR, sw, sb_, q, u16(p.stem), s)));
       }
@@ -450,12 +529,12 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
     }
     return ERNET_OK;
   };
-  if (use_d1) rc = run_stem(__half{}, std::integral_constant<int, tc::KIND_F16>{});
-  else        rc = run_stem(T{}, std::integral_constant<int, KIND>{});
+  rc = run_stem(T{}, std::integral_constant<int, KIND>{});
   if (rc) return rc;
   auto wimg = [&](int k) { return h->t[ERNET_T_TC_BASE + 4 * k + ERNET_T_TC_WIMG].dev; };
   if (KIND == tc::KIND_I8 && h->persistent == 2) {
-    if (h->d_w1_pair && h->pair_taps) {
+    if (fused1) {
+    } else if (h->d_w1_pair && h->pair_taps) {
       ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1P, tc::KIND_I8, tc::OUT_P16>(u16(p.stem), h->d_w1_pair, h->epi1, u16(p.p1), n, h->num_sms, s)));
     } else {
       ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1, tc::KIND_I8, tc::OUT_P16>(u16(p.stem), wimg(0), h->epi1, u16(p.p1), n, h->num_sms, s)));
@@ -468,8 +547,7 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
     ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_block<tc::CfgBlock3Q, tc::KIND_I8, tc::OUT_NHWC>(u16(p.p2), wimg(2), h->epi3, u16(p.p3), n, s)));
   } else if (h->persistent) {
     constexpr int K16 = KIND == tc::KIND_I8 ? tc::KIND_F16 : KIND;
-    if (use_d1) {
-      ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_dblock1<K16, tc::OUT_P8>(u16(p.stem), h->d_dblock1, h->epi1d, u16(p.p1), n, h->num_sms, s)));
+    if (fused1) {
     } else if (h->persistent == 2 && h->pair_block1) {
       ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_cblock<tc::CBlock1, K16, tc::OUT_P8>(u16(p.stem), wimg(0), h->epi1, u16(p.p1), n, h->num_sms, s)));
     } else {
@@ -574,6 +652,7 @@ static int run_chunk_ernet_tc(ernet_handle* h, const void* x, int x_dtype, int x
 
 static int run_chunk(ernet_handle* h, const void* x, int x_dtype, int x_layout, const uint8_t* frames,
                      const IngestTables* tab, int order, int n, float* probs, float* logits, char* ws, cudaStream_t s) {
+  if (frames) h->last_fused = false;
   if (h->ernet()) {
     if (frames) {
       // aider_transforms (aider.py:430: Resize(273) -> CenterCrop(240) -> ToTensor -> Normalize) on the table-driven kernel
@@ -692,8 +771,18 @@ static int init_device_attrs() {
   if ((rc = tc::set_cblock_attr<tc::EBlock5, tc::KIND_F16, tc::OUT_P8>())) return rc;
   if ((rc = tc::set_cblock_attr<tc::EBlock6, tc::KIND_BF16, tc::OUT_NHWC>())) return rc;
   if ((rc = tc::set_cblock_attr<tc::EBlock6, tc::KIND_F16, tc::OUT_NHWC>())) return rc;
-  if ((rc = tc::set_dblock1_attr<tc::KIND_BF16, tc::OUT_P8>())) return rc;
-  if ((rc = tc::set_dblock1_attr<tc::KIND_F16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_fblock_attr<tc::PBlock1, tc::KIND_BF16, tc::OUT_P8, __nv_bfloat16, 16, FS_P8>())) return rc;
+  if ((rc = tc::set_fblock_attr<tc::PBlock1, tc::KIND_F16, tc::OUT_P8, __half, 16, FS_P8>())) return rc;
+  if ((rc = tc::set_fblock_attr<tc::PBlock1P, tc::KIND_I8, tc::OUT_P16, __half, 16, FS_P16>())) return rc;
+  if ((rc = tc::set_fblock_attr<tc::PBlock1P, tc::KIND_BF16, tc::OUT_P8, __nv_bfloat16, 8, FS_P8>())) return rc;
+  if ((rc = tc::set_fblock_attr<tc::PBlock1P, tc::KIND_F16, tc::OUT_P8, __half, 8, FS_P8>())) return rc;
+  if ((rc = tc::set_fblock_attr<tc::PBlock1P, tc::KIND_I8, tc::OUT_P16, __half, 8, FS_P16>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::CBlock2RQ, tc::KIND_I8, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::CBlock3RQ, tc::KIND_I8, tc::OUT_NHWC>())) return rc;
+  if ((rc = tc::set_pblock_attr<tc::PRed2RQ, tc::KIND_F16, tc::OUT_P16>())) return rc;
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem5_kernel<__half, 8, FS_P16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__half, 8, FS_P16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__half, 8, FS_P16, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   if ((rc = tc::set_tail_attrs<tc::TailCfg128>())) return rc;
   if ((rc = tc::set_tail_attrs<tc::TailCfg64>())) return rc;
   return ERNET_OK;
@@ -762,6 +851,13 @@ struct DeviceGuard {
 // ================================================================================================ C ABI
 extern "C" {
 
+#ifndef ERNET_SOURCE_HASH
+#define ERNET_SOURCE_HASH "unknown"
+#endif
+// "ERNET_SOURCE_HASH=<sha256 of the sources>": found by build.py in the file itself to decide whether to rebuild
+extern const char ernet_source_hash_str[] = "ERNET_SOURCE_HASH=" ERNET_SOURCE_HASH;
+const char* ernet_source_hash(void) { return ernet_source_hash_str + 18; }
+
 const char* ernet_last_error(void) { return g_err; }
 int ernet_abi_version(void) { return ERNET_ABI_VERSION; }
 
@@ -793,7 +889,11 @@ int ernet_create(ernet_handle** out, int arch, int precision, int device) {
   h->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("ERNET_PAIR_BLOCK1")) h->pair_block1 = atoi(e) != 0;
   if (const char* e = getenv("ERNET_PAIR_TAPS")) h->pair_taps = atoi(e) != 0;
-  if (const char* e = getenv("ERNET_DW_BLOCK1")) h->dw_block1 = atoi(e) != 0;
+  if (const char* e = getenv("ERNET_FUSE_INGEST")) h->fuse_ingest = atoi(e) != 0;
+  if (cudaMalloc(&h->d_sync, 2 * kSyncImages * sizeof(uint32_t)) != cudaSuccess || cudaMemset(h->d_sync, 0, 2 * kSyncImages * sizeof(uint32_t)) != cudaSuccess) {
+    delete h;
+    return fail(ERNET_ERR_CUDA, "allocating the band counters failed");
+  }
   if (const char* e = getenv("ERNET_TRIM_COLUMNS")) h->trim_columns = atoi(e) != 0;
   if (const char* e = getenv("ERNET_DUAL_COPY")) h->dual_copy = atoi(e) != 0;
   *out = h;
@@ -806,7 +906,7 @@ void ernet_destroy(ernet_handle* h) {
   if (h->d_blob) cudaFree(h->d_blob);
   if (h->d_stem_frag) cudaFree(h->d_stem_frag);
   if (h->d_w1_pair) cudaFree(h->d_w1_pair);
-  if (h->d_dblock1) cudaFree(h->d_dblock1);
+  if (h->d_sync) cudaFree(h->d_sync);
   for (auto& kv : h->ingest) if (kv.second.d_base) cudaFree(kv.second.d_base);
   for (int i = 0; i < 2; ++i) {
     if (h->d_frames[i]) cudaFree(h->d_frames[i]);
@@ -890,10 +990,10 @@ int ernet_load_packed(ernet_handle* h, const void* blob, size_t bytes) {
     const bool q = h->precision == ERNET_PREC_INT8;
     const size_t wimg_bytes[3] = {q ? (size_t)tc::CfgBlock1Q::W_BYTES : (size_t)tc::CfgBlock1::W_BYTES,
                                   q ? (size_t)tc::CfgBlock2Q::W_BYTES : (size_t)tc::CfgBlock2::W_BYTES,
-                                  q ? (size_t)tc::CfgBlock3Q::W_BYTES
+                                  q ? (h->red() ? (size_t)tc::CfgBlock3RQ::W_BYTES : (size_t)tc::CfgBlock3Q::W_BYTES)
                                     : (h->red() ? (size_t)tc::CfgBlock3R::W_BYTES : (size_t)tc::CfgBlock3::W_BYTES)};
     const size_t nout[3] = {64, 96, 128};
-    bool all = h->precision != ERNET_PREC_FP32 && !(q && h->red());
+    bool all = h->precision != ERNET_PREC_FP32;
     if (h->red()) {
       const Tensor& wr = h->t[ERNET_T_TC_RED2_WIMG];
       const Tensor& br = h->t[ERNET_T_TC_RED2_BIAS];
@@ -925,12 +1025,6 @@ int ernet_load_packed(ernet_handle* h, const void* blob, size_t bytes) {
         if (!h->d_w1_pair) ERNET_CUDA(cudaMalloc(&h->d_w1_pair, pr.size()));
         ERNET_CUDA(cudaMemcpy(h->d_w1_pair, pr.data(), pr.size(), cudaMemcpyHostToDevice));
       }
-      if (!q && !h->red()) {   // depthwise + 1x1 block-1 kernel: fp16 constants from the layer-wise tensors
-        tc::DBlock1Consts dc;
-        tc::build_dblock1(host_f32(ERNET_T_BLOCK_BASE + ERNET_T_PW_W), host_f32(ERNET_T_BLOCK_BASE + ERNET_T_DW_W), host_f32(ERNET_T_BLOCK_BASE + ERNET_T_DW_B), &dc);
-        if (!h->d_dblock1) ERNET_CUDA(cudaMalloc(&h->d_dblock1, sizeof(dc)));
-        ERNET_CUDA(cudaMemcpy(h->d_dblock1, &dc, sizeof(dc), cudaMemcpyHostToDevice));
-      }
       {  // conv1 with ToTensor/Normalize folded in, in mma.sync fragment order (ingest_fast.cuh)
         StemFrag sfh;
         build_stem_fragments(host_f32(ERNET_T_STEM_W), host_f32(ERNET_T_STEM_B), h->cs(), &sfh);
@@ -953,19 +1047,20 @@ int ernet_load_packed(ernet_handle* h, const void* blob, size_t bytes) {
         for (int i = 0; i < n; ++i) out_inv[i] = (q && k < 2) ? 1.f / qs[i] : 1.f;
       };
       fill(0, h->epi1.bias, h->epi1.scale, h->epi1.shift, h->epi1.deq, h->epi1.out_inv, 64);
-      h->epi1d = h->epi1;
-      if (!h->red()) memcpy(h->epi1d.bias, host_f32(ERNET_T_BLOCK_BASE + ERNET_T_PW_B), 64 * sizeof(float));
       fill(1, h->epi2.bias, h->epi2.scale, h->epi2.shift, h->epi2.deq, h->epi2.out_inv, 96);
       fill(2, h->epi3.bias, h->epi3.scale, h->epi3.shift, h->epi3.deq, h->epi3.out_inv, 128);
       if (h->red()) {
         memcpy(h->epi_r2.bias, host_f32(ERNET_T_TC_RED2_BIAS), 64 * sizeof(float));
         for (int i = 0; i < 64; ++i) { h->epi_r2.scale[i] = 1.f; h->epi_r2.shift[i] = 0.f; h->epi_r2.deq[i] = 1.f; h->epi_r2.out_inv[i] = 1.f; }
+        if (q) {   // int8: conv_red2 writes the int8 pool2 tensor; ACFF2's own (un-pooled, fp16) output is not re-quantised
+          for (int i = 0; i < 48; ++i) h->epi_r2.out_inv[i] = 1.f / h->q_scales[16 + 64 + i];
+          for (int i = 0; i < 96; ++i) h->epi2.out_inv[i] = 1.f;
+        }
       }
     }
     if (q && !all) {
       memcpy(h->t, old, sizeof(old)); cudaFree(d);
-      return fail(ERNET_ERR_BAD_BLOB, h->red() ? "int8 is implemented for Squeeze_ErNET only"
-                                                : "int8 blob lacks the calibrated tensor-core images (pack with act_scales)");
+      return fail(ERNET_ERR_BAD_BLOB, "int8 blob lacks the calibrated tensor-core images (pack with act_scales)");
     }
   }
   {
@@ -1036,7 +1131,7 @@ static int forward_common(ernet_handle* h, const void* x, int x_dtype, int x_lay
   } else if (order != ERNET_RGB && order != ERNET_BGR) {
     return fail(ERNET_ERR_INVALID_ARG, "bad channel_order %d", order);
   }
-  { int wrc = check_watchdog("an earlier forward call"); if (wrc) return wrc; }
+  { int wrc = check_watchdog("an earlier forward call"); if (wrc) { cudaMemset(h->d_sync, 0, 2 * kSyncImages * sizeof(uint32_t)); return wrc; } }
   const size_t need = ernet_workspace_bytes(h, batch);
   if (!ws || ws_bytes < need) return fail(ERNET_ERR_WORKSPACE, "workspace of %zu bytes needed, %zu given", need, ws ? ws_bytes : 0);
   DeviceGuard g(h->device);
@@ -1205,7 +1300,9 @@ int ernet_classify_frames_host_wait(ernet_handle* h, int ticket) {
   if (!h || ticket < 0 || ticket > 1 || !h->ev_call[ticket]) return fail(ERNET_ERR_INVALID_ARG, "ernet_classify_frames_host_wait: bad ticket");
   DeviceGuard g(h->device);
   ERNET_CUDA(cudaEventSynchronize(h->ev_call[ticket]));
-  return check_watchdog("ernet_classify_frames_host_wait");
+  const int wrc = check_watchdog("ernet_classify_frames_host_wait");
+  if (wrc) cudaMemset(h->d_sync, 0, 2 * kSyncImages * sizeof(uint32_t));     // an aborted fused kernel leaves its band counters dirty
+  return wrc;
 }
 
 int ernet_classify_frames_host(ernet_handle* h, const uint8_t* frames_host, int batch, int height, int width,
@@ -1309,7 +1406,7 @@ int ernet_debug_tap(ernet_handle* h, int tap, const void* workspace, int batch, 
   const int grid = (int)((total + 255) / 256);
   if (p.tc && h->precision == ERNET_PREC_INT8 && (tap == ERNET_TAP_STEM || tap == ERNET_TAP_POOL1 || tap == ERNET_TAP_POOL2)) {
     const int Hh = tap == ERNET_TAP_STEM ? 69 : (tap == ERNET_TAP_POOL1 ? 33 : 15);
-    const int NCc = tap == ERNET_TAP_STEM ? 2 : (tap == ERNET_TAP_POOL1 ? 4 : 6);
+    const int NCc = tap == ERNET_TAP_STEM ? 2 : (tap == ERNET_TAP_POOL1 ? 4 : (h->red() ? 4 : 6));
     const float* sc = h->f(ERNET_T_Q_SCALES) + (tap == ERNET_TAP_STEM ? 0 : (tap == ERNET_TAP_POOL1 ? 16 : 16 + 64));
     tc::tap_p16_to_nchw_f32<<<grid, 256, 0, s>>>(reinterpret_cast<const int8_t*>(src), NCc, C, Hh, total, sc, out);
     ERNET_LAUNCH_CHECK("tap_p16_to_nchw_f32");
@@ -1421,7 +1518,7 @@ int ernet_launches_per_forward(const ernet_handle* h, int batch, int with_ingest
   const bool tail = h->has_tail && h->engine != ERNET_ENGINE_SIMT;
   const int tail_launches = tail ? 1 : 3;
   // frames path: transform + conv1 are one kernel (two with debug taps on); tensor path: conv1 only
-  const int front = with_ingest ? (h->debug_taps ? 2 : 1) : 1;
+  const int front = with_ingest ? (h->debug_taps ? 2 : (h->last_fused ? 0 : 1)) : 1;   // fused: transform + conv1 ride in block 1's kernel
   const int per = h->use_tc() ? front + 3 + (h->red() ? 2 : 0) + tail_launches : front + 6 + (h->red() ? 2 : 0) + tail_launches;
   return chunks * per;
 }

@@ -30,35 +30,36 @@ struct FastGeom {                             // shared-memory carve-up (bytes),
 //   then CS floats: folded bias
 struct StemFrag { uint32_t frag[2][32][8]; float bias[16]; };
 
+// Thread-group synchronisation of one band: the whole CTA (stand-alone kernel) or a named barrier over the NT helper
+// threads of the fused transform + block-1 kernel (tc_fblock.cuh).
+struct BandSyncCta { static __device__ __forceinline__ void sync() { __syncthreads(); } };
+template <int NT> struct BandSyncNamed {
+  static __device__ __forceinline__ void sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
+};
+
+// One band (kStemBand conv1 rows) of one frame by a group of NT threads (tid = 0 .. NT-1); `bar` is an initialised
+// mbarrier (count 1) that this group has used `bar_uses` times before (phase parity of the bulk copy).
 // OUT = FS_P8: 16-bit stem tensor (B,2,72,72,8); FS_P16: int8 stem tensor (B,2,72,72,16) quantised with q.inv[c] (the
 // int8 engine); zero_chunk1: also write the all-zero second chunk (not needed when block 1 pairs taps and never reads it).
-template <typename T, int CS, int OUT = FS_P8>
-__global__ void __launch_bounds__(kFastThreads, 2)
-ingest_stem5_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restrict__ frames_end, int H, int W, int bgr,
-                    const int* __restrict__ xmin, const int* __restrict__ kx, const int* __restrict__ ymin, const int* __restrict__ ylen,
-                    const int* __restrict__ ky, const StemFrag* __restrict__ sf, const __grid_constant__ FastGeom geo,
-                    const __grid_constant__ StemQ q, int zero_chunk1, void* __restrict__ out) {
-  extern __shared__ __align__(128) uint8_t fsm[];
+// Returns true when the band was staged by the bulk copy (the mbarrier then completed one more phase).
+template <typename T, int CS, int OUT, int NT, class Sync>
+__device__ __forceinline__ bool ingest_stem5_band(uint8_t* __restrict__ fsm, const FastGeom& geo, uint64_t* bar, uint32_t bar_uses,
+                                                  int tid, int b, int band_idx, const uint8_t* __restrict__ frames,
+                                                  const uint8_t* __restrict__ frames_end, int H, int W, int bgr,
+                                                  const int* __restrict__ xmin, const int* __restrict__ kx, const int* __restrict__ ymin,
+                                                  const int* __restrict__ ylen, const int* __restrict__ ky, const StemFrag* __restrict__ sf,
+                                                  const StemQ& q, int zero_chunk1, void* __restrict__ out) {
   const uint32_t* raww = reinterpret_cast<const uint32_t*>(fsm);           // [in_rows][W*3] packed RGB bytes (bulk copy)
   uint32_t* hbuf4 = reinterpret_cast<uint32_t*>(fsm + geo.off_hbuf);       // [in_rows + 5][140] RGBX words
   uint8_t* vbuf = fsm + geo.off_vbuf;                                      // [2*band + 2][420] RGB bytes
-  uint64_t* bar = reinterpret_cast<uint64_t*>(fsm + geo.off_bar);
+  constexpr int NW = NT / 32;
 
-  const int b = blockIdx.y;
-  const int y0 = blockIdx.x * kStemBand;
+  const int y0 = band_idx * kStemBand;
   const int y1 = min(y0 + kStemBand, 69);
   const int n0 = 2 * y0, n1 = 2 * (y1 - 1) + 2;
   const int r0 = __ldg(ymin + n0);
   const int in_rows = __ldg(ymin + n1) + __ldg(ylen + n1) - r0;
-  const int tid = threadIdx.x;
   const int rowb = W * 3;                                                  // bytes per raw row
-
-  ERNET_CHAIN_ENTRY(0);
-  if (tid == 0) { tc::mbar_init(bar, 1); tc::fence_mbar_init(); }
-  __syncthreads();
-  pdl_wait();                 // frames may come from the previous kernel of the stream; the stem tensor is read by block 1
-  pdl_launch_dependents();
-  ERNET_CHAIN_WAITED(0);
 
   // ---- phase 0: the raw rows of the band are contiguous: ONE bulk copy (TMA engine), no instructions per byte.  The
   // copy starts at the 16-byte boundary below the band; `off` is carried into the byte offsets of phase 1.  A band whose
@@ -71,7 +72,7 @@ ingest_stem5_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restric
   if (bulk) {
     if (tid == 0) { tc::mbar_expect_tx(bar, bytes); tc::bulk_g2s(fsm, a0, bytes, bar); }
   } else {
-    for (int i = tid; i < (int)(bytes >> 4); i += kFastThreads) {
+    for (int i = tid; i < (int)(bytes >> 4); i += NT) {
       const uint8_t* pv = a0 + (size_t)i * 16;
       if (pv >= frames && pv + 16 <= frames_end) {
         reinterpret_cast<uint4*>(fsm)[i] = __ldg(reinterpret_cast<const uint4*>(pv));
@@ -81,21 +82,22 @@ ingest_stem5_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restric
     }
   }
   // per-thread constants of phase 1 while the copy is in flight
+  constexpr int RG = NT / kCrop;                                          // row groups of phase 1
   const int ox = tid % kCrop, rg = tid / kCrop;
   uint32_t kc[5];
 #pragma unroll
   for (int t = 0; t < 5; ++t) kc[t] = (uint32_t)__ldg(kx + ox * 5 + t) << 2;      // 4k: the result byte is the top byte
   const int bo = off + 3 * __ldg(xmin + ox);
   const int sh = (bo & 3) * 8;
-  if (bulk) { while (!tc::mbar_test_wait(bar, 0)) { } }
-  else __syncthreads();
+  if (bulk) { while (!tc::mbar_test_wait(bar, bar_uses & 1u)) { } }
+  else Sync::sync();
 
   // ---- phase 1: horizontal pass.  Thread = output column; 5 aligned words cover the 15 bytes of the 5 taps, a funnel
   // shift aligns them to the pixel, bytes come out with constant PRMT selectors.  acc = 4 * (2^21 + sum k p) < 2^32.
-  if (tid < 3 * kCrop) {
+  if (tid < RG * kCrop) {
     const uint32_t* p = raww + rg * (rowb >> 2) + (bo >> 2);
     uint32_t* h = hbuf4 + rg * kCrop + ox;
-    for (int r = rg; r < in_rows; r += 3, p += 3 * (rowb >> 2), h += 3 * kCrop) {
+    for (int r = rg; r < in_rows; r += RG, p += RG * (rowb >> 2), h += RG * kCrop) {
       const uint32_t w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3], w4 = p[4];
       const uint32_t v[4] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh)};
       uint32_t a[3] = {1u << 23, 1u << 23, 1u << 23};
@@ -108,12 +110,12 @@ ingest_stem5_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restric
       *h = __byte_perm(__byte_perm(a[0], a[1], 0x0073), a[2], 0x7710);    // R | G << 8 | B << 16
     }
   }
-  __syncthreads();
+  Sync::sync();
 
   // ---- phase 2: vertical pass, four pixels per task -> packed RGB bytes
   const int nrows = n1 - n0 + 1;
-  if (tid < (kFastThreads / 35) * 35)
-  for (int rn = tid / 35, g = tid - (tid / 35) * 35; rn < nrows; rn += kFastThreads / 35) {
+  if (tid < (NT / 35) * 35)
+  for (int rn = tid / 35, g = tid - (tid / 35) * 35; rn < nrows; rn += NT / 35) {
     const int oy = n0 + rn;
     const uint4* hp = reinterpret_cast<const uint4*>(hbuf4 + (__ldg(ymin + oy) - r0) * kCrop) + g;
     uint32_t acc[12];
@@ -122,8 +124,8 @@ ingest_stem5_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restric
 #pragma unroll
     for (int t = 0; t < 5; ++t) {
       const uint32_t c = (uint32_t)__ldg(ky + oy * 5 + t) << 2;
-      const uint4 q = hp[t * (kCrop / 4)];
-      const uint32_t px[4] = {q.x, q.y, q.z, q.w};
+      const uint4 qd = hp[t * (kCrop / 4)];
+      const uint32_t px[4] = {qd.x, qd.y, qd.z, qd.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         acc[3 * j + 0] += c * __byte_perm(px[j], 0u, 0x4440);
@@ -136,12 +138,13 @@ ingest_stem5_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restric
     for (int wd = 0; wd < 3; ++wd)
       vp[wd] = __byte_perm(__byte_perm(acc[4 * wd], acc[4 * wd + 1], 0x0073), __byte_perm(acc[4 * wd + 2], acc[4 * wd + 3], 0x0073), 0x5410);
   }
-  __syncthreads();
+  Sync::sync();
 
-  // ---- phase 3: conv1 3x3 / stride 2 as an implicit GEMM on mma.sync (16 pixels x 8 channels per instruction)
+  // ---- phase 3: conv1 3x3 / stride 2 as an implicit GEMM on mma.sync (16 pixels x 8 channels per instruction); one task =
+  // 16 output pixels of one row, dealt round-robin to the warps
   {
     const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    constexpr int NT = CS / 8;
+    constexpr int NTL = CS / 8;
     int koff[2][2];                                        // byte offset of this lane's k pairs inside a pixel's window
 #pragma unroll
     for (int s = 0; s < 2; ++s)
@@ -157,21 +160,21 @@ ingest_stem5_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restric
       bfrag[0][0][0] = f0.x; bfrag[0][0][1] = f0.y; bfrag[0][1][0] = f0.z; bfrag[0][1][1] = f0.w;
       bfrag[1][0][0] = f1.x; bfrag[1][0][1] = f1.y; bfrag[1][1][0] = f1.z; bfrag[1][1][1] = f1.w;
     }
-    float bia[NT][2];
+    float bia[NTL][2];
 #pragma unroll
-    for (int j = 0; j < NT; ++j) { bia[j][0] = __ldg(sf->bias + 8 * j + 2 * t); bia[j][1] = __ldg(sf->bias + 8 * j + 2 * t + 1); }
+    for (int j = 0; j < NTL; ++j) { bia[j][0] = __ldg(sf->bias + 8 * j + 2 * t); bia[j][1] = __ldg(sf->bias + 8 * j + 2 * t + 1); }
     const __half2 k1024 = __floats2half2_rn(1024.f, 1024.f);
     const int brow = y1 - y0;
     uint4* img = reinterpret_cast<uint4*>(out) + (size_t)b * 2 * 72 * 72;
     uint32_t* orow = reinterpret_cast<uint32_t*>(img + (y0 + 2) * 72 + 2) + t;     // lane's 4-byte slot of chunk 0, band row 0, pixel 0
-    for (int ly = warp; ly < brow; ly += kFastThreads / 32) {
+    for (int task = warp; task < brow * 5; task += NW) {
+      const int ly = task / 5, xg = task - ly * 5;
       const uint8_t* vrow = vbuf + (2 * ly) * (kCrop * 3);
       uint32_t* orow_l = orow + ly * (72 * 4);
-#pragma unroll
-      for (int xg = 0; xg < 5; ++xg) {
+      {
         const int ox0 = xg * 16 + g, ox1 = ox0 + 8;
-        const uint8_t* base0 = vrow + 6 * (xg < 4 ? ox0 : min(ox0, 68));
-        const uint8_t* base1 = vrow + 6 * (xg < 4 ? ox1 : min(ox1, 68));
+        const uint8_t* base0 = vrow + 6 * min(ox0, 68);
+        const uint8_t* base1 = vrow + 6 * min(ox1, 68);
         uint32_t afrag[2][4];
 #pragma unroll
         for (int s = 0; s < 2; ++s)
@@ -184,45 +187,64 @@ ingest_stem5_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restric
             afrag[s][2 * hh + 0] = *reinterpret_cast<const uint32_t*>(&h0);      // row g
             afrag[s][2 * hh + 1] = *reinterpret_cast<const uint32_t*>(&h1);      // row g + 8
           }
-        float acc[NT][4];
+        float acc[NTL][4];
 #pragma unroll
-        for (int j = 0; j < NT; ++j) { acc[j][0] = acc[j][2] = bia[j][0]; acc[j][1] = acc[j][3] = bia[j][1]; }
+        for (int j = 0; j < NTL; ++j) { acc[j][0] = acc[j][2] = bia[j][0]; acc[j][1] = acc[j][3] = bia[j][1]; }
 #pragma unroll
         for (int s = 0; s < 2; ++s)
 #pragma unroll
-          for (int j = 0; j < NT; ++j) StemMma<__half>::mma(acc[j], afrag[s], bfrag[s][j]);
+          for (int j = 0; j < NTL; ++j) StemMma<__half>::mma(acc[j], afrag[s], bfrag[s][j]);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int oxx = half ? ox1 : ox0;
-          if (xg == 4 && oxx >= 69) continue;
+          if (oxx >= 69) continue;
           if (OUT == FS_P16) {
             uint16_t* o16 = reinterpret_cast<uint16_t*>(orow_l + oxx * 4 - t) + t;      // pixel's 16 bytes, this lane's channel pairs
 #pragma unroll
-            for (int j = 0; j < NT; ++j) {
+            for (int j = 0; j < NTL; ++j) {
               int q0 = __float2int_rn(acc[j][2 * half] * q.inv[8 * j + 2 * t]), q1 = __float2int_rn(acc[j][2 * half + 1] * q.inv[8 * j + 2 * t + 1]);
               q0 = max(-127, min(127, q0)); q1 = max(-127, min(127, q1));
               o16[4 * j] = (uint16_t)(((uint32_t)q0 & 0xffu) | (((uint32_t)q1 & 0xffu) << 8));
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < NT; ++j) orow_l[j * (72 * 72 * 4) + oxx * 4] = StemMma<T>::pack(acc[j][2 * half], acc[j][2 * half + 1]);
+            for (int j = 0; j < NTL; ++j) orow_l[j * (72 * 72 * 4) + oxx * 4] = StemMma<T>::pack(acc[j][2 * half], acc[j][2 * half + 1]);
           }
         }
       }
     }
     // zero halo columns of the band's rows (and the all-zero second chunk of an 8-channel stem)
-    for (int i = tid; i < brow * 72; i += kFastThreads) {
+    for (int i = tid; i < brow * 72; i += NT) {
       const int ly = i / 72, pc = i - ly * 72;
       const bool halo = pc < 2 || pc >= 71;
       if (halo) img[(y0 + ly + 2) * 72 + pc] = make_uint4(0, 0, 0, 0);
       if (zero_chunk1 ? (halo || CS == 8 || OUT == FS_P16) : (halo && CS == 16 && OUT == FS_P8)) img[72 * 72 + (y0 + ly + 2) * 72 + pc] = make_uint4(0, 0, 0, 0);
     }
     const int nch = (zero_chunk1 || (CS == 16 && OUT == FS_P8)) ? 2 : 1;         // chunks whose halo rows are written
-    if (blockIdx.x == 0)
-      for (int i = tid; i < nch * 2 * 72; i += kFastThreads) img[(i / 144) * 72 * 72 + (i % 144)] = make_uint4(0, 0, 0, 0);
+    if (band_idx == 0)
+      for (int i = tid; i < nch * 2 * 72; i += NT) img[(i / 144) * 72 * 72 + (i % 144)] = make_uint4(0, 0, 0, 0);
     if (y1 == 69)
-      for (int i = tid; i < nch * 72; i += kFastThreads) img[(i / 72) * 72 * 72 + 71 * 72 + (i % 72)] = make_uint4(0, 0, 0, 0);
+      for (int i = tid; i < nch * 72; i += NT) img[(i / 72) * 72 * 72 + 71 * 72 + (i % 72)] = make_uint4(0, 0, 0, 0);
   }
+  return bulk;
+}
+
+template <typename T, int CS, int OUT = FS_P8>
+__global__ void __launch_bounds__(kFastThreads, 2)
+ingest_stem5_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restrict__ frames_end, int H, int W, int bgr,
+                    const int* __restrict__ xmin, const int* __restrict__ kx, const int* __restrict__ ymin, const int* __restrict__ ylen,
+                    const int* __restrict__ ky, const StemFrag* __restrict__ sf, const __grid_constant__ FastGeom geo,
+                    const __grid_constant__ StemQ q, int zero_chunk1, void* __restrict__ out) {
+  extern __shared__ __align__(128) uint8_t fsm[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(fsm + geo.off_bar);
+  ERNET_CHAIN_ENTRY(0);
+  if (threadIdx.x == 0) { tc::mbar_init(bar, 1); tc::fence_mbar_init(); }
+  __syncthreads();
+  pdl_wait();                 // frames may come from the previous kernel of the stream; the stem tensor is read by block 1
+  pdl_launch_dependents();
+  ERNET_CHAIN_WAITED(0);
+  ingest_stem5_band<T, CS, OUT, kFastThreads, BandSyncCta>(fsm, geo, bar, 0u, threadIdx.x, blockIdx.y, blockIdx.x, frames, frames_end, H, W, bgr,
+                                                           xmin, kx, ymin, ylen, ky, sf, q, zero_chunk1, out);
   ERNET_CHAIN_EXIT(0);
 }
 

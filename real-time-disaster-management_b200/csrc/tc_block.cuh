@@ -91,7 +91,9 @@ constexpr int kBlockThreads = 320;   // producer + MMA + 8 epilogue warps
 // [-> LeakyReLU -> BN affine] -> 16-bit / int8 -> [2x2 max-pool via register-half exchange] -> store.
 // `tbase` = TMEM address of the tile's first column for this warp's lane quarter; (y, x) = this lane's output
 // pixel; `img` = global image index.
-template <class Cfg, int KIND, int OUT>
+// PREFETCH: keep the next 32 columns' TMEM load in flight under the arithmetic of the current ones (64 data registers);
+// off in the fused transform + block-1 kernel, whose 27 warps leave 72 registers per thread.
+template <class Cfg, int KIND, int OUT, bool PREFETCH = true>
 __device__ __forceinline__ void epilogue_tile(const EpiParams<Cfg::N>& par, uint32_t tbase, int y, int x, bool valid,
                                         bool xodd, bool yodd, int qsel, uint16_t* __restrict__ out, int img) {
   constexpr int N = Cfg::N, NREAL = Cfg::NREAL, OP = Cfg::OP, OUT_H = Cfg::OUT_H;
@@ -99,18 +101,19 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams<Cfg::N>& par, uint
   constexpr int OUT_CHUNKS = OUT == OUT_P16 ? NREAL / 16 : NREAL / 8;
   const int py = y >> 1, px = x >> 1;
   const int img0 = img, im = 0;              // (names used by the body below)
-  uint32_t v[2][32];
-  tmem_ld32(tbase, v[0]);
+  uint32_t v[PREFETCH ? 2 : 1][32];
+  if (PREFETCH) tmem_ld32(tbase, v[0]);
 #pragma unroll
   for (int cb = 0; cb < N / 32; ++cb) {
+    if (!PREFETCH) tmem_ld32(tbase + cb * 32, v[0]);
     tmem_ld_wait();                                     // block cb has landed
-    if (cb + 1 < N / 32) tmem_ld32(tbase + (cb + 1) * 32, v[(cb + 1) & 1]);   // prefetch the next 32 columns
+    if (PREFETCH && cb + 1 < N / 32) tmem_ld32(tbase + (cb + 1) * 32, v[(cb + 1) & 1]);   // prefetch the next 32 columns
     float yv[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const int n = cb * 32 + j;
-      float z = KIND == KIND_I8 ? fmaf(__int2float_rn((int)v[cb & 1][j]), par.deq[n], par.bias[n])
-                                : __uint_as_float(v[cb & 1][j]) + par.bias[n];
+      float z = KIND == KIND_I8 ? fmaf(__int2float_rn((int)v[PREFETCH ? (cb & 1) : 0][j]), par.deq[n], par.bias[n])
+                                : __uint_as_float(v[PREFETCH ? (cb & 1) : 0][j]) + par.bias[n];
       if (Cfg::ACT) {
         z = fmaxf(z, 0.01f * z);                         // LeakyReLU(0.01), acff.py:33
         z = fmaf(z, par.scale[n], par.shift[n]);         // eval BatchNorm, acff.py:34
@@ -148,7 +151,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams<Cfg::N>& par, uint
         const uint32_t send = yodd ? m1[j] : m1[j + 2];
         m2[j] = __vmaxs4(keep, __shfl_xor_sync(0xffffffffu, send, 8));
       }
-      if (valid) {                                       // 8 channels = half of a 16-channel chunk
+      if (valid && (cb * 2 + (qsel >> 1)) * 16 < NREAL) {   // 8 channels = half of a 16-channel chunk
         const int ch = cb * 2 + (qsel >> 1);
         uint2* oimg = reinterpret_cast<uint2*>(out) + ((size_t)(img0 + im) * OUT_CHUNKS * OP * OP) * 2;
         oimg[((size_t)(ch * OP + py + 2) * OP + px + 2) * 2 + (qsel & 1)] = make_uint2(m2[0], m2[1]);
@@ -410,6 +413,7 @@ using CfgBlock3R = BlockCfg<6, 128, 15, 12, 2, 4, 1, false, 3>;
 using CfgBlock1Q = BlockCfg<2, 64, 69, 66, 1, 4, 2, true, 1>;
 using CfgBlock2Q = BlockCfg<4, 96, 33, 30, 1, 4, 1, false, 4>;
 using CfgBlock3Q = BlockCfg<6, 128, 15, 12, 2, 4, 1, false, 3>;
+using CfgBlock3RQ = BlockCfg<4, 128, 15, 12, 2, 4, 1, false, 3>;      // int8 Squeeze_RedConv: 48 real + 16 zero channels (weight-image size)
 
 template <class Cfg, int KIND, int OUT>
 inline int launch_acff_block(const void* in, const void* wimg, const EpiParams<Cfg::N>& par, void* out, int batch,

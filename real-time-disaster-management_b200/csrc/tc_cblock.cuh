@@ -433,6 +433,10 @@ using EBlock5 = CCfg<16, 128, 11, 9, 2, 8, false, 9, /*POOL*/ false>;
 using EBlock6 = CCfg<16, 256, 9, 7, 1, 8, false, 6, /*POOL*/ false>;
 using CBlock2Q = CCfg<4, 96, 33, 30, 2, 8, true, 1>;
 using CBlock3Q = CCfg<6, 128, 15, 12, 2, 6, true, 1>;
+// int8 Squeeze_RedConv: ACFF2 un-pooled with an fp16 output (conv_red2 follows as a 16-bit 1-tap instance that writes the
+// int8 pool2 tensor), ACFF3 on 48 real + 16 zero int8 channels
+using CBlock2RQ = CCfg<4, 96, 33, 30, 2, 6, true, 1, /*POOL*/ false>;
+using CBlock3RQ = CCfg<4, 128, 15, 12, 2, 8, true, 1>;
 
 }  // namespace tc
 }  // namespace ernet

@@ -374,6 +374,8 @@ using PBlock3 = PCfg<12, 128, 15, 12, 2, 2, false, 4>;         //  1 unit  / ima
 using PBlock1P = PCfg<2, 64, 69, 66, 3, 3, true, 1, true, 25, true, 64, /*PAIR*/ true>;
 using EBlock1 = PCfg<2, 64, 119, 116, 3, 3, true, 1>;          // ErNET block 1: 40 units / image
 using PRed2R = PCfg<12, 64, 30, 30, 4, 2, true, 1, /*POOL*/ true, /*TAPS*/ 1, /*ACT*/ false, /*NREAL*/ 48>;
+// int8 engine: same instance writing the int8 pool2 tensor as 4 chunks of 16 channels (48 real + 16 exact zeros)
+using PRed2RQ = PCfg<12, 64, 30, 30, 4, 2, true, 1, /*POOL*/ true, /*TAPS*/ 1, /*ACT*/ false, /*NREAL*/ 64>;
 
 }  // namespace tc
 }  // namespace ernet

@@ -443,7 +443,7 @@ class _ErnetB200(_EngineRuntime, nn.Module):
 
     def set_act_scales(self, scales):
         from .pack_tc import normalize_act_scales
-        self._act_scales = tuple(tuple(float(x) for x in a) for a in normalize_act_scales(scales))
+        self._act_scales = tuple(tuple(float(x) for x in a) for a in normalize_act_scales(scales, self.ARCH))
         return self
 
 

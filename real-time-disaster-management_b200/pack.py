@@ -170,7 +170,7 @@ def pack_state_dict(sd, arch, precision, act_scales=None):
     validate_state_dict(sd, arch)
     tensors = {i: (v.astype(np.float32), DT_F32) for i, v in derive_simt(sd, arch).items()}
     if arch == "ernet" and precision == "int8":
-        raise ValueError("int8 is implemented for squeeze-ernet only")
+        raise ValueError("int8 is implemented for squeeze-ernet and squeeze-redconv")
     if precision in ("fp16", "bf16", "int8"):
         from . import pack_tc
         tensors.update(pack_tc.derive_tc(sd, arch, precision, act_scales))

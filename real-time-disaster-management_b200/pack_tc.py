@@ -84,16 +84,21 @@ def weight_image_i8(wq):
     return np.ascontiguousarray(wq.transpose(1, 2, 0).reshape(25, c // 16, 16, n_out).transpose(0, 1, 3, 2))
 
 
-ACT_CHANNELS = (16, 64, 96)      # channels of the three quantised tensors: stem, pool1, pool2 outputs
+ACT_CHANNELS = (16, 64, 96)      # channels of the three quantised tensors: stem, pool1, pool2 outputs (Squeeze_ErNET)
+ACT_CHANNELS_RED = (8, 64, 48)   # Squeeze_RedConv: conv_red1 / pool1 / pool2 (after conv_red2) outputs
 
 
-def normalize_act_scales(act_scales):
+def act_channels(arch):
+    return ACT_CHANNELS_RED if arch == "squeeze-redconv" else ACT_CHANNELS
+
+
+def normalize_act_scales(act_scales, arch="squeeze-ernet"):
     """-> three fp64 arrays of per-channel int8 steps.  Accepts three scalars (plain per-tensor scales) or
     three arrays (per-channel equalised)."""
     if act_scales is None or len(act_scales) != 3:
         raise ValueError("act_scales must have three entries (stem, pool1, pool2)")
     out = []
-    for v, c in zip(act_scales, ACT_CHANNELS):
+    for v, c in zip(act_scales, act_channels(arch)):
         a = np.asarray(v, dtype=np.float64)
         a = np.full(c, float(a)) if a.ndim == 0 else a.reshape(-1)
         if a.shape != (c,) or not np.all(np.isfinite(a)) or np.any(a <= 0):
@@ -108,13 +113,13 @@ def derive_tc_int8(sd, arch, act_scales):
     step in its epilogue (for pool1/pool2 that is a change of the BN affine constants), the consumer's
     folded weights are multiplied by it, so at run time the int8 tensor has ONE scale (1.0) - the
     per-channel part is cross-layer equalisation done at pack time."""
-    from .pack import widths
-    if arch != "squeeze-ernet":
-        raise ValueError("int8 is implemented for squeeze-ernet only")
-    s_act = normalize_act_scales(act_scales)
+    from .pack import widths, _np64
+    if arch not in ("squeeze-ernet", "squeeze-redconv"):
+        raise ValueError("int8 is implemented for squeeze-ernet and squeeze-redconv")
+    s_act = normalize_act_scales(act_scales, arch)
     out = {}
     for k, (c, _co) in enumerate(widths(arch)[:3]):
-        c_pad = max(32, c)                      # K step of kind::i8 is 32
+        c_pad = (c + 31) // 32 * 32             # K step of kind::i8 is 32 (RedConv: 8 -> 32, 48 -> 64)
         weff, beff = fold_block(sd, f"acff{k + 1}", c, c_pad)
         weff[:, :, :c] *= s_act[k].reshape(1, 1, -1)
         wq, s_w = quantize_weights(weff)
@@ -122,7 +127,21 @@ def derive_tc_int8(sd, arch, act_scales):
         out[base + T_TC_WIMG] = (weight_image_i8(wq), DT_RAW)
         out[base + T_TC_BIAS] = (beff.astype(np.float32), DT_F32)
         out[base + T_TC_DEQ] = (s_w.astype(np.float32), DT_F32)
-    out[T_Q_SCALES] = (np.concatenate(s_act).astype(np.float32), DT_F32)
+    # the handle keeps the steps at fixed offsets [16][64][96]; unused tails (RedConv: 8 of 16, 48 of 96) are 1.0
+    qs = np.ones(16 + 64 + 96, dtype=np.float64)
+    for off, a in zip((0, 16, 80), s_act):
+        qs[off:off + len(a)] = a
+    out[T_Q_SCALES] = (qs.astype(np.float32), DT_F32)
+    if arch == "squeeze-redconv":
+        # conv_red2 (squeeze_ernet_redconv.py:16,33) stays a 16-bit 1-tap instance (fp16 weights, fp16 un-pooled ACFF2
+        # output in, int8 pool2 tensor out); N padded to 64: the 16 extra outputs are exact zeros = the zero half of the
+        # fourth 16-channel chunk that block 3's K step of 32 wants
+        wr = np.zeros((64, 1, 96))
+        wr[:48, 0, :] = _np64(sd, "conv_red2.weight")[:, :, 0, 0]
+        br = np.zeros(64)
+        br[:48] = _np64(sd, "conv_red2.bias")
+        out[T_TC_RED2_WIMG] = (weight_image(wr, "fp16"), DT_RAW)
+        out[T_TC_RED2_BIAS] = (br.astype(np.float32), DT_F32)
     return out
 
 

@@ -220,3 +220,18 @@ def test_torch_restatement_matches_reference(arch, wset, model_golden):
     ref32 = model_golden[f"{arch}/shipped/norm/logits32"]
     _, l32 = T.forward(T.to_torch_sd(fixtures.get_state_dict(arch, "shipped")), torch.from_numpy(fixtures.normal_tensors(4, seed=7)), arch)
     assert np.abs(l32.numpy() - ref32).max() <= 2e-6 * np.abs(ref32).max()
+
+
+def test_real_frames_oracle_matches_reference():
+    """Input set I3: the 15 AIDER JPEGs of the reference tree, as the 140x140 crops torchvision/Pillow produced
+    (tests/golden/make_golden_real.py).  The oracle's normalisation + forward reproduces the real classes' fp64 logits."""
+    g = np.load(os.path.join(fixtures.GOLDEN, "real_golden.npz"))
+    crops = g["crops_u8"]
+    assert crops.shape == (15, 140, 140, 3) and crops.dtype == np.uint8
+    lut = I.normalise_lut()
+    x = np.stack([np.stack([lut[c[:, :, ch], ch] for ch in range(3)], 0) for c in crops], 0)
+    for arch in fixtures.ARCHS:
+        res = E.forward(fixtures.get_state_dict(arch, "shipped"), x, arch, dtype=np.float64)
+        ref = g[f"{arch}/shipped/logits64"]
+        assert np.abs(res["logits"] - ref).max() <= 1e-6 * np.abs(ref).max(), arch      # fp32 normalised input on both sides
+        assert (res["probs"].argmax(1) == g[f"{arch}/shipped/probs64"].argmax(1)).all()
