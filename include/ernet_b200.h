@@ -100,6 +100,11 @@ int ernet_set_persistent(ernet_handle* h, int on);
  * conv1 with ToTensor/Normalize folded into the conv weights (ingest_fast.cuh); 0 = the table-lookup kernel that is
  * bit-identical to ernet_ingest_u8 followed by ernet_forward.                                              */
 int ernet_set_fast_ingest(ernet_handle* h, int on);
+/* Frames path, tensor-core engines, 5-tap frames: 1 = the eval transform + conv1 run INSIDE block 1's persistent kernel
+ * on dedicated helper warps, under its tcgen05 MMAs (tc_fblock.cuh; one launch less, bit-identical results); 0
+ * (default) = a kernel of their own in front of block 1.  Measured at parity on B200, hence off
+ * by default.  The environment variable ERNET_FUSE_INGEST=1 sets the initial value of new handles.            */
+int ernet_set_fuse_ingest(ernet_handle* h, int on);
 /* Fused kernels keep some intermediates on chip (acff4 inside the ACFF4+head kernel).  With debug taps
  * on they are also written to the workspace so that ernet_debug_tap() can read them (test use).      */
 int ernet_set_debug_taps(ernet_handle* h, int on);

@@ -1105,6 +1105,11 @@ int ernet_set_fast_ingest(ernet_handle* h, int on) {
   h->fast_ingest = on != 0;
   return ERNET_OK;
 }
+int ernet_set_fuse_ingest(ernet_handle* h, int on) {
+  if (!h) return fail(ERNET_ERR_INVALID_ARG, "null handle");
+  h->fuse_ingest = on != 0;
+  return ERNET_OK;
+}
 int ernet_set_debug_taps(ernet_handle* h, int on) {
   if (!h) return fail(ERNET_ERR_INVALID_ARG, "null handle");
   h->debug_taps = on != 0;

@@ -37,18 +37,55 @@ template <int NT> struct BandSyncNamed {
   static __device__ __forceinline__ void sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 };
 
-// One band (kStemBand conv1 rows) of one frame by a group of NT threads (tid = 0 .. NT-1); `bar` is an initialised
-// mbarrier (count 1) that this group has used `bar_uses` times before (phase parity of the bulk copy).
+// Where the raw rows of one band live and how they are staged.
+struct BandCopy {
+  const uint8_t* a0;      // 16-byte aligned start of the copy
+  uint32_t bytes;         // multiple of 16
+  int off;                // byte offset of the band's first row inside the staged bytes
+  int r0, in_rows;        // first raw row, number of raw rows
+  bool bulk;              // one bulk copy (TMA engine); else the threads copy with guards (first / last band of an unaligned buffer)
+};
+// TAB: 0 = resize tables and conv1 fragments are read from global memory (__ldg), 1 = from generic pointers into shared
+// memory (the fused kernel stages them once per CTA: its few helper warps cannot hide global-load latency)
+template <int TAB> __device__ __forceinline__ int tab_ld(const int* p) { return TAB ? *p : __ldg(p); }
+
+template <int TAB>
+__device__ __forceinline__ BandCopy band_geometry(int b, int band_idx, const uint8_t* frames, const uint8_t* frames_end, int H, int W,
+                                                  const int* ymin, const int* ylen) {
+  const int y0 = band_idx * kStemBand, y1 = min(y0 + kStemBand, 69);
+  const int n0 = 2 * y0, n1 = 2 * (y1 - 1) + 2;
+  BandCopy c;
+  c.r0 = tab_ld<TAB>(ymin + n0);
+  c.in_rows = tab_ld<TAB>(ymin + n1) + tab_ld<TAB>(ylen + n1) - c.r0;
+  const int rowb = W * 3;
+  // The raw rows of the band are contiguous.  The copy starts at the 16-byte boundary below the band; `off` is carried
+  // into the byte offsets of phase 1.  A band whose rounded range leaves [frames, frames_end) is copied by the threads.
+  const uint8_t* band = frames + ((size_t)b * H + c.r0) * rowb;
+  c.a0 = reinterpret_cast<const uint8_t*>(reinterpret_cast<size_t>(band) & ~(size_t)15);
+  c.off = (int)(band - c.a0);
+  c.bytes = (uint32_t)((c.off + c.in_rows * rowb + 15) & ~15);
+  c.bulk = c.a0 >= frames && c.a0 + c.bytes <= frames_end;
+  return c;
+}
+// one thread: ONE bulk copy (TMA engine) of the band's raw rows, no instructions per byte
+__device__ __forceinline__ void band_issue_bulk(uint8_t* fsm, uint64_t* bar, const BandCopy& c) {
+  tc::mbar_expect_tx(bar, c.bytes);
+  tc::bulk_g2s(fsm, c.a0, c.bytes, bar);
+}
+struct BandNoHook { __device__ __forceinline__ void operator()() const {} };
+
+// One band (kStemBand conv1 rows) of one frame by a group of NT threads (tid = 0 .. NT-1).  `bar` is an initialised
+// mbarrier (count 1) on which the band's bulk copy (already issued when `issued`, else issued here) completes; it has
+// completed `bar_uses` phases before.  `after_h()` is called by every thread once the horizontal pass no longer needs the
+// raw rows (the fused kernel starts the NEXT band's bulk copy there, under phases 2 and 3 of this one).
 // OUT = FS_P8: 16-bit stem tensor (B,2,72,72,8); FS_P16: int8 stem tensor (B,2,72,72,16) quantised with q.inv[c] (the
 // int8 engine); zero_chunk1: also write the all-zero second chunk (not needed when block 1 pairs taps and never reads it).
-// Returns true when the band was staged by the bulk copy (the mbarrier then completed one more phase).
-template <typename T, int CS, int OUT, int NT, class Sync>
-__device__ __forceinline__ bool ingest_stem5_band(uint8_t* __restrict__ fsm, const FastGeom& geo, uint64_t* bar, uint32_t bar_uses,
-                                                  int tid, int b, int band_idx, const uint8_t* __restrict__ frames,
-                                                  const uint8_t* __restrict__ frames_end, int H, int W, int bgr,
-                                                  const int* __restrict__ xmin, const int* __restrict__ kx, const int* __restrict__ ymin,
-                                                  const int* __restrict__ ylen, const int* __restrict__ ky, const StemFrag* __restrict__ sf,
-                                                  const StemQ& q, int zero_chunk1, void* __restrict__ out) {
+template <typename T, int CS, int OUT, int NT, class Sync, int TAB = 0, class Hook = BandNoHook>
+__device__ __forceinline__ void ingest_stem5_band(uint8_t* __restrict__ fsm, const FastGeom& geo, uint64_t* bar, uint32_t bar_uses,
+                                                  const BandCopy& cp, bool issued, int tid, int b, int band_idx,
+                                                  const uint8_t* __restrict__ frames, const uint8_t* __restrict__ frames_end, int W, int bgr,
+                                                  const int* xmin, const int* kx, const int* ymin, const int* ky, const StemFrag* sf,
+                                                  const StemQ& q, int zero_chunk1, void* __restrict__ out, Hook after_h = Hook()) {
   const uint32_t* raww = reinterpret_cast<const uint32_t*>(fsm);           // [in_rows][W*3] packed RGB bytes (bulk copy)
   uint32_t* hbuf4 = reinterpret_cast<uint32_t*>(fsm + geo.off_hbuf);       // [in_rows + 5][140] RGBX words
   uint8_t* vbuf = fsm + geo.off_vbuf;                                      // [2*band + 2][420] RGB bytes
@@ -57,23 +94,15 @@ __device__ __forceinline__ bool ingest_stem5_band(uint8_t* __restrict__ fsm, con
   const int y0 = band_idx * kStemBand;
   const int y1 = min(y0 + kStemBand, 69);
   const int n0 = 2 * y0, n1 = 2 * (y1 - 1) + 2;
-  const int r0 = __ldg(ymin + n0);
-  const int in_rows = __ldg(ymin + n1) + __ldg(ylen + n1) - r0;
+  const int r0 = cp.r0, in_rows = cp.in_rows, off = cp.off;
   const int rowb = W * 3;                                                  // bytes per raw row
 
-  // ---- phase 0: the raw rows of the band are contiguous: ONE bulk copy (TMA engine), no instructions per byte.  The
-  // copy starts at the 16-byte boundary below the band; `off` is carried into the byte offsets of phase 1.  A band whose
-  // rounded range leaves [frames, frames_end) (first / last band of an unaligned buffer) is copied by the threads instead.
-  const uint8_t* band = frames + ((size_t)b * H + r0) * rowb;
-  const uint8_t* a0 = reinterpret_cast<const uint8_t*>(reinterpret_cast<size_t>(band) & ~(size_t)15);
-  const int off = (int)(band - a0);
-  const uint32_t bytes = (uint32_t)((off + in_rows * rowb + 15) & ~15);
-  const bool bulk = a0 >= frames && a0 + bytes <= frames_end;
-  if (bulk) {
-    if (tid == 0) { tc::mbar_expect_tx(bar, bytes); tc::bulk_g2s(fsm, a0, bytes, bar); }
+  // ---- phase 0: stage the raw rows
+  if (cp.bulk) {
+    if (!issued && tid == 0) band_issue_bulk(fsm, bar, cp);
   } else {
-    for (int i = tid; i < (int)(bytes >> 4); i += NT) {
-      const uint8_t* pv = a0 + (size_t)i * 16;
+    for (int i = tid; i < (int)(cp.bytes >> 4); i += NT) {
+      const uint8_t* pv = cp.a0 + (size_t)i * 16;
       if (pv >= frames && pv + 16 <= frames_end) {
         reinterpret_cast<uint4*>(fsm)[i] = __ldg(reinterpret_cast<const uint4*>(pv));
       } else {
@@ -86,44 +115,61 @@ __device__ __forceinline__ bool ingest_stem5_band(uint8_t* __restrict__ fsm, con
   const int ox = tid % kCrop, rg = tid / kCrop;
   uint32_t kc[5];
 #pragma unroll
-  for (int t = 0; t < 5; ++t) kc[t] = (uint32_t)__ldg(kx + ox * 5 + t) << 2;      // 4k: the result byte is the top byte
-  const int bo = off + 3 * __ldg(xmin + ox);
+  for (int t = 0; t < 5; ++t) kc[t] = (uint32_t)tab_ld<TAB>(kx + ox * 5 + t) << 2;      // 4k: the result byte is the top byte
+  const int bo = off + 3 * tab_ld<TAB>(xmin + ox);
   const int sh = (bo & 3) * 8;
-  if (bulk) { while (!tc::mbar_test_wait(bar, bar_uses & 1u)) { } }
+  if (cp.bulk) { while (!tc::mbar_test_wait(bar, bar_uses & 1u)) { } }
   else Sync::sync();
 
-  // ---- phase 1: horizontal pass.  Thread = output column; 5 aligned words cover the 15 bytes of the 5 taps, a funnel
-  // shift aligns them to the pixel, bytes come out with constant PRMT selectors.  acc = 4 * (2^21 + sum k p) < 2^32.
+  // ---- phase 1: horizontal pass.  Thread = output column, TWO rows per iteration (independent chains: the few helper
+  // warps of the fused kernel live on instruction-level parallelism); 5 aligned words cover the 15 bytes of the 5 taps, a
+  // funnel shift aligns them to the pixel, bytes come out with constant PRMT selectors.  acc = 4 * (2^21 + sum k p) < 2^32.
   if (tid < RG * kCrop) {
+    const int rstride = RG * (rowb >> 2);
     const uint32_t* p = raww + rg * (rowb >> 2) + (bo >> 2);
     uint32_t* h = hbuf4 + rg * kCrop + ox;
-    for (int r = rg; r < in_rows; r += RG, p += RG * (rowb >> 2), h += RG * kCrop) {
-      const uint32_t w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3], w4 = p[4];
-      const uint32_t v[4] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh)};
+    auto hrow = [&](const uint32_t (&w)[5]) -> uint32_t {
+      const uint32_t v[4] = {__funnelshift_r(w[0], w[1], sh), __funnelshift_r(w[1], w[2], sh), __funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh)};
       uint32_t a[3] = {1u << 23, 1u << 23, 1u << 23};
 #pragma unroll
       for (int t = 0; t < 5; ++t)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          a[c] += kc[t] * __byte_perm(v[(3 * t + c) >> 2], 0u, 0x4440u + (uint32_t)((3 * t + c) & 3));
-        }
-      *h = __byte_perm(__byte_perm(a[0], a[1], 0x0073), a[2], 0x7710);    // R | G << 8 | B << 16
+        for (int c = 0; c < 3; ++c) a[c] += kc[t] * __byte_perm(v[(3 * t + c) >> 2], 0u, 0x4440u + (uint32_t)((3 * t + c) & 3));
+      return __byte_perm(__byte_perm(a[0], a[1], 0x0073), a[2], 0x7710);    // R | G << 8 | B << 16
+    };
+    int r = rg;
+    for (; r + RG < in_rows; r += 2 * RG, p += 2 * rstride, h += 2 * RG * kCrop) {
+      uint32_t wa[5], wb[5];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) { wa[i] = p[i]; wb[i] = p[rstride + i]; }
+      const uint32_t ra = hrow(wa), rb = hrow(wb);
+      h[0] = ra; h[RG * kCrop] = rb;
+    }
+    if (r < in_rows) {
+      uint32_t wa[5];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) wa[i] = p[i];
+      h[0] = hrow(wa);
     }
   }
   Sync::sync();
+  after_h();
 
   // ---- phase 2: vertical pass, four pixels per task -> packed RGB bytes
   const int nrows = n1 - n0 + 1;
   if (tid < (NT / 35) * 35)
   for (int rn = tid / 35, g = tid - (tid / 35) * 35; rn < nrows; rn += NT / 35) {
     const int oy = n0 + rn;
-    const uint4* hp = reinterpret_cast<const uint4*>(hbuf4 + (__ldg(ymin + oy) - r0) * kCrop) + g;
+    const uint4* hp = reinterpret_cast<const uint4*>(hbuf4 + (tab_ld<TAB>(ymin + oy) - r0) * kCrop) + g;
+    uint32_t cy[5];
+#pragma unroll
+    for (int t = 0; t < 5; ++t) cy[t] = (uint32_t)tab_ld<TAB>(ky + oy * 5 + t) << 2;
     uint32_t acc[12];
 #pragma unroll
     for (int j = 0; j < 12; ++j) acc[j] = 1u << 23;
 #pragma unroll
     for (int t = 0; t < 5; ++t) {
-      const uint32_t c = (uint32_t)__ldg(ky + oy * 5 + t) << 2;
+      const uint32_t c = cy[t];
       const uint4 qd = hp[t * (kCrop / 4)];
       const uint32_t px[4] = {qd.x, qd.y, qd.z, qd.w};
 #pragma unroll
@@ -156,13 +202,16 @@ __device__ __forceinline__ bool ingest_stem5_band(uint8_t* __restrict__ fsm, con
     uint32_t bfrag[2][2][2];
     {
       const uint4* fp = reinterpret_cast<const uint4*>(sf->frag[bgr ? 1 : 0][lane]);
-      const uint4 f0 = __ldg(fp), f1 = __ldg(fp + 1);
+      const uint4 f0 = TAB ? fp[0] : __ldg(fp), f1 = TAB ? fp[1] : __ldg(fp + 1);
       bfrag[0][0][0] = f0.x; bfrag[0][0][1] = f0.y; bfrag[0][1][0] = f0.z; bfrag[0][1][1] = f0.w;
       bfrag[1][0][0] = f1.x; bfrag[1][0][1] = f1.y; bfrag[1][1][0] = f1.z; bfrag[1][1][1] = f1.w;
     }
     float bia[NTL][2];
 #pragma unroll
-    for (int j = 0; j < NTL; ++j) { bia[j][0] = __ldg(sf->bias + 8 * j + 2 * t); bia[j][1] = __ldg(sf->bias + 8 * j + 2 * t + 1); }
+    for (int j = 0; j < NTL; ++j) {
+      bia[j][0] = TAB ? sf->bias[8 * j + 2 * t] : __ldg(sf->bias + 8 * j + 2 * t);
+      bia[j][1] = TAB ? sf->bias[8 * j + 2 * t + 1] : __ldg(sf->bias + 8 * j + 2 * t + 1);
+    }
     const __half2 k1024 = __floats2half2_rn(1024.f, 1024.f);
     const int brow = y1 - y0;
     uint4* img = reinterpret_cast<uint4*>(out) + (size_t)b * 2 * 72 * 72;
@@ -226,7 +275,6 @@ __device__ __forceinline__ bool ingest_stem5_band(uint8_t* __restrict__ fsm, con
     if (y1 == 69)
       for (int i = tid; i < nch * 72; i += NT) img[(i / 72) * 72 * 72 + 71 * 72 + (i % 72)] = make_uint4(0, 0, 0, 0);
   }
-  return bulk;
 }
 
 template <typename T, int CS, int OUT = FS_P8>
@@ -243,8 +291,9 @@ ingest_stem5_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restric
   pdl_wait();                 // frames may come from the previous kernel of the stream; the stem tensor is read by block 1
   pdl_launch_dependents();
   ERNET_CHAIN_WAITED(0);
-  ingest_stem5_band<T, CS, OUT, kFastThreads, BandSyncCta>(fsm, geo, bar, 0u, threadIdx.x, blockIdx.y, blockIdx.x, frames, frames_end, H, W, bgr,
-                                                           xmin, kx, ymin, ylen, ky, sf, q, zero_chunk1, out);
+  const BandCopy cp = band_geometry<0>(blockIdx.y, blockIdx.x, frames, frames_end, H, W, ymin, ylen);
+  ingest_stem5_band<T, CS, OUT, kFastThreads, BandSyncCta>(fsm, geo, bar, 0u, cp, false, threadIdx.x, blockIdx.y, blockIdx.x, frames, frames_end, W, bgr,
+                                                           xmin, kx, ymin, ky, sf, q, zero_chunk1, out);
   ERNET_CHAIN_EXIT(0);
 }
 

@@ -26,7 +26,7 @@
 namespace ernet {
 namespace tc {
 
-constexpr int kHelperWarps = 10;                       // 320 threads: 2 row groups x 140 columns in the horizontal pass
+constexpr int kHelperWarps = 15;                       // 480 threads: 3 row groups x 140 columns in the horizontal pass; 32 warps x 64 registers
 constexpr int kHelperThreads = 32 * kHelperWarps;
 constexpr int kStemBands = (69 + kStemBand - 1) / kStemBand;
 
@@ -36,12 +36,19 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   return v;
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+constexpr int kTabInts = kCrop * (1 + 5 + 1 + 1 + 5);     // xmin, kx[5], ymin, ylen, ky[5] of the 140 output rows / columns
 
 template <class Cfg>
 struct FCfg {
   static constexpr int THREADS = kHelperThreads + Cfg::THREADS;
   static constexpr int OFF_HBAR = Cfg::OFF_BAR + 256;                              // helpers' bulk-copy mbarrier
-  static constexpr int OFF_INGEST = (OFF_HBAR + 16 + 127) / 128 * 128;             // FastGeom region of the helpers
+  static constexpr int OFF_TAB = OFF_HBAR + 16;                                    // resize tables (staged once: the helper
+  static constexpr int OFF_SF = OFF_TAB + kTabInts * 4;                            // warps cannot hide global-load latency)
+  static constexpr int OFF_INGEST = (OFF_SF + (int)sizeof(StemFrag) + 127) / 128 * 128;   // FastGeom region of the helpers
+  static_assert(OFF_SF % 16 == 0, "StemFrag is read with 16-byte loads");
   static_assert(Cfg::WRES && Cfg::TAPS == 25 && Cfg::POOL && Cfg::N == 64, "block 1 of the Squeeze models");
 };
 
@@ -100,18 +107,46 @@ ingest_block1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t
 
   if (warp < 0) {
     // ------------------------------------------------------------------ helper warps: transform + conv1, band by band
+    // constants first (not ordered after the previous kernel): resize tables and conv1 fragments -> shared memory
+    int* s_tab = reinterpret_cast<int*>(smem + F::OFF_TAB);
+    StemFrag* s_sf = reinterpret_cast<StemFrag*>(smem + F::OFF_SF);
+    int* s_xmin = s_tab; int* s_kx = s_tab + kCrop; int* s_ymin = s_kx + 5 * kCrop; int* s_ylen = s_ymin + kCrop; int* s_ky = s_ylen + kCrop;
+    for (int i = threadIdx.x; i < kCrop; i += kHelperThreads) { s_xmin[i] = __ldg(xmin + i); s_ymin[i] = __ldg(ymin + i); s_ylen[i] = __ldg(ylen + i); }
+    for (int i = threadIdx.x; i < 5 * kCrop; i += kHelperThreads) { s_kx[i] = __ldg(kx + i); s_ky[i] = __ldg(ky + i); }
+    for (int i = threadIdx.x; i < (int)(sizeof(StemFrag) / 16); i += kHelperThreads)
+      reinterpret_cast<uint4*>(s_sf)[i] = __ldg(reinterpret_cast<const uint4*>(sf) + i);
+    BandSyncNamed<kHelperThreads>::sync();
     pdl_wait();                                          // frames / the stem buffer belong to earlier work of the stream
     ERNET_CHAIN_WAITED(1);
     const int nitems = batch * kStemBands;
-    uint32_t uses = 0;
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    uint8_t* fsm = smem + F::OFF_INGEST;
+    uint32_t uses = 0;                                   // completed phases of hbar
+    int item = blockIdx.x;
+    BandCopy cur{};
+    bool issued = false;
+    if (item < nitems) {
+      cur = band_geometry<1>(item / kStemBands, item % kStemBands, frames, frames_end, H, W, s_ymin, s_ylen);
+      issued = cur.bulk;
+      if (cur.bulk && threadIdx.x == 0) band_issue_bulk(fsm, hbar, cur);
+    }
+    for (; item < nitems; item += gridDim.x) {
       const int b = item / kStemBands, band = item - b * kStemBands;
-      uses += (uint32_t)ingest_stem5_band<T, CS, FSOUT, kHelperThreads, BandSyncNamed<kHelperThreads>>(
-          smem + F::OFF_INGEST, geo, hbar, uses, threadIdx.x, b, band, frames, frames_end, H, W, bgr, xmin, kx, ymin, ylen, ky, sf, sq,
-          zero_chunk1, stem);
-      __threadfence();                                   // this thread's stores of the band: visible device-wide
-      BandSyncNamed<kHelperThreads>::sync();             // .. for every helper thread (and the band's buffers are free again)
-      if (threadIdx.x == 0) atomicAdd(ready + b, 1u);
+      const int nitem = item + (int)gridDim.x;
+      BandCopy nxt{};
+      const bool has_next = nitem < nitems;
+      if (has_next) nxt = band_geometry<1>(nitem / kStemBands, nitem % kStemBands, frames, frames_end, H, W, s_ymin, s_ylen);
+      // the raw rows are dead once the horizontal pass is done: the NEXT band's bulk copy runs under phases 2 and 3
+      auto prefetch = [&]() {
+        if (has_next && nxt.bulk && threadIdx.x == 0) { fence_proxy_async(); band_issue_bulk(fsm, hbar, nxt); }
+      };
+      ingest_stem5_band<T, CS, FSOUT, kHelperThreads, BandSyncNamed<kHelperThreads>, 1>(
+          fsm, geo, hbar, uses, cur, issued, threadIdx.x, b, band, frames, frames_end, W, bgr, s_xmin, s_kx, s_ymin, s_ky, s_sf, sq,
+          zero_chunk1, stem, prefetch);
+      if (cur.bulk) ++uses;
+      BandSyncNamed<kHelperThreads>::sync();             // every helper thread's stores of the band are issued (and its buffers are free)
+      if (threadIdx.x == 0) red_release_gpu_add(ready + b, 1u);    // one release for the whole group (cumulativity over the barrier)
+      cur = nxt;
+      issued = nxt.bulk;
     }
   } else if (warp == 0) {
     // ------------------------------------------------------------------ input producer

@@ -89,6 +89,13 @@ class _EngineRuntime:
         _lib.check(lib.ernet_set_fast_ingest(h, 1 if on else 0))
         return self
 
+    def set_fuse_ingest(self, on=True):
+        """Frames path: run the eval transform + conv1 inside block 1's persistent kernel (helper warps under the tcgen05
+        MMAs, csrc/tc_fblock.cuh) instead of as a kernel of their own.  Bit-identical results; off by default."""
+        lib, h, _ = self._ensure_engine()
+        _lib.check(lib.ernet_set_fuse_ingest(h, 1 if on else 0))
+        return self
+
     def set_debug_taps(self, on=True):
         """Also write the intermediates that fused kernels keep on chip (needed for tap('acff4'))."""
         lib, h, _ = self._ensure_engine()

@@ -137,3 +137,31 @@ def test_load_model_reads_real_checkpoints(arch, wrapped, tmp_path):
     with pytest.raises(RuntimeError):                   # a checkpoint of another architecture must not load silently
         other = "squeeze-redconv" if arch != "squeeze-redconv" else "squeeze-ernet"
         rtdm_b200.load_model(other, str(path), "cpu")
+
+
+def test_bench_configuration_rules():
+    """bench.py: N=1 runs BASELINE configs[1] (256 frames), N>1 runs configs[4] (8192 frames split N ways, strong
+    scaling) unless --batch pins the per-GPU batch; both arms describe the configuration with the same `config` object."""
+    import argparse
+    import bench
+    a = argparse.Namespace(batch=None, arch="squeeze-ernet", precision="bf16")
+    assert bench.resolve_batch(a, 1) == (256, None)
+    assert bench.resolve_batch(a, 2) == (4096, 8192) and bench.resolve_batch(a, 8) == (1024, 8192)
+    a.batch = 512
+    assert bench.resolve_batch(a, 4) == (512, None)
+    c1 = bench.common_config("squeeze-ernet", "bf16", 1024, 8, 8192)
+    assert "configs[4]" in c1["workload"] and c1["global_batch"] == 8192
+    assert "configs[1]" in bench.common_config("squeeze-ernet", "bf16", 256, 1, None)["workload"]
+    ops = bench.issued_flops("squeeze-ernet", "int8")
+    assert ops["tc_block1"] == 45 * 13 * 2 * 128 * 64 * 32 and ops["tc_block2"] == 8 * 25 * 2 * 2 * 128 * 96 * 32
+    assert bench.issued_flops("squeeze-ernet", "bf16")["tc_block1"] == 45 * 25 * 2 * 128 * 64 * 16
+
+
+def test_build_detects_changed_sources(tmp_path):
+    """build(): the library carries the sha256 of the sources it was compiled from; a changed source forces a rebuild
+    (file times are not trusted)."""
+    import importlib
+    b = importlib.import_module("real-time-disaster-management_b200.build")
+    assert b.embedded_hash() == b.source_hash() and not b.needs_build()
+    assert _lib.load().ernet_source_hash().decode() == b.source_hash()
+    assert b.embedded_hash(str(tmp_path / "missing.so")) is None

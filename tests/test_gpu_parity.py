@@ -846,3 +846,35 @@ def test_confusion_update_nan_matches_torch_argmax(dev):
     _lib.check(_lib.load().ernet_confusion_update(sc.data_ptr(), None, 5, 5, None, pred.data_ptr(), None,
                                                   torch.cuda.current_stream().cuda_stream))
     assert torch.equal(pred, sc.argmax(1))
+
+
+@pytest.mark.parametrize("arch,prec", [("squeeze-ernet", "bf16"), ("squeeze-ernet", "fp16"), ("squeeze-redconv", "fp16"), ("squeeze-redconv", "bf16"),
+                                       ("squeeze-ernet", "int8"), ("squeeze-redconv", "int8")])
+def test_fused_transform_block1_kernel_is_bit_identical(arch, prec, dev):
+    """set_fuse_ingest(True): transform + conv1 run on helper warps inside block 1's persistent kernel (tc_fblock.cuh),
+    handing images over through per-image band counters.  Same arithmetic in the same order: logits must be bit-identical
+    to the two-kernel path, for batches that leave CTAs without bands (B = 1), odd batches, a batch larger than the grid,
+    unaligned buffers (guarded first / last band), BGR frames, repeated calls (the counters re-arm) and graph replay."""
+    sd = fixtures.get_state_dict(arch, "shipped")
+    m = rtdm_b200.from_state_dict(arch, sd, dev, prec)
+    mf = rtdm_b200.from_state_dict(arch, sd, dev, prec).set_fuse_ingest(True)
+    if prec == "int8":
+        mf.set_act_scales(m.calibrate())                  # same calibration for both engines
+    for B in (1, 3, 37, 300):
+        frames = np.concatenate([fixtures.noise_frames(B - B // 2, seed=500 + B), fixtures.smooth_frames(B // 2, seed=600 + B)], 0) if B > 1 \
+            else fixtures.noise_frames(1, seed=501)
+        ft = torch.from_numpy(frames).to(dev)
+        want = m.forward_frames(ft, return_logits=True)[1]
+        got = mf.forward_frames(ft, return_logits=True)[1]
+        assert torch.equal(got, want), (arch, prec, B)
+        assert torch.equal(mf.forward_frames(ft, return_logits=True)[1], want)            # counters re-armed
+        if B == 37:
+            big = torch.zeros(frames.size + 5, dtype=torch.uint8, device=dev)
+            big[5:] = ft.flatten()
+            assert torch.equal(mf.forward_frames(big[5:].view(ft.shape), return_logits=True)[1], want)
+            bgr = torch.from_numpy(frames[..., ::-1].copy()).to(dev)
+            assert torch.equal(mf.forward_frames(bgr, bgr=True, return_logits=True)[1], want)
+            run = mf.graph_frames(ft.clone(), return_logits=True)
+            assert torch.equal(run()[1], want) and torch.equal(run()[1], want)
+    assert mf.launches_per_forward(256) == m.launches_per_forward(256) - 1
+    assert _lib.load().ernet_check_watchdog() == 0

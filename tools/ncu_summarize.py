@@ -1,10 +1,17 @@
-"""Turn an ncu report (--set full) of tools/run_forward.py into the committed summaries under profiles/."""
+"""Turn an ncu report (--set full) of tools/run_forward.py into the committed summaries under profiles/.
+
+    python tools/ncu_summarize.py <report.ncu-rep> <tag> <batch> [arch] [precision]
+
+Writes profiles/<tag>_ncu_full.txt and merges the per-launch DRAM bytes / tensor-pipe activity of the configuration
+into profiles/ncu_dram_bytes_per_launch.json under configs["<arch>/<precision>/<batch>"] (bench.py's roofline.traffic)."""
 import csv
 import json
 import subprocess
 import sys
 
 rep, tag, batch = sys.argv[1], sys.argv[2], int(sys.argv[3])
+arch = sys.argv[4] if len(sys.argv) > 4 else "squeeze-ernet"
+precision = sys.argv[5] if len(sys.argv) > 5 else "bf16"
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
@@ -13,7 +20,8 @@ keys = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "sm__cycles_active.a
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_shared_mem"]
-stage_of = [("ingest_stem", "ingest"), ("PCfg<2, 64", "tc_block1"), ("CCfg<2, 64", "tc_block1"), ("CCfg<8, 96", "tc_block2"), ("CCfg<12, 128", "tc_block3"),
+stage_of = [("ingest_block1", "tc_block1"), ("ingest_stem", "ingest"), ("PCfg<12, 64", "red2"), ("CCfg<6, 128", "tc_block3"), ("CCfg<4, 96", "tc_block2"),
+            ("CCfg<4, 128", "tc_block3"), ("pointwise_kernel", "red3"), ("acff_dw", "dw"), ("stem_kernel", "stem"), ("head_kernel", "head"), ("PCfg<2, 64", "tc_block1"), ("CCfg<2, 64", "tc_block1"), ("CCfg<8, 96", "tc_block2"), ("CCfg<12, 128", "tc_block3"),
             ("PCfg<8, 96", "tc_block2"), ("PCfg<12, 128", "tc_block3"), ("BlockCfg<2, 64", "tc_block1"), ("BlockCfg<8, 96", "tc_block2"),
             ("BlockCfg<12, 128", "tc_block3"), ("acff4_head", "tc_block4"), ("BlockCfg<4, 96", "tc_block2"), ("BlockCfg<6, 128", "tc_block3")]
 lines = [f"# ncu --set full --clock-control none, tools/run_forward.py, batch {batch} ({tag})\n",
@@ -38,5 +46,11 @@ for r in rows[2:]:
     tot += float(r[hdr.index("gpu__time_duration.sum")])
 lines.append(f"\n# sum of kernel durations in this capture: {tot:.1f} us\n")
 open(f"profiles/{tag}_ncu_full.txt", "w").writelines(lines)
-json.dump({"batch": batch, "source": f"profiles/{tag}_ncu_full.txt", "stages": dram, "tensor_pipe_active_pct": tpipe}, open("profiles/ncu_dram_bytes_per_launch.json", "w"), indent=1)
+import os
+path = "profiles/ncu_dram_bytes_per_launch.json"
+doc = json.load(open(path)) if os.path.exists(path) else {}
+if "configs" not in doc:
+    doc = {"configs": {}}
+doc["configs"][f"{arch}/{precision}/{batch}"] = {"batch": batch, "source": f"profiles/{tag}_ncu_full.txt", "stages": dram, "tensor_pipe_active_pct": tpipe}
+json.dump(doc, open(path, "w"), indent=1)
 print("".join(lines[-40:]))
