@@ -261,7 +261,8 @@ def test_evaluate_model_matches_oracle(arch, tmp_path, dev):
 # ------------------------------------------------------------------------------------ GPU: engine build / export
 @pytest.mark.gpu
 @pytest.mark.parametrize("arch,quant", [("squeeze-ernet", "fp32"), ("squeeze-ernet", "fp16"), ("squeeze-ernet", "int8"),
-                                        ("squeeze-redconv", "fp16"), ("squeeze-redconv", "bf16"), ("ernet", "fp16")])
+                                        ("squeeze-redconv", "fp16"), ("squeeze-redconv", "bf16"), ("squeeze-redconv", "int8"),
+                                        ("ernet", "fp16")])
 def test_build_trt_model_saves_and_reloads(arch, quant, tmp_path, dev):
     sd = fixtures.get_state_dict(arch, "shipped")
     src = rtdm_b200.from_state_dict(arch, sd, dev, "fp32")
@@ -347,3 +348,40 @@ def test_run_inference_stream_matches_batch_path(dev):
         assert conf == pytest.approx(float(z[want[i].argmax()] / z.sum()) * 100, rel=1e-5)
     with pytest.raises(ValueError):
         clf(np.zeros((100, 100, 3), np.uint8))
+
+
+@pytest.mark.gpu
+def test_device_jpeg_decode_loader_matches_host_loader(tmp_path, dev):
+    """frame_batches_device: files read on host threads, JPEGs decoded by one batched nvJPEG call per chunk, PNGs (not
+    JPEG) through the host decoder.  Every sample exactly once, frames within a few grey levels of PIL's decode, and the
+    evaluation result (confusion matrix) equal to the host-decode loop's up to near-tie predictions."""
+    from PIL import Image
+    rs = np.random.RandomState(5)
+    frames = fixtures.smooth_frames(24, 240, 240, seed=9)
+    samples = []
+    for k in range(60):
+        ext = "png" if k % 10 == 3 else "jpg"
+        path = str(tmp_path / f"f{k:03d}.{ext}")
+        img = frames[k % 24] if k % 7 else fixtures.smooth_frames(1, 180, 320, seed=k)[0]      # a second frame size
+        Image.fromarray(img).save(path, quality=92) if ext == "jpg" else Image.fromarray(img).save(path)
+        samples.append((path, int(rs.randint(0, 5))))
+    host = {}
+    for fb, tb in EV.frame_batches(samples, 16, 0, pin_memory=False):
+        host.setdefault(tuple(fb.shape[1:3]), []).append((fb, tb))
+    n = 0
+    seen = {}
+    for fb, tb in EV.frame_batches_device(samples, 16, dev, 2):
+        assert fb.is_cuda and fb.dtype == torch.uint8 and fb.dim() == 4 and fb.shape[3] == 3 and fb.is_contiguous()
+        n += fb.shape[0]
+        seen.setdefault(tuple(fb.shape[1:3]), []).append((fb.cpu(), tb))
+    assert n == len(samples) and set(seen) == set(host)
+    for hw in host:
+        a = torch.cat([f for f, _ in host[hw]]).to(torch.int16)
+        b = torch.cat([f for f, _ in seen[hw]]).to(torch.int16)
+        assert a.shape == b.shape
+        assert torch.equal(torch.cat([t for _, t in host[hw]]), torch.cat([t for _, t in seen[hw]]))
+        assert (a - b).abs().max() <= 6 and (a - b).abs().float().mean() < 0.5       # nvJPEG vs libjpeg-turbo IDCT / upsampling
+    m = rtdm_b200.from_state_dict("squeeze-ernet", fixtures.get_state_dict("squeeze-ernet", "w3"), dev, "bf16")
+    cm_h = EV.evaluate_model(m, EV.frame_batches(samples, 16, 2), dev)["confusion_matrix"]
+    cm_d = EV.evaluate_model(m, EV.frame_batches_device(samples, 16, dev, 2), dev)["confusion_matrix"]
+    assert int(np.abs(np.asarray(cm_h) - np.asarray(cm_d)).sum()) <= 2               # at most one prediction moved

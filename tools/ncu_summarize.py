@@ -20,10 +20,26 @@ keys = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "sm__cycles_active.a
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_shared_mem"]
-stage_of = [("ingest_block1", "tc_block1"), ("ingest_stem", "ingest"), ("PCfg<12, 64", "red2"), ("CCfg<6, 128", "tc_block3"), ("CCfg<4, 96", "tc_block2"),
-            ("CCfg<4, 128", "tc_block3"), ("pointwise_kernel", "red3"), ("acff_dw", "dw"), ("stem_kernel", "stem"), ("head_kernel", "head"), ("PCfg<2, 64", "tc_block1"), ("CCfg<2, 64", "tc_block1"), ("CCfg<8, 96", "tc_block2"), ("CCfg<12, 128", "tc_block3"),
-            ("PCfg<8, 96", "tc_block2"), ("PCfg<12, 128", "tc_block3"), ("BlockCfg<2, 64", "tc_block1"), ("BlockCfg<8, 96", "tc_block2"),
-            ("BlockCfg<12, 128", "tc_block3"), ("acff4_head", "tc_block4"), ("BlockCfg<4, 96", "tc_block2"), ("BlockCfg<6, 128", "tc_block3")]
+stage_of = [("ingest_block1", "tc_block1"), ("ingest_stem", "ingest"), ("ingest_kernel", "ingest"), ("PCfg<12, 64", "red2"),
+            ("PCfg<2, 64", "tc_block1"), ("CCfg<2, 64", "tc_block1"), ("BlockCfg<2, 64", "tc_block1"),
+            ("CCfg<8, 96", "tc_block2"), ("CCfg<4, 96", "tc_block2"), ("PCfg<8, 96", "tc_block2"), ("BlockCfg<8, 96", "tc_block2"), ("BlockCfg<4, 96", "tc_block2"),
+            ("CCfg<12, 128", "tc_block3"), ("CCfg<6, 128", "tc_block3"), ("CCfg<4, 128", "tc_block3"), ("PCfg<12, 128", "tc_block3"),
+            ("BlockCfg<12, 128", "tc_block3"), ("BlockCfg<6, 128", "tc_block3"), ("acff4_head", "tc_block4"),
+            ("acff_dw", "dw#"), ("pointwise_kernel", "pw#"), ("stem_kernel", "stem"), ("head_kernel", "head")]
+seen = {}
+
+
+def stage_name(name, red):
+    st = next((v for p, v in stage_of if p in name), None)
+    if st and st.endswith("#"):                       # repeated layer-wise kernels: number them in launch order
+        k = st[:-1]
+        seen[k] = seen.get(k, 0) + 1
+        if k == "pw" and red:                         # Squeeze_RedConv: pw1, pw2, red2, pw3, red3, pw4
+            return ["pw1", "pw2", "red2", "pw3", "red3", "pw4"][min(seen[k], 6) - 1]
+        return f"{k}{seen[k]}"
+    return st
+
+
 lines = [f"# ncu --set full --clock-control none, tools/run_forward.py, batch {batch} ({tag})\n",
          "# per-launch values from cold-cache, serialised replays: compare shares, not absolutes\n"]
 dram = {}
@@ -35,7 +51,7 @@ for r in rows[2:]:
     for k in keys:
         if k in hdr:
             lines.append(f"{k} = {r[hdr.index(k)]} {units[hdr.index(k)]}\n")
-    st = next((v for p, v in stage_of if p in name), None)
+    st = stage_name(name, arch == "squeeze-redconv")
 
     def to_bytes(k):
         v, u = float(r[hdr.index(k)]), units[hdr.index(k)].lower()

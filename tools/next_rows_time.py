@@ -104,6 +104,23 @@ for prec in ("bf16", "fp32"):
     dt = time.perf_counter() - t0
     print(json.dumps({"row": "8f-2 evaluation loop", "precision": prec, "images": N, "decode_threads": workers, "wall_img_s": round(N / dt, 1),
                       "model_img_s_reference_definition": round(met["images_per_second"], 1), "accuracy": met["accuracy"]}))
+# the same loop with the JPEGs decoded on the GPU (one batched nvJPEG call per chunk; host threads only read files)
+N2 = 8192
+rows2 = [rows[k % N] for k in range(N2)]
+for prec in ("bf16",):
+    m = rtdm_b200.from_state_dict("squeeze-ernet", sd, dev, prec)
+    EV.evaluate_model(m, EV.frame_batches_device(rows2[:512], 256, dev, 4), dev)
+    for bs in (256, 1024):
+        t0 = time.perf_counter()
+        met = EV.evaluate_model(m, EV.frame_batches_device(rows2, bs, dev, 4), dev)
+        dt = time.perf_counter() - t0
+        print(json.dumps({"row": "8f-2 evaluation loop, device JPEG decode", "precision": prec, "images": N2, "chunk": bs, "read_threads": 4,
+                          "wall_img_s": round(N2 / dt, 1), "model_img_s_reference_definition": round(met["images_per_second"], 1),
+                          "accuracy": met["accuracy"]}))
+    # agreement of the two decoders' predictions on the same files
+    host = EV.evaluate_model(m, EV.frame_batches(rows, 128, workers), dev)["confusion_matrix"]
+    devc = EV.evaluate_model(m, EV.frame_batches_device(rows, 256, dev, 4), dev)["confusion_matrix"]
+    print(json.dumps({"row": "8f-2 host vs device decode", "confusion_matrix_abs_diff": int(np.abs(np.asarray(host) - np.asarray(devc)).sum()), "images": N}))
 # decode alone (the floor of our loop) and the reference-style loop: PIL transform + CPU fp32 forward per batch
 t0 = time.perf_counter()
 n = sum(f.shape[0] for f, _ in EV.frame_batches(rows, 128, workers, pin_memory=False))
