@@ -462,7 +462,8 @@ def gpu_main(args, rank, local_rank, world):
                      "stage_ms_per_step": {k: round(v[0] / prof_steps, 5) for k, v in prof.items()},
                      "per_kernel": per_kernel})
         launches = model.launches_per_forward(BATCH, True) * args.steps
-        cpu_fps, _, cpu_info = cpu_reference_run(6, 1, 32, ARCH)
+        # the CPU baseline is an N=1 figure (rank 0 owns all host cores there; under torchrun the ranks share them)
+        cpu_info = cpu_reference_run(6, 1, 32, ARCH)[2] if world == 1 else None
         line = {
             "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,

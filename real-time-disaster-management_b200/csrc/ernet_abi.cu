@@ -142,7 +142,7 @@ static Plan make_plan(const ernet_handle* h, int n) {
   }
   p.ingest = take(N * 140 * 140 * 3);
   if (p.tc && h->precision == ERNET_PREC_INT8 && h->red()) {   // int8 Squeeze_RedConv (sizes in 2-byte units)
-    p.stem = take(N * 2 * 72 * 72 * 8);        // P16 (B,2,72,72,16) int8: 8 real channels in chunk 0
+    p.stem = take(N * 2 * 72 * 72 * 8);        // P8 fp16 (B,2,72,72,8): 8 real channels in chunk 0 (ACFF1 runs in fp16)
     p.p1 = take(N * 4 * 36 * 36 * 8);          // P16 (B,4,36,36,16)
     p.a2 = take(N * 12 * 33 * 33 * 8);         // P8 fp16 (B,12,33,33,8): un-pooled acff2 output (conv_red2 input)
     p.p2 = take(N * 4 * 18 * 18 * 8 + 4 * 18 * 18 * 8);     // P16 (B,4,18,18,16): 48 real + 16 zero channels, + slack
@@ -434,12 +434,12 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
       ERNET_STAGE(ERNET_STAGE_RED3, launch_pointwise<T>(buf(p.p3), n, 6, 6, 128, 64, h->f(ERNET_T_RED3_W), h->f(ERNET_T_RED3_B), nullptr, nullptr, 0, 0, buf(p.r3), s));
       return run_tail<T>(h, buf(p.r3), buf(p.cat4), buf(p.a4), n, probs, logits, s);
     } else {
-      // ---- int8 Squeeze_RedConv (persistent kernels only): conv1+conv_red1 -> int8 P16 (8 real channels), ACFF1 int8 with
-      // tap pairing, ACFF2 int8 -> fp16 un-pooled, conv_red2 as a 16-bit 1-tap instance writing the int8 pool2 tensor,
-      // ACFF3 int8 -> fp16 NHWC, conv_red3 + ACFF4 + head in fp16 (first conv and head in >= fp16)
+      // ---- int8 Squeeze_RedConv (persistent kernels only): conv1+conv_red1 -> fp16 P8 (8 real channels), ACFF1 in fp16 with
+      // tap pairing (13 MMAs per tile: what int8 would issue too) writing the int8 pool1 tensor, ACFF2 int8 -> fp16
+      // un-pooled, conv_red2 as a 16-bit 1-tap instance writing the int8 pool2 tensor, ACFF3 int8 -> fp16 NHWC, conv_red3 +
+      // ACFF4 + head in fp16 (first conv and head in >= fp16)
       bool fused1 = false;
       StemQ q{};
-      for (int i = 0; i < 16; ++i) q.inv[i] = s_inv.v[i];
       const bool paired = h->d_w1_pair && h->pair_taps;
       auto wimgq = [&](int k) { return h->t[ERNET_T_TC_BASE + 4 * k + ERNET_T_TC_WIMG].dev; };
       if (frames && tab->fs_max_in_rows > 0 && !h->debug_taps) {
@@ -447,34 +447,34 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
         if (h->fast_ingest && h->d_stem_frag && fast5_geometry(*tab, frames, fg)) {
           if (h->fuse_ingest && paired && tc::fused_fits<tc::PBlock1P>(fg) && n <= kSyncImages) {
             fused1 = h->last_fused = true;
-            ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_ingest_block1<tc::PBlock1P, tc::KIND_I8, tc::OUT_P16, T, 8, FS_P16>(*tab, fg, frames, n, order == ERNET_BGR, h->d_stem_frag, q, false,
+            ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_ingest_block1<tc::PBlock1P, tc::KIND_F16, tc::OUT_P16, T, 8, FS_P8>(*tab, fg, frames, n, order == ERNET_BGR, h->d_stem_frag, q, false,
                         u16(p.stem), h->d_w1_pair, h->epi1, u16(p.p1), h->num_sms, h->d_sync, h->d_sync + kSyncImages, s)));
           } else {
-            ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem5<T, 8, FS_P16>(*tab, fg, frames, n, order == ERNET_BGR, h->d_stem_frag, q, !paired, u16(p.stem), s)));
+            ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem5<T, 8>(*tab, fg, frames, n, order == ERNET_BGR, h->d_stem_frag, q, !paired, u16(p.stem), s)));
           }
         } else {
-          ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem<T, 8, FS_P16>(*tab, frames, n, order == ERNET_BGR, sw, sb_, q, u16(p.stem), s)));
+          ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem<T, 8, FS_P8>(*tab, frames, n, order == ERNET_BGR, sw, sb_, q, u16(p.stem), s)));
         }
       } else if (frames) {
         ERNET_STAGE(ERNET_STAGE_INGEST, launch_ingest<T>(*tab, frames, n, order == ERNET_BGR, buf(p.ingest), 140LL * 140 * 3, 1, 140 * 3, 3, s));
         StageTimer _t(h, ERNET_STAGE_STEM, s);
-        tc::stem_p8_kernel<T, 8, tc::KIND_I8><<<grid, 128, 0, s>>>(buf(p.ingest), 140LL * 140 * 3, 1, 140 * 3, 3, sw, sb_, u16(p.stem), total, s_inv);
+        tc::stem_p8_kernel<T, 8, tc::KIND_F16><<<grid, 128, 0, s>>>(buf(p.ingest), 140LL * 140 * 3, 1, 140 * 3, 3, sw, sb_, u16(p.stem), total, s_inv);
         ERNET_LAUNCH_CHECK("stem_p8_kernel");
       } else {
         long long sb = 3LL * 140 * 140, sc, sy, sx;
         if (x_layout == ERNET_NCHW) { sc = 140 * 140; sy = 140; sx = 1; }
         else                        { sc = 1; sy = 140 * 3; sx = 3; }
         StageTimer _t(h, ERNET_STAGE_STEM, s);
-        if (x_dtype == ERNET_F32) tc::stem_p8_kernel<float, 8, tc::KIND_I8><<<grid, 128, 0, s>>>(static_cast<const float*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total, s_inv);
-        else if (x_dtype == ERNET_F16) tc::stem_p8_kernel<__half, 8, tc::KIND_I8><<<grid, 128, 0, s>>>(static_cast<const __half*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total, s_inv);
-        else tc::stem_p8_kernel<__nv_bfloat16, 8, tc::KIND_I8><<<grid, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total, s_inv);
+        if (x_dtype == ERNET_F32) tc::stem_p8_kernel<float, 8, tc::KIND_F16><<<grid, 128, 0, s>>>(static_cast<const float*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total, s_inv);
+        else if (x_dtype == ERNET_F16) tc::stem_p8_kernel<__half, 8, tc::KIND_F16><<<grid, 128, 0, s>>>(static_cast<const __half*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total, s_inv);
+        else tc::stem_p8_kernel<__nv_bfloat16, 8, tc::KIND_F16><<<grid, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(x), sb, sc, sy, sx, sw, sb_, u16(p.stem), total, s_inv);
         ERNET_LAUNCH_CHECK("stem_p8_kernel");
       }
       if (fused1) {
       } else if (paired) {
-        ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1P, tc::KIND_I8, tc::OUT_P16>(u16(p.stem), h->d_w1_pair, h->epi1, u16(p.p1), n, h->num_sms, s)));
+        ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1P, tc::KIND_F16, tc::OUT_P16>(u16(p.stem), h->d_w1_pair, h->epi1, u16(p.p1), n, h->num_sms, s)));
       } else {
-        ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1, tc::KIND_I8, tc::OUT_P16>(u16(p.stem), wimgq(0), h->epi1, u16(p.p1), n, h->num_sms, s)));
+        ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1, tc::KIND_F16, tc::OUT_P16>(u16(p.stem), wimgq(0), h->epi1, u16(p.p1), n, h->num_sms, s)));
       }
       ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_cblock<tc::CBlock2RQ, tc::KIND_I8, tc::OUT_P8>(u16(p.p1), wimgq(1), h->epi2, u16(p.a2), n, h->num_sms, s)));
       ERNET_STAGE(ERNET_STAGE_RED2, (tc::launch_acff_pblock<tc::PRed2RQ, tc::KIND_F16, tc::OUT_P16>(u16(p.a2), h->t[ERNET_T_TC_RED2_WIMG].dev, h->epi_r2, u16(p.p2), n, h->num_sms, s)));
@@ -776,13 +776,12 @@ static int init_device_attrs() {
   if ((rc = tc::set_fblock_attr<tc::PBlock1P, tc::KIND_I8, tc::OUT_P16, __half, 16, FS_P16>())) return rc;
   if ((rc = tc::set_fblock_attr<tc::PBlock1P, tc::KIND_BF16, tc::OUT_P8, __nv_bfloat16, 8, FS_P8>())) return rc;
   if ((rc = tc::set_fblock_attr<tc::PBlock1P, tc::KIND_F16, tc::OUT_P8, __half, 8, FS_P8>())) return rc;
-  if ((rc = tc::set_fblock_attr<tc::PBlock1P, tc::KIND_I8, tc::OUT_P16, __half, 8, FS_P16>())) return rc;
+  if ((rc = tc::set_fblock_attr<tc::PBlock1P, tc::KIND_F16, tc::OUT_P16, __half, 8, FS_P8>())) return rc;
+  if ((rc = tc::set_pblock_attr<tc::PBlock1P, tc::KIND_F16, tc::OUT_P16>())) return rc;
+  if ((rc = tc::set_pblock_attr<tc::PBlock1, tc::KIND_F16, tc::OUT_P16>())) return rc;
   if ((rc = tc::set_cblock_attr<tc::CBlock2RQ, tc::KIND_I8, tc::OUT_P8>())) return rc;
   if ((rc = tc::set_cblock_attr<tc::CBlock3RQ, tc::KIND_I8, tc::OUT_NHWC>())) return rc;
   if ((rc = tc::set_pblock_attr<tc::PRed2RQ, tc::KIND_F16, tc::OUT_P16>())) return rc;
-  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem5_kernel<__half, 8, FS_P16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__half, 8, FS_P16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem_kernel<__half, 8, FS_P16, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   if ((rc = tc::set_tail_attrs<tc::TailCfg128>())) return rc;
   if ((rc = tc::set_tail_attrs<tc::TailCfg64>())) return rc;
   return ERNET_OK;
@@ -1409,7 +1408,7 @@ int ernet_debug_tap(ernet_handle* h, int tap, const void* workspace, int batch, 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const char* src = static_cast<const char*>(workspace) + off;
   const int grid = (int)((total + 255) / 256);
-  if (p.tc && h->precision == ERNET_PREC_INT8 && (tap == ERNET_TAP_STEM || tap == ERNET_TAP_POOL1 || tap == ERNET_TAP_POOL2)) {
+  if (p.tc && h->precision == ERNET_PREC_INT8 && ((tap == ERNET_TAP_STEM && !h->red()) || tap == ERNET_TAP_POOL1 || tap == ERNET_TAP_POOL2)) {
     const int Hh = tap == ERNET_TAP_STEM ? 69 : (tap == ERNET_TAP_POOL1 ? 33 : 15);
     const int NCc = tap == ERNET_TAP_STEM ? 2 : (tap == ERNET_TAP_POOL1 ? 4 : (h->red() ? 4 : 6));
     const float* sc = h->f(ERNET_T_Q_SCALES) + (tap == ERNET_TAP_STEM ? 0 : (tap == ERNET_TAP_POOL1 ? 16 : 16 + 64));

@@ -246,13 +246,13 @@ def frame_batches_device(samples, batch_size=256, device="cuda", num_workers=4) 
                 jpeg_idx.append(i)
                 tensors.append(torch.frombuffer(bytearray(data), dtype=torch.uint8))
             else:
-                frames[i] = torch.from_numpy(decode_frame(path)).to(device)
+                frames[i] = torch.from_numpy(np.array(decode_frame(path))).to(device)
         if tensors:
             try:
                 decoded = tvio.decode_jpeg(tensors, mode=tvio.ImageReadMode.RGB, device=device)
             except Exception as e:                                           # noqa: BLE001  one bad file: decode it on the host
                 logger.error(f"batched device decode failed ({e}); falling back to the host decoder for this chunk")
-                decoded = [torch.from_numpy(decode_frame(parts[i][0])).permute(2, 0, 1).to(device) for i in jpeg_idx]
+                decoded = [torch.from_numpy(np.array(decode_frame(parts[i][0]))).permute(2, 0, 1).to(device) for i in jpeg_idx]
             for i, t in zip(jpeg_idx, decoded):
                 frames[i] = t.permute(1, 2, 0)                               # (3,H,W) -> (H,W,3) view
         buckets = {}

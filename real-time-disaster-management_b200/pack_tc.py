@@ -119,7 +119,19 @@ def derive_tc_int8(sd, arch, act_scales):
     s_act = normalize_act_scales(act_scales, arch)
     out = {}
     for k, (c, _co) in enumerate(widths(arch)[:3]):
-        c_pad = (c + 31) // 32 * 32             # K step of kind::i8 is 32 (RedConv: 8 -> 32, 48 -> 64)
+        if arch == "squeeze-redconv" and k == 0:
+            # Squeeze_RedConv's ACFF1 stays in fp16: its input has 8 channels = ONE 16-byte chunk per pixel at 16 bit, so
+            # tap pairing already issues 13 MMAs per tile - exactly what an int8 block 1 would issue.  int8 would buy
+            # nothing and would push the whole image through an 8-channel int8 bottleneck (measured: 13/15 on the real
+            # frames with it).  The block's OUTPUT (pool1) is still quantised for ACFF2.
+            weff, beff = fold_block(sd, "acff1", c, 16)
+            base = T_TC_BASE
+            out[base + T_TC_WIMG] = (weight_image(weff, "fp16"), DT_RAW)
+            out[base + T_TC_BIAS] = (beff.astype(np.float32), DT_F32)
+            out[base + T_TC_DEQ] = (np.ones(weff.shape[0], dtype=np.float32), DT_F32)
+            s_act[0] = np.ones_like(s_act[0])       # the stem tensor is fp16: no int8 step
+            continue
+        c_pad = (c + 31) // 32 * 32             # K step of kind::i8 is 32 (RedConv: 48 -> 64)
         weff, beff = fold_block(sd, f"acff{k + 1}", c, c_pad)
         weff[:, :, :c] *= s_act[k].reshape(1, 1, -1)
         wq, s_w = quantize_weights(weff)
