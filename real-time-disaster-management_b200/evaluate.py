@@ -267,21 +267,31 @@ def frame_batches_device(samples, batch_size=256, device="cuda", num_workers=4) 
         for chunk in chunks:
             yield from decode(_read_chunk(chunk))
         return
+    # read AND decode in the worker threads: the Huffman stage of nvJPEG's decoder runs on the host inside the op (GIL
+    # released), so several chunks in flight use several cores; each worker decodes on its own CUDA stream
     from collections import deque
     from concurrent.futures import ThreadPoolExecutor
+
+    def work(chunk):
+        stream = torch.cuda.Stream(device)
+        with torch.cuda.stream(stream):
+            out = list(decode(_read_chunk(chunk)))
+        stream.synchronize()
+        return out
+
     with ThreadPoolExecutor(max_workers=num_workers) as pool:
         pending = deque()
         it = iter(chunks)
         for chunk in it:
-            pending.append(pool.submit(_read_chunk, chunk))
+            pending.append(pool.submit(work, chunk))
             if len(pending) >= 2 * num_workers:
                 break
         while pending:
-            parts = pending.popleft().result()
+            batches = pending.popleft().result()
             nxt = next(it, None)
             if nxt is not None:
-                pending.append(pool.submit(_read_chunk, nxt))
-            yield from decode(parts)
+                pending.append(pool.submit(work, nxt))
+            yield from batches
 
 
 def main(argv=None):
@@ -296,8 +306,9 @@ def main(argv=None):
     parser.add_argument('--num-workers', type=int, default=4)
     parser.add_argument('--trt', action='store_true', help='accepted for compatibility: the B200 engine is always used')
     parser.add_argument('--quant', type=str, default='fp16', choices=['fp16', 'bf16', 'fp32', 'int8'])
-    parser.add_argument('--decode', type=str, default='device', choices=['device', 'host'],
-                        help='JPEG decode: batched nvJPEG on the GPU (default) or PIL on host threads')
+    parser.add_argument('--decode', type=str, default='host', choices=['host', 'device'],
+                        help='JPEG decode: PIL on host threads (default: the decoder the reference uses, dataloaders/aider.py:44-56) '
+                             'or batched nvJPEG on the GPU (1.7x faster wall clock; a few pixels differ from libjpeg-turbo)')
     args = parser.parse_args(argv)
     logging.basicConfig(level=logging.INFO, format='%(asctime)s - %(name)s - %(levelname)s - %(message)s')
     if not torch.cuda.is_available():

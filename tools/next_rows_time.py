@@ -110,11 +110,11 @@ rows2 = [rows[k % N] for k in range(N2)]
 for prec in ("bf16",):
     m = rtdm_b200.from_state_dict("squeeze-ernet", sd, dev, prec)
     EV.evaluate_model(m, EV.frame_batches_device(rows2[:512], 256, dev, 4), dev)
-    for bs in (256, 1024):
+    for bs, nw in ((256, 4), (256, workers), (128, workers), (64, workers)):
         t0 = time.perf_counter()
-        met = EV.evaluate_model(m, EV.frame_batches_device(rows2, bs, dev, 4), dev)
+        met = EV.evaluate_model(m, EV.frame_batches_device(rows2, bs, dev, nw), dev)
         dt = time.perf_counter() - t0
-        print(json.dumps({"row": "8f-2 evaluation loop, device JPEG decode", "precision": prec, "images": N2, "chunk": bs, "read_threads": 4,
+        print(json.dumps({"row": "8f-2 evaluation loop, device JPEG decode", "precision": prec, "images": N2, "chunk": bs, "decode_threads": nw,
                           "wall_img_s": round(N2 / dt, 1), "model_img_s_reference_definition": round(met["images_per_second"], 1),
                           "accuracy": met["accuracy"]}))
     # agreement of the two decoders' predictions on the same files

@@ -21,4 +21,4 @@ for path in sys.argv[1:]:
     if d.get("gather_probabilities_ms") is not None:
         print(f"    gather of the probabilities: {d['gather_probabilities_ms'] * 1e3:.1f} us")
     print(f"    depthwise_hbm block1 {d['depthwise_hbm']['block1']['frac']} block2 {d['depthwise_hbm']['block2']['frac']}; latency b1 {d['latency_b1_ms'] * 1e3:.1f} us, graph {d['latency_b1_graph_ms'] * 1e3:.1f} us; "
-          f"cpu_baseline {d['cpu_baseline']['value']:.0f} img/s on {d['cpu_baseline']['cores']} cores")
+          + (f"cpu_baseline {d['cpu_baseline']['value']:.0f} img/s on {d['cpu_baseline']['cores']} cores" if d.get("cpu_baseline") else "cpu_baseline: N=1 only"))
