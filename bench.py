@@ -112,7 +112,7 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
@@ -122,7 +122,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -143,18 +143,26 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
+        idle_sm, idle_mx = [], []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                clk, cmax, util = float(f[1]), float(f[2]), float(f[9])
             except ValueError:
                 continue
+            if util < 5.0:                     # the sampler runs from process start: keep only samples taken under load
+                idle_sm.append(clk); idle_mx.append(cmax)
+                continue
+            sm.append(clk); mx.append(cmax)
             for n, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
+        if not sm and idle_sm:                 # run too short for a loaded sample: report what there is, and say so
+            return {"sm_mhz": float(np.median(idle_sm)), "sm_max_mhz": float(max(idle_mx)), "samples": 0, "idle_samples": len(idle_sm),
+                    "reasons": ["no sample under load"]}
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "samples": len(sm),
@@ -271,6 +279,9 @@ def gpu_main(args, rank, local_rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                       # started first: nvidia-smi needs a few hundred ms before its first sample
     ARCH, PRECISION = args.arch, args.precision
     BATCH, sharded_total = resolve_batch(args, world)
     sd = fixtures.get_state_dict(ARCH, "shipped")
@@ -292,9 +303,6 @@ def gpu_main(args, rank, local_rank, world):
     def step(i):
         return model.forward_frames(dev_sets[i % n_sets])
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()                       # sampled from the warm-up on, so short runs still see the GPU under load
     for i in range(args.warmup):
         step(i)
     barrier()
@@ -302,14 +310,14 @@ def gpu_main(args, rank, local_rank, world):
     # host runs ahead (the start event is recorded behind it), so the K steps execute back to back.  Long runs simply
     # block in the launch queue until the spin ends - no host/device hand-shake that could dead-lock.
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda._sleep(int(4e6))               # ~2 ms at 1.9 GHz
+    if hasattr(torch.cuda, "_sleep"):
+        torch.cuda._sleep(int(4e6))           # ~2 ms at 1.9 GHz
     e0.record(stream)
     for i in range(args.steps):
         out = step(i)
     e1.record(stream)
     barrier()
     ms_max = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if rank == 0 else None
     value = world * BATCH * args.steps / (ms_max * 1e-3)
     assert torch.isfinite(out).all()
 
@@ -402,6 +410,9 @@ def gpu_main(args, rank, local_rank, world):
     torch.cuda.synchronize(dev)
     prof = model.profile_read()
     model.profile(False)
+    # clocks: sampled from the warm-up, through the timed region, to the end of the per-kernel pass (the same steps again) -
+    # a 20-step timed region lasts 4 ms, shorter than one nvidia-smi sample, so the window has to be the loaded phases around it
+    clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
         peaks = load_peaks()

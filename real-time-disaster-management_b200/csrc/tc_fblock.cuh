@@ -16,6 +16,9 @@
 // orders the async proxy after it (fence.proxy.async) and issues the load.  Helpers never wait for consumers and all CTAs
 // of the grid are co-resident (grid <= #SMs, one CTA per SM), so the only waits are forward in image order: no deadlock.
 // Consumers run ~one band behind the helpers; the kernel takes max(transform, block 1) + the first band (~6 us).
+// Measured (B200, bf16, 256 frames): 118-122 us against 49 + 64 us for the two kernels - parity, not a win: the helpers are
+// the bottleneck (15 warps carry 54 % of the kernel's 59 M warp instructions at 1.2 eligible warps per scheduler; the
+// stand-alone transform kernel needs 28 warps per SM to issue at 71 %).  Hence opt-in (ernet_set_fuse_ingest); DESIGN.md 5a.
 // The flags re-arm themselves: every unit's producer counts itself in taken[img]; the 15th resets both words, so a
 // replayed CUDA graph (constant kernel arguments) and the next launch find zeros.  (A watchdog abort leaves them dirty:
 // the host clears them when it reports the timeout.)
@@ -190,7 +193,9 @@ ingest_block1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t
     // ------------------------------------------------------------------ MMA issuers (even / odd units), as in tc_pblock.cuh
     const int me = warp == 1 ? 0 : 1;
     if (elect_one()) {
-      bool ok = mbar_wait(bar_w, 0, abort_flag, 0x502u);
+      // every wait of this kernel suspends or backs off: block 1 is not its bottleneck (the helpers are), and a spinning
+      // issuer warp costs its scheduler up to a quarter of the issue slots the helpers need
+      bool ok = mbar_wait_suspend(bar_w, 0, abort_flag, 0x502u);
       const uint32_t in_addr = smem_u32(smem), w_addr = smem_u32(s_w);
       constexpr uint32_t A_HI = desc_hi(BW * 16), B_HI = desc_hi(128);
       const uint32_t w_lo0 = desc_lo(w_addr, N * 16);
@@ -199,10 +204,10 @@ ingest_block1_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t
         const int r = u % Cfg::UNITS_PER_IMG, ux = r % Cfg::UX;
         const int ntile = min(GX, Cfg::TCOLS - ux * GX);
         const int st = k % NSTAGE, buf = k & 1, use = k >> 1;
-        ok = mbar_wait(&in_full[st], (k / NSTAGE) & 1, abort_flag, 0x503u, k);
-        if (ok && use > 0) ok = mbar_wait(&acc_empty[buf], (use - 1) & 1, abort_flag, 0x504u, k);
+        ok = mbar_wait_suspend(&in_full[st], (k / NSTAGE) & 1, abort_flag, 0x503u, k);
+        if (ok && use > 0) ok = mbar_wait_suspend(&acc_empty[buf], (use - 1) & 1, abort_flag, 0x504u, k);
         if (!ok) break;
-        while (*turn < (uint32_t)k) { if (*abort_flag) { ok = false; break; } }
+        while (*turn < (uint32_t)k) { __nanosleep(32); if (*abort_flag) { ok = false; break; } }
         if (!ok) break;
         tc_fence_after();
         const uint32_t a_lo0 = desc_lo(in_addr + st * Cfg::STAGE_STRIDE + (uint32_t)((2 * BW + 2) * 16), Cfg::CHUNK_BYTES);
