@@ -235,9 +235,8 @@ def test_frames_path_and_chunking(prec, dev):
     p2, l2 = m.forward_with_logits(x)
     if prec == "fp32":
         assert torch.equal(logits, l2) and torch.equal(probs, p2)
-    else:   # 16-bit frames path runs conv1 on mma.sync with weights rounded to 16 bit; the tensor path keeps fp32 weights:
-        # stem values differ by one 16-bit ulp here and there (measured 3-7e-3 on the logits; both meet the oracle tolerance)
-        assert _rel(logits.double().cpu().numpy(), l2.double().cpu().numpy()) <= 1e-2
+    else:   # 16-bit frames path runs conv1 on mma.sync with weights rounded to 16 bit; the tensor path keeps fp32 weights
+        assert _rel(logits.double().cpu().numpy(), l2.double().cpu().numpy()) <= 5e-3
     ref = E.forward(sd, I.ingest(frames), arch, dtype=np.float64)
     assert _rel(logits.double().cpu().numpy(), ref["logits"]) <= TOL[prec]
     # ragged chunking (17 = 5+5+5+2) gives bit-identical results; so does B=1
