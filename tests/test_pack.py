@@ -106,3 +106,44 @@ def test_bf16_rounding_is_nearest_even():
     x = np.random.RandomState(0).standard_normal(4096).astype(np.float32) * 3
     want = torch.from_numpy(x).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
     assert np.array_equal(PT.to_bits16(x, "bf16"), want)
+
+
+@pytest.mark.parametrize("arch", fixtures.ARCHS)
+def test_int8_operand_images(arch):
+    """int8 blobs: per-output-channel symmetric weights (max|q| = 127 in every non-zero row), image sizes the kernels
+    expect, activation steps at their fixed offsets; Squeeze_RedConv keeps ACFF1 in fp16 (its tap-paired 16-bit form issues
+    the int8 MMA count) and carries conv_red2 as a 16-bit 1-tap image padded to 64 outputs."""
+    import rtdm_b200.pack_tc as PT
+    sd = fixtures.get_state_dict(arch, "w3")
+    chans = PT.act_channels(arch)
+    rs = np.random.RandomState(3)
+    scales = [rs.uniform(0.01, 0.05, c) for c in chans]
+    out = PT.derive_tc_int8(sd, arch, scales)
+    red = arch == "squeeze-redconv"
+    cpad = [(c + 31) // 32 * 32 for c, _ in P.widths(arch)[:3]]
+    for k, (c, co) in enumerate(P.widths(arch)[:3]):
+        img, _ = out[PT.T_TC_BASE + 4 * k + PT.T_TC_WIMG]
+        deq = out[PT.T_TC_BASE + 4 * k + PT.T_TC_DEQ][0]
+        assert deq.shape == (co,) and out[PT.T_TC_BASE + 4 * k + PT.T_TC_BIAS][0].shape == (co,)
+        if red and k == 0:
+            assert img.dtype == np.uint16 and img.shape == (25, 2, co, 8) and np.all(deq == 1.0)      # fp16 block 1
+            continue
+        assert img.dtype == np.int8 and img.shape == (25, cpad[k] // 16, co, 16)
+        rows = img.transpose(2, 0, 1, 3).reshape(co, -1).astype(np.int32)
+        assert np.abs(rows).max(axis=1).min() == 127 and np.abs(rows).max() == 127
+        assert np.all(rows.reshape(co, 25, -1)[:, :, c:] == 0)                                      # zero-padded channels
+        # dequantised weights reproduce the folded, activation-scaled weights to half an int8 step
+        weff, _ = PT.fold_block(sd, f"acff{k + 1}", c, cpad[k])
+        weff[:, :, :c] *= np.asarray(scales[k]).reshape(1, 1, -1)
+        back = rows.reshape(co, 25, -1) * deq.astype(np.float64).reshape(-1, 1, 1)
+        assert np.abs(back - weff).max() <= 0.5001 * deq.max()
+    qs = out[PT.T_Q_SCALES][0]
+    assert qs.shape == (16 + 64 + 96,)
+    for off, c, s in zip((0, 16, 80), chans, scales):
+        want = np.ones(c) if (red and off == 0) else s
+        assert np.allclose(qs[off:off + c], want.astype(np.float32))
+    assert (PT.T_TC_RED2_WIMG in out) == red
+    if red:
+        assert out[PT.T_TC_RED2_WIMG][0].shape == (1, 12, 64, 8) and np.all(out[PT.T_TC_RED2_BIAS][0][48:] == 0)
+    with pytest.raises(ValueError):
+        PT.derive_tc_int8(sd, arch, scales[:2])
