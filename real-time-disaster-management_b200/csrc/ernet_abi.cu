@@ -18,6 +18,7 @@
 #include "tc_pblock.cuh"
 #include "tc_cblock.cuh"
 #include "tc_fblock.cuh"
+#include "tc_pw32.cuh"
 #include "dw_tma.cuh"
 
 namespace ernet {
@@ -64,6 +65,8 @@ struct ernet_handle {
   bool fuse_ingest = false;          // ERNET_FUSE_INGEST=1: transform + conv1 under block 1 in one kernel (tc_fblock.cuh; off until it beats the two kernels)
   bool last_fused = false;           // the most recent frames chunk took the fused kernel (ernet_launches_per_forward)
   void* d_w1_pair = nullptr;         // block-1 weights regrouped for tap pairing ([13][2][64][16 B], tc_pblock.cuh)
+  float* d_pw32[3] = {nullptr, nullptr, nullptr};   // fp32 Squeeze_ErNET: (hi, lo) TF32 images of the three 1x1 weights (tc_pw32.cuh)
+  bool fp32_tc = true;               // fp32 engine: blocks 1-3 1x1 convolutions as split-TF32 tcgen05 GEMMs (ERNET_FP32_TC=0: FFMA kernel)
   StemFrag* d_stem_frag = nullptr;   // folded conv1 in mma.sync fragment order (16-bit engines)
   bool dual_copy = false;       // host path: alternate two copy streams (ERNET_DUAL_COPY=1)
   bool trim_columns = false;    // host path: also skip the columns outside the crop footprint (ERNET_TRIM_COLUMNS=1).  Off:
@@ -339,6 +342,14 @@ static int run_chunk_simt(ernet_handle* h, const void* x, int x_dtype, int x_lay
   const int cs = h->cs(), c3 = h->c3(), c4 = h->c4();
   // acff1 + pool1
   ERNET_STAGE(ERNET_STAGE_DW1, launch_acff_dw<T>(buf(p.stem), n, 69, 69, cs, 66, 66, h->blk(0, ERNET_T_DW_W), h->blk(0, ERNET_T_DW_B), buf(p.cat1), s));
+  // fp32 Squeeze_ErNET: the three big 1x1 convolutions run on the tensor cores in split-TF32 form (tc_pw32.cuh)
+  bool tf = false;
+  if constexpr (std::is_same<T, float>::value) tf = h->fp32_tc && !h->red() && h->d_pw32[0] && h->d_pw32[1] && h->d_pw32[2];
+  if (tf) {
+    if constexpr (std::is_same<T, float>::value)
+      ERNET_STAGE(ERNET_STAGE_PW1, (tc::launch_pw32<tc::FPw1>(buf(p.cat1), h->d_pw32[0], h->blk(0, ERNET_T_PW_B), h->blk(0, ERNET_T_BN_S),
+                                    h->blk(0, ERNET_T_BN_T), buf(p.p1), n, h->num_sms, s)));
+  } else
   ERNET_STAGE(ERNET_STAGE_PW1, launch_pointwise<T>(buf(p.cat1), n, 66, 66, 3 * cs, 64, h->blk(0, ERNET_T_PW_W), h->blk(0, ERNET_T_PW_B),
                                 h->blk(0, ERNET_T_BN_S), h->blk(0, ERNET_T_BN_T), 1, 1, buf(p.p1), s));
   // acff2 [+conv_red2] + pool2
@@ -348,12 +359,21 @@ static int run_chunk_simt(ernet_handle* h, const void* x, int x_dtype, int x_lay
                                   h->blk(1, ERNET_T_BN_S), h->blk(1, ERNET_T_BN_T), 1, 0, buf(p.a2), s));
     ERNET_STAGE(ERNET_STAGE_RED2, launch_pointwise<T>(buf(p.a2), n, 30, 30, 96, 48, h->f(ERNET_T_RED2_W), h->f(ERNET_T_RED2_B), nullptr, nullptr,
                                   0, 1, buf(p.p2), s));
+  } else if (tf) {
+    if constexpr (std::is_same<T, float>::value)
+      ERNET_STAGE(ERNET_STAGE_PW2, (tc::launch_pw32<tc::FPw2>(buf(p.cat2), h->d_pw32[1], h->blk(1, ERNET_T_PW_B), h->blk(1, ERNET_T_BN_S),
+                                    h->blk(1, ERNET_T_BN_T), buf(p.p2), n, h->num_sms, s)));
   } else {
     ERNET_STAGE(ERNET_STAGE_PW2, launch_pointwise<T>(buf(p.cat2), n, 30, 30, 192, 96, h->blk(1, ERNET_T_PW_W), h->blk(1, ERNET_T_PW_B),
                                   h->blk(1, ERNET_T_BN_S), h->blk(1, ERNET_T_BN_T), 1, 1, buf(p.p2), s));
   }
   // acff3 + pool3 [+conv_red3]
   ERNET_STAGE(ERNET_STAGE_DW3, launch_acff_dw<T>(buf(p.p2), n, 15, 15, c3, 12, 12, h->blk(2, ERNET_T_DW_W), h->blk(2, ERNET_T_DW_B), buf(p.cat3), s));
+  if (tf) {
+    if constexpr (std::is_same<T, float>::value)
+      ERNET_STAGE(ERNET_STAGE_PW3, (tc::launch_pw32<tc::FPw3>(buf(p.cat3), h->d_pw32[2], h->blk(2, ERNET_T_PW_B), h->blk(2, ERNET_T_BN_S),
+                                    h->blk(2, ERNET_T_BN_T), buf(p.p3), n, h->num_sms, s)));
+  } else
   ERNET_STAGE(ERNET_STAGE_PW3, launch_pointwise<T>(buf(p.cat3), n, 12, 12, 3 * c3, 128, h->blk(2, ERNET_T_PW_W), h->blk(2, ERNET_T_PW_B),
                                 h->blk(2, ERNET_T_BN_S), h->blk(2, ERNET_T_BN_T), 1, 1, buf(p.p3), s));
   const T* in4 = buf(p.p3);
@@ -734,6 +754,9 @@ static int init_device_attrs() {
   ERNET_CUDA(cudaFuncSetAttribute(ingest_stem5_kernel<__half, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   ERNET_CUDA(cudaFuncSetAttribute(ingest_stem5_kernel<__nv_bfloat16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   ERNET_CUDA(cudaFuncSetAttribute(ingest_stem5_kernel<__half, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+  if ((rc = tc::set_pw32_attr<tc::FPw1>())) return rc;
+  if ((rc = tc::set_pw32_attr<tc::FPw2>())) return rc;
+  if ((rc = tc::set_pw32_attr<tc::FPw3>())) return rc;
   if ((rc = tc::set_all_block_attrs())) return rc;
   if ((rc = tc::set_pblock_attr<tc::PBlock1, tc::KIND_BF16, tc::OUT_P8>())) return rc;
   if ((rc = tc::set_pblock_attr<tc::PBlock1, tc::KIND_F16, tc::OUT_P8>())) return rc;
@@ -893,6 +916,7 @@ int ernet_create(ernet_handle** out, int arch, int precision, int device) {
     delete h;
     return fail(ERNET_ERR_CUDA, "allocating the band counters failed");
   }
+  if (const char* e = getenv("ERNET_FP32_TC")) h->fp32_tc = atoi(e) != 0;
   if (const char* e = getenv("ERNET_TRIM_COLUMNS")) h->trim_columns = atoi(e) != 0;
   if (const char* e = getenv("ERNET_DUAL_COPY")) h->dual_copy = atoi(e) != 0;
   *out = h;
@@ -905,6 +929,7 @@ void ernet_destroy(ernet_handle* h) {
   if (h->d_blob) cudaFree(h->d_blob);
   if (h->d_stem_frag) cudaFree(h->d_stem_frag);
   if (h->d_w1_pair) cudaFree(h->d_w1_pair);
+  for (int k = 0; k < 3; ++k) if (h->d_pw32[k]) cudaFree(h->d_pw32[k]);
   if (h->d_sync) cudaFree(h->d_sync);
   for (auto& kv : h->ingest) if (kv.second.d_base) cudaFree(kv.second.d_base);
   for (int i = 0; i < 2; ++i) {
@@ -1076,6 +1101,18 @@ int ernet_load_packed(ernet_handle* h, const void* blob, size_t bytes) {
   }
   if (h->d_blob) { cudaDeviceSynchronize(); cudaFree(h->d_blob); }
   h->d_blob = d; h->blob_bytes = bytes; h->loaded = true;
+  if (h->precision == ERNET_PREC_FP32 && h->arch == ERNET_ARCH_SQUEEZE) {
+    // (hi, lo) TF32 images of the 1x1 weights of blocks 1-3, in the stage order tc_pw32.cuh streams them
+    const int kk[3] = {48, 192, 288}, nn[3] = {64, 96, 128};
+    for (int k = 0; k < 3; ++k) {
+      const Tensor& w = h->t[ERNET_T_BLOCK_BASE + 8 * k + ERNET_T_PW_W];
+      if (!w.dev || w.nbytes != (size_t)kk[k] * nn[k] * sizeof(float)) continue;
+      if (!h->d_pw32[k]) ERNET_CUDA(cudaMalloc(&h->d_pw32[k], tc::pw32_weight_floats(kk[k], nn[k]) * sizeof(float)));
+      tc::pw32_pack_weights<<<(kk[k] * nn[k] + 255) / 256, 256>>>(h->blk(k, ERNET_T_PW_W), kk[k], nn[k], h->d_pw32[k]);
+      ERNET_LAUNCH_CHECK("pw32_pack_weights");
+    }
+    ERNET_CUDA(cudaDeviceSynchronize());
+  }
   return ERNET_OK;
 }
 
