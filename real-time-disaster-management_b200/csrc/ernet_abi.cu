@@ -65,9 +65,10 @@ struct ernet_handle {
   bool fuse_ingest = false;          // ERNET_FUSE_INGEST=1: transform + conv1 under block 1 in one kernel (tc_fblock.cuh; off until it beats the two kernels)
   bool last_fused = false;           // the most recent frames chunk took the fused kernel (ernet_launches_per_forward)
   void* d_w1_pair = nullptr;         // block-1 weights regrouped for tap pairing ([13][2][64][16 B], tc_pblock.cuh)
-  float* d_pw32[3] = {nullptr, nullptr, nullptr};   // fp32 Squeeze_ErNET: (hi, lo) TF32 images of the three 1x1 weights (tc_pw32.cuh)
-  bool fp32_tc = true;               // fp32 engine: blocks 1-3 1x1 convolutions as split-TF32 tcgen05 GEMMs (ERNET_FP32_TC=0: FFMA kernel)
+  float* d_pw32[4] = {nullptr, nullptr, nullptr, nullptr};   // fp32 Squeeze_ErNET: (hi, lo) TF32 images of the four 1x1 weights (tc_pw32.cuh)
+  bool fp32_tc = true;               // fp32 engine: blocks 1-4 1x1 convolutions as split-TF32 tcgen05 GEMMs (ERNET_FP32_TC=0: FFMA kernel)
   StemFrag* d_stem_frag = nullptr;   // folded conv1 in mma.sync fragment order (16-bit engines)
+  StemFrag32* d_stem_frag32 = nullptr;   // fp32 engine: the same as (hi, lo) fp16 images (ingest_fast.cuh)
   bool dual_copy = false;       // host path: alternate two copy streams (ERNET_DUAL_COPY=1)
   bool trim_columns = false;    // host path: also skip the columns outside the crop footprint (ERNET_TRIM_COLUMNS=1).  Off:
                                 // measured 78 K img/s against 281 K - a 3-D copy of 639-byte rows runs at ~10 GB/s
@@ -303,6 +304,13 @@ static int run_tail(ernet_handle* h, const T* in4, T* cat4, T* a4, int n, float*
     return rc;
   }
   ERNET_STAGE(ERNET_STAGE_DW4, launch_acff_dw<T>(in4, n, 6, 6, c4, 4, 4, h->blk(3, ERNET_T_DW_W), h->blk(3, ERNET_T_DW_B), cat4, s));
+  bool tf = false;
+  if constexpr (std::is_same<T, float>::value) tf = h->fp32_tc && !h->red() && h->d_pw32[3];
+  if (tf) {
+    if constexpr (std::is_same<T, float>::value)
+      ERNET_STAGE(ERNET_STAGE_PW4, (tc::launch_pw32<tc::FPw4>(cat4, h->d_pw32[3], h->blk(3, ERNET_T_PW_B), h->blk(3, ERNET_T_BN_S),
+                                    h->blk(3, ERNET_T_BN_T), a4, n, h->num_sms, s)));
+  } else
   ERNET_STAGE(ERNET_STAGE_PW4, launch_pointwise<T>(cat4, n, 4, 4, 3 * c4, 256, h->blk(3, ERNET_T_PW_W), h->blk(3, ERNET_T_PW_B),
                                 h->blk(3, ERNET_T_BN_S), h->blk(3, ERNET_T_BN_T), 1, 0, a4, s));
   {
@@ -324,6 +332,16 @@ static int run_chunk_simt(ernet_handle* h, const void* x, int x_dtype, int x_lay
   if (frames && tab->fs_max_in_rows > 0 && !h->debug_taps) {
     // transform + conv1 fused (the transformed tensor never reaches HBM)
     StemQ q{};
+    FastGeom fg;
+    bool fast = false;
+    if constexpr (std::is_same<T, float>::value) fast = h->fast_ingest && h->d_stem_frag32 && fast5_geometry(*tab, frames, fg);
+    if (fast) {
+      // fp32 engine, 5-tap frames: word-wide transform, conv1 on mma.sync with (hi, lo) fp16 weight images (ingest_fast.cuh)
+      if constexpr (std::is_same<T, float>::value) {
+        if (h->red()) ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem5<float, 8, FS_NHWC>(*tab, fg, frames, n, order == ERNET_BGR, &h->d_stem_frag32->base, q, false, buf(p.stem), s)));
+        else          ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem5<float, 16, FS_NHWC>(*tab, fg, frames, n, order == ERNET_BGR, &h->d_stem_frag32->base, q, false, buf(p.stem), s)));
+      }
+    } else
     if (h->red()) ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem<T, 8, FS_NHWC>(*tab, frames, n, order == ERNET_BGR, h->f(ERNET_T_STEM_W), h->f(ERNET_T_STEM_B), q, buf(p.stem), s)));
     else          ERNET_STAGE(ERNET_STAGE_INGEST, (launch_ingest_stem<T, 16, FS_NHWC>(*tab, frames, n, order == ERNET_BGR, h->f(ERNET_T_STEM_W), h->f(ERNET_T_STEM_B), q, buf(p.stem), s)));
   } else if (frames) {
@@ -754,9 +772,12 @@ static int init_device_attrs() {
   ERNET_CUDA(cudaFuncSetAttribute(ingest_stem5_kernel<__half, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   ERNET_CUDA(cudaFuncSetAttribute(ingest_stem5_kernel<__nv_bfloat16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   ERNET_CUDA(cudaFuncSetAttribute(ingest_stem5_kernel<__half, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem5_kernel<float, 16, FS_NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+  ERNET_CUDA(cudaFuncSetAttribute(ingest_stem5_kernel<float, 8, FS_NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   if ((rc = tc::set_pw32_attr<tc::FPw1>())) return rc;
   if ((rc = tc::set_pw32_attr<tc::FPw2>())) return rc;
   if ((rc = tc::set_pw32_attr<tc::FPw3>())) return rc;
+  if ((rc = tc::set_pw32_attr<tc::FPw4>())) return rc;
   if ((rc = tc::set_all_block_attrs())) return rc;
   if ((rc = tc::set_pblock_attr<tc::PBlock1, tc::KIND_BF16, tc::OUT_P8>())) return rc;
   if ((rc = tc::set_pblock_attr<tc::PBlock1, tc::KIND_F16, tc::OUT_P8>())) return rc;
@@ -928,8 +949,9 @@ void ernet_destroy(ernet_handle* h) {
   DeviceGuard g(h->device);
   if (h->d_blob) cudaFree(h->d_blob);
   if (h->d_stem_frag) cudaFree(h->d_stem_frag);
+  if (h->d_stem_frag32) cudaFree(h->d_stem_frag32);
   if (h->d_w1_pair) cudaFree(h->d_w1_pair);
-  for (int k = 0; k < 3; ++k) if (h->d_pw32[k]) cudaFree(h->d_pw32[k]);
+  for (int k = 0; k < 4; ++k) if (h->d_pw32[k]) cudaFree(h->d_pw32[k]);
   if (h->d_sync) cudaFree(h->d_sync);
   for (auto& kv : h->ingest) if (kv.second.d_base) cudaFree(kv.second.d_base);
   for (int i = 0; i < 2; ++i) {
@@ -1101,15 +1123,31 @@ int ernet_load_packed(ernet_handle* h, const void* blob, size_t bytes) {
   }
   if (h->d_blob) { cudaDeviceSynchronize(); cudaFree(h->d_blob); }
   h->d_blob = d; h->blob_bytes = bytes; h->loaded = true;
+  if (h->precision == ERNET_PREC_FP32 && h->arch != ERNET_ARCH_ERNET) {
+    // conv1 (+conv_red1) with ToTensor/Normalize folded in as (hi, lo) fp16 images in mma.sync fragment order (ingest_fast.cuh)
+    const Tensor& sw_ = h->t[ERNET_T_STEM_W];
+    const Tensor& sb_ = h->t[ERNET_T_STEM_B];
+    if (sw_.dev && sb_.dev && sw_.nbytes == (size_t)27 * h->cs() * sizeof(float)) {
+      auto host_f32 = [&](const Tensor& t) { return reinterpret_cast<const float*>(static_cast<const char*>(blob) + (static_cast<const char*>(t.dev) - static_cast<const char*>(d))); };
+      StemFrag32 sfh;
+      build_stem_fragments32(host_f32(sw_), host_f32(sb_), h->cs(), &sfh);
+      if (!h->d_stem_frag32) ERNET_CUDA(cudaMalloc(&h->d_stem_frag32, sizeof(StemFrag32)));
+      ERNET_CUDA(cudaMemcpy(h->d_stem_frag32, &sfh, sizeof(StemFrag32), cudaMemcpyHostToDevice));
+    }
+  }
   if (h->precision == ERNET_PREC_FP32 && h->arch == ERNET_ARCH_SQUEEZE) {
     // (hi, lo) TF32 images of the 1x1 weights of blocks 1-3, in the stage order tc_pw32.cuh streams them
-    const int kk[3] = {48, 192, 288}, nn[3] = {64, 96, 128};
-    for (int k = 0; k < 3; ++k) {
+    const int kk[4] = {48, 192, 288, 384}, nn[4] = {64, 96, 128, 256};
+    for (int k = 0; k < 4; ++k) {
       const Tensor& w = h->t[ERNET_T_BLOCK_BASE + 8 * k + ERNET_T_PW_W];
       if (!w.dev || w.nbytes != (size_t)kk[k] * nn[k] * sizeof(float)) continue;
       if (!h->d_pw32[k]) ERNET_CUDA(cudaMalloc(&h->d_pw32[k], tc::pw32_weight_floats(kk[k], nn[k]) * sizeof(float)));
-      tc::pw32_pack_weights<<<(kk[k] * nn[k] + 255) / 256, 256>>>(h->blk(k, ERNET_T_PW_W), kk[k], nn[k], h->d_pw32[k]);
-      ERNET_LAUNCH_CHECK("pw32_pack_weights");
+      const int splits = k == 3 ? tc::FPw4::NSPLIT : 1, nsub = nn[k] / splits;      // block 4: one image per 64-channel split
+      for (int sp = 0; sp < splits; ++sp) {
+        tc::pw32_pack_weights<<<(kk[k] * nsub + 255) / 256, 256>>>(h->blk(k, ERNET_T_PW_W), kk[k], nsub,
+                                                                  h->d_pw32[k] + (size_t)sp * tc::pw32_weight_floats(kk[k], nsub), nn[k], sp * nsub);
+        ERNET_LAUNCH_CHECK("pw32_pack_weights");
+      }
     }
     ERNET_CUDA(cudaDeviceSynchronize());
   }

@@ -29,6 +29,11 @@ struct FastGeom {                             // shared-memory carve-up (bytes),
 //   frag[order][lane][s][j][hh]  fp16 pairs w'[k][n], w'[k+1][n], k = 16s + 2t + 8hh, n = 8j + g (lane = 4g + t)
 //   then CS floats: folded bias
 struct StemFrag { uint32_t frag[2][32][8]; float bias[16]; };
+// fp32 engine: the folded weights as TWO fp16 images, w' = hi + lo / kStemLoScale with hi = fp16(w') and
+// lo = fp16((w' - hi) * kStemLoScale) (22 significant bits; the uint8 pixels are exact in fp16 and the products are exact in
+// the fp32 accumulators, one accumulator per image).  `base` first: the band function reads it through a StemFrag pointer.
+struct StemFrag32 { StemFrag base; uint32_t lo[2][32][8]; };
+constexpr float kStemLoScale = 65536.f;
 
 // Thread-group synchronisation of one band: the whole CTA (stand-alone kernel) or a named barrier over the NT helper
 // threads of the fused transform + block-1 kernel (tc_fblock.cuh).
@@ -206,6 +211,14 @@ __device__ __forceinline__ void ingest_stem5_band(uint8_t* __restrict__ fsm, con
       bfrag[0][0][0] = f0.x; bfrag[0][0][1] = f0.y; bfrag[0][1][0] = f0.z; bfrag[0][1][1] = f0.w;
       bfrag[1][0][0] = f1.x; bfrag[1][0][1] = f1.y; bfrag[1][1][0] = f1.z; bfrag[1][1][1] = f1.w;
     }
+    constexpr bool F32 = OUT == FS_NHWC;                    // fp32 engine: second (lo) weight image, fp32 NHWC stem tensor
+    uint32_t bfrag_lo[F32 ? 2 : 1][2][2];
+    if (F32) {
+      const uint4* fp = reinterpret_cast<const uint4*>(reinterpret_cast<const StemFrag32*>(sf)->lo[bgr ? 1 : 0][lane]);
+      const uint4 f0 = TAB ? fp[0] : __ldg(fp), f1 = TAB ? fp[1] : __ldg(fp + 1);
+      bfrag_lo[0][0][0] = f0.x; bfrag_lo[0][0][1] = f0.y; bfrag_lo[0][1][0] = f0.z; bfrag_lo[0][1][1] = f0.w;
+      bfrag_lo[F32 ? 1 : 0][0][0] = f1.x; bfrag_lo[F32 ? 1 : 0][0][1] = f1.y; bfrag_lo[F32 ? 1 : 0][1][0] = f1.z; bfrag_lo[F32 ? 1 : 0][1][1] = f1.w;
+    }
     float bia[NTL][2];
 #pragma unroll
     for (int j = 0; j < NTL; ++j) {
@@ -216,6 +229,7 @@ __device__ __forceinline__ void ingest_stem5_band(uint8_t* __restrict__ fsm, con
     const int brow = y1 - y0;
     uint4* img = reinterpret_cast<uint4*>(out) + (size_t)b * 2 * 72 * 72;
     uint32_t* orow = reinterpret_cast<uint32_t*>(img + (y0 + 2) * 72 + 2) + t;     // lane's 4-byte slot of chunk 0, band row 0, pixel 0
+    float* orow32 = reinterpret_cast<float*>(out) + ((size_t)b * 69 + y0) * 69 * CS + 2 * t;   // FS_NHWC: (B,69,69,CS) fp32
     for (int task = warp; task < brow * 5; task += NW) {
       const int ly = task / 5, xg = task - ly * 5;
       const uint8_t* vrow = vbuf + (2 * ly) * (kCrop * 3);
@@ -243,11 +257,28 @@ __device__ __forceinline__ void ingest_stem5_band(uint8_t* __restrict__ fsm, con
         for (int s = 0; s < 2; ++s)
 #pragma unroll
           for (int j = 0; j < NTL; ++j) StemMma<__half>::mma(acc[j], afrag[s], bfrag[s][j]);
+        if (F32) {
+          float acl[NTL][4];
+#pragma unroll
+          for (int j = 0; j < NTL; ++j) acl[j][0] = acl[j][1] = acl[j][2] = acl[j][3] = 0.f;
+#pragma unroll
+          for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int j = 0; j < NTL; ++j) StemMma<__half>::mma(acl[j], afrag[s], bfrag_lo[F32 ? s : 0][j]);
+#pragma unroll
+          for (int j = 0; j < NTL; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[j][e] = fmaf(acl[j][e], 1.f / kStemLoScale, acc[j][e]);
+        }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int oxx = half ? ox1 : ox0;
           if (oxx >= 69) continue;
-          if (OUT == FS_P16) {
+          if (F32) {
+#pragma unroll
+            for (int j = 0; j < NTL; ++j)
+              *reinterpret_cast<float2*>(orow32 + ((size_t)ly * 69 + oxx) * CS + 8 * j) = make_float2(acc[j][2 * half], acc[j][2 * half + 1]);
+          } else if (OUT == FS_P16) {
             uint16_t* o16 = reinterpret_cast<uint16_t*>(orow_l + oxx * 4 - t) + t;      // pixel's 16 bytes, this lane's channel pairs
 #pragma unroll
             for (int j = 0; j < NTL; ++j) {
@@ -263,6 +294,7 @@ __device__ __forceinline__ void ingest_stem5_band(uint8_t* __restrict__ fsm, con
       }
     }
     // zero halo columns of the band's rows (and the all-zero second chunk of an 8-channel stem)
+    if (!F32)
     for (int i = tid; i < brow * 72; i += NT) {
       const int ly = i / 72, pc = i - ly * 72;
       const bool halo = pc < 2 || pc >= 71;
@@ -270,9 +302,9 @@ __device__ __forceinline__ void ingest_stem5_band(uint8_t* __restrict__ fsm, con
       if (zero_chunk1 ? (halo || CS == 8 || OUT == FS_P16) : (halo && CS == 16 && OUT == FS_P8)) img[72 * 72 + (y0 + ly + 2) * 72 + pc] = make_uint4(0, 0, 0, 0);
     }
     const int nch = (zero_chunk1 || (CS == 16 && OUT == FS_P8)) ? 2 : 1;         // chunks whose halo rows are written
-    if (band_idx == 0)
+    if (!F32 && band_idx == 0)
       for (int i = tid; i < nch * 2 * 72; i += NT) img[(i / 144) * 72 * 72 + (i % 144)] = make_uint4(0, 0, 0, 0);
-    if (y1 == 69)
+    if (!F32 && y1 == 69)
       for (int i = tid; i < nch * 72; i += NT) img[(i / 72) * 72 * 72 + 71 * 72 + (i % 72)] = make_uint4(0, 0, 0, 0);
   }
 }
@@ -327,6 +359,36 @@ inline void build_stem_fragments(const float* w, const float* bias, int cs, Stem
     double s = bias[n];
     for (int k = 0; k < 27; ++k) s -= (double)w[k * cs + n] * mean[k % 3] / stdv[k % 3];
     out->bias[n] = (float)s;
+  }
+}
+
+// fp32 engine: the same fold, every weight as the (hi, lo) fp16 pair of StemFrag32
+inline void build_stem_fragments32(const float* w, const float* bias, int cs, StemFrag32* out) {
+  build_stem_fragments(w, bias, cs, &out->base);            // bias (fp32) and the hi image = fp16(w')
+  const double stdv[3] = {0.229, 0.224, 0.225};
+  memset(out->lo, 0, sizeof(out->lo));
+  for (int order = 0; order < 2; ++order) {
+    auto lo_of = [&](int k, int n) -> __half {
+      const int kyy = k / 10, off = k % 10;
+      if (kyy >= 3 || off >= 9 || n >= cs) return __float2half_rn(0.f);
+      const int kxx = off / 3, cb = off % 3;
+      const int c = order ? 2 - cb : cb;
+      const double wd = (double)w[((kyy * 3 + kxx) * 3 + c) * cs + n] / (255.0 * stdv[c]);
+      const double hi = (double)__half2float(__float2half_rn((float)wd));
+      return __float2half_rn((float)((wd - hi) * (double)kStemLoScale));
+    };
+    for (int lane = 0; lane < 32; ++lane) {
+      const int g = lane >> 2, t = lane & 3;
+      for (int s = 0; s < 2; ++s)
+        for (int j = 0; j < 2; ++j)
+          for (int hh = 0; hh < 2; ++hh) {
+            const int k0 = 16 * s + 2 * t + 8 * hh, n = 8 * j + g;
+            const __half lo = lo_of(k0, n), hi = lo_of(k0 + 1, n);
+            uint16_t lob, hib;
+            memcpy(&lob, &lo, 2); memcpy(&hib, &hi, 2);
+            out->lo[order][lane][(s * 2 + j) * 2 + hh] = (uint32_t)lob | ((uint32_t)hib << 16);
+          }
+    }
   }
 }
 

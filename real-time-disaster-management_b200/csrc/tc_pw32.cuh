@@ -23,25 +23,40 @@
 namespace ernet {
 namespace tc {
 
-template <int K_, int N_, int H_, bool WRES_, int RAW_STAGES_, int OP_STAGES_, int ACC_BUFS_>
+// FLAT (block 4: 4x4 maps, no pool): the concat tensor (batch, 16 pixels, K) is read as ONE 16-pixel-wide image whose rows
+// are the images of the batch, so a unit is 16 images x 16 pixels; the N_ * NSPLIT_ output channels are dealt to NSPLIT_
+// units per row group (more CTAs busy on a tiny GEMM, TMEM holds two accumulator buffers).
+template <int K_, int N_, int H_, bool WRES_, int RAW_STAGES_, int OP_STAGES_, int ACC_BUFS_, bool FLAT_ = false, int NSPLIT_ = 1>
 struct TfCfg {
   static constexpr int K = K_, N = N_, H = H_, RAW_STAGES = RAW_STAGES_, OP_STAGES = OP_STAGES_, ACC_BUFS = ACC_BUFS_;
-  static constexpr bool WRES = WRES_;
+  static constexpr bool WRES = WRES_, FLAT = FLAT_;
+  static constexpr int NSPLIT = NSPLIT_, NTOT = N_ * NSPLIT_;
   static constexpr int KS = 16, CH = KS / 4, NKS = K / KS;           // channels / 16-byte chunks per stage, stages per unit
   static constexpr int RAW_BYTES = 256 * KS * 4;                      // 16 x 16 pixels x 16 channels fp32 (64-byte swizzled rows)
   static constexpr int B_HALF = CH * N * 16, B_STAGE = 2 * B_HALF;    // weights of one stage: hi then lo, [chunk][n][4 k]
   static constexpr int W_SMEM = WRES ? NKS * B_STAGE : OP_STAGES * B_STAGE;
   static constexpr int UX = (H + 15) / 16, UNITS_PER_IMG = UX * UX;
+  static constexpr int W_SPLIT_BYTES = NKS * B_STAGE;                  // weight image of one N split
   static constexpr int OH = H / 2;
   // TMEM columns: accumulators [buf][tile][N], then the A operand ring [stage][tile][hi 16 | lo 16]
   static constexpr int A_BASE = ACC_BUFS * 2 * N, A_STAGE_COLS = 64;
   static constexpr int OFF_W = RAW_STAGES * RAW_BYTES;
   static constexpr int OFF_BAR = OFF_W + W_SMEM;
   static constexpr int OFF_PAR = OFF_BAR + 256;                        // bias | bn scale | bn shift, N floats each
-  static constexpr int SMEM_BYTES = OFF_PAR + 3 * N * 4;
+  static constexpr int SMEM_BYTES = OFF_PAR + 3 * NTOT * 4;
   static constexpr int NCONV = 8, NEPI = 8;                            // converter / epilogue warps: (tile, TMEM lane quarter) each
   static constexpr int THREADS = (2 + NCONV + NEPI) * 32;
   static_assert(K % KS == 0 && N % 32 == 0 && N <= 128 && H % 2 == 0, "operand shape");
+  static_assert(FLAT ? (H == 16 && !WRES) : NSPLIT == 1, "flat maps: 16 pixels per image, streamed weights; N splits only there");
+
+  struct Unit { int img, uy, ux, nh; };
+  static __device__ __forceinline__ int total_units(int batch) { return FLAT ? ((batch + 15) / 16) * NSPLIT : batch * UNITS_PER_IMG; }
+  static __device__ __forceinline__ Unit unit(int u) {
+    Unit r;
+    if (FLAT) { r.nh = u % NSPLIT; r.uy = u / NSPLIT; r.ux = 0; r.img = 0; }
+    else { r.img = u / UNITS_PER_IMG; const int q = u - r.img * UNITS_PER_IMG; r.uy = q / UX; r.ux = q - r.uy * UX; r.nh = 0; }
+    return r;
+  }
   static_assert(RAW_STAGES <= 6 && OP_STAGES <= 4 && ACC_BUFS >= 1 && ACC_BUFS <= 2, "barrier arrays");
   static_assert(A_BASE + OP_STAGES * A_STAGE_COLS <= 512, "TMEM columns");
   static_assert(OFF_W % 128 == 0 && OFF_BAR % 16 == 0, "alignment");
@@ -74,12 +89,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// w [K][N] fp32 -> per stage of 16 k: [hi | lo][chunk c < 4][n][k = 16 s + 4 c + j, j < 4]
-__global__ void pw32_pack_weights(const float* __restrict__ w, int K, int N, float* __restrict__ out) {
+// w [K][ldn] fp32, columns n0 .. n0 + N -> per stage of 16 k: [hi | lo][chunk c < 4][n][k = 16 s + 4 c + j, j < 4]
+__global__ void pw32_pack_weights(const float* __restrict__ w, int K, int N, float* __restrict__ out, int ldn = 0, int n0 = 0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K * N) return;
   const int k = i / N, n = i - k * N;
-  const float v = w[i];
+  const float v = w[(size_t)k * (ldn ? ldn : N) + n0 + n];
   const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
   const int s = k >> 4, c = (k >> 2) & 3, j = k & 3;
   const size_t base = (size_t)s * (8 * N * 4) + ((size_t)c * N + n) * 4 + j;
@@ -108,12 +123,13 @@ pw32_kernel(const __grid_constant__ CUtensorMap tmap_in, const float* __restrict
   float* s_par = reinterpret_cast<float*>(smem + Cfg::OFF_PAR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_units = batch * Cfg::UNITS_PER_IMG;
+  const int total_units = Cfg::total_units(batch);
+  constexpr int NTOT = Cfg::NTOT;
 
-  for (int i = threadIdx.x; i < N; i += Cfg::THREADS) {      // constants: not ordered after the previous kernel
+  for (int i = threadIdx.x; i < NTOT; i += Cfg::THREADS) {   // constants: not ordered after the previous kernel
     s_par[i] = par.bias[i];
-    s_par[N + i] = par.bn_s[i];
-    s_par[2 * N + i] = par.bn_t[i];
+    s_par[NTOT + i] = par.bn_s[i];
+    s_par[2 * NTOT + i] = par.bn_t[i];
   }
   if (threadIdx.x == 0) {
     *abort_flag = 0u;
@@ -142,19 +158,19 @@ pw32_kernel(const __grid_constant__ CUtensorMap tmap_in, const float* __restrict
       int it = 0;
       bool ok = true;
       for (int u = blockIdx.x; u < total_units && ok; u += gridDim.x) {
-        const int img = u / Cfg::UNITS_PER_IMG, r = u - img * Cfg::UNITS_PER_IMG;
-        const int uy = r / Cfg::UX, ux = r - uy * Cfg::UX;
+        const typename Cfg::Unit un = Cfg::unit(u);
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(wimg) + (size_t)un.nh * Cfg::W_SPLIT_BYTES;
         for (int ks = 0; ks < NKS; ++ks, ++it) {
           const int rs = it % Cfg::RAW_STAGES, ruse = it / Cfg::RAW_STAGES;
           if (ruse > 0 && !(ok = mbar_wait(&raw_empty[rs], (ruse - 1) & 1, abort_flag, 0x700u, it))) break;
           mbar_expect_tx(&raw_full[rs], Cfg::RAW_BYTES);
-          tma_load_4d(smem + rs * Cfg::RAW_BYTES, &tmap_in, ks * Cfg::KS, ux * 16, uy * 16, img, &raw_full[rs]);
+          tma_load_4d(smem + rs * Cfg::RAW_BYTES, &tmap_in, ks * Cfg::KS, un.ux * 16, un.uy * 16, un.img, &raw_full[rs]);
           if (!Cfg::WRES) {
             // the weight block of this stage shares the ring index (and the release) of the A operand stage in TMEM
             const int os = it % Cfg::OP_STAGES, ouse = it / Cfg::OP_STAGES;
             if (ouse > 0 && !(ok = mbar_wait(&op_empty[os], (ouse - 1) & 1, abort_flag, 0x701u, it))) break;
             mbar_expect_tx(&w_full[os], Cfg::B_STAGE);
-            bulk_g2s(s_w + os * Cfg::B_STAGE, reinterpret_cast<const uint8_t*>(wimg) + (size_t)ks * Cfg::B_STAGE, Cfg::B_STAGE, &w_full[os]);
+            bulk_g2s(s_w + os * Cfg::B_STAGE, wsrc + (size_t)ks * Cfg::B_STAGE, Cfg::B_STAGE, &w_full[os]);
           }
         }
       }
@@ -168,7 +184,7 @@ pw32_kernel(const __grid_constant__ CUtensorMap tmap_in, const float* __restrict
       constexpr uint32_t HI = desc_hi(128);
       int it = 0, k = 0;
       for (int u = blockIdx.x; u < total_units && ok; u += gridDim.x, ++k) {
-        const int r = u % Cfg::UNITS_PER_IMG, ux = r % Cfg::UX;
+        const int ux = Cfg::unit(u).ux;
         const int ntile = (ux * 16 + 8 < H) ? 2 : 1;
         const int buf = k % Cfg::ACC_BUFS, use = k / Cfg::ACC_BUFS;
         if (use > 0 && !(ok = mbar_wait(&acc_empty[buf], (use - 1) & 1, abort_flag, 0x703u, k))) break;
@@ -213,7 +229,7 @@ pw32_kernel(const __grid_constant__ CUtensorMap tmap_in, const float* __restrict
     int it = 0;
     bool ok = true;
     for (int u = blockIdx.x; u < total_units && ok; u += gridDim.x) {
-      const int ux = (u % Cfg::UNITS_PER_IMG) % Cfg::UX;
+      const int ux = Cfg::unit(u).ux;
       const bool live = t == 0 || (ux * 16 + 8 < H);            // the right tile of the last unit column is outside the image
       for (int ks = 0; ks < NKS; ++ks, ++it) {
         const int rs = it % Cfg::RAW_STAGES, os = it % Cfg::OP_STAGES, ouse = it / Cfg::OP_STAGES;
@@ -250,16 +266,18 @@ pw32_kernel(const __grid_constant__ CUtensorMap tmap_in, const float* __restrict
     const int chsel = (xodd ? 16 : 0) + (yodd ? 8 : 0);
     int k = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++k) {
-      const int img = u / Cfg::UNITS_PER_IMG, r = u - img * Cfg::UNITS_PER_IMG;
-      const int uy = r / Cfg::UX, ux = r - uy * Cfg::UX;
+      const typename Cfg::Unit un = Cfg::unit(u);
+      const int img = un.img, uy = un.uy, ux = un.ux;
       const int ntile = (ux * 16 + 8 < H) ? 2 : 1;
+      const float* pp = s_par + un.nh * N;                       // this unit's slice of bias | bn scale | bn shift
       const int buf = k % Cfg::ACC_BUFS, use = k / Cfg::ACC_BUFS;
       if (!mbar_wait_suspend(&acc_full[buf], use & 1, abort_flag, 0x730u + warp, k)) break;
       tc_fence_after();
       if (e < ntile) {
         const int y = uy * 16 + ry, x = ux * 16 + rx;
-        const bool valid = (y < H) && (x < H);
-        float* o = out + (((size_t)img * Cfg::OH + (y >> 1)) * Cfg::OH + (x >> 1)) * N + chsel;
+        const bool valid = Cfg::FLAT ? (y < batch) : ((y < H) && (x < H));
+        float* o = Cfg::FLAT ? out + ((size_t)y * 16 + x) * NTOT + un.nh * N        // un-pooled: (batch, 16 pixels, NTOT)
+                             : out + (((size_t)img * Cfg::OH + (y >> 1)) * Cfg::OH + (x >> 1)) * N + chsel;
         const uint32_t tbase = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * 2 * N + e * N);
 #pragma unroll 1
         for (int cb = 0; cb < N / 32; ++cb) {
@@ -269,9 +287,9 @@ pw32_kernel(const __grid_constant__ CUtensorMap tmap_in, const float* __restrict
           float f[32];
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 pb = *reinterpret_cast<const float4*>(s_par + cb * 32 + j4 * 4);
-            const float4 ps = *reinterpret_cast<const float4*>(s_par + N + cb * 32 + j4 * 4);
-            const float4 pt = *reinterpret_cast<const float4*>(s_par + 2 * N + cb * 32 + j4 * 4);
+            const float4 pb = *reinterpret_cast<const float4*>(pp + cb * 32 + j4 * 4);
+            const float4 ps = *reinterpret_cast<const float4*>(pp + NTOT + cb * 32 + j4 * 4);
+            const float4 pt = *reinterpret_cast<const float4*>(pp + 2 * NTOT + cb * 32 + j4 * 4);
             const float bb[4] = {pb.x, pb.y, pb.z, pb.w}, ss[4] = {ps.x, ps.y, ps.z, ps.w}, tt[4] = {pt.x, pt.y, pt.z, pt.w};
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
@@ -280,6 +298,14 @@ pw32_kernel(const __grid_constant__ CUtensorMap tmap_in, const float* __restrict
               z = z > 0.f ? z : 0.01f * z;
               f[j] = fmaf(z, ss[jj], tt[jj]);
             }
+          }
+          if (Cfg::FLAT) {
+            if (valid) {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4)
+                *reinterpret_cast<float4*>(o + cb * 32 + j4 * 4) = make_float4(f[4 * j4], f[4 * j4 + 1], f[4 * j4 + 2], f[4 * j4 + 3]);
+            }
+            continue;
           }
           // 2x2 max-pool: lanes l^1 (x neighbour) and l^8 (y neighbour) hold the other three pixels of the window; each
           // exchange halves the channels a lane keeps, so the four lanes end with 8 pooled channels each
@@ -322,8 +348,10 @@ template <class Cfg>
 inline int make_pw32_map(CUtensorMap* map, const void* base, int batch) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(ERNET_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-  const cuuint64_t dims[4] = {(cuuint64_t)Cfg::K, (cuuint64_t)Cfg::H, (cuuint64_t)Cfg::H, (cuuint64_t)batch};
-  const cuuint64_t strides[3] = {(cuuint64_t)Cfg::K * 4, (cuuint64_t)Cfg::H * Cfg::K * 4, (cuuint64_t)Cfg::H * Cfg::H * Cfg::K * 4};
+  const cuuint64_t dims[4] = {(cuuint64_t)Cfg::K, (cuuint64_t)Cfg::H, Cfg::FLAT ? (cuuint64_t)batch : (cuuint64_t)Cfg::H,
+                              Cfg::FLAT ? (cuuint64_t)1 : (cuuint64_t)batch};
+  const cuuint64_t strides[3] = {(cuuint64_t)Cfg::K * 4, (cuuint64_t)Cfg::H * Cfg::K * 4,
+                                 (Cfg::FLAT ? (cuuint64_t)batch : (cuuint64_t)Cfg::H) * Cfg::H * Cfg::K * 4};
   const cuuint32_t box[4] = {(cuuint32_t)Cfg::KS, 16, 16, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr,
@@ -339,7 +367,7 @@ inline int launch_pw32(const float* a, const float* wimg, const float* bias, con
   CUtensorMap map;
   int rc = make_pw32_map<Cfg>(&map, a, batch);
   if (rc) return rc;
-  const int total = batch * Cfg::UNITS_PER_IMG;
+  const int total = Cfg::FLAT ? ((batch + 15) / 16) * Cfg::NSPLIT : batch * Cfg::UNITS_PER_IMG;
   const int grid = total < num_sms ? total : num_sms;
   Pw32Params par{bias, bn_s, bn_t};
   ERNET_CUDA(launch_pdl(pw32_kernel<Cfg>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, map, wimg, par, out, batch));
@@ -354,10 +382,12 @@ inline int set_pw32_attr() {
 
 inline size_t pw32_weight_floats(int K, int N) { return (size_t)2 * K * N; }
 
-// Squeeze_ErNET fp32: block 1 (48 -> 64 on 66x66, weights resident), block 2 (192 -> 96 on 30x30), block 3 (288 -> 128 on 12x12)
+// Squeeze_ErNET fp32: block 1 (48 -> 64 on 66x66, weights resident), block 2 (192 -> 96 on 30x30), block 3 (288 -> 128 on 12x12);
 using FPw1 = TfCfg<48, 64, 66, true, 6, 3, 2>;
 using FPw2 = TfCfg<192, 96, 30, true, 4, 2, 2>;
 using FPw3 = TfCfg<288, 128, 12, false, 4, 4, 1>;
+// block 4 (384 -> 256 on 4x4, LeakyReLU + BN, no pool): 16 images x 16 pixels per unit, four 64-channel splits
+using FPw4 = TfCfg<384, 64, 16, false, 4, 4, 2, true, 4>;
 
 }  // namespace tc
 }  // namespace ernet

@@ -17,6 +17,7 @@ from test_oracle_golden import INGEST_NAMES, _case_frame
 pytestmark = pytest.mark.gpu
 
 TOL = {"fp32": 1e-4, "fp16": 2e-2, "bf16": 2e-2}     # BASELINE.json north_star tolerances (relative, on logits)
+FP32_FAST_INGEST_TOL = 5e-6   # fp32 frames path on 5-tap frames vs transform-then-model (both fp32; see ingest_fast.cuh)
 TDT = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
 DCODE = {"fp32": 0, "fp16": 1, "bf16": 2}
 
@@ -234,7 +235,13 @@ def test_frames_path_and_chunking(prec, dev):
     x = m.ingest(ft, dtype=TDT[prec])
     p2, l2 = m.forward_with_logits(x)
     if prec == "fp32":
-        assert torch.equal(logits, l2) and torch.equal(probs, p2)
+        # 240x240 frames take the word-wide kernel whose conv1 runs on mma.sync with (hi, lo) fp16 weight images (22
+        # significant bits, Normalize folded in): fp32-rounding-level agreement; the table-lookup kernel is bit-identical
+        assert _rel(logits.double().cpu().numpy(), l2.double().cpu().numpy()) <= FP32_FAST_INGEST_TOL
+        m.set_fast_ingest(False)
+        p_t, l_t = m.forward_frames(ft, return_logits=True)
+        m.set_fast_ingest(True)
+        assert torch.equal(l_t, l2) and torch.equal(p_t, p2)
     else:   # 16-bit frames path runs conv1 on mma.sync with weights rounded to 16 bit; the tensor path keeps fp32 weights
         assert _rel(logits.double().cpu().numpy(), l2.double().cpu().numpy()) <= 5e-3
     ref = E.forward(sd, I.ingest(frames), arch, dtype=np.float64)
@@ -592,7 +599,15 @@ def test_fused_transform_conv1_equals_two_kernel_path(hw, arch, prec, dev):
     x = m.ingest(ft, dtype=TDT[prec])
     l_two = m.forward_with_logits(x)[1]
     if prec == "fp32":
-        assert torch.equal(l_fused, l_two)
+        # 5-tap geometries (240x240, 161x300) take the word-wide kernel whose conv1 runs on mma.sync with (hi, lo) fp16
+        # weight images: fp32-rounding-level agreement there, bit-identity everywhere else and with that kernel switched off
+        if hw in ((240, 240), (161, 300)):
+            assert _rel(l_fused.double().cpu().numpy(), l_two.double().cpu().numpy()) <= FP32_FAST_INGEST_TOL
+        else:
+            assert torch.equal(l_fused, l_two)
+        m.set_fast_ingest(False)
+        assert torch.equal(m.forward_frames(ft, return_logits=True)[1], l_two)
+        m.set_fast_ingest(True)
     else:   # conv1 of the 16-bit frames path: mma.sync, weights rounded to 16 bit (tensor path: fp32 weights, FFMA)
         assert _rel(l_fused.double().cpu().numpy(), l_two.double().cpu().numpy()) <= 5e-3
     assert torch.equal(l_bgr, l_fused)
@@ -631,7 +646,8 @@ def test_block_kernel_schedules_agree(arch, prec, dev):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("arch,prec", [("squeeze-ernet", "bf16"), ("squeeze-redconv", "fp16")])
+@pytest.mark.parametrize("arch,prec", [("squeeze-ernet", "bf16"), ("squeeze-redconv", "fp16"), ("squeeze-ernet", "fp32"),
+                                       ("squeeze-redconv", "fp32")])
 def test_fast_ingest_matches_table_lookup_kernel(arch, prec, dev):
     """240x240 frames take the word-wide fused transform+conv1 kernel with Normalize folded into conv1; the
     table-lookup kernel (bit-identical to ingest() + forward()) stays selectable.  Both meet the oracle tolerance, agree
@@ -649,7 +665,7 @@ def test_fast_ingest_matches_table_lookup_kernel(arch, prec, dev):
         assert _rel(lg.double().cpu().numpy(), ref) <= TOL[prec]
         assert _top1_ok(lg.double().cpu().numpy(), ref, TOL[prec])
     assert not torch.equal(l_fast, l_slow)                       # two different kernels really ran
-    assert _rel(l_fast.double().cpu().numpy(), l_slow.double().cpu().numpy()) <= 1e-2
+    assert _rel(l_fast.double().cpu().numpy(), l_slow.double().cpu().numpy()) <= (FP32_FAST_INGEST_TOL if prec == "fp32" else 1e-2)
     l_bgr = m.forward_frames(torch.from_numpy(frames[..., ::-1].copy()).to(dev), bgr=True, return_logits=True)[1]
     assert torch.equal(l_bgr, l_fast)
     for shift in (1, 7, 16):                                      # first / last band of an unaligned buffer: guarded copy

@@ -15,10 +15,11 @@ batch = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 g = torch.Generator().manual_seed(7)
 frames = torch.randint(0, 256, (batch, 240, 240, 3), dtype=torch.uint8, generator=g).cuda()
 res = {}
-for mode in ("0", "1"):
-    os.environ["ERNET_FP32_TC"] = mode
+for mode in ("0", "1", "1s"):                       # FFMA 1x1 kernels | split-TF32 tcgen05 GEMMs | the latter with the table-lookup ingest
+    os.environ["ERNET_FP32_TC"] = mode[0]
     m = rtdm_b200.from_state_dict("squeeze-ernet", fixtures.get_state_dict("squeeze-ernet", "shipped"), "cuda:0", "fp32")
     m.set_chunk(batch)
+    m.set_fast_ingest(mode != "1s")
     _, lg = m.forward_frames(frames, return_logits=True)
     torch.cuda.synchronize()
     m.check_watchdog() if hasattr(m, "check_watchdog") else None
@@ -40,5 +41,8 @@ for n in ("pool1", "pool2", "pool3"):
 out["logits_max_abs"] = float((res["0"][0] - res["1"][0]).abs().max())
 out["stage_us_ffma"] = res["0"][2]
 out["stage_us_tf32x3"] = res["1"][2]
+out["logits_max_abs_fast_vs_table_ingest"] = float((res["1"][0] - res["1s"][0]).abs().max())
+out["logits_abs_max"] = float(res["1s"][0].abs().max())
+out["stage_us_tf32x3_table_ingest"] = res["1s"][2]
 out["step_us"] = {k: round(sum(res[k][2].values()), 1) for k in res}
 print(json.dumps(out))
