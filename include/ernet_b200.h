@@ -105,6 +105,12 @@ int ernet_set_fast_ingest(ernet_handle* h, int on);
  * (default) = a kernel of their own in front of block 1.  Measured at parity on B200, hence off
  * by default.  The environment variable ERNET_FUSE_INGEST=1 sets the initial value of new handles.            */
 int ernet_set_fuse_ingest(ernet_handle* h, int on);
+/* Host path (ernet_classify_frames_host*): 1 = when the caller's frame buffer is pinned host memory, a small kernel
+ * pulls only the FOOTPRINT of the crop window (rows and columns the eval transform reads, 240x240: 79 % of the frame)
+ * over PCIe with 16-byte loads instead of a copy-engine transfer of the row range (89 %); pageable or unaligned
+ * buffers silently take the copy-engine path.  0 = always the copy engine.  `ctas` = CTAs of that kernel (0 keeps
+ * the current value).  The environment variable ERNET_HOST_GATHER sets the initial value of new handles.        */
+int ernet_set_host_gather(ernet_handle* h, int on, int ctas);
 /* Fused kernels keep some intermediates on chip (acff4 inside the ACFF4+head kernel).  With debug taps
  * on they are also written to the workspace so that ernet_debug_tap() can read them (test use).      */
 int ernet_set_debug_taps(ernet_handle* h, int on);
@@ -139,7 +145,8 @@ int ernet_forward_frames(ernet_handle* h, const uint8_t* frames_hwc, int batch, 
                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* Bytes of one height x width frame that ernet_classify_frames_host really sends to the device: only the rows the
- * crop window of the eval transform reads (240x240: 213 of 240 rows).  0 on error.                         */
+ * crop window of the eval transform reads (240x240: 213 of 240 rows) - with ernet_set_host_gather on, only the
+ * 16-byte vectors that overlap the window's rows AND columns.  0 on error.                                 */
 size_t ernet_host_copy_bytes_per_frame(ernet_handle* h, int height, int width);
 /* Same with HOST buffers: `predict()` of aider-predict.py:47-86 / the loop body of
  * evaluate-classification-metrics.py:69-82 for a batch.  Host->device copies of the frames and the

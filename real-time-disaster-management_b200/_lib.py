@@ -39,6 +39,7 @@ SIGNATURES = {
     "ernet_classify_frames_host_wait": (_i, [_vp, _i]),
     "ernet_set_fast_ingest": (_i, [_vp, _i]),
     "ernet_set_fuse_ingest": (_i, [_vp, _i]),
+    "ernet_set_host_gather": (_i, [_vp, _i, _i]),
     "ernet_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "ernet_ingest_u8": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "ernet_prepare_ingest": (_i, [_vp, _i, _i]),

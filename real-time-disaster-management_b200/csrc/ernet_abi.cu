@@ -20,6 +20,7 @@
 #include "tc_fblock.cuh"
 #include "tc_pw32.cuh"
 #include "dw_tma.cuh"
+#include "host_gather.cuh"
 
 namespace ernet {
 
@@ -72,6 +73,8 @@ struct ernet_handle {
   bool dual_copy = false;       // host path: alternate two copy streams (ERNET_DUAL_COPY=1)
   bool trim_columns = false;    // host path: also skip the columns outside the crop footprint (ERNET_TRIM_COLUMNS=1).  Off:
                                 // measured 78 K img/s against 281 K - a 3-D copy of 639-byte rows runs at ~10 GB/s
+  bool host_gather = false;     // host path: pinned frames are pulled by host_gather_kernel (footprint rows AND columns, host_gather.cuh)
+  int gather_ctas = 32;
   bool pair_taps = true;        // two taps per MMA in block 1 when its input has one real chunk (ERNET_PAIR_TAPS=0 switches it off)
   bool pair_block1 = false;     // block 1 on the CTA-pair kernel as well (experiment switch: ERNET_PAIR_BLOCK1=0)
   bool fast_ingest = true;      // word-wide fused transform+conv1 with Normalize folded into conv1 (ingest_fast.cuh)
@@ -939,6 +942,8 @@ int ernet_create(ernet_handle** out, int arch, int precision, int device) {
   }
   if (const char* e = getenv("ERNET_FP32_TC")) h->fp32_tc = atoi(e) != 0;
   if (const char* e = getenv("ERNET_TRIM_COLUMNS")) h->trim_columns = atoi(e) != 0;
+  if (const char* e = getenv("ERNET_HOST_GATHER")) h->host_gather = atoi(e) != 0;
+  if (const char* e = getenv("ERNET_GATHER_CTAS")) { const int c = atoi(e); if (c >= 1 && c <= 1024) h->gather_ctas = c; }
   if (const char* e = getenv("ERNET_DUAL_COPY")) h->dual_copy = atoi(e) != 0;
   *out = h;
   return ERNET_OK;
@@ -1184,6 +1189,13 @@ int ernet_set_fuse_ingest(ernet_handle* h, int on) {
   h->fuse_ingest = on != 0;
   return ERNET_OK;
 }
+int ernet_set_host_gather(ernet_handle* h, int on, int ctas) {
+  if (!h) return fail(ERNET_ERR_INVALID_ARG, "null handle");
+  if (ctas < 0 || ctas > 1024) return fail(ERNET_ERR_INVALID_ARG, "host gather: ctas must be 0 (keep) .. 1024, got %d", ctas);
+  h->host_gather = on != 0;
+  if (ctas) h->gather_ctas = ctas;
+  return ERNET_OK;
+}
 int ernet_set_debug_taps(ernet_handle* h, int on) {
   if (!h) return fail(ERNET_ERR_INVALID_ARG, "null handle");
   h->debug_taps = on != 0;
@@ -1278,11 +1290,22 @@ int ernet_ingest_u8(ernet_handle* h, const uint8_t* frames, int batch, int heigh
   return ERNET_OK;
 }
 
+static GatherGeom gather_geometry(const IngestTables* tab, int width) {
+  GatherGeom g;
+  g.f_img = (unsigned long long)tab->H * width * 3;
+  g.rowb = width * 3;
+  g.row_lo = tab->row_lo; g.nrows = tab->row_hi - tab->row_lo;
+  g.xb0 = tab->col_lo * 3; g.xb1 = tab->col_hi * 3;
+  g.vpr = (g.xb1 - g.xb0 + 15) / 16 + 1;
+  return g;
+}
+
 size_t ernet_host_copy_bytes_per_frame(ernet_handle* h, int height, int width) {
   if (!h) return 0;
   DeviceGuard g(h->device);
   const IngestTables* tab;
   if (get_tables(h, height, width, &tab)) return 0;
+  if (h->host_gather && ((size_t)height * width * 3) % 16 == 0) return gather_bytes_per_frame(gather_geometry(tab, width));
   return (size_t)(tab->row_hi - tab->row_lo) * (h->trim_columns ? (size_t)(tab->col_hi - tab->col_lo) : (size_t)width) * 3;
 }
 
@@ -1296,8 +1319,10 @@ int ernet_classify_frames_host_submit(ernet_handle* h, const uint8_t* frames_hos
   int rc = get_tables(h, height, width, &tab);
   if (rc) return rc;
   if (!h->s_copy) {
-    ERNET_CUDA(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
-    ERNET_CUDA(cudaStreamCreateWithFlags(&h->s_copy2, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;                            // copy streams first: the gather kernel's few CTAs must not queue behind compute CTAs
+    ERNET_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    ERNET_CUDA(cudaStreamCreateWithPriority(&h->s_copy, cudaStreamNonBlocking, prio_hi));
+    ERNET_CUDA(cudaStreamCreateWithPriority(&h->s_copy2, cudaStreamNonBlocking, prio_hi));
     ERNET_CUDA(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
       ERNET_CUDA(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
@@ -1314,6 +1339,16 @@ int ernet_classify_frames_host_submit(ernet_handle* h, const uint8_t* frames_hos
   }
   const size_t f_img = (size_t)height * width * 3;
   const size_t fbytes = (size_t)chunk * f_img;
+  // pinned (mapped) frames can be pulled by a kernel that skips the columns outside the crop footprint as well
+  const uint8_t* gather_src = nullptr;
+  if (h->host_gather && f_img % 16 == 0) {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, frames_host) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer &&
+        (reinterpret_cast<size_t>(pa.devicePointer) & 15) == 0)
+      gather_src = static_cast<const uint8_t*>(pa.devicePointer);
+    else
+      cudaGetLastError();
+  }
   if (h->d_frames_bytes < fbytes || h->d_ws_bytes < ernet_workspace_bytes(h, chunk) || h->d_res_elems < (size_t)batch * 10)
     ERNET_CUDA(cudaStreamSynchronize(h->s_compute));        // growing a buffer: nothing may still be using the old one
   if (h->d_frames_bytes < fbytes) {
@@ -1346,7 +1381,11 @@ int ernet_classify_frames_host_submit(ernet_handle* h, const uint8_t* frames_hos
     // only the rows the crop window of the eval transform reads travel over PCIe (240x240: rows 14..226, 89 % of
     // the frame); one strided copy, each "row" of it is the contiguous row range of one frame
     const size_t rowb = (size_t)width * 3, lo = (size_t)tab->row_lo * rowb, span = (size_t)(tab->row_hi - tab->row_lo) * rowb;
-    if (h->trim_columns) {
+    if (gather_src) {
+      host_gather_kernel<<<h->gather_ctas, kGatherThreads, 0, cs>>>(gather_src + (size_t)b0 * f_img, h->d_frames[s], n, (unsigned long long)n * f_img,
+                                                                    gather_geometry(tab, width));
+      ERNET_LAUNCH_CHECK("host_gather_kernel");
+    } else if (h->trim_columns) {
       // rows AND columns of the crop window's footprint: a 3-D strided copy (x = bytes of the column range, y = rows, z = frames)
       cudaMemcpy3DParms cp = {};
       const size_t xoff = (size_t)tab->col_lo * 3, xbytes = (size_t)(tab->col_hi - tab->col_lo) * 3;

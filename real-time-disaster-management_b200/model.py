@@ -96,6 +96,14 @@ class _EngineRuntime:
         _lib.check(lib.ernet_set_fuse_ingest(h, 1 if on else 0))
         return self
 
+    def set_host_gather(self, on=True, ctas=0):
+        """Host path (classify_host / classify_host_submit): pull only the footprint of the crop window from PINNED frames
+        over PCIe with a small kernel (csrc/host_gather.cuh) instead of a copy-engine transfer of the row range.  Same
+        results; pageable frames take the copy-engine path either way."""
+        lib, h, _ = self._ensure_engine()
+        _lib.check(lib.ernet_set_host_gather(h, 1 if on else 0, int(ctas)))
+        return self
+
     def set_debug_taps(self, on=True):
         """Also write the intermediates that fused kernels keep on chip (needed for tap('acff4'))."""
         lib, h, _ = self._ensure_engine()

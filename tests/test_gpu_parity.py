@@ -860,6 +860,46 @@ def test_host_path_small_chunk_large_batch(dev):
     assert _lib.load().ernet_check_watchdog() == 0
 
 
+@pytest.mark.parametrize("arch,prec,hw", [("squeeze-ernet", "bf16", (240, 240)), ("squeeze-redconv", "fp16", (240, 240)),
+                                          ("squeeze-ernet", "fp32", (240, 240)), ("squeeze-ernet", "bf16", (480, 640)),
+                                          ("squeeze-ernet", "bf16", (161, 300)), ("ernet", "bf16", (240, 240))])
+def test_host_gather_matches_copy_engine_path(arch, prec, hw, dev):
+    """ernet_set_host_gather: pinned frames are pulled over PCIe by a kernel that reads only the crop window's footprint
+    (rows and columns); results equal the copy-engine path bit for bit - blocking and streaming calls, several sub-chunks,
+    a pinned view at an odd byte offset and pageable frames (both fall back to the copy engine), frame sizes whose byte
+    count is not a multiple of 16 (161x300: fallback as well) - and fewer bytes are reported as sent."""
+    H, W = hw
+    sd = fixtures.get_state_dict(arch, "shipped" if arch != "ernet" else "w3")
+    n = 150 if hw == (240, 240) else 9
+    frames = np.concatenate([fixtures.noise_frames(n // 2, H, W, seed=11 + H), fixtures.smooth_frames(n - n // 2, H, W, seed=12 + W)], 0)
+    m = rtdm_b200.from_state_dict(arch, sd, dev, prec)
+    want_p, want_l = m.classify_host(frames, return_logits=True)
+    rows_only = m.host_copy_bytes_per_frame(H, W)
+    m.set_host_gather(True)
+    pinned = torch.from_numpy(frames).pin_memory()
+    got_p, got_l = m.classify_host(pinned, return_logits=True)
+    assert np.array_equal(got_l, want_l) and np.array_equal(got_p, want_p)
+    if (H * W * 3) % 16 == 0:
+        assert m.host_copy_bytes_per_frame(H, W) < rows_only
+    else:
+        assert m.host_copy_bytes_per_frame(H, W) == rows_only
+    # streaming, 4 CTAs, two tickets in flight, a second batch right behind
+    m.set_host_gather(True, ctas=4)
+    t1 = m.classify_host_submit(pinned, return_logits=True)
+    t2 = m.classify_host_submit(pinned[: max(1, n // 3)], return_logits=True)
+    p1, l1 = t1.result()
+    p2, l2 = t2.result()
+    assert np.array_equal(l1, want_l) and np.array_equal(l2, want_l[: max(1, n // 3)])
+    # pageable frames and a pinned view that is not 16-byte aligned: copy-engine path, same answer
+    pg_p, pg_l = m.classify_host(frames, return_logits=True)
+    assert np.array_equal(pg_l, want_l)
+    big = torch.empty(frames.size + 3, dtype=torch.uint8).pin_memory()
+    big[3:] = torch.from_numpy(frames).flatten()
+    od_p, od_l = m.classify_host(big[3:].view(frames.shape), return_logits=True)
+    assert np.array_equal(od_l, want_l)
+    assert _lib.load().ernet_check_watchdog() == 0
+
+
 def test_confusion_update_nan_matches_torch_argmax(dev):
     """A NaN score wins the arg-max (first NaN), as in torch.argmax (evaluate-classification-metrics.py:81)."""
     sc = torch.tensor([[0.1, float("nan"), 0.7, 0.0, 0.2], [0.5, 0.2, 0.1, 0.1, 0.1], [float("nan")] * 5,
