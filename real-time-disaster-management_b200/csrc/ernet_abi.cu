@@ -1150,7 +1150,8 @@ int ernet_load_packed(ernet_handle* h, const void* blob, size_t bytes) {
       const int splits = k == 3 ? tc::FPw4::NSPLIT : 1, nsub = nn[k] / splits;      // block 4: one image per 64-channel split
       for (int sp = 0; sp < splits; ++sp) {
         tc::pw32_pack_weights<<<(kk[k] * nsub + 255) / 256, 256>>>(h->blk(k, ERNET_T_PW_W), kk[k], nsub,
-                                                                  h->d_pw32[k] + (size_t)sp * tc::pw32_weight_floats(kk[k], nsub), nn[k], sp * nsub);
+                                                                  h->d_pw32[k] + (size_t)sp * tc::pw32_weight_floats(kk[k], nsub), nn[k], sp * nsub,
+                                                                  k < 3 ? h->blk(k, ERNET_T_BN_S) : nullptr);   // pooled blocks: pool-first epilogue
         ERNET_LAUNCH_CHECK("pw32_pack_weights");
       }
     }

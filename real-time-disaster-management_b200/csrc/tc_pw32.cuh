@@ -11,10 +11,14 @@
 //   warp 0      TMA: per K stage of 16 channels one box (16 ch, 16 px, 16 rows) of the NHWC concat tensor -> raw ring
 //               (rows outside the image are zero-filled by the TMA unit), plus that stage's weight block when the
 //               weights are streamed;
-//   warps 2-5   convert a raw stage into the two UMMA operand images (hi, lo) in the K-major core-matrix layout;
+//   warps 2-9   convert a raw stage into the two UMMA operand images (hi, lo) in the K-major core-matrix layout;
 //   warp 1      MMA issuer: 2 tiles x 2 K steps x 3 MMAs (kind::tf32, M128 x N x K8) per stage, two TMEM accumulator
 //               buffers so that the epilogue of unit k runs under the MMAs of unit k+1;
-//   warps 6-13  epilogue: TMEM -> bias, LeakyReLU, BN affine -> 2x2 max-pool by lane shuffles -> fp32 NHWC.
+//   warps 10-17 epilogue, POOL FIRST: TMEM -> 2x2 max of the raw accumulators by lane shuffles -> bias, LeakyReLU, BN
+//               affine on the pooled quarter -> fp32 NHWC.  max commutes with every monotone map, and bias + LeakyReLU +
+//               BN is non-decreasing in the accumulator when the BN scale is >= 0; for channels with a negative scale
+//               the packer negates the weight column (the accumulator becomes -acc, exactly) and the epilogue multiplies
+//               the pooled value by -1 again: max(-acc) = -min(acc), which is what a decreasing map needs.
 #pragma once
 #include <cuda.h>
 
@@ -42,8 +46,8 @@ struct TfCfg {
   static constexpr int A_BASE = ACC_BUFS * 2 * N, A_STAGE_COLS = 64;
   static constexpr int OFF_W = RAW_STAGES * RAW_BYTES;
   static constexpr int OFF_BAR = OFF_W + W_SMEM;
-  static constexpr int OFF_PAR = OFF_BAR + 256;                        // bias | bn scale | bn shift, N floats each
-  static constexpr int SMEM_BYTES = OFF_PAR + 3 * NTOT * 4;
+  static constexpr int OFF_PAR = OFF_BAR + 256;                        // bias | bn scale | bn shift | accumulator sign, NTOT floats each
+  static constexpr int SMEM_BYTES = OFF_PAR + 4 * NTOT * 4;
   static constexpr int NCONV = 8, NEPI = 8;                            // converter / epilogue warps: (tile, TMEM lane quarter) each
   static constexpr int THREADS = (2 + NCONV + NEPI) * 32;
   static_assert(K % KS == 0 && N % 32 == 0 && N <= 128 && H % 2 == 0, "operand shape");
@@ -90,11 +94,14 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // w [K][ldn] fp32, columns n0 .. n0 + N -> per stage of 16 k: [hi | lo][chunk c < 4][n][k = 16 s + 4 c + j, j < 4]
-__global__ void pw32_pack_weights(const float* __restrict__ w, int K, int N, float* __restrict__ out, int ldn = 0, int n0 = 0) {
+// neg_if (pooled blocks: the BN scale) != nullptr: columns whose entry is negative are stored negated (pool-first epilogue)
+__global__ void pw32_pack_weights(const float* __restrict__ w, int K, int N, float* __restrict__ out, int ldn = 0, int n0 = 0,
+                                  const float* __restrict__ neg_if = nullptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K * N) return;
   const int k = i / N, n = i - k * N;
-  const float v = w[(size_t)k * (ldn ? ldn : N) + n0 + n];
+  float v = w[(size_t)k * (ldn ? ldn : N) + n0 + n];
+  if (neg_if && neg_if[n0 + n] < 0.f) v = -v;
   const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
   const int s = k >> 4, c = (k >> 2) & 3, j = k & 3;
   const size_t base = (size_t)s * (8 * N * 4) + ((size_t)c * N + n) * 4 + j;
@@ -130,6 +137,7 @@ pw32_kernel(const __grid_constant__ CUtensorMap tmap_in, const float* __restrict
     s_par[i] = par.bias[i];
     s_par[NTOT + i] = par.bn_s[i];
     s_par[2 * NTOT + i] = par.bn_t[i];
+    s_par[3 * NTOT + i] = (!Cfg::FLAT && par.bn_s[i] < 0.f) ? -1.f : 1.f;      // same rule as pw32_pack_weights
   }
   if (threadIdx.x == 0) {
     *abort_flag = 0u;
@@ -284,36 +292,33 @@ pw32_kernel(const __grid_constant__ CUtensorMap tmap_in, const float* __restrict
           uint32_t v[32];
           tmem_ld32(tbase + cb * 32, v);
           tmem_ld_wait();
-          float f[32];
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 pb = *reinterpret_cast<const float4*>(pp + cb * 32 + j4 * 4);
-            const float4 ps = *reinterpret_cast<const float4*>(pp + NTOT + cb * 32 + j4 * 4);
-            const float4 pt = *reinterpret_cast<const float4*>(pp + 2 * NTOT + cb * 32 + j4 * 4);
-            const float bb[4] = {pb.x, pb.y, pb.z, pb.w}, ss[4] = {ps.x, ps.y, ps.z, ps.w}, tt[4] = {pt.x, pt.y, pt.z, pt.w};
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const int j = j4 * 4 + jj;
-              float z = __uint_as_float(v[j]) + bb[jj];
-              z = z > 0.f ? z : 0.01f * z;
-              f[j] = fmaf(z, ss[jj], tt[jj]);
-            }
-          }
-          if (Cfg::FLAT) {
+          if (Cfg::FLAT) {                 // un-pooled block: every value goes through bias, LeakyReLU, BN
             if (valid) {
 #pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4)
-                *reinterpret_cast<float4*>(o + cb * 32 + j4 * 4) = make_float4(f[4 * j4], f[4 * j4 + 1], f[4 * j4 + 2], f[4 * j4 + 3]);
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 pb = *reinterpret_cast<const float4*>(pp + cb * 32 + j4 * 4);
+                const float4 ps = *reinterpret_cast<const float4*>(pp + NTOT + cb * 32 + j4 * 4);
+                const float4 pt = *reinterpret_cast<const float4*>(pp + 2 * NTOT + cb * 32 + j4 * 4);
+                const float bb[4] = {pb.x, pb.y, pb.z, pb.w}, ss[4] = {ps.x, ps.y, ps.z, ps.w}, tt[4] = {pt.x, pt.y, pt.z, pt.w};
+                float f[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                  float z = __uint_as_float(v[j4 * 4 + jj]) + bb[jj];
+                  z = z > 0.f ? z : 0.01f * z;
+                  f[jj] = fmaf(z, ss[jj], tt[jj]);
+                }
+                *reinterpret_cast<float4*>(o + cb * 32 + j4 * 4) = make_float4(f[0], f[1], f[2], f[3]);
+              }
             }
             continue;
           }
-          // 2x2 max-pool: lanes l^1 (x neighbour) and l^8 (y neighbour) hold the other three pixels of the window; each
-          // exchange halves the channels a lane keeps, so the four lanes end with 8 pooled channels each
+          // 2x2 max-pool of the raw accumulators: lanes l^1 (x neighbour) and l^8 (y neighbour) hold the other three pixels
+          // of the window; each exchange halves the channels a lane keeps, so the four lanes end with 8 pooled channels each
           float g[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float keep = xodd ? f[j + 16] : f[j];
-            const float send = xodd ? f[j] : f[j + 16];
+            const float keep = __uint_as_float(xodd ? v[j + 16] : v[j]);
+            const float send = __uint_as_float(xodd ? v[j] : v[j + 16]);
             g[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
           }
           float m[8];
@@ -322,6 +327,23 @@ pw32_kernel(const __grid_constant__ CUtensorMap tmap_in, const float* __restrict
             const float keep = yodd ? g[j + 8] : g[j];
             const float send = yodd ? g[j] : g[j + 8];
             m[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+          }
+          // bias, LeakyReLU, BN on the lane's 8 pooled channels (cb * 32 + chsel + 0..7)
+#pragma unroll
+          for (int j4 = 0; j4 < 2; ++j4) {
+            const float* q = pp + cb * 32 + chsel + j4 * 4;
+            const float4 pb = *reinterpret_cast<const float4*>(q);
+            const float4 ps = *reinterpret_cast<const float4*>(q + NTOT);
+            const float4 pt = *reinterpret_cast<const float4*>(q + 2 * NTOT);
+            const float4 pg = *reinterpret_cast<const float4*>(q + 3 * NTOT);
+            const float bb[4] = {pb.x, pb.y, pb.z, pb.w}, ss[4] = {ps.x, ps.y, ps.z, ps.w}, tt[4] = {pt.x, pt.y, pt.z, pt.w},
+                        gg[4] = {pg.x, pg.y, pg.z, pg.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              float z = fmaf(m[j4 * 4 + jj], gg[jj], bb[jj]);       // (+-1) * pooled accumulator + bias: exact sign restore
+              z = fmaxf(z, 0.01f * z);                              // LeakyReLU(0.01)
+              m[j4 * 4 + jj] = fmaf(z, ss[jj], tt[jj]);
+            }
           }
           if (valid) {
             *reinterpret_cast<float4*>(o + cb * 32) = make_float4(m[0], m[1], m[2], m[3]);

@@ -25,7 +25,7 @@ stage_of = [("ingest_block1", "tc_block1"), ("ingest_stem", "ingest"), ("ingest_
             ("CCfg<8, 96", "tc_block2"), ("CCfg<4, 96", "tc_block2"), ("PCfg<8, 96", "tc_block2"), ("BlockCfg<8, 96", "tc_block2"), ("BlockCfg<4, 96", "tc_block2"),
             ("CCfg<12, 128", "tc_block3"), ("CCfg<6, 128", "tc_block3"), ("CCfg<4, 128", "tc_block3"), ("PCfg<12, 128", "tc_block3"),
             ("BlockCfg<12, 128", "tc_block3"), ("BlockCfg<6, 128", "tc_block3"), ("acff4_head", "tc_block4"),
-            ("acff_dw", "dw#"), ("pointwise_kernel", "pw#"), ("stem_kernel", "stem"), ("head_kernel", "head")]
+            ("acff_dw", "dw#"), ("pointwise_kernel", "pw#"), ("pw32_kernel", "pw#"), ("stem_kernel", "stem"), ("head_kernel", "head")]
 seen = {}
 
 
