@@ -73,6 +73,7 @@ struct ernet_handle {
   bool dual_copy = false;       // host path: alternate two copy streams (ERNET_DUAL_COPY=1)
   bool trim_columns = false;    // host path: also skip the columns outside the crop footprint (ERNET_TRIM_COLUMNS=1).  Off:
                                 // measured 78 K img/s against 281 K - a 3-D copy of 639-byte rows runs at ~10 GB/s
+  bool tail_tiles = true;       // block 1: output rows 64, 65 as one tail unit per image (PCfg::TAIL, tc_pblock.cuh; ERNET_TAIL_TILES=0: 16x8 tiles only)
   bool host_gather = false;     // host path: pinned frames are pulled by host_gather_kernel (footprint rows AND columns, host_gather.cuh)
   int gather_ctas = 32;
   bool pair_taps = true;        // two taps per MMA in block 1 when its input has one real chunk (ERNET_PAIR_TAPS=0 switches it off)
@@ -459,7 +460,10 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
       if (h->persistent == 2) {
         if (fused1) {
         } else if (h->d_w1_pair && h->pair_taps) {
-          ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1P, KIND, tc::OUT_P8>(u16(p.stem), h->d_w1_pair, h->epi1, u16(p.p1), n, h->num_sms, s)));
+          {
+            if (h->tail_tiles) ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1PT, KIND, tc::OUT_P8>(u16(p.stem), h->d_w1_pair, h->epi1, u16(p.p1), n, h->num_sms, s)));
+            else ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1P, KIND, tc::OUT_P8>(u16(p.stem), h->d_w1_pair, h->epi1, u16(p.p1), n, h->num_sms, s)));
+          }
         } else {
           ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1, KIND, tc::OUT_P8>(u16(p.stem), wimgr(0), h->epi1, u16(p.p1), n, h->num_sms, s)));
         }
@@ -513,7 +517,10 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
       }
       if (fused1) {
       } else if (paired) {
-        ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1P, tc::KIND_F16, tc::OUT_P16>(u16(p.stem), h->d_w1_pair, h->epi1, u16(p.p1), n, h->num_sms, s)));
+        {
+          if (h->tail_tiles) ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1PT, tc::KIND_F16, tc::OUT_P16>(u16(p.stem), h->d_w1_pair, h->epi1, u16(p.p1), n, h->num_sms, s)));
+          else ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1P, tc::KIND_F16, tc::OUT_P16>(u16(p.stem), h->d_w1_pair, h->epi1, u16(p.p1), n, h->num_sms, s)));
+        }
       } else {
         ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1, tc::KIND_F16, tc::OUT_P16>(u16(p.stem), wimgq(0), h->epi1, u16(p.p1), n, h->num_sms, s)));
       }
@@ -576,7 +583,10 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
   if (KIND == tc::KIND_I8 && h->persistent == 2) {
     if (fused1) {
     } else if (h->d_w1_pair && h->pair_taps) {
-      ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1P, tc::KIND_I8, tc::OUT_P16>(u16(p.stem), h->d_w1_pair, h->epi1, u16(p.p1), n, h->num_sms, s)));
+      {
+        if (h->tail_tiles) ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1PT, tc::KIND_I8, tc::OUT_P16>(u16(p.stem), h->d_w1_pair, h->epi1, u16(p.p1), n, h->num_sms, s)));
+        else ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1P, tc::KIND_I8, tc::OUT_P16>(u16(p.stem), h->d_w1_pair, h->epi1, u16(p.p1), n, h->num_sms, s)));
+      }
     } else {
       ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1, tc::KIND_I8, tc::OUT_P16>(u16(p.stem), wimg(0), h->epi1, u16(p.p1), n, h->num_sms, s)));
     }
@@ -591,6 +601,8 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
     if (fused1) {
     } else if (h->persistent == 2 && h->pair_block1) {
       ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_cblock<tc::CBlock1, K16, tc::OUT_P8>(u16(p.stem), wimg(0), h->epi1, u16(p.p1), n, h->num_sms, s)));
+    } else if (h->tail_tiles) {
+      ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1T, K16, tc::OUT_P8>(u16(p.stem), wimg(0), h->epi1, u16(p.p1), n, h->num_sms, s)));
     } else {
       ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1, K16, tc::OUT_P8>(u16(p.stem), wimg(0), h->epi1, u16(p.p1), n, h->num_sms, s)));
     }
@@ -782,6 +794,12 @@ static int init_device_attrs() {
   if ((rc = tc::set_pw32_attr<tc::FPw3>())) return rc;
   if ((rc = tc::set_pw32_attr<tc::FPw4>())) return rc;
   if ((rc = tc::set_all_block_attrs())) return rc;
+  if ((rc = tc::set_pblock_attr<tc::PBlock1T, tc::KIND_BF16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_pblock_attr<tc::PBlock1T, tc::KIND_F16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_pblock_attr<tc::PBlock1PT, tc::KIND_BF16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_pblock_attr<tc::PBlock1PT, tc::KIND_F16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_pblock_attr<tc::PBlock1PT, tc::KIND_F16, tc::OUT_P16>())) return rc;
+  if ((rc = tc::set_pblock_attr<tc::PBlock1PT, tc::KIND_I8, tc::OUT_P16>())) return rc;
   if ((rc = tc::set_pblock_attr<tc::PBlock1, tc::KIND_BF16, tc::OUT_P8>())) return rc;
   if ((rc = tc::set_pblock_attr<tc::PBlock1, tc::KIND_F16, tc::OUT_P8>())) return rc;
   if ((rc = tc::set_pblock_attr<tc::PBlock2, tc::KIND_BF16, tc::OUT_P8>())) return rc;
@@ -943,6 +961,7 @@ int ernet_create(ernet_handle** out, int arch, int precision, int device) {
   if (const char* e = getenv("ERNET_FP32_TC")) h->fp32_tc = atoi(e) != 0;
   if (const char* e = getenv("ERNET_TRIM_COLUMNS")) h->trim_columns = atoi(e) != 0;
   if (const char* e = getenv("ERNET_HOST_GATHER")) h->host_gather = atoi(e) != 0;
+  if (const char* e = getenv("ERNET_TAIL_TILES")) h->tail_tiles = atoi(e) != 0;
   if (const char* e = getenv("ERNET_GATHER_CTAS")) { const int c = atoi(e); if (c >= 1 && c <= 1024) h->gather_ctas = c; }
   if (const char* e = getenv("ERNET_DUAL_COPY")) h->dual_copy = atoi(e) != 0;
   *out = h;

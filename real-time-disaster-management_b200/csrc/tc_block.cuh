@@ -215,6 +215,101 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams<Cfg::N>& par, uint
   }
       }
 
+// Epilogue of the tail unit of tc_pblock.cuh (PCfg::TAIL): TMEM lane = x, the accumulators of output rows HU-2 and HU-1
+// are tiles 0 and 1 (tbase, tbase + N).  Same arithmetic per element as epilogue_tile (bias, LeakyReLU, BN, rounding to
+// the output type, then the max - rounding is monotone), so the results are bit-identical to the 16 x 8 tiling; the y half
+// of the 2x2 pool is a max of the two tiles in this thread, the x half one exchange with lane^1, after which the lane owns
+// 16 of the 32 channels of the block of columns: two 8-channel chunks (P8) or one 16-channel chunk (P16).
+template <class Cfg, int KIND, int OUT>
+__device__ __forceinline__ void epilogue_tail(const EpiParams<Cfg::N>& par, uint32_t tbase, int x, bool valid, bool xodd,
+                                              uint16_t* __restrict__ out, int img) {
+  constexpr int N = Cfg::N, NREAL = Cfg::NREAL, OP = Cfg::OP;
+  constexpr bool BF16 = KIND == KIND_BF16;
+  constexpr int OUT_CHUNKS = OUT == OUT_P16 ? NREAL / 16 : NREAL / 8;
+  static_assert(OUT == OUT_P8 || OUT == OUT_P16, "the tail unit writes padded P8 / P16 images");
+  const int py = (Cfg::HU - 2) >> 1, px = x >> 1;
+#pragma unroll 1
+  for (int cb = 0; cb < N / 32; ++cb) {
+    uint32_t v[2][32];
+    tmem_ld32(tbase + cb * 32, v[0]);
+    tmem_ld32(tbase + N + cb * 32, v[1]);
+    tmem_ld_wait();
+    uint32_t pk[2][16];                                  // per row: 32 channels as 16-bit pairs (P8) / int8 quads (P16: 8 used)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float yv[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int n = cb * 32 + j;
+        float z = KIND == KIND_I8 ? fmaf(__int2float_rn((int)v[r][j]), par.deq[n], par.bias[n]) : __uint_as_float(v[r][j]) + par.bias[n];
+        if (Cfg::ACT) {
+          z = fmaxf(z, 0.01f * z);
+          z = fmaf(z, par.scale[n], par.shift[n]);
+        }
+        yv[j] = z;
+      }
+      if (OUT == OUT_P16) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint32_t w = 0;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            int q = __float2int_rn(yv[4 * j + e] * par.out_inv[cb * 32 + 4 * j + e]);
+            q = max(-127, min(127, q));
+            w |= ((uint32_t)q & 0xffu) << (8 * e);
+          }
+          pk[r][j] = w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (BF16) { __nv_bfloat162 h = __floats2bfloat162_rn(yv[2 * j], yv[2 * j + 1]); pk[r][j] = *reinterpret_cast<uint32_t*>(&h); }
+          else      { __half2 h = __floats2half2_rn(yv[2 * j], yv[2 * j + 1]);            pk[r][j] = *reinterpret_cast<uint32_t*>(&h); }
+        }
+      }
+    }
+    if (OUT == OUT_P16) {
+      uint32_t m[8], m1[4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = __vmaxs4(pk[0][j], pk[1][j]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t keep = xodd ? m[j + 4] : m[j];
+        const uint32_t send = xodd ? m[j] : m[j + 4];
+        m1[j] = __vmaxs4(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+      }
+      const int ch = cb * 2 + (xodd ? 1 : 0);
+      if (valid && ch * 16 < NREAL) {
+        uint4* oimg = reinterpret_cast<uint4*>(out) + (size_t)img * OUT_CHUNKS * OP * OP;
+        oimg[(ch * OP + py + 2) * OP + px + 2] = make_uint4(m1[0], m1[1], m1[2], m1[3]);
+      }
+    } else {
+      uint32_t m[16], m1[8];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (BF16) { __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&pk[0][j]), *reinterpret_cast<const __nv_bfloat162*>(&pk[1][j])); m[j] = *reinterpret_cast<uint32_t*>(&r); }
+        else      { __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&pk[0][j]), *reinterpret_cast<const __half2*>(&pk[1][j])); m[j] = *reinterpret_cast<uint32_t*>(&r); }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t keep = xodd ? m[j + 8] : m[j];
+        const uint32_t send = xodd ? m[j] : m[j + 8];
+        const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+        if (BF16) { __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&keep), *reinterpret_cast<const __nv_bfloat162*>(&recv)); m1[j] = *reinterpret_cast<uint32_t*>(&r); }
+        else      { __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&keep), *reinterpret_cast<const __half2*>(&recv)); m1[j] = *reinterpret_cast<uint32_t*>(&r); }
+      }
+      if (valid) {
+        uint4* oimg = reinterpret_cast<uint4*>(out) + (size_t)img * OUT_CHUNKS * OP * OP;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int ch = cb * 4 + (xodd ? 2 : 0) + h;
+          if (ch * 8 < NREAL) oimg[(ch * OP + py + 2) * OP + px + 2] = make_uint4(m1[4 * h], m1[4 * h + 1], m1[4 * h + 2], m1[4 * h + 3]);
+        }
+      }
+    }
+  }
+}
+
 // KIND_I8 with a 16-bit output writes fp16 (the int8 engine keeps its non-quantised tensors in fp16).
 template <class Cfg, int KIND, int OUT>
 __global__ void __launch_bounds__(kBlockThreads, 1)

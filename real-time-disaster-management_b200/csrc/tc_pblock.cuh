@@ -29,10 +29,17 @@ namespace tc {
 // stem) where an MMA K step wants two.  Instead of multiplying a zero chunk, the second chunk of the A descriptor is
 // pointed at the SAME staged chunk shifted by another tap (LBO = byte distance between the two taps' windows): one
 // MMA does two taps, 13 instead of 25 per tile.  Weights: [13 pairs][tap A chunk, tap B chunk][N][16 B].
+//
+// TAIL_: HU = 16 q + 2 leaves two output rows for a fifth row of 16 x 8 tiles that would be 12.5 % useful (block 1: 9 of
+// its 45 tiles per image).  Instead ONE tail unit per image covers both rows over the whole width with two tiles whose M
+// rows run ALONG a row: its box is 8 rows x 128 pixels (pitch 128 pixels, zero fill right of the image), the A
+// descriptor's SBO is 128 bytes (the next core matrix = the next 8 pixels of the same row), tile 0 = row HU-2, tile 1 =
+// row HU-1.  Same 25 shifted windows, same weights; TMEM lane = x, so the y half of the 2x2 pool is a max of the two
+// tiles' accumulators in one thread and the x half one exchange with lane^1.  38 instead of 45 tiles per image.
 template <int NC_, int N_, int HIN_, int HU_, int GX_, int NSTAGE_, bool WRES_, int WSTAGES_,
-          bool POOL_ = true, int TAPS_ = 25, bool ACT_ = true, int NREAL_ = N_, bool PAIR_ = false>
+          bool POOL_ = true, int TAPS_ = 25, bool ACT_ = true, int NREAL_ = N_, bool PAIR_ = false, bool TAIL_ = false>
 struct PCfg {
-  static constexpr bool PAIR = PAIR_;
+  static constexpr bool PAIR = PAIR_, TAIL = TAIL_;
   static constexpr int NPAIR = 13;
   // epilogue warps per TMEM lane quarter: one per tile of the unit (up to 3), so that with tap pairing (13 MMAs per
   // tile) the epilogue of a unit still finishes inside the unit's MMA time
@@ -44,15 +51,19 @@ struct PCfg {
   static constexpr bool WRES = WRES_, POOL = POOL_, ACT = ACT_;
   static constexpr int TAPS = TAPS_, NREAL = NREAL_;
   static constexpr int WP = HIN + 3;                                   // padded image pitch / height
-  static constexpr int HALO = TAPS == 1 ? 0 : 1;                       // a 1x1 convolution needs no neighbours: the box is the tiles
+  static constexpr int HALO = TAPS_ == 1 ? 0 : 1;                      // a 1x1 convolution needs no neighbours: the box is the tiles
   static constexpr int BW = (8 * GX + 6 * HALO) < WP ? (8 * GX + 6 * HALO) : WP;     // box width  (pixels)
   static constexpr int BH = (16 + 6 * HALO) < WP ? (16 + 6 * HALO) : WP;             // box height (16 output rows + 6)
   static constexpr int CHUNK_BYTES = BH * BW * 16;
   static constexpr int STAGE_BYTES = (PAIR ? 1 : NC) * CHUNK_BYTES;          // bytes one box delivers
-  static constexpr int STAGE_STRIDE = (STAGE_BYTES + 127) / 128 * 128;      // TMA destinations are 128-byte aligned
-  static constexpr int TR = (HU + 15) / 16, TCOLS = (HU + 7) / 8;
+  static constexpr int TBW = 128, TBH = 8;                                  // tail box: pixels per row, rows (2 output rows + 6)
+  static constexpr int TAIL_CHUNK_BYTES = TBH * TBW * 16, TAIL_STAGE_BYTES = (PAIR ? 1 : NC) * TAIL_CHUNK_BYTES;
+  static constexpr int STAGE_MAX = (TAIL && TAIL_STAGE_BYTES > STAGE_BYTES) ? TAIL_STAGE_BYTES : STAGE_BYTES;
+  static constexpr int STAGE_STRIDE = (STAGE_MAX + 127) / 128 * 128;        // TMA destinations are 128-byte aligned
+  static constexpr int TR = TAIL ? HU / 16 : (HU + 15) / 16, TCOLS = (HU + 7) / 8;   // rows of regular tiles
   static constexpr int UX = (TCOLS + GX - 1) / GX;                     // units per tile row
-  static constexpr int UNITS_PER_IMG = TR * UX;
+  static constexpr int UNITS_PER_IMG = TR * UX + (TAIL ? 1 : 0);
+  static_assert(!TAIL || (HU % 16 == 2 && HU <= TBW && POOL_ && TAPS_ == 25 && GX_ >= 2 && WRES_), "tail unit: two rows left over, pooled 25-tap block");
   static constexpr int KSTEPS = NC / 2;
   static constexpr int TAP_BYTES = NC * N * 16;
   static constexpr int W_BYTES = (PAIR ? NPAIR : TAPS) * TAP_BYTES;
@@ -86,8 +97,8 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
 
 template <class Cfg, int KIND, int OUT>
 __global__ void __launch_bounds__(kPThreads, ERNET_PBLOCK_MINB)
-acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t* __restrict__ wimg,
-                   const __grid_constant__ EpiParams<Cfg::N> par, uint16_t* __restrict__ out, int batch) {
+acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_tail,
+                   const uint16_t* __restrict__ wimg, const __grid_constant__ EpiParams<Cfg::N> par, uint16_t* __restrict__ out, int batch) {
   constexpr int N = Cfg::N, GX = Cfg::GX, NSTAGE = Cfg::NSTAGE, BW = Cfg::BW, OP = Cfg::OP;
   constexpr bool BF16 = KIND == KIND_BF16;
   constexpr uint32_t IDESC = KIND == KIND_I8 ? instr_desc(2u, 1u, 128u, (uint32_t)N) : instr_desc(1u, BF16 ? 1u : 0u, 128u, (uint32_t)N);
@@ -122,6 +133,7 @@ acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t* 
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], Cfg::NEPI); }
     fence_mbar_init();
     tma_prefetch_desc(&tmap_in);
+    if (Cfg::TAIL) tma_prefetch_desc(&tmap_tail);
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -147,8 +159,13 @@ acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t* 
         const int st = k % NSTAGE, use = k / NSTAGE;
         if (use > 0 && !mbar_wait(&in_empty[st], (use - 1) & 1, abort_flag, 0x500u, k)) break;
         ERNET_TL(k, 0);
-        mbar_expect_tx(&in_full[st], Cfg::STAGE_BYTES);
-        tma_load_4d(smem + st * Cfg::STAGE_STRIDE, &tmap_in, (ux * GX * 8 + 2 * (1 - Cfg::HALO)) * 4, ty * 16 + 2 * (1 - Cfg::HALO), 0, img, &in_full[st]);
+        if (Cfg::TAIL && ty == Cfg::TR) {     // tail unit: rows HU-4 .. HU+3 of the image over the whole width (u64 elements: 2 per pixel)
+          mbar_expect_tx(&in_full[st], Cfg::TAIL_STAGE_BYTES);
+          tma_load_4d(smem + st * Cfg::STAGE_STRIDE, &tmap_tail, 0, Cfg::TR * 16, 0, img, &in_full[st]);
+        } else {
+          mbar_expect_tx(&in_full[st], Cfg::STAGE_BYTES);
+          tma_load_4d(smem + st * Cfg::STAGE_STRIDE, &tmap_in, (ux * GX * 8 + 2 * (1 - Cfg::HALO)) * 4, ty * 16 + 2 * (1 - Cfg::HALO), 0, img, &in_full[st]);
+        }
       }
     }
   } else if (warp == 2) {
@@ -186,7 +203,8 @@ acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t* 
       int k = me;
       for (int u = blockIdx.x + me * (int)gridDim.x; u < total_units && ok; u += NISSUE * (int)gridDim.x, k += NISSUE) {
         const int r = u % Cfg::UNITS_PER_IMG, ux = r % Cfg::UX;
-        const int ntile = min(GX, Cfg::TCOLS - ux * GX);
+        const bool tail = Cfg::TAIL && r == Cfg::UNITS_PER_IMG - 1;
+        const int ntile = tail ? 2 : min(GX, Cfg::TCOLS - ux * GX);
         const int st = k % NSTAGE, buf = k & 1, use = k >> 1;
         ok = mbar_wait(&in_full[st], (k / NSTAGE) & 1, abort_flag, 0x503u, k);
         ERNET_TL(k, 1);
@@ -201,6 +219,45 @@ acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t* 
         // tile tl of the unit: output origin = box origin + (2, 2 + 8*tl)
         const uint32_t a_lo0 = desc_lo(in_addr + st * Cfg::STAGE_STRIDE + (uint32_t)(Cfg::HALO * (2 * BW + 2) * 16), Cfg::CHUNK_BYTES);
         const uint32_t d0 = tmem_base + (uint32_t)(buf * GX * N);
+        if (Cfg::TAIL && tail) {
+          // tail unit: M rows run along an image row (SBO = 128 bytes), pitch TBW pixels, tile tl = output row HU - 2 + tl
+          constexpr int TBW = Cfg::TBW;
+          constexpr uint32_t A_HI_T = desc_hi(128);
+          const uint32_t t_lo0 = desc_lo(in_addr + st * Cfg::STAGE_STRIDE + (uint32_t)((2 * TBW + 2) * 16), Cfg::TAIL_CHUNK_BYTES);
+          if constexpr (Cfg::PAIR) {
+#pragma unroll
+            for (int pr = 0; pr < Cfg::NPAIR; ++pr) {
+              const int tapA = pr == 0 ? 0 : 2 * pr - 1, tapB = pr == 0 ? 1 : 2 * pr;
+              const int offA = tap_dy(tapA) * TBW + tap_dx(tapA), offB = tap_dy(tapB) * TBW + tap_dx(tapB);
+              const uint32_t a_lo = ((t_lo0 & 0x3FFFu) + (uint32_t)offA) | ((uint32_t)(offB - offA) << 16);
+              const uint32_t b_lo = w_lo0 + (uint32_t)(pr * (Cfg::TAP_BYTES >> 4));
+              if (NISSUE > 1 && pr == Cfg::NPAIR - 2) *turn = (uint32_t)(k + 1);
+#pragma unroll
+              for (int tl = 0; tl < 2; ++tl) {
+                const uint64_t ad = desc_make(a_lo + (uint32_t)(tl * TBW), A_HI_T), bd = desc_make(b_lo, B_HI);
+                if (KIND == KIND_I8) mma_i8(d0 + tl * N, ad, bd, IDESC, pr != 0 ? 1u : 0u);
+                else                 mma_f16(d0 + tl * N, ad, bd, IDESC, pr != 0 ? 1u : 0u);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int tap = 0; tap < Cfg::TAPS; ++tap) {
+              const uint32_t b_lo = w_lo0 + (uint32_t)(tap * (Cfg::TAP_BYTES >> 4));
+              const uint32_t toff = (uint32_t)(tap_dy(tap) * TBW + tap_dx(tap));
+              if (NISSUE > 1 && tap == Cfg::TAPS - 4) *turn = (uint32_t)(k + 1);
+#pragma unroll
+              for (int tl = 0; tl < 2; ++tl) {
+#pragma unroll
+                for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+                  const uint64_t ad = desc_make(t_lo0 + toff + (uint32_t)(tl * TBW) + ks * ((2 * Cfg::TAIL_CHUNK_BYTES) >> 4), A_HI_T);
+                  const uint64_t bd = desc_make(b_lo + ks * B_KSTEP, B_HI);
+                  if (KIND == KIND_I8) mma_i8(d0 + tl * N, ad, bd, IDESC, (tap | ks) != 0 ? 1u : 0u);
+                  else                 mma_f16(d0 + tl * N, ad, bd, IDESC, (tap | ks) != 0 ? 1u : 0u);
+                }
+              }
+            }
+          }
+        } else
         if constexpr (Cfg::PAIR) {
 #pragma unroll
           for (int pr = 0; pr < Cfg::NPAIR; ++pr) {
@@ -284,11 +341,19 @@ acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint16_t* 
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++k) {
       const int img = u / Cfg::UNITS_PER_IMG, r = u - img * Cfg::UNITS_PER_IMG;
       const int ty = r / Cfg::UX, ux = r - ty * Cfg::UX;
-      const int ntile = min(GX, Cfg::TCOLS - ux * GX);
+      const bool tail = Cfg::TAIL && ty == Cfg::TR;
+      const int ntile = tail ? 0 : min(GX, Cfg::TCOLS - ux * GX);
       const int buf = k & 1, use = k >> 1;
       if (!mbar_wait(&acc_full[buf], use & 1, abort_flag, 0x600u + warp, k)) break;
       if (threadIdx.x == 96) ERNET_TL(k, 4);
       tc_fence_after();
+      if constexpr (Cfg::TAIL) {
+        if (tail && ehalf == 0) {                  // one warp per TMEM lane quarter: lane = x, tiles 0 / 1 = the two rows
+          const int x = 32 * q4 + lane;
+          const uint32_t tbase = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * GX * N);
+          epilogue_tail<Cfg, KIND, OUT>(par, tbase, x, x < Cfg::HU, xodd, out, img);
+        }
+      }
       for (int tl = ehalf; tl < ntile; tl += Cfg::EPW) {
         const int y = ty * 16 + rr, x = (ux * GX + tl) * 8 + cc;
         const bool valid = (y < Cfg::HU) && (x < Cfg::HU);
@@ -346,15 +411,35 @@ inline int make_input_map(CUtensorMap* map, const void* base, int batch) {
   return ERNET_OK;
 }
 
+// Tail box (PCfg::TAIL): 8 rows x 128 pixels, 64-bit elements (two per pixel) so that the 2048-byte row stays within the
+// 256-element box limit; columns right of the padded image are zero-filled by the TMA unit.
+template <class Cfg>
+inline int make_tail_map(CUtensorMap* map, const void* base, int batch) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(ERNET_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[4] = {(cuuint64_t)Cfg::WP * 2, (cuuint64_t)Cfg::WP, (cuuint64_t)Cfg::NC, (cuuint64_t)batch};
+  const cuuint64_t strides[3] = {(cuuint64_t)Cfg::WP * 16, (cuuint64_t)Cfg::WP * Cfg::WP * 16,
+                                 (cuuint64_t)Cfg::NC * Cfg::WP * Cfg::WP * 16};
+  const cuuint32_t box[4] = {(cuuint32_t)Cfg::TBW * 2, (cuuint32_t)Cfg::TBH, (cuuint32_t)(Cfg::PAIR ? 1 : Cfg::NC), 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ERNET_ERR_CUDA, "cuTensorMapEncodeTiled (tail box) failed with CUresult %d", (int)r);
+  return ERNET_OK;
+}
+
 template <class Cfg, int KIND, int OUT>
 inline int launch_acff_pblock(const void* in, const void* wimg, const EpiParams<Cfg::N>& par, void* out, int batch, int num_sms,
                               cudaStream_t stream) {
-  CUtensorMap map;
+  CUtensorMap map, map_tail;
   int rc = make_input_map<Cfg>(&map, in, batch);
   if (rc) return rc;
+  if (Cfg::TAIL) { if ((rc = make_tail_map<Cfg>(&map_tail, in, batch))) return rc; }
+  else map_tail = map;
   const int total = batch * Cfg::UNITS_PER_IMG;
   const int grid = total < num_sms ? total : num_sms;
-  ERNET_CUDA(launch_pdl(acff_pblock_kernel<Cfg, KIND, OUT>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, map,
+  ERNET_CUDA(launch_pdl(acff_pblock_kernel<Cfg, KIND, OUT>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, map, map_tail,
                         static_cast<const uint16_t*>(wimg), par, static_cast<uint16_t*>(out), batch));
   return ERNET_OK;
 }
@@ -367,11 +452,14 @@ inline int set_pblock_attr() {
 
 // Persistent configurations (same math as CfgBlock*): GX tiles per unit, input ring depth, weight residency.
 using PBlock1 = PCfg<2, 64, 69, 66, 3, 3, true, 1>;            // 15 units / image, 21 KB boxes, weights resident
+// default for the 16-bit Squeeze_ErNET: rows 64, 65 as one tail unit - 12 + 1 units, 38 instead of 45 tiles per image
+using PBlock1T = PCfg<2, 64, 69, 66, 3, 3, true, 1, true, 25, true, 64, false, /*TAIL*/ true>;
 using PBlock2 = PCfg<8, 96, 33, 30, 2, 2, false, 8>;           //  4 units / image, 62 KB boxes
 using PBlock3 = PCfg<12, 128, 15, 12, 2, 2, false, 4>;         //  1 unit  / image, box = whole padded image
 // Squeeze_RedConv: conv_red2 (96 -> 48, 1x1, bias only) + 2x2 pool as a 1-tap instance: 2 units / image, 98 KB boxes
 // block 1 with one real input chunk (int8 Squeeze_ErNET, 16-bit Squeeze_RedConv): 13 two-tap MMAs per tile
 using PBlock1P = PCfg<2, 64, 69, 66, 3, 3, true, 1, true, 25, true, 64, /*PAIR*/ true>;
+using PBlock1PT = PCfg<2, 64, 69, 66, 3, 3, true, 1, true, 25, true, 64, /*PAIR*/ true, /*TAIL*/ true>;
 using EBlock1 = PCfg<2, 64, 119, 116, 3, 3, true, 1>;          // ErNET block 1: 40 units / image
 using PRed2R = PCfg<12, 64, 30, 30, 4, 2, true, 1, /*POOL*/ true, /*TAPS*/ 1, /*ACT*/ false, /*NREAL*/ 48>;
 // int8 engine: same instance writing the int8 pool2 tensor as 4 chunks of 16 channels (48 real + 16 exact zeros)

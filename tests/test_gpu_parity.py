@@ -646,6 +646,38 @@ def test_block_kernel_schedules_agree(arch, prec, dev):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("arch,prec", [("squeeze-ernet", "bf16"), ("squeeze-ernet", "fp16"), ("squeeze-ernet", "int8"),
+                                       ("squeeze-redconv", "bf16"), ("squeeze-redconv", "fp16"), ("squeeze-redconv", "int8")])
+def test_block1_tail_unit_is_bit_identical(arch, prec, dev, monkeypatch):
+    """Block 1's output rows 64, 65 run as ONE tail unit per image (two tiles whose M rows run along an image row,
+    PCfg::TAIL in csrc/tc_pblock.cuh) instead of a fifth row of 16x8 tiles that is 12.5 % useful.  Same MMAs per output
+    pixel in the same order, same epilogue arithmetic: logits and the pool1 tensor equal the 16x8-only tiling bit for bit,
+    for batches that leave CTAs with and without a tail unit, tensors and frames."""
+    sd = fixtures.get_state_dict(arch, "shipped")
+    frames = torch.from_numpy(np.concatenate([fixtures.noise_frames(20, seed=91), fixtures.smooth_frames(17, seed=92)], 0)).to(dev)
+    out = {}
+    for tail in ("0", "1"):
+        monkeypatch.setenv("ERNET_TAIL_TILES", tail)
+        m = rtdm_b200.from_state_dict(arch, sd, dev, prec)
+        if prec == "int8":
+            m.calibrate()
+        res = []
+        for B in (1, 3, 37):
+            x = torch.from_numpy(fixtures.normal_tensors(B, seed=500 + B)).to(dev)
+            res.append(m.forward_with_logits(x)[1].clone())
+            res.append(m.tap("pool1").clone())
+        res.append(m.forward_frames(frames, return_logits=True)[1].clone())
+        res.append(m.tap("pool1").clone())
+        out[tail] = res
+        ref = E.forward(sd, fixtures.normal_tensors(37, seed=537), arch, dtype=np.float64)["logits"]
+        if prec != "int8":
+            assert _rel(res[4].double().cpu().numpy(), ref) <= TOL[prec]
+    for a, b in zip(out["0"], out["1"]):
+        assert torch.equal(a, b)
+    assert _lib.load().ernet_check_watchdog() == 0
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("arch,prec", [("squeeze-ernet", "bf16"), ("squeeze-redconv", "fp16"), ("squeeze-ernet", "fp32"),
                                        ("squeeze-redconv", "fp32")])
 def test_fast_ingest_matches_table_lookup_kernel(arch, prec, dev):
