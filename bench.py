@@ -71,7 +71,7 @@ GEMM_STAGES = {"pw1", "pw2", "pw3", "pw4", "tc_block1", "tc_block2", "tc_block3"
 # FLOPs the tensor-core block kernels actually ISSUE per image (25-tap dense form, padded 16x8 tiles): reported next to
 # the algorithmic figure so that the roofline fraction and the tensor-pipe utilisation can both be read off
 def issued_flops(arch, precision):
-    """Operations the tensor pipe really executes per image (padded 16x8 tiles, all taps), by stage.  16-bit: 2*128*N*16
+    """Operations the tensor pipe really executes per image (padded tiles, all taps), by stage.  16-bit: 2*128*N*16
     per MMA; int8 (kind::i8): 2*128*N*32.  Block 1 issues 13 two-tap MMAs per tile when its input has one real 16-byte
     chunk (int8 Squeeze_ErNET, 16-bit Squeeze_RedConv), else 25."""
     k = 32 if precision == "int8" else 16
@@ -81,7 +81,10 @@ def issued_flops(arch, precision):
     c3 = 48 if red else 96
     ks3 = c3 // (32 if precision == "int8" else 16)
     c4 = 64 if red else 128
-    out = {"tc_block1": 45 * b1_taps * 2 * 128 * 64 * k, "tc_block2": 8 * 25 * ks2 * 2 * 128 * 96 * k,
+    # block 1: 4 x 9 regular 16x8 tiles + the 2 tiles of the tail unit (rows 64, 65; csrc/tc_pblock.cuh PCfg::TAIL); 45 with
+    # ERNET_TAIL_TILES=0
+    b1_tiles = 38 if os.environ.get("ERNET_TAIL_TILES", "1") != "0" else 45
+    out = {"tc_block1": b1_tiles * b1_taps * 2 * 128 * 64 * k, "tc_block2": 8 * 25 * ks2 * 2 * 128 * 96 * k,
            "tc_block3": 2 * 25 * ks3 * 2 * 128 * 128 * k, "tc_block4": (3 * c4 // 16) * 2 * 128 * 256 * 16 // 2}
     if red:
         out["red2"] = 8 * 6 * 2 * 128 * 64 * 16                 # conv_red2 as a 1-tap instance: 8 tiles x 6 K steps, N = 64
