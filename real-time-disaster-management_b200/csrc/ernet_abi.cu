@@ -9,6 +9,8 @@
 #include <utility>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges are no-ops unless a profiler injects the NVTX library
+
 #include "common.cuh"
 #include "ingest.cuh"
 #include "simt_layers.cuh"
@@ -73,6 +75,7 @@ struct ernet_handle {
   bool dual_copy = false;       // host path: alternate two copy streams (ERNET_DUAL_COPY=1)
   bool trim_columns = false;    // host path: also skip the columns outside the crop footprint (ERNET_TRIM_COLUMNS=1).  Off:
                                 // measured 78 K img/s against 281 K - a 3-D copy of 639-byte rows runs at ~10 GB/s
+  bool nvtx = false;            // ERNET_NVTX=1: an NVTX range per stage launch
   bool tail_tiles = true;       // block 1: output rows 64, 65 as one tail unit per image (PCfg::TAIL, tc_pblock.cuh; ERNET_TAIL_TILES=0: 16x8 tiles only)
   bool host_gather = false;     // host path: pinned frames are pulled by host_gather_kernel (footprint rows AND columns, host_gather.cuh)
   int gather_ctas = 32;
@@ -273,10 +276,14 @@ static int launch_stem(const ernet_handle* h, const TI* x, long long sb, long lo
   return ERNET_OK;
 }
 
-// Brackets one stage with CUDA events on the launch stream when profiling is on.
+// Brackets one stage with CUDA events on the launch stream when profiling is on, and with an NVTX range named after the
+// stage when ERNET_NVTX=1 (profiler timelines: SURVEY section 5).
+static const char* const kStageNames[ERNET_STAGE_COUNT] = {"ingest", "stem", "dw1", "pw1", "dw2", "pw2", "red2", "dw3", "pw3", "red3",
+                                                           "dw4", "pw4", "head", "tc_block1", "tc_block2", "tc_block3", "tc_block4"};
 struct StageTimer {
-  ernet_handle* h; cudaStream_t s; cudaEvent_t a = nullptr, b = nullptr; int stage;
+  ernet_handle* h; cudaStream_t s; cudaEvent_t a = nullptr, b = nullptr; int stage; bool range = false;
   StageTimer(ernet_handle* h_, int stage_, cudaStream_t s_) : h(h_), s(s_), stage(stage_) {
+    if (h->nvtx && stage >= 0 && stage < ERNET_STAGE_COUNT) { nvtxRangePushA(kStageNames[stage]); range = true; }
     if (!h->profiling) return;
     auto get = [&]() { cudaEvent_t e = nullptr;
       if (!h->prof_pool.empty()) { e = h->prof_pool.back(); h->prof_pool.pop_back(); } else cudaEventCreate(&e);
@@ -285,6 +292,7 @@ struct StageTimer {
     cudaEventRecord(a, s);
   }
   ~StageTimer() {
+    if (range) nvtxRangePop();
     if (!a) return;
     cudaEventRecord(b, s);
     h->prof.push_back({stage, a, b});
@@ -962,6 +970,7 @@ int ernet_create(ernet_handle** out, int arch, int precision, int device) {
   if (const char* e = getenv("ERNET_TRIM_COLUMNS")) h->trim_columns = atoi(e) != 0;
   if (const char* e = getenv("ERNET_HOST_GATHER")) h->host_gather = atoi(e) != 0;
   if (const char* e = getenv("ERNET_TAIL_TILES")) h->tail_tiles = atoi(e) != 0;
+  if (const char* e = getenv("ERNET_NVTX")) h->nvtx = atoi(e) != 0;
   if (const char* e = getenv("ERNET_GATHER_CTAS")) { const int c = atoi(e); if (c >= 1 && c <= 1024) h->gather_ctas = c; }
   if (const char* e = getenv("ERNET_DUAL_COPY")) h->dual_copy = atoi(e) != 0;
   *out = h;
