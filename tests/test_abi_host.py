@@ -139,7 +139,7 @@ def test_load_model_reads_real_checkpoints(arch, wrapped, tmp_path):
         rtdm_b200.load_model(other, str(path), "cpu")
 
 
-def test_bench_configuration_rules():
+def test_bench_configuration_rules(monkeypatch):
     """bench.py: N=1 runs BASELINE configs[1] (256 frames), N>1 runs configs[4] (8192 frames split N ways, strong
     scaling) unless --batch pins the per-GPU batch; both arms describe the configuration with the same `config` object."""
     import argparse
@@ -152,8 +152,12 @@ def test_bench_configuration_rules():
     c1 = bench.common_config("squeeze-ernet", "bf16", 1024, 8, 8192)
     assert "configs[4]" in c1["workload"] and c1["global_batch"] == 8192
     assert "configs[1]" in bench.common_config("squeeze-ernet", "bf16", 256, 1, None)["workload"]
+    # block 1: 36 regular tiles + the 2 tiles of the tail unit per image (45 regular tiles with ERNET_TAIL_TILES=0)
+    monkeypatch.delenv("ERNET_TAIL_TILES", raising=False)
     ops = bench.issued_flops("squeeze-ernet", "int8")
-    assert ops["tc_block1"] == 45 * 13 * 2 * 128 * 64 * 32 and ops["tc_block2"] == 8 * 25 * 2 * 2 * 128 * 96 * 32
+    assert ops["tc_block1"] == 38 * 13 * 2 * 128 * 64 * 32 and ops["tc_block2"] == 8 * 25 * 2 * 2 * 128 * 96 * 32
+    assert bench.issued_flops("squeeze-ernet", "bf16")["tc_block1"] == 38 * 25 * 2 * 128 * 64 * 16
+    monkeypatch.setenv("ERNET_TAIL_TILES", "0")
     assert bench.issued_flops("squeeze-ernet", "bf16")["tc_block1"] == 45 * 25 * 2 * 128 * 64 * 16
 
 
