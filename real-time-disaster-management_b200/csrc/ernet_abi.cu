@@ -971,6 +971,10 @@ int ernet_create(ernet_handle** out, int arch, int precision, int device) {
   if (const char* e = getenv("ERNET_HOST_GATHER")) h->host_gather = atoi(e) != 0;
   if (const char* e = getenv("ERNET_TAIL_TILES")) h->tail_tiles = atoi(e) != 0;
   if (const char* e = getenv("ERNET_NVTX")) h->nvtx = atoi(e) != 0;
+  if (const char* e = getenv("ERNET_EPI_SUSPEND")) {       // study switch, device-wide (tc_common.cuh)
+    const unsigned int v = atoi(e) != 0 ? 1u : 0u;
+    cudaMemcpyToSymbol(tc::g_epi_suspend, &v, sizeof(v));
+  }
   if (const char* e = getenv("ERNET_GATHER_CTAS")) { const int c = atoi(e); if (c >= 1 && c <= 1024) h->gather_ctas = c; }
   if (const char* e = getenv("ERNET_DUAL_COPY")) h->dual_copy = atoi(e) != 0;
   *out = h;

@@ -304,6 +304,7 @@ acff_cblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
     const bool xodd = (lane & 1) != 0, yodd = ((lane >> 3) & 1) != 0;
     const int qsel = (xodd ? 2 : 0) + (yodd ? 1 : 0);
     pdl_wait();                                             // stores below must not overtake the previous kernel's readers
+    const bool susp = g_epi_suspend != 0;
     for (int k = 0; k < nk; ++k) {
       bool dup;
       const int u = unit_of(k, dup);
@@ -311,7 +312,7 @@ acff_cblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
       const int ty = r / Cfg::UX, ux = r - ty * Cfg::UX;
       constexpr int ntile = GX;
       const int buf = k & 1, use = k >> 1;
-      if (!mbar_wait(&acc_full[buf], use & 1, abort_flag, 0x800u + warp, k)) break;
+      if (!mbar_wait_epi(&acc_full[buf], use & 1, abort_flag, 0x800u + warp, k, susp)) break;
       if (threadIdx.x == 96) ERNET_TL(k, 4);
       tc_fence_after();
       for (int tl = ehalf; tl < ntile; tl += 2) {

@@ -337,6 +337,7 @@ acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
     const int rr = 4 * q4 + (lane >> 3), cc = lane & 7;
     const bool xodd = (lane & 1) != 0, yodd = ((lane >> 3) & 1) != 0;
     const int qsel = (xodd ? 2 : 0) + (yodd ? 1 : 0);
+    const bool susp = g_epi_suspend != 0;
     int k = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++k) {
       const int img = u / Cfg::UNITS_PER_IMG, r = u - img * Cfg::UNITS_PER_IMG;
@@ -344,7 +345,7 @@ acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
       const bool tail = Cfg::TAIL && ty == Cfg::TR;
       const int ntile = tail ? 0 : min(GX, Cfg::TCOLS - ux * GX);
       const int buf = k & 1, use = k >> 1;
-      if (!mbar_wait(&acc_full[buf], use & 1, abort_flag, 0x600u + warp, k)) break;
+      if (!mbar_wait_epi(&acc_full[buf], use & 1, abort_flag, 0x600u + warp, k, susp)) break;
       if (threadIdx.x == 96) ERNET_TL(k, 4);
       tc_fence_after();
       if constexpr (Cfg::TAIL) {
