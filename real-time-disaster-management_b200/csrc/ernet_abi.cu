@@ -972,7 +972,7 @@ int ernet_create(ernet_handle** out, int arch, int precision, int device) {
   if (const char* e = getenv("ERNET_TAIL_TILES")) h->tail_tiles = atoi(e) != 0;
   if (const char* e = getenv("ERNET_NVTX")) h->nvtx = atoi(e) != 0;
   if (const char* e = getenv("ERNET_EPI_SUSPEND")) {       // study switch, device-wide (tc_common.cuh)
-    const unsigned int v = atoi(e) != 0 ? 1u : 0u;
+    const unsigned int v = (unsigned int)atoi(e) & 3u;       // bit 0: block kernels' epilogue warps, bit 1: ACFF4 + head kernel
     cudaMemcpyToSymbol(tc::g_epi_suspend, &v, sizeof(v));
   }
   if (const char* e = getenv("ERNET_GATHER_CTAS")) { const int c = atoi(e); if (c >= 1 && c <= 1024) h->gather_ctas = c; }

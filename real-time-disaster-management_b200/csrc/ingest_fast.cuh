@@ -123,7 +123,9 @@ __device__ __forceinline__ void ingest_stem5_band(uint8_t* __restrict__ fsm, con
   for (int t = 0; t < 5; ++t) kc[t] = (uint32_t)tab_ld<TAB>(kx + ox * 5 + t) << 2;      // 4k: the result byte is the top byte
   const int bo = off + 3 * tab_ld<TAB>(xmin + ox);
   const int sh = (bo & 3) * 8;
-  if (cp.bulk) { while (!tc::mbar_test_wait(bar, bar_uses & 1u)) { } }
+  // suspending wait: the kernel is issue-bound, and 14 warps polling for their band's bytes would take issue slots from the
+  // co-resident CTA that is computing
+  if (cp.bulk) { while (!tc::mbar_try_wait(bar, bar_uses & 1u)) { } }
   else Sync::sync();
 
   // ---- phase 1: horizontal pass.  Thread = output column, TWO rows per iteration (independent chains: the few helper

@@ -134,7 +134,10 @@ acff4_head_kernel(const uint16_t* __restrict__ in /*(B,6,6,C4)*/, const float* _
   }
 
   // ---- depthwise trio -> A operand: one (pixel, 8-channel chunk) item per thread
-  bool ok = mbar_wait(bar_in, 0, abort_flag, 0x400u);
+  // 16 warps wait here from the moment the CTA is resident (8-20 k cycles before block 3 ends) until the input has landed:
+  // bit 1 of g_epi_suspend selects the suspending form (study switch ERNET_EPI_SUSPEND=3)
+  const bool susp = (g_epi_suspend & 2u) != 0;
+  bool ok = mbar_wait_epi(bar_in, 0, abort_flag, 0x400u, 0, susp);
   if (threadIdx.x == 0) ERNET_TL(20, 2);
   if (ok) {
     for (int item = threadIdx.x; item < ROWS * CV; item += kTailThreads) {
@@ -210,7 +213,7 @@ acff4_head_kernel(const uint16_t* __restrict__ in /*(B,6,6,C4)*/, const float* _
     //      columns, lane = pixel (16 consecutive lanes = one image)
     const int cg = warp >> 2;
     const int row = lane, im = row >> 4;
-    if (mbar_wait(acc_full, 0, abort_flag, 0x403u, warp)) {
+    if (mbar_wait_epi(acc_full, 0, abort_flag, 0x403u, warp, susp)) {
       if (threadIdx.x == 0) ERNET_TL(20, 4);
       tc_fence_after();
       float dot[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
