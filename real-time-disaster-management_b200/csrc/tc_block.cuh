@@ -222,14 +222,14 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams<Cfg::N>& par, uint
 // 16 of the 32 channels of the block of columns: two 8-channel chunks (P8) or one 16-channel chunk (P16).
 template <class Cfg, int KIND, int OUT>
 __device__ __forceinline__ void epilogue_tail(const EpiParams<Cfg::N>& par, uint32_t tbase, int x, bool valid, bool xodd,
-                                              uint16_t* __restrict__ out, int img) {
+                                              uint16_t* __restrict__ out, int img, int cb0, int cb_step) {
   constexpr int N = Cfg::N, NREAL = Cfg::NREAL, OP = Cfg::OP;
   constexpr bool BF16 = KIND == KIND_BF16;
   constexpr int OUT_CHUNKS = OUT == OUT_P16 ? NREAL / 16 : NREAL / 8;
   static_assert(OUT == OUT_P8 || OUT == OUT_P16, "the tail unit writes padded P8 / P16 images");
   const int py = (Cfg::HU - 2) >> 1, px = x >> 1;
 #pragma unroll 1
-  for (int cb = 0; cb < N / 32; ++cb) {
+  for (int cb = cb0; cb < N / 32; cb += cb_step) {          // blocks of 32 columns are dealt to the EPW warps of a lane quarter
     uint32_t v[2][32];
     tmem_ld32(tbase + cb * 32, v[0]);
     tmem_ld32(tbase + N + cb * 32, v[1]);

@@ -349,10 +349,10 @@ acff_pblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
       if (threadIdx.x == 96) ERNET_TL(k, 4);
       tc_fence_after();
       if constexpr (Cfg::TAIL) {
-        if (tail && ehalf == 0) {                  // one warp per TMEM lane quarter: lane = x, tiles 0 / 1 = the two rows
-          const int x = 32 * q4 + lane;
+        if (tail) {                                // lane = x, tiles 0 / 1 = the two rows; the EPW warps of a lane quarter share the
+          const int x = 32 * q4 + lane;            // blocks of 32 columns (one warp alone made the tail unit epilogue-bound)
           const uint32_t tbase = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * GX * N);
-          epilogue_tail<Cfg, KIND, OUT>(par, tbase, x, x < Cfg::HU, xodd, out, img);
+          epilogue_tail<Cfg, KIND, OUT>(par, tbase, x, x < Cfg::HU, xodd, out, img, ehalf, Cfg::EPW);
         }
       }
       for (int tl = ehalf; tl < ntile; tl += Cfg::EPW) {
