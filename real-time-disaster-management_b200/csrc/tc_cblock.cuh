@@ -199,10 +199,13 @@ acff_cblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
     // ------------------------------------------------------------------ weight producer (constants: no pdl_wait)
     if (lane == 0) {
       if (Cfg::WRES) {
-        if (leader) mbar_expect_tx(&w_full[0], 2 * Cfg::NBUNDLE * Cfg::WB_BYTES);
+        // one barrier per K step (NTG bundles): the first MMAs of the CTA pair start when the first slice of the resident
+        // weights has landed, not after all of them (154 KB per CTA in block 2: ~2 us at the head of every launch)
+        if (leader)
+          for (int ks = 0; ks < KS; ++ks) mbar_expect_tx(&w_full[ks], 2 * Cfg::NTG * Cfg::WB_BYTES);
         for (int b = 0; b < Cfg::NBUNDLE; ++b)
           tma2_load_3d(s_w + b * Cfg::WB_BYTES, &tmap_w, (int)rank * NH * (16 / Cfg::WELEM), 2 * (b / Cfg::NTG), (b % Cfg::NTG) * Cfg::TG,
-                       mapa_u32(smem_u32(&w_full[0]), 0));
+                       mapa_u32(smem_u32(&w_full[b / Cfg::NTG]), 0));
       } else {
         int it = 0;
         bool ok = true;
@@ -220,7 +223,7 @@ acff_cblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (leader && elect_one()) {
       bool ok = true;
-      if (Cfg::WRES) { ok = mbar_wait(&w_full[0], 0, abort_flag, 0x702u); tc_fence_after(); }
+      static_assert(!Cfg::WRES || KS <= 16, "one weight barrier per K step");
       const uint32_t in_addr = smem_u32(smem), w_addr = smem_u32(s_w);
       constexpr uint32_t A_HI = desc_hi(BW * 16), B_HI = desc_hi(128);
       const uint32_t w_lo0 = desc_lo(w_addr, NH * 16);
@@ -238,6 +241,7 @@ acff_cblock_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
           const int sl = q % NSLOT;
           ok = mbar_wait(&in_full[sl], (q / NSLOT) & 1, abort_flag, 0x703u, q);
           if (ks == 0) ERNET_TL(k, 1);
+          if (ok && Cfg::WRES && k == 0) ok = mbar_wait(&w_full[ks], 0, abort_flag, 0x702u, ks);    // resident weights of this K step
           if (!ok) break;
           tc_fence_after();
           const uint32_t a_lo0 = desc_lo(in_addr + sl * Cfg::SLOT_BYTES + (uint32_t)((2 * BW + 2) * 16), Cfg::CHUNK_BYTES);
