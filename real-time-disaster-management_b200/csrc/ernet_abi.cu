@@ -75,6 +75,7 @@ struct ernet_handle {
   bool dual_copy = false;       // host path: alternate two copy streams (ERNET_DUAL_COPY=1)
   bool trim_columns = false;    // host path: also skip the columns outside the crop footprint (ERNET_TRIM_COLUMNS=1).  Off:
                                 // measured 78 K img/s against 281 K - a 3-D copy of 639-byte rows runs at ~10 GB/s
+  bool small_batch_units = true;   // pair kernels: one-tile units for small batches (CBlock2S / CBlock3S; ERNET_SMALL_BATCH_UNITS=0: off)
   bool nvtx = false;            // ERNET_NVTX=1: an NVTX range per stage launch
   bool tail_tiles = true;       // block 1: output rows 64, 65 as one tail unit per image (PCfg::TAIL, tc_pblock.cuh; ERNET_TAIL_TILES=0: 16x8 tiles only)
   bool host_gather = false;     // host path: pinned frames are pulled by host_gather_kernel (footprint rows AND columns, host_gather.cuh)
@@ -615,8 +616,14 @@ static int run_chunk_tc(ernet_handle* h, const void* x, int x_dtype, int x_layou
       ERNET_STAGE(ERNET_STAGE_TC_BLOCK1, (tc::launch_acff_pblock<tc::PBlock1, K16, tc::OUT_P8>(u16(p.stem), wimg(0), h->epi1, u16(p.p1), n, h->num_sms, s)));
     }
     if (h->persistent == 2) {
-      ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_cblock<tc::CBlock2, K16, tc::OUT_P8>(u16(p.p1), wimg(1), h->epi2, u16(p.p2), n, h->num_sms, s)));
-      ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_cblock<tc::CBlock3, K16, tc::OUT_NHWC>(u16(p.p2), wimg(2), h->epi3, u16(p.p3), n, h->num_sms, s)));
+      if (h->small_batch_units && n <= tc::kSmallBatch2)
+        ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_cblock<tc::CBlock2S, K16, tc::OUT_P8>(u16(p.p1), wimg(1), h->epi2, u16(p.p2), n, h->num_sms, s)));
+      else
+        ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_cblock<tc::CBlock2, K16, tc::OUT_P8>(u16(p.p1), wimg(1), h->epi2, u16(p.p2), n, h->num_sms, s)));
+      if (h->small_batch_units && n <= tc::kSmallBatch3)
+        ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_cblock<tc::CBlock3S, K16, tc::OUT_NHWC>(u16(p.p2), wimg(2), h->epi3, u16(p.p3), n, h->num_sms, s)));
+      else
+        ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_cblock<tc::CBlock3, K16, tc::OUT_NHWC>(u16(p.p2), wimg(2), h->epi3, u16(p.p3), n, h->num_sms, s)));
     } else {
       ERNET_STAGE(ERNET_STAGE_TC_BLOCK2, (tc::launch_acff_pblock<tc::PBlock2, K16, tc::OUT_P8>(u16(p.p1), wimg(1), h->epi2, u16(p.p2), n, h->num_sms, s)));
       ERNET_STAGE(ERNET_STAGE_TC_BLOCK3, (tc::launch_acff_pblock<tc::PBlock3, K16, tc::OUT_NHWC>(u16(p.p2), wimg(2), h->epi3, u16(p.p3), n, h->num_sms, s)));
@@ -816,6 +823,10 @@ static int init_device_attrs() {
   if ((rc = tc::set_pblock_attr<tc::PBlock3, tc::KIND_F16, tc::OUT_NHWC>())) return rc;
   if ((rc = tc::set_cblock_attr<tc::CBlock1, tc::KIND_BF16, tc::OUT_P8>())) return rc;
   if ((rc = tc::set_cblock_attr<tc::CBlock1, tc::KIND_F16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::CBlock2S, tc::KIND_BF16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::CBlock2S, tc::KIND_F16, tc::OUT_P8>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::CBlock3S, tc::KIND_BF16, tc::OUT_NHWC>())) return rc;
+  if ((rc = tc::set_cblock_attr<tc::CBlock3S, tc::KIND_F16, tc::OUT_NHWC>())) return rc;
   if ((rc = tc::set_cblock_attr<tc::CBlock2, tc::KIND_BF16, tc::OUT_P8>())) return rc;
   if ((rc = tc::set_cblock_attr<tc::CBlock2, tc::KIND_F16, tc::OUT_P8>())) return rc;
   if ((rc = tc::set_cblock_attr<tc::CBlock3, tc::KIND_BF16, tc::OUT_NHWC>())) return rc;
@@ -971,6 +982,7 @@ int ernet_create(ernet_handle** out, int arch, int precision, int device) {
   if (const char* e = getenv("ERNET_HOST_GATHER")) h->host_gather = atoi(e) != 0;
   if (const char* e = getenv("ERNET_TAIL_TILES")) h->tail_tiles = atoi(e) != 0;
   if (const char* e = getenv("ERNET_NVTX")) h->nvtx = atoi(e) != 0;
+  if (const char* e = getenv("ERNET_SMALL_BATCH_UNITS")) h->small_batch_units = atoi(e) != 0;
   if (const char* e = getenv("ERNET_EPI_SUSPEND")) {       // study switch, device-wide (tc_common.cuh)
     const unsigned int v = (unsigned int)atoi(e) & 3u;       // bit 0: block kernels' epilogue warps, bit 1: ACFF4 + head kernel
     cudaMemcpyToSymbol(tc::g_epi_suspend, &v, sizeof(v));

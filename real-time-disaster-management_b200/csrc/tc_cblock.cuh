@@ -426,6 +426,14 @@ inline int set_cblock_attr() {
 using CBlock1 = CCfg<2, 64, 69, 66, 3, 4, true, 1>;              // 26 KB of weights resident per CTA + 4 x 21 KB slots (one K step per unit)
 using CBlock2 = CCfg<8, 96, 33, 30, 2, 5, true, 1>;             // 154 KB of weights resident per CTA + 5 x 15 KB slots
 using CBlock3 = CCfg<12, 128, 15, 12, 2, 12, false, 9>;         // 12 x 10 KB slots (two units) + 9 x 10 KB weight bundles
+// Small batches (real-time use: one frame at a time, aider-predict.py / real-time-inference.py): ONE tile per CTA and unit, so
+// that an image's tiles spread over twice as many CTA pairs and the serial MMA chain of a launch halves (block 3 at batch 1:
+// both tiles of the image on one pair, 150 instead of 300 MMAs deep).  Same MMAs per output in the same order: bit-identical.
+// Used while all pair-units still fit one round (kSmallBatch2 / kSmallBatch3 images); beyond that the two-tile units win
+// (half the weight traffic per image).
+using CBlock2S = CCfg<8, 96, 33, 30, 1, 5, true, 1>;
+using CBlock3S = CCfg<12, 128, 15, 12, 1, 12, false, 9>;
+constexpr int kSmallBatch2 = 18, kSmallBatch3 = 74;
 // Squeeze_RedConv: ACFF2 without the pool (conv_red2 sits between it and pool2), ACFF3 on 48 input channels
 using CBlock2R = CCfg<8, 96, 33, 30, 2, 5, true, 1, /*POOL*/ false>;
 using CBlock3R = CCfg<6, 128, 15, 12, 2, 9, false, 9>;
