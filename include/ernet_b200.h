@@ -22,7 +22,7 @@
  * defaults are the fast paths): ERNET_TAIL_TILES=0 block 1 on 16x8 tiles only (no tail unit), ERNET_FP32_TC=0 fp32
  * engine with the FFMA 1x1 kernels instead of the split-TF32 tcgen05 GEMMs, ERNET_FUSE_INGEST=1, ERNET_HOST_GATHER=1
  * (+ ERNET_GATHER_CTAS=n), ERNET_PAIR_TAPS=0, ERNET_PAIR_BLOCK1=1, ERNET_DUAL_COPY=1, ERNET_TRIM_COLUMNS=1, ERNET_EPI_SUSPEND=0
- * (polling instead of suspending epilogue waits), ERNET_NVTX=1 (an NVTX range per stage launch).  Results are bit-identical across all of them except ERNET_FP32_TC (fp32 rounding
+ * (polling instead of suspending epilogue waits), ERNET_SMALL_BATCH_UNITS=0 (two-tile pair-kernel units at every batch size), ERNET_NVTX=1 (an NVTX range per stage launch).  Results are bit-identical across all of them except ERNET_FP32_TC (fp32 rounding
  * level) - tests/test_gpu_parity.py cross-checks each.
  */
 #ifndef ERNET_B200_H_
