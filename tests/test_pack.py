@@ -147,3 +147,58 @@ def test_int8_operand_images(arch):
         assert out[PT.T_TC_RED2_WIMG][0].shape == (1, 12, 64, 8) and np.all(out[PT.T_TC_RED2_BIAS][0][48:] == 0)
     with pytest.raises(ValueError):
         PT.derive_tc_int8(sd, arch, scales[:2])
+
+
+# ------------------------------------------------------------------------------------ numerics of the fp32 engine's splits
+def _tf32_trunc(a):
+    """What tcgen05 kind::tf32 reads of an fp32 operand: the top 19 bits (sign, exponent, 10 mantissa bits)."""
+    return (np.asarray(a, np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def test_split_tf32_product_is_fp32_accurate():
+    """csrc/tc_pw32.cuh: v = hi + lo with hi = v & 0xFFFFE000 (exactly a TF32 number) and lo = v - hi (exact in fp32);
+    a.b ~= a_lo.b_hi + a_hi.b_lo + a_hi.b_hi drops only lo x lo.  Emulated with the operand truncation of the tensor core:
+    a K = 288 dot product of trained-like values agrees with the fp64 result to fp32 rounding level (a single TF32 MMA
+    does not: ~1e-3), which is what lets the fp32 engine keep the 1e-4 logit bound of north_star."""
+    rs = np.random.RandomState(5)
+    a = (rs.standard_normal((64, 288)) * np.exp(rs.uniform(-3, 3, (64, 288)))).astype(np.float32)
+    b = (rs.standard_normal((288, 32)) * 0.05).astype(np.float32)
+    a_hi = _tf32_trunc(a); a_lo = (a - a_hi).astype(np.float32)
+    b_hi = _tf32_trunc(b); b_lo = (b - b_hi).astype(np.float32)
+    assert np.array_equal(a_hi.astype(np.float64) + a_lo.astype(np.float64), a.astype(np.float64))       # the split is exact
+    t = lambda x: _tf32_trunc(x).astype(np.float64)                                                       # noqa: E731
+    three = t(a_lo) @ t(b_hi) + t(a_hi) @ t(b_lo) + t(a_hi) @ t(b_hi)
+    one = t(a) @ t(b)
+    ref = a.astype(np.float64) @ b.astype(np.float64)
+    scale = (np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64))                                 # sum of |terms|
+    assert (np.abs(three - ref) / scale).max() <= 2.0 ** -19
+    assert (np.abs(one - ref) / scale).max() >= 2.0 ** -13                                                # why one MMA is not enough
+
+
+@pytest.mark.parametrize("arch", fixtures.ARCHS)
+def test_split_fp16_stem_weights_are_fp32_accurate(arch):
+    """csrc/ingest_fast.cuh (fp32 engine, 5-tap frames): conv1 runs on mma.sync from the uint8 pixels (exact in fp16) against
+    two fp16 weight images, w' = hi + lo / 2^16 with hi = fp16(w'), lo = fp16((w' - hi) * 2^16), ToTensor + Normalize folded
+    into w' and the bias.  Emulated in numpy on the real conv1 (+conv_red1) weights: every folded weight is represented to
+    2^-21 relative (weights below the fp16 normal range: 2^-35 absolute), and conv1 of uint8 windows agrees with the reference's normalise-then-convolve to fp32 rounding level."""
+    sd = fixtures.get_state_dict(arch, "shipped")
+    w = np.asarray(sd["conv1.weight"], np.float64)                       # (16, 3, 3, 3) OIHW
+    bias = np.asarray(sd["conv1.bias"], np.float64) if "conv1.bias" in sd else np.zeros(w.shape[0])
+    if arch == "squeeze-redconv":                                        # conv_red1 (1x1, no nonlinearity in between) folds in
+        r = np.asarray(sd["conv_red1.weight"], np.float64)[:, :, 0, 0]   # (8, 16)
+        bias = r @ bias + np.asarray(sd["conv_red1.bias"], np.float64)
+        w = np.einsum("oc,cikl->oikl", r, w)
+    mean, std = np.array([0.485, 0.456, 0.406]), np.array([0.229, 0.224, 0.225])
+    wf = w / (255.0 * std)[None, :, None, None]                          # folded weights
+    bf = bias - (w * (mean / std)[None, :, None, None]).sum((1, 2, 3))
+    hi = wf.astype(np.float32).astype(np.float16)
+    lo = ((wf - hi.astype(np.float64)) * 65536.0).astype(np.float32).astype(np.float16)
+    rec = hi.astype(np.float64) + lo.astype(np.float64) / 65536.0
+    # 2^-21 relative; below the fp16 normal range (2^-14) hi is subnormal and the error is bounded absolutely instead
+    assert (np.abs(rec - wf) <= 2.0 ** -21 * np.maximum(np.abs(wf), 2.0 ** -14)).all()
+    rs = np.random.RandomState(9)
+    px = rs.randint(0, 256, (500, 3, 3, 3)).astype(np.float64)           # 500 uint8 windows (C, ky, kx)
+    got = np.einsum("ockl,nckl->no", rec, px) + bf
+    x = (px / 255.0 - mean[None, :, None, None]) / std[None, :, None, None]
+    ref = np.einsum("ockl,nckl->no", w, x) + bias
+    assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
