@@ -202,3 +202,29 @@ def test_split_fp16_stem_weights_are_fp32_accurate(arch):
     x = (px / 255.0 - mean[None, :, None, None]) / std[None, :, None, None]
     ref = np.einsum("ockl,nckl->no", w, x) + bias
     assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+def test_pool_first_epilogue_is_exact():
+    """csrc/tc_pw32.cuh epilogue: the 2x2 max runs on the RAW accumulators and bias / LeakyReLU / BN on the pooled quarter.
+    max commutes with a non-decreasing map; for channels with a negative BN scale the packer negates the weight column
+    (accumulator = -acc, exactly) and the epilogue multiplies the pooled value by -1 again.  In fp32, same operation
+    order as the kernel: bit-identical to activate-then-pool, including zero and negative scales and ties."""
+    rs = np.random.RandomState(11)
+    acc = (rs.standard_normal((4, 8, 8, 32)) * 30).astype(np.float32)
+    acc[0, :2, :2, :] = acc[0, 0, 0, :]                                   # a window of ties
+    bias = rs.standard_normal(32).astype(np.float32)
+    s = rs.standard_normal(32).astype(np.float32)
+    s[3] = 0.0
+    t = rs.standard_normal(32).astype(np.float32)
+
+    def act(z):                                                            # bias added by the caller; LeakyReLU(0.01) then BN affine
+        z = np.maximum(z, np.float32(0.01) * z)
+        return z * s + t                                                   # numpy: mul then add, both rounded - same for both orders
+
+    def pool(x):
+        return np.maximum(np.maximum(x[:, 0::2, 0::2], x[:, 0::2, 1::2]), np.maximum(x[:, 1::2, 0::2], x[:, 1::2, 1::2]))
+
+    want = pool(act(acc + bias))
+    sgn = np.where(s < 0, np.float32(-1), np.float32(1))
+    got = act(pool(acc * sgn) * sgn + bias)                                # acc * sgn = what the negated weight column accumulates
+    assert np.array_equal(got, want)
