@@ -678,6 +678,29 @@ def test_block1_tail_unit_is_bit_identical(arch, prec, dev, monkeypatch):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_small_batch_units_are_bit_identical(prec, dev, monkeypatch):
+    """Small batches run blocks 2 and 3 with ONE tile per CTA and unit (CBlock2S up to 18 images, CBlock3S up to 74: an
+    image's tiles spread over twice as many CTA pairs, the MMA chain of a launch halves - single-frame latency).  Same MMAs
+    per output in the same order: logits equal the two-tile units bit for bit on both sides of both thresholds, eagerly and
+    through the captured CUDA graph."""
+    sd = fixtures.get_state_dict("squeeze-ernet", "shipped")
+    frames = torch.from_numpy(np.concatenate([fixtures.noise_frames(40, seed=81), fixtures.smooth_frames(35, seed=82)], 0)).to(dev)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("ERNET_SMALL_BATCH_UNITS", mode)
+        m = rtdm_b200.from_state_dict("squeeze-ernet", sd, dev, prec)
+        res = [m.forward_frames(frames[:B], return_logits=True)[1].clone() for B in (1, 2, 18, 19, 74, 75)]
+        runner = m.graph_frames(frames[:1].clone())
+        res.append(runner().clone())
+        out[mode] = res
+    for a, b in zip(out["0"], out["1"]):
+        assert torch.equal(a, b)
+    assert torch.equal(out["1"][5][:18], out["1"][2])                      # and across batch sizes
+    assert _lib.load().ernet_check_watchdog() == 0
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("arch,prec", [("squeeze-ernet", "bf16"), ("squeeze-redconv", "fp16"), ("squeeze-ernet", "fp32"),
                                        ("squeeze-redconv", "fp32")])
 def test_fast_ingest_matches_table_lookup_kernel(arch, prec, dev):
